@@ -1,0 +1,166 @@
+/*
+ * tensorf_b200.h — C ABI of the B200-native tensorf-jax hot path (libtensorf_b200.so).
+ *
+ * The reference (brentyi/tensorf-jax) is pure Python/JAX and has no FFI of its own; the
+ * entry points below are what a `jax.ffi` / XLA custom-call binding for its per-ray hot path
+ * binds (see INTEGRATION.md for the reference-side stub).  Each entry point cites the
+ * reference interface (file:line under /root/reference) it replaces.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  All pointers are DEVICE pointers unless stated; all
+ *    floating point is fp32, indices int32, camera ids uint32; arrays are dense row-major in
+ *    the reference's own layouts (factors channel-first: vector (3,C,G), matrix (3,C,G,G),
+ *    tensor_vm.py:129-138; flax Dense kernels (in,out), networks.py:57-117).
+ *  - The caller (XLA) owns every buffer.  Entry points never allocate, free or retain device
+ *    memory; scratch is a caller-provided workspace whose size `tensorf_render_workspace_bytes`
+ *    reports.  Result and workspace buffers may arrive uninitialised: gradient accumulators
+ *    are zeroed on-stream by the entry point.
+ *  - Work is only enqueued on the given stream (no device synchronisation, no host-blocking
+ *    waits), so calls are CUDA-graph capturable and re-entrant across devices/threads.
+ *  - Return value: 0 on success, negative `tensorf_status` on failure with a thread-local
+ *    message available from `tensorf_last_error()`.  Nothing aborts.
+ *  - Randomness stays in the host framework: the shared jitter/Gumbel vectors that
+ *    render.py:158-161, :375-379 and :461-469 draw with jax.random enter as input arrays.
+ */
+#ifndef TENSORF_B200_H_
+#define TENSORF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* tensorf_stream_t; /* cudaStream_t */
+
+enum tensorf_status {
+  TENSORF_OK = 0,
+  TENSORF_ERR_INVALID_ARGUMENT = -1,
+  TENSORF_ERR_CUDA = -2,
+  TENSORF_ERR_UNSUPPORTED = -3
+};
+
+/* render.py:18-23 (RenderMode) */
+enum tensorf_render_mode { TENSORF_MODE_RGB = 0, TENSORF_MODE_DIST_MEDIAN = 1, TENSORF_MODE_DIST_MEAN = 2 };
+
+/* MLP arithmetic: exact fp32 on CUDA cores, or tcgen05 tensor cores with split-bf16 operands. */
+enum tensorf_mlp_impl { TENSORF_MLP_AUTO = 0, TENSORF_MLP_SIMT_FP32 = 1, TENSORF_MLP_TCGEN05 = 2 };
+
+/* Static configuration of one render call: render.py:26-36 (RenderConfig), the static fields
+ * of networks.py:38-43 (FeatureMlp) and the array shapes render.py:105-113 receives. */
+typedef struct tensorf_render_desc {
+  int32_t R;           /* rays in this call */
+  int32_t N;           /* density_samples_per_ray */
+  int32_t K;           /* appearance_samples_per_ray, 1 <= K <= N */
+  int32_t G;           /* grid_dim */
+  int32_t cd;          /* density per-axis channels (density feature dim = 3*cd) */
+  int32_t ca;          /* appearance per-axis channels */
+  int32_t mode;        /* tensorf_render_mode */
+  int32_t contracted;  /* LearnableParams.scene_contraction */
+  int32_t squash;      /* feature_squash_dim (27) */
+  int32_t units;       /* 128 */
+  int32_t feat_freqs;  /* feature_n_freqs */
+  int32_t view_freqs;  /* viewdir_n_freqs */
+  int32_t num_cameras; /* 0 = no camera embeddings */
+  int32_t mlp_impl;    /* tensorf_mlp_impl */
+  float loss_scale;    /* 1/(3*R_global): training.py:140 is a mean over the WHOLE batch */
+  int32_t reserved;
+} tensorf_render_desc;
+
+/* Leaves of render.py:39-46 (LearnableParams), reference layouts. `embed` may be NULL when
+ * num_cameras == 0.  For gradients the same struct is used with writable buffers. */
+typedef struct tensorf_params {
+  float* density_vector;    /* (3, cd, G) */
+  float* density_matrix;    /* (3, cd, G, G) */
+  float* appearance_vector; /* (3, ca, G) */
+  float* appearance_matrix; /* (3, ca, G, G) */
+  float* w0;                /* Dense_0.kernel (3*ca, squash), no bias */
+  float* w1;                /* Dense_1.kernel (enc, units) */
+  float* b1;                /* Dense_1.bias (units) */
+  float* w2;                /* Dense_2.kernel (units, units) */
+  float* b2;                /* Dense_2.bias (units) */
+  float* w3;                /* Dense_3.kernel (units, 3) */
+  float* b3;                /* Dense_3.bias (3) */
+  float* embed;             /* Embed_0.embedding (num_cameras, units) or NULL */
+} tensorf_params;
+
+/* cameras.py:10-20 (Rays3D) + the arrays render_rays derives from its key and config. */
+typedef struct tensorf_render_inputs {
+  const float* origins;           /* (R,3) */
+  const float* directions;        /* (R,3) */
+  const uint32_t* camera_indices; /* (R,) ; may be NULL when num_cameras == 0 */
+  const float* aabb;              /* (2,3) */
+  const float* jitter;            /* bounded: (N,) shared by all rays; contracted: (R,N) */
+  const float* gumbel;            /* (N,) shared by all rays; RGB mode only */
+  const float* base_ts;           /* contracted only: (N,) constant schedule, render.py:130-151 */
+  const float* deltas;            /* contracted only: (N,) step sizes, render.py:154-155 */
+  const float* colors;            /* (R,3) or NULL; when given the MSE loss is fused */
+} tensorf_render_inputs;
+
+const char* tensorf_last_error(void);
+int tensorf_version(void);
+
+/* ---- factor layout (kernel-native texel-major copy of the channel-first factors) -------- */
+/* Number of floats of the packed copy of one TensorVM: [3][G][Cp] lines then [3][G][G][Cp]
+ * planes, Cp = C rounded up to a multiple of 4. */
+int64_t tensorf_vm_packed_floats(int C, int G);
+/* tensor_vm.py:129-138 layout -> packed. */
+int tensorf_vm_pack(tensorf_stream_t s, const float* vector, const float* matrix, float* packed, int C, int G);
+/* packed gradient -> (3,C,G) / (3,C,G,G) gradient buffers (overwrites). */
+int tensorf_vm_unpack(tensorf_stream_t s, const float* packed, float* vector, float* matrix, int C, int G);
+
+/* ---- tensor_vm.py:42-89 TensorVM.interpolate ---------------------------------------------- */
+/* ijk (3,B) in [-1,1] -> out (3C,B) (feature_major=0, the reference's layout) or (B,3C)
+ * (feature_major=1, the (M,3ca) row layout render.py:484-486 builds). */
+int tensorf_vm_interp_fwd(tensorf_stream_t s, const float* packed, const float* ijk, float* out, int C, int G, int64_t B,
+                          int feature_major);
+/* Reverse mode w.r.t. the factors: d_out has out's layout; d_packed (+=) must be zeroed by
+ * the caller (or hold a running sum). */
+int tensorf_vm_interp_bwd(tensorf_stream_t s, const float* packed, const float* ijk, const float* d_out, float* d_packed,
+                          int C, int G, int64_t B, int feature_major);
+
+/* ---- render.py:461-469 selection stage (test entry point) -------------------------------- */
+/* idx (R,K) = indices of the K largest g per row, ties -> lower index, emitted in ASCENDING
+ * index order (the order is not observable through render_rays). g (R,N). */
+int tensorf_topk_select(tensorf_stream_t s, const float* g, int R, int N, int K, int32_t* idx);
+
+/* ---- networks.py:46-121 FeatureMlp.__call__ ----------------------------------------------- */
+/* features (M, 3*ca); viewdirs (M/rows_per_ray, 3); camera_indices (M/rows_per_ray); rgb (M,3).
+ * workspace: tensorf_mlp_workspace_bytes. */
+int64_t tensorf_mlp_workspace_bytes(const tensorf_render_desc* d, int64_t M);
+int tensorf_mlp_fwd(tensorf_stream_t s, const tensorf_render_desc* d, const tensorf_params* p, const float* features,
+                    const float* viewdirs, const uint32_t* camera_indices, int64_t M, int rows_per_ray, void* workspace,
+                    float* rgb);
+/* rgb = the forward output, d_rgb (M,3) -> d_features (M,3*ca) and the MLP leaves of `grads`
+ * (overwritten). Must follow tensorf_mlp_fwd on the same workspace. */
+int tensorf_mlp_bwd(tensorf_stream_t s, const tensorf_render_desc* d, const tensorf_params* p, const float* features,
+                    const float* viewdirs, const uint32_t* camera_indices, int64_t M, int rows_per_ray, void* workspace,
+                    const float* rgb, const float* d_rgb, float* d_features, const tensorf_params* grads);
+
+/* ---- render.py:105-279 render_rays --------------------------------------------------------- */
+int tensorf_render_workspace_bytes(const tensorf_render_desc* d, int64_t* bytes);
+/* mode RGB: rgb (R,3).  If inputs->colors != NULL, *loss (device scalar, overwritten) receives
+ * loss_scale * sum((rgb-colors)^2) (training.py:140) and the loss cotangent is kept in the
+ * workspace for tensorf_render_rgb_bwd(d_rgb = NULL). */
+int tensorf_render_rgb_fwd(tensorf_stream_t s, const tensorf_render_desc* d, const tensorf_params* p,
+                           const tensorf_render_inputs* in, void* workspace, float* rgb, float* loss);
+/* Reverse mode of render_rays w.r.t. every leaf of LearnableParams (what
+ * training.py:153-156 `jax.value_and_grad` asks for).  d_rgb (R,3) or NULL (= use the fused
+ * loss cotangent).  All leaves of `grads` are overwritten.  Must follow the forward call on the
+ * same workspace. */
+int tensorf_render_rgb_bwd(tensorf_stream_t s, const tensorf_render_desc* d, const tensorf_params* p,
+                           const tensorf_render_inputs* in, void* workspace, const float* d_rgb,
+                           const tensorf_params* grads);
+/* modes DIST_MEDIAN / DIST_MEAN (render.py:248-276): depth (R,). Only the density factors of
+ * `p` are read. */
+int tensorf_render_depth(tensorf_stream_t s, const tensorf_render_desc* d, const tensorf_params* p,
+                         const tensorf_render_inputs* in, void* workspace, float* depth);
+
+/* Debug/test views into the workspace after tensorf_render_rgb_fwd (device pointers). */
+int tensorf_render_workspace_view(const tensorf_render_desc* d, void* workspace, const char* name, void** ptr,
+                                  int64_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TENSORF_B200_H_ */

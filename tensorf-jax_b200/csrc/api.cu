@@ -1,0 +1,372 @@
+// extern "C" entry points of libtensorf_b200.so (see include/tensorf_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "mlp.cuh"
+#include "render_kernels.cuh"
+
+namespace tf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static inline int64_t al(int64_t floats) { return round_up64(floats, 64); }  // 256-byte granules
+
+struct RenderWs {
+  float *packed_d, *packed_a, *gpacked_d, *gpacked_a;
+  float *z, *dz, *pt_sel, *stats, *feat, *d_feat, *rgb_sel, *d_rgb_sel, *go;
+  int32_t* idx;
+  float* mlp_base;
+  int64_t total_floats;
+};
+
+static RenderWs carve(const tensorf_render_desc& d, float* base) {
+  RenderWs w{};
+  const int64_t R = d.R, N = d.N, K = d.K, M = R * K;
+  const MlpShape ms = mlp_shape(d);
+  int64_t off = 0;
+  auto take = [&](int64_t n) {
+    float* p = base ? base + off : nullptr;
+    off += al(n);
+    return p;
+  };
+  w.packed_d = take(packed_floats(d.cd, d.G));
+  w.packed_a = take(packed_floats(d.ca, d.G));
+  w.gpacked_d = take(packed_floats(d.cd, d.G));
+  w.gpacked_a = take(packed_floats(d.ca, d.G));
+  w.z = take(R * N);
+  w.dz = take(R * N);
+  w.idx = reinterpret_cast<int32_t*>(take(M));
+  w.pt_sel = take(M);
+  w.stats = take(R * 8);
+  w.go = take(R * 3);
+  w.feat = take(M * ms.Ca);
+  w.d_feat = take(M * ms.Ca);
+  w.rgb_sel = take(M * 3);
+  w.d_rgb_sel = take(M * 3);
+  w.mlp_base = take(mlp_ws_floats(ms, M));
+  w.total_floats = off;
+  return w;
+}
+
+static int check_desc(const tensorf_render_desc* d) {
+  TF_CHECK_ARG(d != nullptr, "desc is NULL");
+  TF_CHECK_ARG(d->R >= 0 && d->N >= 1 && d->G >= 2, "bad shape R=%d N=%d G=%d", d->R, d->N, d->G);
+  TF_CHECK_ARG(d->cd >= 1 && d->ca >= 1, "bad channel dims cd=%d ca=%d", d->cd, d->ca);
+  TF_CHECK_ARG(d->mode >= TENSORF_MODE_RGB && d->mode <= TENSORF_MODE_DIST_MEAN, "bad render mode %d", d->mode);
+  if (d->mode == TENSORF_MODE_RGB) {
+    TF_CHECK_ARG(d->K >= 1 && d->K <= d->N, "appearance_samples_per_ray=%d must be in [1, %d]", d->K, d->N);
+    if (d->units != 128) {
+      set_error("FeatureMlp units=%d unsupported (128 only)", d->units);
+      return TENSORF_ERR_UNSUPPORTED;
+    }
+    TF_CHECK_ARG(d->squash >= 1 && d->squash <= 32, "feature_squash_dim=%d must be in [1,32]", d->squash);
+    TF_CHECK_ARG(d->feat_freqs >= 0 && d->view_freqs >= 0 && d->num_cameras >= 0, "bad MLP config");
+    TF_CHECK_ARG((int64_t)d->R * d->K < (int64_t)1 << 31, "R*K too large");
+  }
+  TF_CHECK_ARG((int64_t)d->R * d->N < (int64_t)1 << 31, "R*N too large");
+  return 0;
+}
+
+static int check_inputs(const tensorf_render_desc* d, const tensorf_render_inputs* in) {
+  TF_CHECK_ARG(in != nullptr, "inputs is NULL");
+  TF_CHECK_ARG(in->origins && in->directions && in->aabb && in->jitter, "origins/directions/aabb/jitter must be non-NULL");
+  if (d->contracted) TF_CHECK_ARG(in->base_ts && in->deltas, "contracted scene needs base_ts and deltas");
+  if (d->mode == TENSORF_MODE_RGB) {
+    TF_CHECK_ARG(in->gumbel != nullptr, "RGB mode needs the gumbel vector");
+    if (d->num_cameras > 0) TF_CHECK_ARG(in->camera_indices != nullptr, "camera embeddings need camera_indices");
+  }
+  return 0;
+}
+
+static void fill_scene(SceneArgs& a, const tensorf_render_desc& d, const tensorf_render_inputs& in) {
+  a.origins = in.origins;
+  a.directions = in.directions;
+  a.aabb = in.aabb;
+  a.jitter = in.jitter;
+  a.base_ts = in.base_ts;
+  a.deltas = in.deltas;
+  a.R = d.R;
+  a.N = d.N;
+  a.K = d.K;
+  a.G = d.G;
+  a.contracted = d.contracted;
+}
+
+static MlpParams mlp_params(const tensorf_params& p) {
+  return MlpParams{p.w0, p.w1, p.b1, p.w2, p.b2, p.w3, p.b3, p.embed};
+}
+static MlpGrads mlp_grads(const tensorf_params& p) { return MlpGrads{p.w0, p.w1, p.b1, p.w2, p.b2, p.w3, p.b3, p.embed}; }
+
+static int check_mlp_params(const tensorf_render_desc& d, const tensorf_params* p, const char* what) {
+  TF_CHECK_ARG(p != nullptr, "%s is NULL", what);
+  TF_CHECK_ARG(p->w0 && p->w1 && p->b1 && p->w2 && p->b2 && p->w3 && p->b3, "%s: MLP leaves must be non-NULL", what);
+  if (d.num_cameras > 0) TF_CHECK_ARG(p->embed != nullptr, "%s: embed must be non-NULL with camera embeddings", what);
+  return 0;
+}
+
+}  // namespace tf
+
+using namespace tf;
+
+extern "C" {
+
+const char* tensorf_last_error(void) { return g_err; }
+int tensorf_version(void) { return 100; }
+
+int64_t tensorf_vm_packed_floats(int C, int G) { return packed_floats(C, G); }
+
+int tensorf_vm_pack(tensorf_stream_t s, const float* vector, const float* matrix, float* packed, int C, int G) {
+  TF_CHECK_ARG(vector && matrix && packed, "NULL buffer");
+  TF_CHECK_ARG(C >= 1 && G >= 2, "bad C=%d G=%d", C, G);
+  return vm_pack((cudaStream_t)s, vector, matrix, packed, C, G);
+}
+int tensorf_vm_unpack(tensorf_stream_t s, const float* packed, float* vector, float* matrix, int C, int G) {
+  TF_CHECK_ARG(vector && matrix && packed, "NULL buffer");
+  TF_CHECK_ARG(C >= 1 && G >= 2, "bad C=%d G=%d", C, G);
+  return vm_unpack((cudaStream_t)s, packed, vector, matrix, C, G);
+}
+
+int tensorf_vm_interp_fwd(tensorf_stream_t s, const float* packed, const float* ijk, float* out, int C, int G, int64_t B,
+                          int feature_major) {
+  TF_CHECK_ARG(B >= 0 && C >= 1 && G >= 2, "bad shape C=%d G=%d B=%lld", C, G, (long long)B);
+  TF_CHECK_ARG(B == 0 || (packed && ijk && out), "NULL buffer");
+  return vm_interp_fwd((cudaStream_t)s, packed, ijk, out, C, G, B, feature_major);
+}
+int tensorf_vm_interp_bwd(tensorf_stream_t s, const float* packed, const float* ijk, const float* d_out, float* d_packed,
+                          int C, int G, int64_t B, int feature_major) {
+  TF_CHECK_ARG(B >= 0 && C >= 1 && G >= 2, "bad shape C=%d G=%d B=%lld", C, G, (long long)B);
+  TF_CHECK_ARG(B == 0 || (packed && ijk && d_out && d_packed), "NULL buffer");
+  return vm_interp_bwd((cudaStream_t)s, packed, ijk, d_out, d_packed, C, G, B, feature_major);
+}
+
+int tensorf_topk_select(tensorf_stream_t s, const float* g, int R, int N, int K, int32_t* idx) {
+  TF_CHECK_ARG(R >= 0 && N >= 1 && K >= 1 && K <= N, "bad shape R=%d N=%d K=%d (need 1 <= K <= N)", R, N, K);
+  TF_CHECK_ARG(R == 0 || (g && idx), "NULL buffer");
+  return launch_topk_select((cudaStream_t)s, g, R, N, K, idx);
+}
+
+int64_t tensorf_mlp_workspace_bytes(const tensorf_render_desc* d, int64_t M) {
+  if (!d || M < 0) return -1;
+  return (int64_t)sizeof(float) * mlp_ws_floats(mlp_shape(*d), M);
+}
+
+int tensorf_mlp_fwd(tensorf_stream_t s, const tensorf_render_desc* d, const tensorf_params* p, const float* features,
+                    const float* viewdirs, const uint32_t* camera_indices, int64_t M, int rows_per_ray, void* workspace,
+                    float* rgb) {
+  TF_CHECK_ARG(d != nullptr, "desc is NULL");
+  if (d->units != 128) {
+    set_error("FeatureMlp units=%d unsupported (128 only)", d->units);
+    return TENSORF_ERR_UNSUPPORTED;
+  }
+  TF_CHECK_ARG(d->squash >= 1 && d->squash <= 32 && d->ca >= 1, "bad MLP config");
+  TF_CHECK_ARG(M >= 0 && rows_per_ray >= 1 && M % rows_per_ray == 0, "M=%lld must be a multiple of rows_per_ray=%d",
+               (long long)M, rows_per_ray);
+  TF_RETURN_IF_ERROR(check_mlp_params(*d, p, "params"));
+  TF_CHECK_ARG(M == 0 || (features && viewdirs && workspace && rgb), "NULL buffer");
+  if (d->num_cameras > 0) TF_CHECK_ARG(M == 0 || camera_indices, "camera embeddings need camera_indices");
+  MlpShape ms = mlp_shape(*d);
+  MlpWs ws = mlp_ws_carve(ms, M, (float*)workspace);
+  return mlp_simt_fwd((cudaStream_t)s, ms, mlp_params(*p), features, viewdirs, camera_indices, M, rows_per_ray, ws, rgb);
+}
+
+int tensorf_mlp_bwd(tensorf_stream_t s, const tensorf_render_desc* d, const tensorf_params* p, const float* features,
+                    const float* viewdirs, const uint32_t* camera_indices, int64_t M, int rows_per_ray, void* workspace,
+                    const float* rgb, const float* d_rgb, float* d_features, const tensorf_params* grads) {
+  TF_CHECK_ARG(d != nullptr, "desc is NULL");
+  if (d->units != 128) {
+    set_error("FeatureMlp units=%d unsupported (128 only)", d->units);
+    return TENSORF_ERR_UNSUPPORTED;
+  }
+  TF_CHECK_ARG(M >= 0 && rows_per_ray >= 1 && M % rows_per_ray == 0, "M=%lld must be a multiple of rows_per_ray=%d",
+               (long long)M, rows_per_ray);
+  TF_RETURN_IF_ERROR(check_mlp_params(*d, p, "params"));
+  TF_RETURN_IF_ERROR(check_mlp_params(*d, grads, "grads"));
+  TF_CHECK_ARG(M == 0 || (features && viewdirs && workspace && rgb && d_rgb && d_features), "NULL buffer");
+  MlpShape ms = mlp_shape(*d);
+  MlpWs ws = mlp_ws_carve(ms, M, (float*)workspace);
+  return mlp_simt_bwd((cudaStream_t)s, ms, mlp_params(*p), features, viewdirs, camera_indices, M, rows_per_ray, ws, rgb,
+                      d_rgb, d_features, mlp_grads(*grads));
+}
+
+int tensorf_render_workspace_bytes(const tensorf_render_desc* d, int64_t* bytes) {
+  TF_RETURN_IF_ERROR(check_desc(d));
+  TF_CHECK_ARG(bytes != nullptr, "bytes is NULL");
+  tensorf_render_desc dd = *d;
+  if (dd.mode != TENSORF_MODE_RGB) dd.K = 1;
+  *bytes = carve(dd, nullptr).total_floats * (int64_t)sizeof(float);
+  return 0;
+}
+
+int tensorf_render_workspace_view(const tensorf_render_desc* d, void* workspace, const char* name, void** ptr,
+                                  int64_t* count) {
+  TF_RETURN_IF_ERROR(check_desc(d));
+  TF_CHECK_ARG(workspace && name && ptr && count, "NULL argument");
+  RenderWs w = carve(*d, (float*)workspace);
+  const int64_t R = d->R, N = d->N, M = R * d->K, Ca = 3 * d->ca;
+  struct { const char* n; void* p; int64_t c; } views[] = {
+      {"z", w.z, R * N},           {"dz", w.dz, R * N},          {"idx", w.idx, M},
+      {"pt_sel", w.pt_sel, M},     {"stats", w.stats, R * 8},    {"feat", w.feat, M * Ca},
+      {"d_feat", w.d_feat, M * Ca}, {"rgb_sel", w.rgb_sel, M * 3}, {"d_rgb_sel", w.d_rgb_sel, M * 3},
+      {"go", w.go, R * 3},         {"packed_d", w.packed_d, packed_floats(d->cd, d->G)},
+      {"packed_a", w.packed_a, packed_floats(d->ca, d->G)},
+  };
+  for (auto& v : views)
+    if (strcmp(v.n, name) == 0) {
+      *ptr = v.p;
+      *count = v.c;
+      return 0;
+    }
+  set_error("unknown workspace view '%s'", name);
+  return TENSORF_ERR_INVALID_ARGUMENT;
+}
+
+int tensorf_render_depth(tensorf_stream_t s, const tensorf_render_desc* d, const tensorf_params* p,
+                         const tensorf_render_inputs* in, void* workspace, float* depth) {
+  TF_RETURN_IF_ERROR(check_desc(d));
+  TF_CHECK_ARG(d->mode == TENSORF_MODE_DIST_MEDIAN || d->mode == TENSORF_MODE_DIST_MEAN, "render_depth needs a DIST_* mode");
+  TF_RETURN_IF_ERROR(check_inputs(d, in));
+  TF_CHECK_ARG(p && p->density_vector && p->density_matrix, "density factors must be non-NULL");
+  TF_CHECK_ARG(workspace && (depth || d->R == 0), "NULL buffer");
+  cudaStream_t st = (cudaStream_t)s;
+  tensorf_render_desc dd = *d;
+  dd.K = 1;
+  RenderWs w = carve(dd, (float*)workspace);
+  TF_RETURN_IF_ERROR(vm_pack(st, p->density_vector, p->density_matrix, w.packed_d, d->cd, d->G));
+  DensityArgs a{};
+  fill_scene(a, dd, *in);
+  a.packed_d = w.packed_d;
+  a.gumbel = nullptr;
+  a.Cp = packed_cp(d->cd);
+  a.mode = d->mode;
+  a.z_out = w.z;
+  a.depth_out = depth;
+  return launch_density_select(st, a);
+}
+
+int tensorf_render_rgb_fwd(tensorf_stream_t s, const tensorf_render_desc* d, const tensorf_params* p,
+                           const tensorf_render_inputs* in, void* workspace, float* rgb, float* loss) {
+  TF_RETURN_IF_ERROR(check_desc(d));
+  TF_CHECK_ARG(d->mode == TENSORF_MODE_RGB, "render_rgb_fwd needs mode RGB");
+  TF_RETURN_IF_ERROR(check_inputs(d, in));
+  TF_RETURN_IF_ERROR(check_mlp_params(*d, p, "params"));
+  TF_CHECK_ARG(p->density_vector && p->density_matrix && p->appearance_vector && p->appearance_matrix,
+               "factor leaves must be non-NULL");
+  TF_CHECK_ARG(workspace && (rgb || d->R == 0), "NULL buffer");
+  TF_CHECK_ARG(!in->colors || loss, "loss must be non-NULL when colors are given");
+  cudaStream_t st = (cudaStream_t)s;
+  RenderWs w = carve(*d, (float*)workspace);
+  const MlpShape ms = mlp_shape(*d);
+  const int64_t M = (int64_t)d->R * d->K;
+
+  TF_RETURN_IF_ERROR(vm_pack(st, p->density_vector, p->density_matrix, w.packed_d, d->cd, d->G));
+  TF_RETURN_IF_ERROR(vm_pack(st, p->appearance_vector, p->appearance_matrix, w.packed_a, d->ca, d->G));
+
+  DensityArgs a{};
+  fill_scene(a, *d, *in);
+  a.packed_d = w.packed_d;
+  a.gumbel = in->gumbel;
+  a.Cp = packed_cp(d->cd);
+  a.mode = d->mode;
+  a.z_out = w.z;
+  a.idx_out = w.idx;
+  a.pt_sel_out = w.pt_sel;
+  a.stats_out = w.stats;
+  TF_RETURN_IF_ERROR(launch_density_select(st, a));
+
+  AppearanceArgs ap{};
+  fill_scene(ap, *d, *in);
+  ap.packed_a = w.packed_a;
+  ap.idx = w.idx;
+  ap.C = d->ca;
+  ap.Cp = packed_cp(d->ca);
+  ap.M = M;
+  ap.feat = w.feat;
+  TF_RETURN_IF_ERROR(launch_appearance(st, ap, false));
+
+  MlpWs mws = mlp_ws_carve(ms, M, w.mlp_base);
+  TF_RETURN_IF_ERROR(
+      mlp_simt_fwd(st, ms, mlp_params(*p), w.feat, in->directions, in->camera_indices, M, d->K, mws, w.rgb_sel));
+
+  if (in->colors) TF_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  CompositeArgs c{};
+  c.rgb_sel = w.rgb_sel;
+  c.pt_sel = w.pt_sel;
+  c.stats = w.stats;
+  c.colors = in->colors;
+  c.rgb_out = rgb;
+  c.go = w.go;
+  c.loss = loss;
+  c.loss_scale = d->loss_scale;
+  c.R = d->R;
+  c.K = d->K;
+  return launch_composite_fwd(st, c);
+}
+
+int tensorf_render_rgb_bwd(tensorf_stream_t s, const tensorf_render_desc* d, const tensorf_params* p,
+                           const tensorf_render_inputs* in, void* workspace, const float* d_rgb,
+                           const tensorf_params* grads) {
+  TF_RETURN_IF_ERROR(check_desc(d));
+  TF_CHECK_ARG(d->mode == TENSORF_MODE_RGB, "render_rgb_bwd needs mode RGB");
+  TF_RETURN_IF_ERROR(check_inputs(d, in));
+  TF_RETURN_IF_ERROR(check_mlp_params(*d, p, "params"));
+  TF_RETURN_IF_ERROR(check_mlp_params(*d, grads, "grads"));
+  TF_CHECK_ARG(grads->density_vector && grads->density_matrix && grads->appearance_vector && grads->appearance_matrix,
+               "factor gradient leaves must be non-NULL");
+  TF_CHECK_ARG(workspace != nullptr, "workspace is NULL");
+  TF_CHECK_ARG(d_rgb || in->colors, "either d_rgb or inputs->colors (fused loss) is required");
+  cudaStream_t st = (cudaStream_t)s;
+  RenderWs w = carve(*d, (float*)workspace);
+  const MlpShape ms = mlp_shape(*d);
+  const int64_t M = (int64_t)d->R * d->K;
+
+  RayBwdArgs rb{};
+  fill_scene(rb, *d, *in);
+  rb.z = w.z;
+  rb.idx = w.idx;
+  rb.pt_sel = w.pt_sel;
+  rb.rgb_sel = w.rgb_sel;
+  rb.stats = w.stats;
+  rb.go = d_rgb ? d_rgb : w.go;
+  rb.d_rgb_sel = w.d_rgb_sel;
+  rb.dz = w.dz;
+  TF_RETURN_IF_ERROR(launch_ray_bwd(st, rb));
+
+  TF_CHECK_CUDA(cudaMemsetAsync(w.gpacked_d, 0, sizeof(float) * packed_floats(d->cd, d->G), st));
+  TF_CHECK_CUDA(cudaMemsetAsync(w.gpacked_a, 0, sizeof(float) * packed_floats(d->ca, d->G), st));
+
+  DensityBwdArgs db{};
+  fill_scene(db, *d, *in);
+  db.packed_d = w.packed_d;
+  db.dz = w.dz;
+  db.d_packed = w.gpacked_d;
+  db.Cp = packed_cp(d->cd);
+  TF_RETURN_IF_ERROR(launch_density_scatter(st, db));
+
+  MlpWs mws = mlp_ws_carve(ms, M, w.mlp_base);
+  TF_RETURN_IF_ERROR(mlp_simt_bwd(st, ms, mlp_params(*p), w.feat, in->directions, in->camera_indices, M, d->K, mws,
+                                  w.rgb_sel, w.d_rgb_sel, w.d_feat, mlp_grads(*grads)));
+
+  AppearanceArgs ap{};
+  fill_scene(ap, *d, *in);
+  ap.packed_a = w.packed_a;
+  ap.idx = w.idx;
+  ap.C = d->ca;
+  ap.Cp = packed_cp(d->ca);
+  ap.M = M;
+  ap.d_feat = w.d_feat;
+  ap.d_packed = w.gpacked_a;
+  TF_RETURN_IF_ERROR(launch_appearance(st, ap, true));
+
+  TF_RETURN_IF_ERROR(vm_unpack(st, w.gpacked_d, grads->density_vector, grads->density_matrix, d->cd, d->G));
+  TF_RETURN_IF_ERROR(vm_unpack(st, w.gpacked_a, grads->appearance_vector, grads->appearance_matrix, d->ca, d->G));
+  return 0;
+}
+
+}  // extern "C"

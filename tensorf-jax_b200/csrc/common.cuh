@@ -1,0 +1,78 @@
+// Shared host/device helpers for libtensorf_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/tensorf_b200.h"
+
+namespace tf {
+
+void set_error(const char* fmt, ...);  // thread-local message, api.cu
+
+#define TF_CHECK_ARG(cond, ...)            \
+  do {                                     \
+    if (!(cond)) {                         \
+      tf::set_error(__VA_ARGS__);          \
+      return TENSORF_ERR_INVALID_ARGUMENT; \
+    }                                      \
+  } while (0)
+
+#define TF_CHECK_CUDA(expr)                                                               \
+  do {                                                                                    \
+    cudaError_t e_ = (expr);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      tf::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return TENSORF_ERR_CUDA;                                                            \
+    }                                                                                     \
+  } while (0)
+
+// Launch errors are collected right after enqueue; no device synchronisation.
+#define TF_CHECK_LAUNCH() TF_CHECK_CUDA(cudaGetLastError())
+
+#define TF_RETURN_IF_ERROR(expr) \
+  do {                           \
+    int rc_ = (expr);            \
+    if (rc_ != 0) return rc_;    \
+  } while (0)
+
+constexpr int kSMs = 148;
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+__host__ __device__ inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- packed ("texel-major") factor layout --------------------------------------------------
+// lines  : [3][G][Cp]       at float offset 0
+// planes : [3][G][G][Cp]    at float offset 3*G*Cp
+// Cp = C rounded up to a multiple of 4 so that one texel is a whole number of float4.
+__host__ __device__ inline int packed_cp(int C) { return (C + 3) & ~3; }
+__host__ __device__ inline int64_t packed_line_floats(int C, int G) { return (int64_t)3 * G * packed_cp(C); }
+__host__ __device__ inline int64_t packed_plane_floats(int C, int G) { return (int64_t)3 * G * G * packed_cp(C); }
+__host__ __device__ inline int64_t packed_floats(int C, int G) { return packed_line_floats(C, G) + packed_plane_floats(C, G); }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// Vector reduction to global memory (PTX ISA 8.1+, sm_90+): one 16-byte RED per texel fragment.
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_incl_scan(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+#endif
+
+}  // namespace tf

@@ -1,0 +1,435 @@
+// FeatureMlp on CUDA cores in true fp32 (networks.py:38-121).  This is the exact-arithmetic
+// path (what the JAX CPU oracle computes) and the on-device reference for the tcgen05 path.
+#include <algorithm>
+
+#include "mlp.cuh"
+
+namespace tf {
+
+int64_t mlp_ws_floats(const MlpShape& s, int64_t M) {
+  int64_t Mp = round_up64(M, 128);
+  return Mp * ((int64_t)2 * round_up(s.squash, 4) + 2 * round_up(s.enc, 4) + 4 * s.units);
+}
+MlpWs mlp_ws_carve(const MlpShape& s, int64_t M, float* base) {
+  int64_t Mp = round_up64(M, 128);
+  MlpWs w;
+  float* p = base;
+  w.f = p;   p += Mp * round_up(s.squash, 4);
+  w.df = p;  p += Mp * round_up(s.squash, 4);
+  w.x = p;   p += Mp * round_up(s.enc, 4);
+  w.dx = p;  p += Mp * round_up(s.enc, 4);
+  w.h1 = p;  p += Mp * s.units;
+  w.h2 = p;  p += Mp * s.units;
+  w.dp2 = p; p += Mp * s.units;
+  w.dp1 = p; p += Mp * s.units;
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic strided SGEMM: C(m,n) = epilogue( sum_k A(m,k) * B(k,n) )
+// ---------------------------------------------------------------------------------------------
+struct GemmArgs {
+  const float* A; int64_t sam, sak;
+  const float* B; int64_t sbk, sbn;
+  float* C; int64_t ldc;
+  const float* bias;                  // per column or null
+  const float* mask; int64_t ldmask;  // keep C(m,n) only where mask(m,n) > 0, or null
+  int64_t M, N, K;
+  int64_t k_chunk;  // split-K chunk (gridDim.z chunks); atomic accumulate when gridDim.z > 1
+  int relu;
+};
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(256) k_sgemm(GemmArgs g) {
+  constexpr int BK = 16;
+  constexpr int NTX = BN / TN;  // threads along n
+  static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int t = threadIdx.x;
+  const int tx = t % NTX, ty = t / NTX;
+  const int64_t m0 = (int64_t)blockIdx.x * BM, n0 = (int64_t)blockIdx.y * BN;
+  const int64_t kbeg = (int64_t)blockIdx.z * g.k_chunk;
+  const int64_t kend = min(g.K, kbeg + g.k_chunk);
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  constexpr int A_PER = BM * BK / 256, B_PER = (BN * BK + 255) / 256;
+  const bool a_kc = (g.sak == 1), b_nc = (g.sbn == 1);
+
+  for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+    float ra[A_PER], rb[B_PER];
+#pragma unroll
+    for (int i = 0; i < A_PER; ++i) {
+      int e = t + 256 * i, mm, kk;
+      if (a_kc) { kk = e % BK; mm = e / BK; } else { mm = e % BM; kk = e / BM; }
+      int64_t m = m0 + mm, k = k0 + kk;
+      ra[i] = (m < g.M && k < kend) ? g.A[m * g.sam + k * g.sak] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < B_PER; ++i) {
+      int e = t + 256 * i, nn, kk;
+      if (b_nc) { nn = e % BN; kk = e / BN; } else { kk = e % BK; nn = e / BK; }
+      int64_t n = n0 + nn, k = k0 + kk;
+      rb[i] = (e < BN * BK && n < g.N && k < kend) ? g.B[k * g.sbk + n * g.sbn] : 0.f;
+    }
+    __syncthreads();  // previous tile fully consumed
+#pragma unroll
+    for (int i = 0; i < A_PER; ++i) {
+      int e = t + 256 * i, mm, kk;
+      if (a_kc) { kk = e % BK; mm = e / BK; } else { mm = e % BM; kk = e / BM; }
+      As[kk][mm] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < B_PER; ++i) {
+      int e = t + 256 * i, nn, kk;
+      if (b_nc) { nn = e % BN; kk = e / BN; } else { kk = e % BK; nn = e / BK; }
+      if (e < BN * BK) Bs[kk][nn] = rb[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int h = 0; h < TM / 4; ++h) {
+        float4 v = *reinterpret_cast<const float4*>(&As[kk][h * (BM / 2) + ty * 4]);
+        a[4 * h + 0] = v.x; a[4 * h + 1] = v.y; a[4 * h + 2] = v.z; a[4 * h + 3] = v.w;
+      }
+#pragma unroll
+      for (int h = 0; h < TN / 4; ++h) {
+        float4 v = *reinterpret_cast<const float4*>(&Bs[kk][h * (BN / 2) + tx * 4]);
+        b[4 * h + 0] = v.x; b[4 * h + 1] = v.y; b[4 * h + 2] = v.z; b[4 * h + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+  }
+
+  const bool atomic = gridDim.z > 1;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int64_t m = m0 + (i / 4) * (BM / 2) + ty * 4 + (i % 4);
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int64_t n = n0 + (j / 4) * (BN / 2) + tx * 4 + (j % 4);
+      if (n >= g.N) continue;
+      float v = acc[i][j];
+      if (g.bias) v += g.bias[n];
+      if (g.relu) v = fmaxf(v, 0.f);
+      if (g.mask && !(g.mask[m * g.ldmask + n] > 0.f)) v = 0.f;
+      if (atomic)
+        atomicAdd(&g.C[m * g.ldc + n], v);
+      else
+        g.C[m * g.ldc + n] = v;
+    }
+  }
+}
+
+// TM == 4 / TN == 4 use a single half: rows ty*4.. (BM/2 offset unused). Guard the layout.
+template <int BM, int BN, int TM, int TN>
+static int launch_sgemm(cudaStream_t st, GemmArgs g, int splits) {
+  static_assert((TM == 8 || BM / TM * 4 == BM) && (TN == 8 || BN / TN * 4 == BN), "tile layout");
+  if (g.M == 0 || g.N == 0) return 0;
+  splits = max(1, splits);
+  g.k_chunk = round_up64(ceil_div64(g.K, splits), 16);
+  int z = (int)ceil_div64(g.K, g.k_chunk);
+  dim3 grid((unsigned)ceil_div64(g.M, BM), (unsigned)ceil_div64(g.N, BN), (unsigned)z);
+  k_sgemm<BM, BN, TM, TN><<<grid, 256, 0, st>>>(g);
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fourier encoding (networks.py:13-35, :68-76)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_encode_fwd(const float* __restrict__ f, const float* __restrict__ viewdirs,
+                                                    float* __restrict__ x, int64_t M, int rows_per_ray, MlpShape s) {
+  const int D = s.squash + 3;
+  int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= M * D) return;
+  int64_t m = item / D;
+  int d = (int)(item % D);
+  float* row = x + m * s.enc;
+  float val;
+  int F, off;
+  if (d < s.squash) {
+    val = f[m * s.squash + d];
+    F = s.Ff;
+    off = D + d * 2 * s.Ff;
+  } else {
+    val = viewdirs[(m / rows_per_ray) * 3 + (d - s.squash)];
+    F = s.Fv;
+    off = D + s.squash * 2 * s.Ff + (d - s.squash) * 2 * s.Fv;
+  }
+  row[d] = val;
+  const float half_pi = 1.57079632679489661923f;
+  float scale = 1.0f;
+  for (int j = 0; j < F; ++j) {
+    float in = val * scale;  // exact: power-of-two scaling
+    row[off + j] = sinf(in);
+    row[off + F + j] = sinf(__fadd_rn(in, half_pi));
+    scale *= 2.0f;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_encode_bwd(const float* __restrict__ f, const float* __restrict__ dx,
+                                                    float* __restrict__ df, int64_t M, MlpShape s) {
+  int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= M * s.squash) return;
+  int64_t m = item / s.squash;
+  int d = (int)(item % s.squash);
+  const float* row = dx + m * s.enc;
+  float val = f[m * s.squash + d];
+  float g = row[d];
+  int off = s.squash + 3 + d * 2 * s.Ff;
+  const float half_pi = 1.57079632679489661923f;
+  float scale = 1.0f;
+  for (int j = 0; j < s.Ff; ++j) {
+    float in = val * scale;
+    g += scale * (row[off + j] * cosf(in) + row[off + s.Ff + j] * cosf(__fadd_rn(in, half_pi)));
+    scale *= 2.0f;
+  }
+  df[item] = g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Output layer: FiLM (networks.py:103-111) + Dense 3 + sigmoid (:114-120). One warp per row,
+// lane owns hidden units 4*lane..4*lane+3 (units == 128).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_out_fwd(const float* __restrict__ h2, const float* __restrict__ w3,
+                                                 const float* __restrict__ b3, const float* __restrict__ embed,
+                                                 const uint32_t* __restrict__ cams, float* __restrict__ rgb, int64_t M,
+                                                 int rows_per_ray) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float w[4][3];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) w[j][c] = w3[(4 * lane + j) * 3 + c];
+  for (int64_t m = warp; m < M; m += nwarps) {
+    float4 h = *reinterpret_cast<const float4*>(h2 + m * 128 + 4 * lane);
+    float hv[4] = {h.x, h.y, h.z, h.w};
+    if (embed != nullptr && lane >= 16) {
+      const float* em = embed + (int64_t)cams[m / rows_per_ray] * 128;
+      float4 sc = *reinterpret_cast<const float4*>(em + 4 * lane - 64);
+      float4 sh = *reinterpret_cast<const float4*>(em + 4 * lane);
+      hv[0] = __fadd_rn(__fmul_rn(sc.x, hv[0]), sh.x);
+      hv[1] = __fadd_rn(__fmul_rn(sc.y, hv[1]), sh.y);
+      hv[2] = __fadd_rn(__fmul_rn(sc.z, hv[2]), sh.z);
+      hv[3] = __fadd_rn(__fmul_rn(sc.w, hv[3]), sh.w);
+    }
+    float o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float a = hv[0] * w[0][c];
+      a = fmaf(hv[1], w[1][c], a);
+      a = fmaf(hv[2], w[2][c], a);
+      a = fmaf(hv[3], w[3][c], a);
+      o[c] = warp_sum(a);
+    }
+    if (lane < 3) {
+      float y = (lane == 0 ? o[0] : (lane == 1 ? o[1] : o[2])) + b3[lane];
+      rgb[3 * m + lane] = 1.0f / (1.0f + expf(-y));
+    }
+  }
+}
+
+// Reverse of the output layer. Each warp walks a contiguous chunk of rows, keeps the dW3 / db3 /
+// dEmbed partial sums in registers and flushes them with atomics (embedding rows are flushed
+// whenever the camera index changes: consecutive rows of one ray share the camera).
+__global__ void __launch_bounds__(256) k_out_bwd(const float* __restrict__ h2, const float* __restrict__ w3,
+                                                 const float* __restrict__ embed, const uint32_t* __restrict__ cams,
+                                                 const float* __restrict__ rgb, const float* __restrict__ d_rgb,
+                                                 float* __restrict__ dp2, float* __restrict__ dw3, float* __restrict__ db3,
+                                                 float* __restrict__ dembed, int64_t M, int rows_per_ray, int64_t chunk) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t mbeg = warp * chunk, mend = min(M, mbeg + chunk);
+  if (mbeg >= M) return;
+  float w[4][3], gw[4][3];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      w[j][c] = w3[(4 * lane + j) * 3 + c];
+      gw[j][c] = 0.f;
+    }
+  float gb[3] = {0.f, 0.f, 0.f};
+  float gsc[4] = {0.f, 0.f, 0.f, 0.f}, gsh[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool film = embed != nullptr;
+  int64_t cur_cam = -1;
+  auto flush_embed = [&]() {
+    if (film && cur_cam >= 0 && lane >= 16) {
+      float* de = dembed + cur_cam * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(de + 4 * lane - 64 + j, gsc[j]);
+        atomicAdd(de + 4 * lane + j, gsh[j]);
+        gsc[j] = 0.f;
+        gsh[j] = 0.f;
+      }
+    }
+  };
+  for (int64_t m = mbeg; m < mend; ++m) {
+    float4 h = *reinterpret_cast<const float4*>(h2 + m * 128 + 4 * lane);
+    float hv[4] = {h.x, h.y, h.z, h.w};   // pre-FiLM (post-relu)
+    float hf[4] = {h.x, h.y, h.z, h.w};   // post-FiLM
+    float sc[4] = {1.f, 1.f, 1.f, 1.f};
+    if (film) {
+      int64_t cam = cams[m / rows_per_ray];
+      if (cam != cur_cam) {
+        flush_embed();
+        cur_cam = cam;
+      }
+      if (lane >= 16) {
+        const float* em = embed + cam * 128;
+        float4 s4 = *reinterpret_cast<const float4*>(em + 4 * lane - 64);
+        float4 t4 = *reinterpret_cast<const float4*>(em + 4 * lane);
+        sc[0] = s4.x; sc[1] = s4.y; sc[2] = s4.z; sc[3] = s4.w;
+        hf[0] = __fadd_rn(__fmul_rn(s4.x, hv[0]), t4.x);
+        hf[1] = __fadd_rn(__fmul_rn(s4.y, hv[1]), t4.y);
+        hf[2] = __fadd_rn(__fmul_rn(s4.z, hv[2]), t4.z);
+        hf[3] = __fadd_rn(__fmul_rn(s4.w, hv[3]), t4.w);
+      }
+    }
+    float dy[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float y = rgb[3 * m + c];
+      dy[c] = d_rgb[3 * m + c] * y * (1.0f - y);
+      gb[c] += dy[c];
+    }
+    float dh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      dh[j] = dy[0] * w[j][0] + dy[1] * w[j][1] + dy[2] * w[j][2];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gw[j][c] = fmaf(hf[j], dy[c], gw[j][c]);
+    }
+    if (film && lane >= 16) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        gsc[j] = fmaf(dh[j], hv[j], gsc[j]);
+        gsh[j] += dh[j];
+        dh[j] *= sc[j];
+      }
+    }
+    float4 o;
+    o.x = hv[0] > 0.f ? dh[0] : 0.f;
+    o.y = hv[1] > 0.f ? dh[1] : 0.f;
+    o.z = hv[2] > 0.f ? dh[2] : 0.f;
+    o.w = hv[3] > 0.f ? dh[3] : 0.f;
+    *reinterpret_cast<float4*>(dp2 + m * 128 + 4 * lane) = o;
+  }
+  flush_embed();
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) atomicAdd(&dw3[(4 * lane + j) * 3 + c], gw[j][c]);
+  if (lane == 0) {
+    atomicAdd(&db3[0], gb[0]);
+    atomicAdd(&db3[1], gb[1]);
+    atomicAdd(&db3[2], gb[2]);
+  }
+}
+
+// Column sums (bias gradients): out[n] += sum_m G[m][n], n < 128.
+__global__ void __launch_bounds__(256) k_colsum128(const float* __restrict__ G, float* __restrict__ out, int64_t M,
+                                                   int64_t chunk) {
+  __shared__ float part[128];
+  const int n = threadIdx.x & 127, half = threadIdx.x >> 7;
+  int64_t mbeg = (int64_t)blockIdx.x * chunk, mend = min(M, mbeg + chunk);
+  float a = 0.f;
+  for (int64_t m = mbeg + half; m < mend; m += 2) a += G[m * 128 + n];
+  if (half == 1) part[n] = a;
+  __syncthreads();
+  if (half == 0) atomicAdd(&out[n], a + part[n]);
+}
+
+// ---------------------------------------------------------------------------------------------
+int mlp_simt_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs,
+                 const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, float* rgb) {
+  if (M == 0) return 0;
+  GemmArgs g{};
+  // Dense_0: f = feat @ W0 (no bias)
+  g = GemmArgs{feat, s.Ca, 1, p.w0, s.squash, 1, ws.f, s.squash, nullptr, nullptr, 0, M, s.squash, s.Ca, 0, 0};
+  TF_RETURN_IF_ERROR((launch_sgemm<128, 32, 4, 4>(st, g, 1)));
+  k_encode_fwd<<<(unsigned)ceil_div64(M * (s.squash + 3), 256), 256, 0, st>>>(ws.f, viewdirs, ws.x, M, rows_per_ray, s);
+  TF_CHECK_LAUNCH();
+  // Dense_1 + relu
+  g = GemmArgs{ws.x, s.enc, 1, p.w1, s.units, 1, ws.h1, s.units, p.b1, nullptr, 0, M, s.units, s.enc, 0, 1};
+  TF_RETURN_IF_ERROR((launch_sgemm<128, 128, 8, 8>(st, g, 1)));
+  // Dense_2 + relu
+  g = GemmArgs{ws.h1, s.units, 1, p.w2, s.units, 1, ws.h2, s.units, p.b2, nullptr, 0, M, s.units, s.units, 0, 1};
+  TF_RETURN_IF_ERROR((launch_sgemm<128, 128, 8, 8>(st, g, 1)));
+  int64_t warps = std::min<int64_t>(M, (int64_t)kSMs * 64);
+  k_out_fwd<<<(unsigned)ceil_div64(warps * 32, 256), 256, 0, st>>>(ws.h2, p.w3, p.b3, s.ncam ? p.embed : nullptr, cams, rgb, M,
+                                                                    rows_per_ray);
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+
+int mlp_simt_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs,
+                 const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, const float* rgb, const float* d_rgb,
+                 float* d_feat, const MlpGrads& gr) {
+  const int U = s.units;
+  TF_CHECK_CUDA(cudaMemsetAsync(gr.w0, 0, sizeof(float) * s.Ca * s.squash, st));
+  TF_CHECK_CUDA(cudaMemsetAsync(gr.w1, 0, sizeof(float) * s.enc * U, st));
+  TF_CHECK_CUDA(cudaMemsetAsync(gr.b1, 0, sizeof(float) * U, st));
+  TF_CHECK_CUDA(cudaMemsetAsync(gr.w2, 0, sizeof(float) * U * U, st));
+  TF_CHECK_CUDA(cudaMemsetAsync(gr.b2, 0, sizeof(float) * U, st));
+  TF_CHECK_CUDA(cudaMemsetAsync(gr.w3, 0, sizeof(float) * U * 3, st));
+  TF_CHECK_CUDA(cudaMemsetAsync(gr.b3, 0, sizeof(float) * 3, st));
+  if (s.ncam) TF_CHECK_CUDA(cudaMemsetAsync(gr.embed, 0, sizeof(float) * (int64_t)s.ncam * U, st));
+  if (M == 0) return 0;
+  (void)viewdirs;
+
+  // output layer reverse: chunk = whole rays so the embedding flush is per ray group
+  int64_t chunk = std::max<int64_t>(rows_per_ray, 32);
+  chunk = ceil_div64(chunk, rows_per_ray) * rows_per_ray;
+  int64_t warps = ceil_div64(M, chunk);
+  k_out_bwd<<<(unsigned)ceil_div64(warps * 32, 256), 256, 0, st>>>(ws.h2, p.w3, s.ncam ? p.embed : nullptr, cams, rgb, d_rgb,
+                                                                    ws.dp2, gr.w3, gr.b3, gr.embed, M, rows_per_ray, chunk);
+  TF_CHECK_LAUNCH();
+
+  const int splits = (int)std::min<int64_t>(2 * kSMs, std::max<int64_t>(1, M / 256));
+  const int64_t cs_chunk = std::max<int64_t>(256, ceil_div64(M, 4 * kSMs));
+  GemmArgs g{};
+  // dW2 = h1^T dp2 ; db2
+  g = GemmArgs{ws.h1, 1, U, ws.dp2, U, 1, gr.w2, U, nullptr, nullptr, 0, U, U, M, 0, 0};
+  TF_RETURN_IF_ERROR((launch_sgemm<128, 128, 8, 8>(st, g, splits)));
+  k_colsum128<<<(unsigned)ceil_div64(M, cs_chunk), 256, 0, st>>>(ws.dp2, gr.b2, M, cs_chunk);
+  TF_CHECK_LAUNCH();
+  // dp1 = (dp2 @ W2^T) * (h1 > 0)
+  g = GemmArgs{ws.dp2, U, 1, p.w2, 1, U, ws.dp1, U, nullptr, ws.h1, U, M, U, U, 0, 0};
+  TF_RETURN_IF_ERROR((launch_sgemm<128, 128, 8, 8>(st, g, 1)));
+  // dW1 = x^T dp1 ; db1
+  g = GemmArgs{ws.x, 1, s.enc, ws.dp1, U, 1, gr.w1, U, nullptr, nullptr, 0, s.enc, U, M, 0, 0};
+  TF_RETURN_IF_ERROR((launch_sgemm<128, 128, 8, 8>(st, g, splits)));
+  k_colsum128<<<(unsigned)ceil_div64(M, cs_chunk), 256, 0, st>>>(ws.dp1, gr.b1, M, cs_chunk);
+  TF_CHECK_LAUNCH();
+  // dx = dp1 @ W1^T
+  g = GemmArgs{ws.dp1, U, 1, p.w1, 1, U, ws.dx, s.enc, nullptr, nullptr, 0, M, s.enc, U, 0, 0};
+  TF_RETURN_IF_ERROR((launch_sgemm<128, 128, 8, 8>(st, g, 1)));
+  // df through the Fourier features
+  k_encode_bwd<<<(unsigned)ceil_div64(M * s.squash, 256), 256, 0, st>>>(ws.f, ws.dx, ws.df, M, s);
+  TF_CHECK_LAUNCH();
+  // dW0 = feat^T df
+  g = GemmArgs{feat, 1, s.Ca, ws.df, s.squash, 1, gr.w0, s.squash, nullptr, nullptr, 0, s.Ca, s.squash, M, 0, 0};
+  TF_RETURN_IF_ERROR((launch_sgemm<128, 32, 4, 4>(st, g, splits)));
+  // d_feat = df @ W0^T
+  g = GemmArgs{ws.df, s.squash, 1, p.w0, 1, s.squash, d_feat, s.Ca, nullptr, nullptr, 0, M, s.Ca, s.squash, 0, 0};
+  TF_RETURN_IF_ERROR((launch_sgemm<128, 128, 8, 8>(st, g, 1)));
+  return 0;
+}
+
+}  // namespace tf

@@ -1,0 +1,573 @@
+// Per-ray kernels of render.py:105-279 / :437-549 and their reverse mode.
+//
+//   k_density_select   one warp per ray: sampling (AABB or L-inf contraction) -> fused VM
+//                      density gather (no (3cd,R,N) feature tensor) -> softplus -> prefix sum
+//                      / exp -> Gumbel top-k (radix select, ties -> lower index) -> depth modes
+//   k_appearance_gather  VM appearance lookup at the selected samples, rows (M, 3ca)
+//   k_composite_fwd    weighted RGB sum x unbias + white background (+ fused MSE loss)
+//   k_ray_bwd          reverse of composite + unbias + segment probabilities (suffix scan)
+//   k_density_scatter / k_appearance_scatter  re-gather + vector RED into packed gradients
+#include "render_kernels.cuh"
+#include "vm.cuh"
+
+namespace tf {
+
+// ---------------------------------------------------------------------------------------------
+// Warp-level radix select of the K largest keys, ties -> lower index.
+// keys: shared [N]; hist: shared int[256]. On return thr = key of the K-th largest element,
+// n_eq = how many elements equal to thr to take (in ascending index order).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_radix_select(const uint32_t* keys, int N, int K, int* hist, int lane, uint32_t& thr,
+                                                  int& n_eq) {
+  uint32_t prefix = 0, mask = 0;
+  int krem = K;
+#pragma unroll 1
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = lane; i < 256; i += 32) hist[i] = 0;
+    __syncwarp();
+    for (int s = lane; s < N; s += 32) {
+      uint32_t k = keys[s];
+      if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1);
+    }
+    __syncwarp();
+    int c[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      c[j] = hist[8 * lane + j];
+      tot += c[j];
+    }
+    int incl = tot;  // suffix sum over lanes: bins of higher lanes hold larger digits
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_down_sync(0xffffffffu, incl, o);
+      if (lane + o < 32) incl += t;
+    }
+    int a = incl - tot, digit = -1, nk = 0;
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+      if (digit < 0 && a < krem && a + c[j] >= krem) {
+        digit = 8 * lane + j;
+        nk = krem - a;
+      }
+      a += c[j];
+    }
+    unsigned found = __ballot_sync(0xffffffffu, digit >= 0);
+    int src = __ffs(found) - 1;
+    digit = __shfl_sync(0xffffffffu, digit, src);
+    krem = __shfl_sync(0xffffffffu, nk, src);
+    prefix |= (uint32_t)digit << shift;
+    mask |= 0xffu << shift;
+    __syncwarp();
+  }
+  thr = prefix;
+  n_eq = krem;
+}
+
+// Emit the selected indices in ascending order. F(pos, s).
+template <typename F>
+__device__ __forceinline__ void warp_emit_selected(const uint32_t* keys, int N, uint32_t thr, int n_eq, int lane, F emit) {
+  int pos = 0, eq_seen = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int base = 0; base < N; base += 32) {
+    int s = base + lane;
+    uint32_t k = (s < N) ? keys[s] : 0u;
+    bool gt = (s < N) && (k > thr);
+    bool eq = (s < N) && (k == thr);
+    unsigned eqb = __ballot_sync(0xffffffffu, eq);
+    bool take = gt || (eq && (eq_seen + __popc(eqb & lt) < n_eq));
+    unsigned tb = __ballot_sync(0xffffffffu, take);
+    if (take) emit(pos + __popc(tb & lt), s);
+    pos += __popc(tb);
+    eq_seen += __popc(eqb);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Segment probabilities for one 32-sample tile (render.py:300-347). Called with identical
+// arguments by the forward and the reverse kernel so both see bit-identical E / pt.
+// ---------------------------------------------------------------------------------------------
+struct SegTile {
+  float a, E, pt;
+};
+__device__ __forceinline__ SegTile seg_tile(float z, float delta, bool valid, int lane, float& carry_c, float& carry_E) {
+  SegTile o;
+  float sigma = softplus_f(z);
+  o.a = valid ? __fmul_rn(-sigma, delta) : 0.0f;  // neg_scaled_sigmas = -sigmas * step_sizes
+  float c = __fadd_rn(carry_c, warp_incl_scan(o.a, lane));
+  o.E = expf(c);  // p_exits
+  float Eprev = __shfl_up_sync(0xffffffffu, o.E, 1);
+  if (lane == 0) Eprev = carry_E;
+  o.pt = __fmul_rn(__fsub_rn(1.0f, expf(o.a)), Eprev);  // p_terminates
+  carry_c = __shfl_sync(0xffffffffu, c, 31);
+  carry_E = __shfl_sync(0xffffffffu, o.E, 31);
+  return o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_density_select
+// ---------------------------------------------------------------------------------------------
+template <int LPS>
+__device__ __forceinline__ float density_sample_sum(const float* __restrict__ packed, const VmTaps& taps, int G, int Cp,
+                                                    int sub) {
+  const int nvec = Cp >> 2;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int v = sub; v < nvec; v += LPS) {
+#pragma unroll
+    for (int P = 0; P < 3; ++P) {
+      PairAddr pa = pair_addr(taps, P, G, Cp, v);
+      float4 lin, bil;
+      pair_values(packed, pa, lin, bil);
+      acc.x = fmaf(lin.x, bil.x, acc.x);
+      acc.y = fmaf(lin.y, bil.y, acc.y);
+      acc.z = fmaf(lin.z, bil.z, acc.z);
+      acc.w = fmaf(lin.w, bil.w, acc.w);
+    }
+  }
+  return (acc.x + acc.y) + (acc.z + acc.w);
+}
+
+template <int LPS>
+__global__ void __launch_bounds__(128) k_density_select(DensityArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Npad = round_up(A.N, 32);
+  // per warp: float vals[Npad]; uint32 keys[Npad]; int hist[256]
+  unsigned char* wbase = smem_raw + (size_t)warp * ((size_t)Npad * 8 + 1024);
+  float* vals = reinterpret_cast<float*>(wbase);
+  uint32_t* keys = reinterpret_cast<uint32_t*>(wbase + (size_t)Npad * 4);
+  int* hist = reinterpret_cast<int*>(wbase + (size_t)Npad * 8);
+
+  const int r = blockIdx.x * 4 + warp;
+  if (r >= A.R) return;
+
+  SceneParams sc;
+  load_scene(sc, A.aabb, A.N, A.G, A.contracted, A.jitter, A.base_ts, A.deltas);
+  RayParams ray;
+  load_ray(ray, sc, A.origins, A.directions, A.aabb, r);
+
+  // ---- phase 1: density gather, LPS lanes per sample --------------------------------------
+  constexpr int SPI = 32 / LPS;
+  const int sub = lane % LPS, sl = lane / LPS;
+  for (int sbase = 0; sbase < A.N; sbase += SPI) {
+    int s = sbase + sl;
+    float acc = 0.f;
+    if (s < A.N) {
+      float delta;
+      float t = sample_t(ray, sc, r, s, delta);
+      float x[3];
+      sample_grid_coords(ray, sc, t, x);
+      VmTaps taps;
+      make_vm_taps(taps, x, A.G);
+      acc = density_sample_sum<LPS>(A.packed_d, taps, A.G, A.Cp, sub);
+    }
+#pragma unroll
+    for (int o = LPS >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (s < A.N && sub == 0) vals[s] = acc + 10.0f;  // render.py:207
+  }
+  __syncwarp();
+
+  // ---- phase 2: segment probabilities, Gumbel keys, depth accumulators ---------------------
+  float carry_c = 0.f, carry_E = 1.f;
+  float mean_acc = 0.f, med_acc = 0.f;
+  bool carry_mask = false;
+  for (int base = 0; base < A.N; base += 32) {
+    int s = base + lane;
+    bool valid = s < A.N;
+    float z = valid ? vals[s] : 0.f;
+    float delta = 0.f, t = 0.f;
+    if (valid) t = sample_t(ray, sc, r, s, delta);
+    SegTile sg = seg_tile(z, delta, valid, lane, carry_c, carry_E);
+    bool mask = __fsub_rn(1.0f, sg.E) > 0.5f;  // render.py:253-258
+    bool pmask = __shfl_up_sync(0xffffffffu, (int)mask, 1) != 0;
+    if (lane == 0) pmask = carry_mask;
+    carry_mask = __shfl_sync(0xffffffffu, (int)mask, 31) != 0;
+    if (valid) {
+      A.z_out[(int64_t)r * A.N + s] = z;
+      vals[s] = sg.pt;
+      if (A.mode == TENSORF_MODE_RGB) keys[s] = ordered_key(__fadd_rn(A.gumbel[s], logf(sg.pt)));
+      mean_acc = fmaf(sg.pt, t, mean_acc);         // render.py:271-276
+      if (s >= 1 && mask != pmask) med_acc += t;  // render.py:259-266 (where-semantics)
+    }
+  }
+  const float E_last = carry_E;
+  __syncwarp();
+
+  if (A.mode != TENSORF_MODE_RGB) {
+    float dlt;
+    float t_last = sample_t(ray, sc, r, A.N - 1, dlt);
+    float out;
+    if (A.mode == TENSORF_MODE_DIST_MEAN) {
+      out = warp_sum(mean_acc) + E_last * t_last;
+    } else {
+      out = warp_sum(med_acc);
+      if (!carry_mask) out += INFINITY;  // padded (True, inf) element
+    }
+    if (lane == 0) A.depth_out[r] = out;
+    return;
+  }
+
+  // ---- phase 3: Gumbel top-k (render.py:461-469) -------------------------------------------
+  uint32_t thr;
+  int n_eq;
+  warp_radix_select(keys, A.N, A.K, hist, lane, thr, n_eq);
+  float S = 0.f;
+  int32_t* idx_row = A.idx_out + (int64_t)r * A.K;
+  float* pt_row = A.pt_sel_out + (int64_t)r * A.K;
+  warp_emit_selected(keys, A.N, thr, n_eq, lane, [&](int pos, int s) {
+    float pt = vals[s];
+    idx_row[pos] = s;
+    pt_row[pos] = pt;
+    S += pt;
+  });
+  S = warp_sum(S);
+  if (lane == 0) {
+    A.stats_out[(int64_t)r * 8 + 0] = E_last;
+    A.stats_out[(int64_t)r * 8 + 1] = S;
+  }
+}
+
+int launch_density_select(cudaStream_t st, const DensityArgs& A) {
+  if (A.R == 0) return 0;
+  const int nvec = A.Cp / 4;
+  int lps = 1;
+  for (int p = 8; p >= 1; p >>= 1)
+    if (nvec % p == 0) {
+      lps = p;
+      break;
+    }
+  if (lps == 1 && nvec > 2) lps = nvec >= 8 ? 8 : 4;
+  const int Npad = round_up(A.N, 32);
+  size_t smem = 4 * ((size_t)Npad * 8 + 1024);
+  TF_CHECK_ARG(smem <= 200 * 1024, "density_samples_per_ray=%d too large for the per-ray kernel", A.N);
+  dim3 grid((A.R + 3) / 4), block(128);
+#define TF_LAUNCH_DS(L)                                                                                      \
+  do {                                                                                                       \
+    if (smem > 48 * 1024)                                                                                    \
+      TF_CHECK_CUDA(cudaFuncSetAttribute(k_density_select<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_density_select<L><<<grid, block, smem, st>>>(A);                                                       \
+  } while (0)
+  switch (lps) {
+    case 8: TF_LAUNCH_DS(8); break;
+    case 4: TF_LAUNCH_DS(4); break;
+    case 2: TF_LAUNCH_DS(2); break;
+    default: TF_LAUNCH_DS(1); break;
+  }
+#undef TF_LAUNCH_DS
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// standalone selection stage (test entry point)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_topk_select(const float* __restrict__ g, int R, int N, int K, int32_t* __restrict__ idx) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Npad = round_up(N, 32);
+  unsigned char* wbase = smem_raw + (size_t)warp * ((size_t)Npad * 4 + 1024);
+  uint32_t* keys = reinterpret_cast<uint32_t*>(wbase);
+  int* hist = reinterpret_cast<int*>(wbase + (size_t)Npad * 4);
+  const int r = blockIdx.x * 4 + warp;
+  if (r >= R) return;
+  for (int s = lane; s < N; s += 32) keys[s] = ordered_key(g[(int64_t)r * N + s]);
+  __syncwarp();
+  uint32_t thr;
+  int n_eq;
+  warp_radix_select(keys, N, K, hist, lane, thr, n_eq);
+  int32_t* row = idx + (int64_t)r * K;
+  warp_emit_selected(keys, N, thr, n_eq, lane, [&](int pos, int s) { row[pos] = s; });
+}
+
+int launch_topk_select(cudaStream_t st, const float* g, int R, int N, int K, int32_t* idx) {
+  if (R == 0) return 0;
+  size_t smem = 4 * ((size_t)round_up(N, 32) * 4 + 1024);
+  TF_CHECK_ARG(smem <= 200 * 1024, "N=%d too large for the selection kernel", N);
+  if (smem > 48 * 1024)
+    TF_CHECK_CUDA(cudaFuncSetAttribute(k_topk_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_topk_select<<<(R + 3) / 4, 128, smem, st>>>(g, R, N, K, idx);
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// appearance gather / scatter at the selected samples (render.py:472-486)
+// work item = (row m, float4 channel group v)
+// ---------------------------------------------------------------------------------------------
+template <bool BWD>
+__global__ void __launch_bounds__(256) k_appearance(AppearanceArgs A) {
+  const int nvec = A.Cp >> 2;
+  int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= A.M * nvec) return;
+  int64_t m = item / nvec;
+  int v = (int)(item % nvec);
+  int r = (int)(m / A.K);
+  int s = A.idx[m];
+  SceneParams sc;
+  load_scene(sc, A.aabb, A.N, A.G, A.contracted, A.jitter, A.base_ts, A.deltas);
+  RayParams ray;
+  load_ray(ray, sc, A.origins, A.directions, A.aabb, r);
+  float delta;
+  float t = sample_t(ray, sc, r, s, delta);
+  float x[3];
+  sample_grid_coords(ray, sc, t, x);
+  VmTaps taps;
+  make_vm_taps(taps, x, A.G);
+  const int Ca = 3 * A.C;
+#pragma unroll
+  for (int P = 0; P < 3; ++P) {
+    PairAddr pa = pair_addr(taps, P, A.G, A.Cp, v);
+    float4 lin, bil;
+    pair_values(A.packed_a, pa, lin, bil);
+    int c0 = 4 * v;
+    if (!BWD) {
+      float4 f = f4_mul(lin, bil);
+      float* dst = A.feat + m * Ca + P * A.C + c0;
+      if ((A.C & 3) == 0) {
+        *reinterpret_cast<float4*>(dst) = f;
+      } else {
+        float fv[4] = {f.x, f.y, f.z, f.w};
+        for (int j = 0; j < 4; ++j)
+          if (c0 + j < A.C) dst[j] = fv[j];
+      }
+    } else {
+      const float* src = A.d_feat + m * Ca + P * A.C + c0;
+      float4 g;
+      if ((A.C & 3) == 0) {
+        g = *reinterpret_cast<const float4*>(src);
+      } else {
+        float gv[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < 4; ++j)
+          if (c0 + j < A.C) gv[j] = src[j];
+        g = make_float4(gv[0], gv[1], gv[2], gv[3]);
+      }
+      float4 gl = f4_mul(g, bil), gb = f4_mul(g, lin);
+      red_add_v4(A.d_packed + pa.l0, f4_scale(gl, pa.wl0));
+      red_add_v4(A.d_packed + pa.l1, f4_scale(gl, pa.wl1));
+      red_add_v4(A.d_packed + pa.m00, f4_scale(gb, pa.w00));
+      red_add_v4(A.d_packed + pa.m01, f4_scale(gb, pa.w01));
+      red_add_v4(A.d_packed + pa.m10, f4_scale(gb, pa.w10));
+      red_add_v4(A.d_packed + pa.m11, f4_scale(gb, pa.w11));
+    }
+  }
+}
+
+int launch_appearance(cudaStream_t st, const AppearanceArgs& A, bool bwd) {
+  if (A.M == 0) return 0;
+  int64_t items = A.M * (A.Cp / 4);
+  unsigned grid = (unsigned)ceil_div64(items, 256);
+  if (bwd)
+    k_appearance<true><<<grid, 256, 0, st>>>(A);
+  else
+    k_appearance<false><<<grid, 256, 0, st>>>(A);
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// composite (render.py:233-246, :529-546) + fused MSE (training.py:140)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_composite_fwd(CompositeArgs A) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = blockIdx.x * 4 + warp;
+  __shared__ float loss_part[4];
+  float sq = 0.f;
+  if (r < A.R) {
+    float W[3] = {0.f, 0.f, 0.f};
+    for (int k = lane; k < A.K; k += 32) {
+      int64_t m = (int64_t)r * A.K + k;
+      float pt = A.pt_sel[m];
+      W[0] = fmaf(A.rgb_sel[3 * m + 0], pt, W[0]);
+      W[1] = fmaf(A.rgb_sel[3 * m + 1], pt, W[1]);
+      W[2] = fmaf(A.rgb_sel[3 * m + 2], pt, W[2]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) W[c] = warp_sum(W[c]);
+    float* st = A.stats + (int64_t)r * 8;
+    float E_last = st[0], S = st[1];
+    float u = __fdiv_rn(__fadd_rn(__fsub_rn(1.0f, E_last), 1e-8f), __fadd_rn(S, 1e-8f));
+    if (lane < 3) {
+      float w = lane == 0 ? W[0] : (lane == 1 ? W[1] : W[2]);
+      float rgb = __fadd_rn(__fmul_rn(w, u), E_last);
+      A.rgb_out[3 * r + lane] = rgb;
+      st[4 + lane] = w;
+      if (A.colors) {
+        float diff = rgb - A.colors[3 * r + lane];
+        A.go[3 * r + lane] = 2.0f * diff * A.loss_scale;
+        sq = diff * diff;
+      }
+    }
+    if (lane == 3) st[2] = u;
+  }
+  if (A.colors) {
+    sq = warp_sum(sq);
+    if (lane == 0) loss_part[warp] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(A.loss, (loss_part[0] + loss_part[1] + loss_part[2] + loss_part[3]) * A.loss_scale);
+  }
+}
+
+int launch_composite_fwd(cudaStream_t st, const CompositeArgs& A) {
+  if (A.R == 0) return 0;
+  k_composite_fwd<<<(A.R + 3) / 4, 128, 0, st>>>(A);
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_ray_bwd: reverse of composite/unbias/segment probabilities
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_ray_bwd(RayBwdArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Npad = round_up(A.N, 32);
+  float* gE_s = reinterpret_cast<float*>(smem_raw) + (size_t)warp * 2 * Npad;  // gpt_s * E_s
+  float* q_s = gE_s + Npad;                                                    // gpt_s, then gpt_s * pt_s
+  const int r = blockIdx.x * 4 + warp;
+  if (r >= A.R) return;
+
+  SceneParams sc;
+  load_scene(sc, A.aabb, A.N, A.G, A.contracted, A.jitter, A.base_ts, A.deltas);
+  RayParams ray;
+  load_ray(ray, sc, A.origins, A.directions, A.aabb, r);
+
+  const float* st = A.stats + (int64_t)r * 8;
+  const float E_last = st[0], S = st[1];
+  const float Wc[3] = {st[4], st[5], st[6]};
+  const float go[3] = {A.go[3 * r + 0], A.go[3 * r + 1], A.go[3 * r + 2]};
+  const float Au = __fadd_rn(__fsub_rn(1.0f, E_last), 1e-8f), Bu = __fadd_rn(S, 1e-8f);
+  const float u = __fdiv_rn(Au, Bu);
+  const float AoB2 = Au / (Bu * Bu);
+
+  for (int s = lane; s < Npad; s += 32) q_s[s] = 0.f;
+  __syncwarp();
+  for (int k = lane; k < A.K; k += 32) {
+    int64_t m = (int64_t)r * A.K + k;
+    float pt = A.pt_sel[m];
+    float gpt = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float ck = A.rgb_sel[3 * m + c];
+      A.d_rgb_sel[3 * m + c] = go[c] * u * pt;
+      gpt += go[c] * (u * ck - Wc[c] * AoB2);
+    }
+    q_s[A.idx[m]] = gpt;
+  }
+  float gE = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) gE += go[c] * (1.0f - Wc[c] / Bu);
+  __syncwarp();
+
+  // forward recompute of E_s, pt_s (bit-identical to k_density_select)
+  float carry_c = 0.f, carry_E = 1.f;
+  for (int base = 0; base < A.N; base += 32) {
+    int s = base + lane;
+    bool valid = s < A.N;
+    float z = valid ? A.z[(int64_t)r * A.N + s] : 0.f;
+    float delta = 0.f;
+    if (valid) (void)sample_t(ray, sc, r, s, delta);
+    SegTile sg = seg_tile(z, delta, valid, lane, carry_c, carry_E);
+    if (valid) {
+      float gpt = q_s[s];
+      gE_s[s] = gpt * sg.E;
+      q_s[s] = gpt * sg.pt;
+    }
+  }
+  __syncwarp();
+
+  // reverse pass: dL/da_j = -gpt_j E_j + sum_{s>j} gpt_s pt_s + gE E_last
+  float carry_suf = 0.f;
+  const float tail = gE * E_last;
+  for (int base = Npad - 32; base >= 0; base -= 32) {
+    int s = base + lane;
+    bool valid = s < A.N;
+    float q = valid ? q_s[s] : 0.f;
+    float incl = q;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float t = __shfl_down_sync(0xffffffffu, incl, o);
+      if (lane + o < 32) incl += t;
+    }
+    float excl = incl - q + carry_suf;
+    carry_suf += __shfl_sync(0xffffffffu, incl, 0);
+    if (valid) {
+      float z = A.z[(int64_t)r * A.N + s];
+      float delta;
+      (void)sample_t(ray, sc, r, s, delta);
+      float da = -gE_s[s] + excl + tail;
+      float sigma = softplus_f(z);
+      A.dz[(int64_t)r * A.N + s] = da * (-delta) * expf(z - sigma);
+    }
+  }
+}
+
+int launch_ray_bwd(cudaStream_t st, const RayBwdArgs& A) {
+  if (A.R == 0) return 0;
+  size_t smem = 4 * (size_t)2 * round_up(A.N, 32) * sizeof(float);
+  if (smem > 48 * 1024) TF_CHECK_CUDA(cudaFuncSetAttribute(k_ray_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_ray_bwd<<<(A.R + 3) / 4, 128, smem, st>>>(A);
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// density scatter: every density channel of a sample receives the same upstream scalar dz.
+// ---------------------------------------------------------------------------------------------
+template <int LPS>
+__global__ void __launch_bounds__(256) k_density_scatter(DensityBwdArgs A) {
+  const int nvec = A.Cp >> 2;
+  constexpr int SPB = 256 / LPS;
+  const int sub = threadIdx.x % LPS;
+  int64_t i = (int64_t)blockIdx.x * SPB + threadIdx.x / LPS;
+  if (i >= (int64_t)A.R * A.N) return;
+  const float g = A.dz[i];
+  if (g == 0.0f) return;
+  int r = (int)(i / A.N), s = (int)(i % A.N);
+  SceneParams sc;
+  load_scene(sc, A.aabb, A.N, A.G, A.contracted, A.jitter, A.base_ts, A.deltas);
+  RayParams ray;
+  load_ray(ray, sc, A.origins, A.directions, A.aabb, r);
+  float delta;
+  float t = sample_t(ray, sc, r, s, delta);
+  float x[3];
+  sample_grid_coords(ray, sc, t, x);
+  VmTaps taps;
+  make_vm_taps(taps, x, A.G);
+  for (int v = sub; v < nvec; v += LPS) {
+#pragma unroll
+    for (int P = 0; P < 3; ++P) {
+      PairAddr pa = pair_addr(taps, P, A.G, A.Cp, v);
+      float4 lin, bil;
+      pair_values(A.packed_d, pa, lin, bil);
+      float4 gl = f4_scale(bil, g), gb = f4_scale(lin, g);
+      red_add_v4(A.d_packed + pa.l0, f4_scale(gl, pa.wl0));
+      red_add_v4(A.d_packed + pa.l1, f4_scale(gl, pa.wl1));
+      red_add_v4(A.d_packed + pa.m00, f4_scale(gb, pa.w00));
+      red_add_v4(A.d_packed + pa.m01, f4_scale(gb, pa.w01));
+      red_add_v4(A.d_packed + pa.m10, f4_scale(gb, pa.w10));
+      red_add_v4(A.d_packed + pa.m11, f4_scale(gb, pa.w11));
+    }
+  }
+}
+
+int launch_density_scatter(cudaStream_t st, const DensityBwdArgs& A) {
+  int64_t samples = (int64_t)A.R * A.N;
+  if (samples == 0) return 0;
+  const int nvec = A.Cp / 4;
+  int lps = 1;
+  for (int p = 8; p >= 1; p >>= 1)
+    if (nvec % p == 0) {
+      lps = p;
+      break;
+    }
+  if (lps == 1 && nvec > 2) lps = nvec >= 8 ? 8 : 4;
+  switch (lps) {
+    case 8: k_density_scatter<8><<<(unsigned)ceil_div64(samples, 32), 256, 0, st>>>(A); break;
+    case 4: k_density_scatter<4><<<(unsigned)ceil_div64(samples, 64), 256, 0, st>>>(A); break;
+    case 2: k_density_scatter<2><<<(unsigned)ceil_div64(samples, 128), 256, 0, st>>>(A); break;
+    default: k_density_scatter<1><<<(unsigned)ceil_div64(samples, 256), 256, 0, st>>>(A); break;
+  }
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace tf

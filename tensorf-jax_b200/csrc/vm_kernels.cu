@@ -1,0 +1,160 @@
+// TensorVM kernels: layout pack/unpack and the standalone `TensorVM.interpolate`
+// forward / reverse (tensor_vm.py:42-89, :140-167, :226-250).
+#include "vm.cuh"
+
+namespace tf {
+
+// ---- pack: channel-first (C, T) -> texel-major (T, Cp) ---------------------------------------
+// One CTA moves 32 texels x all channels through shared memory: reads are coalesced along the
+// texel axis (the reference's contiguous axis), writes are one contiguous 32*Cp-float run.
+template <bool UNPACK>
+__global__ void __launch_bounds__(256) k_pack(const float* __restrict__ src, float* __restrict__ dst, int C, int Cp,
+                                              int64_t T /* texels per pair */, int64_t tiles_per_pair) {
+  extern __shared__ float tile[];  // [Cp][33]
+  int64_t tile_id = blockIdx.x;
+  int P = (int)(tile_id / tiles_per_pair);
+  int64_t t0 = (tile_id % tiles_per_pair) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 warps
+  if (!UNPACK) {
+    const float* s = src + (int64_t)P * C * T;
+    for (int c = ty; c < Cp; c += 8) {
+      int64_t t = t0 + tx;
+      tile[c * 33 + tx] = (c < C && t < T) ? s[(int64_t)c * T + t] : 0.0f;
+    }
+    __syncthreads();
+    float* d = dst + ((int64_t)P * T + t0) * Cp;
+    int64_t n = min((int64_t)32, T - t0) * Cp;
+    for (int i = threadIdx.x; i < n; i += 256) d[i] = tile[(i % Cp) * 33 + (i / Cp)];
+  } else {
+    const float* s = src + ((int64_t)P * T + t0) * Cp;
+    int64_t n = min((int64_t)32, T - t0) * Cp;
+    for (int i = threadIdx.x; i < n; i += 256) tile[(i % Cp) * 33 + (i / Cp)] = s[i];
+    __syncthreads();
+    float* d = dst + (int64_t)P * C * T;
+    for (int c = ty; c < C; c += 8) {
+      int64_t t = t0 + tx;
+      if (t < T) d[(int64_t)c * T + t] = tile[c * 33 + tx];
+    }
+  }
+}
+
+template <bool UNPACK>
+static int launch_pack(cudaStream_t st, const float* src, float* dst, int C, int64_t T) {
+  int Cp = packed_cp(C);
+  int64_t tiles = ceil_div64(T, 32);
+  size_t smem = (size_t)Cp * 33 * sizeof(float);
+  TF_CHECK_ARG(smem <= 48 * 1024, "channel dim %d too large for pack kernel", C);
+  k_pack<UNPACK><<<(unsigned)(3 * tiles), 256, smem, st>>>(src, dst, C, Cp, T, tiles);
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+
+int vm_pack(cudaStream_t st, const float* vector, const float* matrix, float* packed, int C, int G) {
+  TF_RETURN_IF_ERROR(launch_pack<false>(st, vector, packed, C, G));
+  TF_RETURN_IF_ERROR(launch_pack<false>(st, matrix, packed + packed_line_floats(C, G), C, (int64_t)G * G));
+  return 0;
+}
+int vm_unpack(cudaStream_t st, const float* packed, float* vector, float* matrix, int C, int G) {
+  TF_RETURN_IF_ERROR(launch_pack<true>(st, packed, vector, C, G));
+  TF_RETURN_IF_ERROR(launch_pack<true>(st, packed + packed_line_floats(C, G), matrix, C, (int64_t)G * G));
+  return 0;
+}
+
+// ---- standalone interpolate -----------------------------------------------------------------
+// Work item = (sample b, float4 channel group v).  Items are flattened so a warp covers whole
+// texel fragments with contiguous lanes (a texel is nvec consecutive float4s): every load
+// instruction moves full 32-byte sectors.  feature_major=1 writes rows (B, 3C); feature_major=0
+// writes the reference's (3C, B).
+__global__ void __launch_bounds__(256) k_vm_interp_fwd(const float* __restrict__ packed, const float* __restrict__ ijk,
+                                                       float* __restrict__ out, int C, int Cp, int G, int64_t B,
+                                                       int feature_major) {
+  const int nvec = Cp >> 2;
+  int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= B * nvec) return;
+  int64_t b = item / nvec;
+  int v = (int)(item % nvec);
+  float gm1 = (float)(G - 1);
+  float x[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) x[a] = grid_coord(ijk[(int64_t)a * B + b], gm1);
+  VmTaps taps;
+  make_vm_taps(taps, x, G);
+#pragma unroll
+  for (int P = 0; P < 3; ++P) {
+    PairAddr pa = pair_addr(taps, P, G, Cp, v);
+    float4 lin, bil;
+    pair_values(packed, pa, lin, bil);
+    float4 f = f4_mul(lin, bil);
+    float fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = 4 * v + j;
+      if (c < C) {
+        if (feature_major)
+          out[b * (3 * C) + P * C + c] = fv[j];
+        else
+          out[((int64_t)(P * C + c)) * B + b] = fv[j];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_vm_interp_bwd(const float* __restrict__ packed, const float* __restrict__ ijk,
+                                                       const float* __restrict__ d_out, float* __restrict__ d_packed,
+                                                       int C, int Cp, int G, int64_t B, int feature_major) {
+  const int nvec = Cp >> 2;
+  int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= B * nvec) return;
+  int64_t b = item / nvec;
+  int v = (int)(item % nvec);
+  float gm1 = (float)(G - 1);
+  float x[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) x[a] = grid_coord(ijk[(int64_t)a * B + b], gm1);
+  VmTaps taps;
+  make_vm_taps(taps, x, G);
+#pragma unroll
+  for (int P = 0; P < 3; ++P) {
+    float gv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = 4 * v + j;
+      gv[j] = 0.f;
+      if (c < C) gv[j] = feature_major ? d_out[b * (3 * C) + P * C + c] : d_out[((int64_t)(P * C + c)) * B + b];
+    }
+    float4 g = make_float4(gv[0], gv[1], gv[2], gv[3]);
+    PairAddr pa = pair_addr(taps, P, G, Cp, v);
+    float4 lin, bil;
+    pair_values(packed, pa, lin, bil);
+    float4 gl = f4_mul(g, bil);  // d/d lin
+    float4 gb = f4_mul(g, lin);  // d/d bil
+    red_add_v4(d_packed + pa.l0, f4_scale(gl, pa.wl0));
+    red_add_v4(d_packed + pa.l1, f4_scale(gl, pa.wl1));
+    red_add_v4(d_packed + pa.m00, f4_scale(gb, pa.w00));
+    red_add_v4(d_packed + pa.m01, f4_scale(gb, pa.w01));
+    red_add_v4(d_packed + pa.m10, f4_scale(gb, pa.w10));
+    red_add_v4(d_packed + pa.m11, f4_scale(gb, pa.w11));
+  }
+}
+
+int vm_interp_fwd(cudaStream_t st, const float* packed, const float* ijk, float* out, int C, int G, int64_t B,
+                  int feature_major) {
+  if (B == 0) return 0;
+  int Cp = packed_cp(C);
+  int64_t items = B * (Cp / 4);
+  k_vm_interp_fwd<<<(unsigned)ceil_div64(items, 256), 256, 0, st>>>(packed, ijk, out, C, Cp, G, B, feature_major);
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+int vm_interp_bwd(cudaStream_t st, const float* packed, const float* ijk, const float* d_out, float* d_packed, int C,
+                  int G, int64_t B, int feature_major) {
+  if (B == 0) return 0;
+  int Cp = packed_cp(C);
+  int64_t items = B * (Cp / 4);
+  k_vm_interp_bwd<<<(unsigned)ceil_div64(items, 256), 256, 0, st>>>(packed, ijk, d_out, d_packed, C, Cp, G, B,
+                                                                     feature_major);
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace tf

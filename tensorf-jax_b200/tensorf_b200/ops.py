@@ -1,0 +1,276 @@
+"""Torch-tensor front end of the C ABI (include/tensorf_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream, every computation is a
+call into libtensorf_b200.so.  All tensors must be CUDA, contiguous, fp32 (int32 / uint32-as-
+int32 for indices).  Work is enqueued on `torch.cuda.current_stream()`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import PARAM_FIELDS, Params, RenderDesc, RenderInputs, check
+
+MODE_RGB, MODE_DIST_MEDIAN, MODE_DIST_MEAN = 0, 1, 2
+MLP_AUTO, MLP_SIMT_FP32, MLP_TCGEN05 = 0, 1, 2
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=torch.float32, name: str = "tensor") -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t.data_ptr()
+
+
+def make_desc(R: int, N: int, K: int, G: int, cd: int, ca: int, mode: int = MODE_RGB, contracted: bool = False,
+              feat_freqs: int = 6, view_freqs: int = 6, num_cameras: Optional[int] = None, loss_scale: float = 0.0,
+              squash: int = 27, units: int = 128, mlp_impl: int = MLP_AUTO) -> RenderDesc:
+    return RenderDesc(R=R, N=N, K=K, G=G, cd=cd, ca=ca, mode=mode, contracted=int(bool(contracted)), squash=squash,
+                      units=units, feat_freqs=feat_freqs, view_freqs=view_freqs, num_cameras=int(num_cameras or 0),
+                      mlp_impl=mlp_impl, loss_scale=loss_scale, reserved=0)
+
+
+def encoded_dim(desc: RenderDesc) -> int:
+    return desc.squash + 3 + 2 * desc.feat_freqs * desc.squash + 2 * desc.view_freqs * 3
+
+
+def param_shapes(desc: RenderDesc) -> Dict[str, Tuple[int, ...]]:
+    """Leaf shapes of LearnableParams (render.py:39-46) in the reference's layouts."""
+    G, cd, ca, u = desc.G, desc.cd, desc.ca, desc.units
+    s = {
+        "density_vector": (3, cd, G), "density_matrix": (3, cd, G, G),
+        "appearance_vector": (3, ca, G), "appearance_matrix": (3, ca, G, G),
+        "w0": (3 * ca, desc.squash), "w1": (encoded_dim(desc), u), "b1": (u,), "w2": (u, u), "b2": (u,),
+        "w3": (u, 3), "b3": (3,),
+    }
+    if desc.num_cameras > 0:
+        s["embed"] = (desc.num_cameras, u)
+    return s
+
+
+def _params_struct(desc: RenderDesc, params: Dict[str, torch.Tensor], what: str = "params", factors: bool = True) -> Params:
+    shapes = param_shapes(desc)
+    ps = Params()
+    for name in PARAM_FIELDS:
+        if name not in shapes or (not factors and name.startswith(("density_", "appearance_"))):
+            setattr(ps, name, None)
+            continue
+        if name not in params:
+            raise KeyError(f"{what} is missing leaf '{name}'")
+        t = params[name]
+        if tuple(t.shape) != shapes[name]:
+            raise ValueError(f"{what}['{name}'] has shape {tuple(t.shape)}, expected {shapes[name]}")
+        setattr(ps, name, _ptr(t, name=f"{what}['{name}']"))
+    return ps
+
+
+# ---------------------------------------------------------------------------------------------
+# TensorVM
+# ---------------------------------------------------------------------------------------------
+def vm_packed_floats(C_: int, G: int) -> int:
+    return int(_lib.load().tensorf_vm_packed_floats(C_, G))
+
+
+def vm_pack(vector: torch.Tensor, matrix: torch.Tensor) -> torch.Tensor:
+    """(3,C,G), (3,C,G,G) channel-first (tensor_vm.py:129-138) -> packed texel-major copy."""
+    if vector.dim() != 3 or matrix.dim() != 4 or vector.shape[0] != 3 or matrix.shape[0] != 3:
+        raise ValueError(f"expected vector (3,C,G) and matrix (3,C,G,G), got {tuple(vector.shape)}, {tuple(matrix.shape)}")
+    _, Cc, G = vector.shape
+    if tuple(matrix.shape) != (3, Cc, G, G):
+        raise ValueError(f"matrix shape {tuple(matrix.shape)} does not match vector {tuple(vector.shape)}")
+    packed = torch.empty(vm_packed_floats(Cc, G), dtype=torch.float32, device=vector.device)
+    check(_lib.load().tensorf_vm_pack(_stream(), _ptr(vector, name="vector"), _ptr(matrix, name="matrix"), _ptr(packed), Cc, G))
+    return packed
+
+
+def vm_unpack(packed: torch.Tensor, C_: int, G: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    if packed.numel() != vm_packed_floats(C_, G):
+        raise ValueError("packed buffer has the wrong size")
+    vector = torch.empty((3, C_, G), dtype=torch.float32, device=packed.device)
+    matrix = torch.empty((3, C_, G, G), dtype=torch.float32, device=packed.device)
+    check(_lib.load().tensorf_vm_unpack(_stream(), _ptr(packed), _ptr(vector), _ptr(matrix), C_, G))
+    return vector, matrix
+
+
+def vm_interp_fwd(packed: torch.Tensor, ijk: torch.Tensor, C_: int, G: int, feature_major: bool = False) -> torch.Tensor:
+    """ijk (3,B) -> (3C,B) or (B,3C)."""
+    if ijk.dim() != 2 or ijk.shape[0] != 3:
+        raise ValueError(f"ijk must be (3,B), got {tuple(ijk.shape)}")
+    B = ijk.shape[1]
+    out = torch.empty((B, 3 * C_) if feature_major else (3 * C_, B), dtype=torch.float32, device=ijk.device)
+    check(_lib.load().tensorf_vm_interp_fwd(_stream(), _ptr(packed), _ptr(ijk, name="ijk"), _ptr(out), C_, G, B, int(feature_major)))
+    return out
+
+
+def vm_interp_bwd(packed: torch.Tensor, ijk: torch.Tensor, d_out: torch.Tensor, C_: int, G: int,
+                  feature_major: bool = False, d_packed: Optional[torch.Tensor] = None) -> torch.Tensor:
+    B = ijk.shape[1]
+    expect = (B, 3 * C_) if feature_major else (3 * C_, B)
+    if tuple(d_out.shape) != expect:
+        raise ValueError(f"d_out must be {expect}, got {tuple(d_out.shape)}")
+    if d_packed is None:
+        d_packed = torch.zeros_like(packed)
+    check(_lib.load().tensorf_vm_interp_bwd(_stream(), _ptr(packed), _ptr(ijk, name="ijk"), _ptr(d_out, name="d_out"),
+                                            _ptr(d_packed), C_, G, B, int(feature_major)))
+    return d_packed
+
+
+def topk_select(g: torch.Tensor, K: int) -> torch.Tensor:
+    """render.py:461-469 selection stage: (R,N) -> (R,K) int32, ascending index order."""
+    if g.dim() != 2:
+        raise ValueError("g must be (R,N)")
+    R, N = g.shape
+    idx = torch.empty((R, K), dtype=torch.int32, device=g.device)
+    check(_lib.load().tensorf_topk_select(_stream(), _ptr(g, name="g"), R, N, K, _ptr(idx, torch.int32)))
+    return idx
+
+
+# ---------------------------------------------------------------------------------------------
+# FeatureMlp
+# ---------------------------------------------------------------------------------------------
+class MlpCall:
+    """One FeatureMlp.apply (networks.py:46-121) with its saved activations."""
+
+    def __init__(self, desc: RenderDesc, M: int, device):
+        self.desc, self.M = desc, M
+        nbytes = int(_lib.load().tensorf_mlp_workspace_bytes(C.byref(desc), M))
+        if nbytes < 0:
+            raise ValueError("bad MLP description")
+        self.workspace = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=device)
+        self.rgb = None
+
+    def forward(self, params, features, viewdirs, camera_indices, rows_per_ray: int = 1) -> torch.Tensor:
+        d = self.desc
+        if tuple(features.shape) != (self.M, 3 * d.ca):
+            raise ValueError(f"features must be {(self.M, 3 * d.ca)}, got {tuple(features.shape)}")
+        if tuple(viewdirs.shape) != (self.M // rows_per_ray, 3):
+            raise ValueError(f"viewdirs must be {(self.M // rows_per_ray, 3)}, got {tuple(viewdirs.shape)}")
+        ps = _params_struct(d, params, factors=False)
+        rgb = torch.empty((self.M, 3), dtype=torch.float32, device=features.device)
+        cams = _ptr(camera_indices, torch.int32, "camera_indices") if d.num_cameras > 0 else None
+        check(_lib.load().tensorf_mlp_fwd(_stream(), C.byref(d), C.byref(ps), _ptr(features, name="features"),
+                                          _ptr(viewdirs, name="viewdirs"), cams, self.M, rows_per_ray,
+                                          _ptr(self.workspace), _ptr(rgb)))
+        self._saved = (params, features, viewdirs, camera_indices, rows_per_ray)
+        self.rgb = rgb
+        return rgb
+
+    def backward(self, d_rgb: torch.Tensor):
+        d = self.desc
+        params, features, viewdirs, camera_indices, rows_per_ray = self._saved
+        ps = _params_struct(d, params, factors=False)
+        grads = {k: torch.empty_like(v) for k, v in params.items() if not k.startswith(("density_", "appearance_"))}
+        gs = _params_struct(d, grads, "grads", factors=False)
+        d_feat = torch.empty_like(features)
+        cams = _ptr(camera_indices, torch.int32, "camera_indices") if d.num_cameras > 0 else None
+        check(_lib.load().tensorf_mlp_bwd(_stream(), C.byref(d), C.byref(ps), _ptr(features), _ptr(viewdirs), cams, self.M,
+                                          rows_per_ray, _ptr(self.workspace), _ptr(self.rgb), _ptr(d_rgb, name="d_rgb"),
+                                          _ptr(d_feat), C.byref(gs)))
+        return d_feat, grads
+
+
+# ---------------------------------------------------------------------------------------------
+# render_rays
+# ---------------------------------------------------------------------------------------------
+class RenderCall:
+    """One invocation of render.py:105-279 (forward, optional fused loss, reverse).  Owns the
+    workspace the C ABI asks the caller to provide; reusable across calls of the same shape."""
+
+    def __init__(self, desc: RenderDesc, device):
+        self.desc = desc
+        nbytes = C.c_int64(0)
+        check(_lib.load().tensorf_render_workspace_bytes(C.byref(desc), C.byref(nbytes)))
+        self.workspace_bytes = int(nbytes.value)
+        self.workspace = torch.empty(max(self.workspace_bytes // 4, 1), dtype=torch.float32, device=device)
+        self.device = device
+        self._keep = None
+
+    def _inputs(self, inputs: Dict[str, Optional[torch.Tensor]]) -> RenderInputs:
+        d = self.desc
+        R, N = d.R, d.N
+        exp = {
+            "origins": ((R, 3), torch.float32), "directions": ((R, 3), torch.float32), "aabb": ((2, 3), torch.float32),
+            "jitter": ((R, N) if d.contracted else (N,), torch.float32),
+        }
+        if d.mode == MODE_RGB:
+            exp["gumbel"] = ((N,), torch.float32)
+            if d.num_cameras > 0:
+                exp["camera_indices"] = ((R,), torch.int32)
+        if d.contracted:
+            exp["base_ts"] = ((N,), torch.float32)
+            exp["deltas"] = ((N,), torch.float32)
+        ri = RenderInputs()
+        for name, (shape, dt) in exp.items():
+            t = inputs.get(name)
+            if t is None:
+                raise KeyError(f"inputs is missing '{name}'")
+            if tuple(t.shape) != shape:
+                raise ValueError(f"inputs['{name}'] has shape {tuple(t.shape)}, expected {shape}")
+            setattr(ri, name, _ptr(t, dt, f"inputs['{name}']"))
+        colors = inputs.get("colors")
+        if colors is not None:
+            if tuple(colors.shape) != (R, 3):
+                raise ValueError(f"colors must be {(R, 3)}")
+            ri.colors = _ptr(colors, name="colors")
+        return ri
+
+    def forward(self, params: Dict[str, torch.Tensor], inputs: Dict[str, Optional[torch.Tensor]]):
+        """Returns (rgb (R,3), loss or None). `inputs['colors']` enables the fused MSE."""
+        d = self.desc
+        ps = _params_struct(d, params)
+        ri = self._inputs(inputs)
+        rgb = torch.empty((d.R, 3), dtype=torch.float32, device=self.device)
+        loss = torch.empty((), dtype=torch.float32, device=self.device) if inputs.get("colors") is not None else None
+        check(_lib.load().tensorf_render_rgb_fwd(_stream(), C.byref(d), C.byref(ps), C.byref(ri), _ptr(self.workspace),
+                                                 _ptr(rgb), _ptr(loss)))
+        self._keep = (params, inputs)
+        return rgb, loss
+
+    def backward(self, d_rgb: Optional[torch.Tensor] = None, grads: Optional[Dict[str, torch.Tensor]] = None):
+        """Gradients w.r.t. every leaf of LearnableParams. d_rgb=None uses the fused loss cotangent."""
+        d = self.desc
+        params, inputs = self._keep
+        ps = _params_struct(d, params)
+        ri = self._inputs(inputs)
+        if grads is None:
+            grads = {k: torch.empty_like(v) for k, v in params.items() if k in param_shapes(d)}
+        gs = _params_struct(d, grads, "grads")
+        if d_rgb is not None and tuple(d_rgb.shape) != (d.R, 3):
+            raise ValueError(f"d_rgb must be {(d.R, 3)}")
+        check(_lib.load().tensorf_render_rgb_bwd(_stream(), C.byref(d), C.byref(ps), C.byref(ri), _ptr(self.workspace),
+                                                 _ptr(d_rgb, name="d_rgb"), C.byref(gs)))
+        return grads
+
+    def depth(self, params: Dict[str, torch.Tensor], inputs: Dict[str, Optional[torch.Tensor]]) -> torch.Tensor:
+        d = self.desc
+        ps = Params()
+        for name in ("density_vector", "density_matrix"):
+            t = params[name]
+            if tuple(t.shape) != param_shapes(d)[name]:
+                raise ValueError(f"params['{name}'] has shape {tuple(t.shape)}")
+            setattr(ps, name, _ptr(t, name=name))
+        ri = self._inputs(inputs)
+        out = torch.empty((d.R,), dtype=torch.float32, device=self.device)
+        check(_lib.load().tensorf_render_depth(_stream(), C.byref(d), C.byref(ps), C.byref(ri), _ptr(self.workspace), _ptr(out)))
+        return out
+
+    def view(self, name: str) -> torch.Tensor:
+        """A copy of one residual stored in the workspace (tests / debugging)."""
+        ptr, cnt = C.c_void_p(), C.c_int64()
+        check(_lib.load().tensorf_render_workspace_view(C.byref(self.desc), _ptr(self.workspace), name.encode(), C.byref(ptr),
+                                                        C.byref(cnt)))
+        off = (ptr.value - self.workspace.data_ptr()) // 4
+        t = self.workspace[off:off + cnt.value]
+        return t.view(torch.int32).clone() if name == "idx" else t.clone()

@@ -1,0 +1,63 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/tensorf_b200.h
+declares (no compute calls without a GPU); argument validation that needs no device."""
+import ctypes
+import pathlib
+import re
+
+import pytest
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "tensorf_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tensorf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound():
+    from tensorf_b200 import _lib
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 16
+    assert sorted(_lib.SIGNATURES) == names, "ctypes SIGNATURES out of sync with the header"
+    for n in names:
+        assert hasattr(lib, n), f"{n} not exported"
+    assert lib.tensorf_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    from tensorf_b200 import _lib
+    assert ctypes.sizeof(_lib.RenderDesc) == 16 * 4
+    assert ctypes.sizeof(_lib.Params) == 12 * 8
+    assert ctypes.sizeof(_lib.RenderInputs) == 9 * 8
+
+
+def test_host_side_validation_without_gpu():
+    from tensorf_b200 import _lib, ops
+    lib = _lib.load()
+    assert lib.tensorf_vm_packed_floats(16, 128) == 3 * 128 * 16 + 3 * 128 * 128 * 16
+    assert lib.tensorf_vm_packed_floats(5, 4) == 3 * 4 * 8 + 3 * 16 * 8          # channels padded to 8
+    nbytes = ctypes.c_int64()
+    bad = ops.make_desc(R=4, N=5, K=6, G=9, cd=2, ca=3)                            # K > N
+    assert lib.tensorf_render_workspace_bytes(ctypes.byref(bad), ctypes.byref(nbytes)) == -1
+    assert b"appearance_samples_per_ray" in lib.tensorf_last_error()
+    ok = ops.make_desc(R=4096, N=221, K=33, G=128, cd=16, ca=48, feat_freqs=2, view_freqs=2)
+    assert lib.tensorf_render_workspace_bytes(ctypes.byref(ok), ctypes.byref(nbytes)) == 0 and nbytes.value > 0
+    un = ops.make_desc(R=4, N=5, K=2, G=9, cd=2, ca=3, units=64)
+    assert lib.tensorf_render_workspace_bytes(ctypes.byref(un), ctypes.byref(nbytes)) == -3
+    with pytest.raises(_lib.TensorfError):
+        _lib.check(-1)
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    from tensorf_b200 import _lib
+    with pytest.raises(_lib.TensorfLibraryError, match="no CPU fallback"):
+        _lib.load(tmp_path / "libtensorf_b200.so")
+
+
+def test_ops_reject_cpu_tensors():
+    import torch
+    from tensorf_b200 import ops
+    with pytest.raises(ValueError, match="no CPU path"):
+        ops._ptr(torch.zeros(3))
