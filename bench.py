@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py — train rays/s (fwd+bwd) of the tensorf-jax per-ray hot path on N B200s.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # CPU arm: the oracle restatement on the host cores
+
+A "step" is one pass of the hot path (render_rays forward + loss + reverse w.r.t. every leaf of
+LearnableParams; training.py:108-156) over one batch of synthetic rays.  Workload at every N:
+BASELINE.json configs[1] per GPU (lego shape, R=4096 rays x N=256 density samples, K=38
+appearance samples, 128^3 grid); for N>1 the rays are sharded (weak scaling: 4096 rays per
+GPU), the loss is the mean over the GLOBAL batch and the gradients are sum-allreduced with
+NCCL every step.  Adam/LR (training.py:158-204) is outside the measured path.
+Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "tensorf-jax_b200"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from tensorf_b200 import synthetic as S  # noqa: E402
+
+METRIC = "train_rays_per_sec_fwd_bwd"
+UNIT = "rays/s"
+
+
+def workload_from_name(name: str) -> S.Workload:
+    if name == "lego_256":  # BASELINE.json configs[1] as named ("4096 rays x 256 samples")
+        return S.lego_workload(R=4096, G=128, N=256, K=38, name="lego_G128_R4096_N256_K38 (BASELINE configs[1])")
+    if name == "lego_221":  # what the reference would execute at G=128 (training.py:115-118)
+        return S.lego_workload(R=4096, G=128)
+    if name == "lego_300":  # configs[2] per-GPU shard at 8 GPUs
+        return S.lego_workload(R=2048, G=300)
+    if name == "dozer_128":
+        return S.dozer_workload(R=2048, G=128)
+    raise SystemExit(f"unknown workload {name}")
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle (PyTorch-CPU fp32 restatement of the reference; JAX is not in the image)
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_rays_per_s(w: S.Workload, sample_rays: int, steps: int, warmup: int):
+    sys.path.insert(0, str(ROOT / "oracle"))
+    sys.path.insert(0, str(ROOT / "tests"))
+    import tensorf_oracle as O
+    from helpers import oracle_cfgs, oracle_inputs
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    inp = S.make_inputs(w, R=sample_rays)
+    ws = S.Workload(**{**w.__dict__, "R": sample_rays})
+    cfg, mc = oracle_cfgs(ws)
+    oi = oracle_inputs(inp, torch.float32)
+
+    def step():
+        O.loss_and_grads(cfg, mc, oi["params"], w.contracted, oi["aabb"], oi["origins"], oi["directions"],
+                         oi["camera_indices"], oi["colors"], oi["jitter"], oi["gumbel"])
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return sample_rays / dt, dt * 1e3, cores
+
+
+def run_reference_arm(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 512
+    steps = max(1, min(args.steps, 10))
+    warmup = max(1, min(args.warmup, 2))
+    v, ms, cores = cpu_reference_rays_per_s(w, sample, steps, warmup)
+    desc = f"{sample}-ray slice of the {w.name} batch per step, fwd+bwd via torch.autograd, fp32, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w.name, "R_per_step": sample, "N": w.N, "K": w.K, "G": w.G, "cd": w.cd, "ca": w.ca,
+                   "note": "CPU restatement of the reference (oracle/tensorf_oracle.py); JAX is not installable in this "
+                           "image so the reference's own JAX-CPU path cannot run"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="lego_256")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-l2-flush", action="store_true")
+    args = ap.parse_args()
+    w = workload_from_name(args.workload)
+    if args.impl == "reference":
+        return run_reference_arm(args, w)
+
+    import torch.distributed as dist
+    from tensorf_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+    steps = args.steps
+
+    # ---- inputs: same parameters on every rank, a different ray shard per rank ------------------
+    R_global = w.R * world
+    inp = S.make_inputs(w, seed_rays=1 + rank)
+    desc = ops.make_desc(R=w.R, N=w.N, K=w.K, G=w.G, cd=w.cd, ca=w.ca, contracted=w.contracted, feat_freqs=w.feat_freqs,
+                         view_freqs=w.view_freqs, num_cameras=w.num_cameras, loss_scale=1.0 / (3 * R_global))
+    call = ops.RenderCall(desc, dev)
+
+    def dv(x):
+        t = torch.from_numpy(np.ascontiguousarray(x))
+        if t.dtype == torch.uint32:
+            t = t.view(torch.int32)
+        return t.to(dev)
+
+    params = {k: dv(v) for k, v in inp["params"].items()}
+    host_keys = ["origins", "directions", "camera_indices", "colors", "jitter", "gumbel"]
+    host = {k: (torch.from_numpy(inp[k].view(np.int32) if inp[k].dtype == np.uint32 else inp[k])).pin_memory() for k in host_keys}
+    dins = {k: v.to(dev) for k, v in host.items()}
+    dins["aabb"] = dv(inp["aabb"])
+    if w.contracted:
+        sys.path.insert(0, str(ROOT / "oracle"))
+        # host constants of render.py:127-155 (numpy, float64 -> fp32), computed once
+        from tensorf_b200.render import contracted_schedule
+        base, delta = contracted_schedule(w.near, w.far, w.N)
+        dins["base_ts"], dins["deltas"] = dv(base), dv(delta)
+
+    # all gradient leaves live in ONE flat buffer -> one NCCL allreduce per step
+    shapes = ops.param_shapes(desc)
+    total = sum(int(np.prod(s)) for s in shapes.values())
+    flat = torch.empty(total, dtype=torch.float32, device=dev)
+    grads, off = {}, 0
+    for k, s in shapes.items():
+        n = int(np.prod(s))
+        grads[k] = flat[off:off + n].view(s)
+        off += n
+
+    flush = None if args.no_l2_flush else torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def step():
+        rgb, loss = call.forward(params, dins)
+        call.backward(None, grads)
+        if world > 1:
+            dist.all_reduce(flat)
+            dist.all_reduce(loss)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+
+    # ---- timed region: exactly `steps` steps, CUDA events per step, L2 flushed between steps ----
+    sampler = ClockSampler(local) if rank == 0 else None
+    ops.profile_enable(True)
+    launches0 = ops.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    for i in range(steps):
+        if flush is not None:
+            flush.zero_()
+        ev[i][0].record()
+        step()
+        ev[i][1].record()
+    barrier()
+    launches = ops.launch_count() - launches0
+    prof = ops.profile_read()
+    ops.profile_enable(False)
+    clocks = sampler.stop() if sampler else None
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / steps
+    value = R_global / (ms_per_step * 1e-3)
+
+    # ---- e2e: public API with HOST buffers; H2D of the minibatch + D2H of the loss every step -----
+    h2d = sum(host[k].numel() * host[k].element_size() for k in host_keys)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        for k in host_keys:
+            dins[k].copy_(host[k], non_blocking=True)
+        loss = step()
+        loss_host = float(loss.item())  # blocking D2H read, like training.py:342
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / steps
+    e2e_value = R_global / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        # Algorithmic bytes of the gather model: 6 taps x 4 B per sample-channel,
+        # the reverse pass re-gathers and scatter-adds the same count (2x).
+        alg = {
+            "density_select": 24 * w.N * 3 * w.cd * w.R,
+            "appearance_gather": 24 * w.K * 3 * w.ca * w.R,
+            "density_scatter": 48 * w.N * 3 * w.cd * w.R,
+            "appearance_scatter": 48 * w.K * 3 * w.ca * w.R,
+        }
+        stages = {k: {"ms": v[0] / max(v[1], 1), "share": v[0] / total_ms} for k, v in prof.items()}
+        dom = max(alg, key=lambda k: stages.get(k, {"ms": 0})["ms"])
+        dom_ms = stages[dom]["ms"]
+        achieved = alg[dom] / (dom_ms * 1e-3) / 1e9
+        traffic = None
+        tp = ROOT / "profiles" / "traffic.json"  # per-launch dram bytes from the committed ncu --set full capture
+        if tp.exists():
+            traffic = json.loads(tp.read_text()).get(args.workload, {}).get(dom)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w.name, "R_per_gpu": w.R, "R_global": R_global, "N": w.N, "K": w.K, "G": w.G,
+                       "cd": w.cd, "ca": w.ca, "feat_freqs": w.feat_freqs, "view_freqs": w.view_freqs,
+                       "contracted": w.contracted, "parallelism": f"rays sharded x{world}, NCCL grad allreduce" if world > 1 else "single GPU",
+                       "l2": "flushed (256 MiB write) between timed steps" if flush is not None else "not flushed",
+                       "timed": "render_rays fwd + MSE + reverse wrt all LearnableParams leaves; Adam excluded",
+                       "loss": loss_host},
+            "roofline_step": {"bound": "hbm", "achieved": value / world * w.train_bytes_per_ray() / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": value / world * w.train_bytes_per_ray() / 1e9 / peak,
+                              "note": "whole step per GPU, gather-model bytes 3*24*(N*3cd+K*3ca) per ray (SURVEY §8d); factors are L2-resident at 128^3"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": dom_ms, "peak_source": peak_src},
+            "stages_ms": {k: round(v["ms"], 4) for k, v in sorted(stages.items(), key=lambda kv: -kv[1]["ms"])},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, ms, cores = cpu_reference_rays_per_s(w, 512, 6, 1)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"512-ray slice of the same batch, fwd+bwd, 6 timed steps ({ms:.0f} ms each), "
+                                             f"PyTorch-CPU fp32 restatement of the reference (JAX not in image)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

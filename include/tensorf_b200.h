@@ -100,6 +100,16 @@ typedef struct tensorf_render_inputs {
 const char* tensorf_last_error(void);
 int tensorf_version(void);
 
+/* ---- measurement hooks (bench.py; off by default) ---------------------------------------- */
+/* Kernels + memsets this thread has enqueued through the library so far. */
+int64_t tensorf_launch_count(void);
+/* When enabled, every entry point brackets its stages (pack, density_select, mlp_fwd, ...) with
+ * cudaEventRecord on the launch stream. Not CUDA-graph-capture safe while enabled. */
+int tensorf_profile_enable(int enable);
+/* HOST buffers: names[max_entries][32], total_ms[max_entries], calls[max_entries]. Blocks until
+ * the recorded events have completed, returns per-stage totals since the last read and resets. */
+int tensorf_profile_read(int max_entries, char* names, float* total_ms, int* calls, int* count);
+
 /* ---- factor layout (kernel-native texel-major copy of the channel-first factors) -------- */
 /* Number of floats of the packed copy of one TensorVM: [3][G][Cp] lines then [3][G][G][Cp]
  * planes, Cp = C rounded up to a multiple of 4. */
@@ -123,6 +133,11 @@ int tensorf_vm_interp_bwd(tensorf_stream_t s, const float* packed, const float* 
 /* idx (R,K) = indices of the K largest g per row, ties -> lower index, emitted in ASCENDING
  * index order (the order is not observable through render_rays). g (R,N). */
 int tensorf_topk_select(tensorf_stream_t s, const float* g, int R, int N, int K, int32_t* idx);
+
+/* ---- render.py:300-347 compute_segment_probabilities ---------------------------------------- */
+/* sigmas, step_sizes (R,N) -> p_exits = exp(cumsum(-sigma*step)), p_terminates (R,N). */
+int tensorf_segment_probabilities(tensorf_stream_t s, const float* sigmas, const float* step_sizes, int R, int N,
+                                  float* p_exits, float* p_terminates);
 
 /* ---- networks.py:46-121 FeatureMlp.__call__ ----------------------------------------------- */
 /* features (M, 3*ca); viewdirs (M/rows_per_ray, 3); camera_indices (M/rows_per_ray); rgb (M,3).

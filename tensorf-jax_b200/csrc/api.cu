@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <vector>
+
 #include "mlp.cuh"
 #include "render_kernels.cuh"
 
@@ -14,6 +16,42 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+static thread_local int64_t g_launches = 0;
+void count_launch() { ++g_launches; }
+
+// ---- stage profiler -------------------------------------------------------------------------
+struct ProfRec {
+  const char* name;
+  cudaEvent_t e0, e1;
+};
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  std::vector<ProfRec> recs;
+  cudaEvent_t get() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+};
+static thread_local Profiler g_prof;
+
+StageTimer::StageTimer(cudaStream_t st, const char* name) : st_(st), rec_(-1) {
+  if (!g_prof.on) return;
+  cudaEvent_t e0 = g_prof.get(), e1 = g_prof.get();
+  if (!e0 || !e1) return;
+  cudaEventRecord(e0, st);
+  rec_ = (int)g_prof.recs.size();
+  g_prof.recs.push_back(ProfRec{name, e0, e1});
+}
+StageTimer::~StageTimer() {
+  if (rec_ >= 0) cudaEventRecord(g_prof.recs[rec_].e1, st_);
 }
 
 static inline int64_t al(int64_t floats) { return round_up64(floats, 64); }  // 256-byte granules
@@ -120,6 +158,42 @@ extern "C" {
 const char* tensorf_last_error(void) { return g_err; }
 int tensorf_version(void) { return 100; }
 
+int64_t tensorf_launch_count(void) { return g_launches; }
+
+int tensorf_profile_enable(int enable) {
+  g_prof.on = enable != 0;
+  g_prof.used = 0;
+  g_prof.recs.clear();
+  return 0;
+}
+
+int tensorf_profile_read(int max_entries, char* names, float* total_ms, int* calls, int* count) {
+  TF_CHECK_ARG(names && total_ms && calls && count && max_entries > 0, "NULL argument");
+  int n = 0;
+  for (auto& r : g_prof.recs) {
+    TF_CHECK_CUDA(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    TF_CHECK_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    int j = 0;
+    for (; j < n; ++j)
+      if (strncmp(names + 32 * j, r.name, 31) == 0) break;
+    if (j == n) {
+      if (n == max_entries) continue;
+      strncpy(names + 32 * n, r.name, 31);
+      names[32 * n + 31] = 0;
+      total_ms[n] = 0.f;
+      calls[n] = 0;
+      ++n;
+    }
+    total_ms[j] += ms;
+    calls[j] += 1;
+  }
+  *count = n;
+  g_prof.used = 0;
+  g_prof.recs.clear();
+  return 0;
+}
+
 int64_t tensorf_vm_packed_floats(int C, int G) { return packed_floats(C, G); }
 
 int tensorf_vm_pack(tensorf_stream_t s, const float* vector, const float* matrix, float* packed, int C, int G) {
@@ -150,6 +224,13 @@ int tensorf_topk_select(tensorf_stream_t s, const float* g, int R, int N, int K,
   TF_CHECK_ARG(R >= 0 && N >= 1 && K >= 1 && K <= N, "bad shape R=%d N=%d K=%d (need 1 <= K <= N)", R, N, K);
   TF_CHECK_ARG(R == 0 || (g && idx), "NULL buffer");
   return launch_topk_select((cudaStream_t)s, g, R, N, K, idx);
+}
+
+int tensorf_segment_probabilities(tensorf_stream_t s, const float* sigmas, const float* step_sizes, int R, int N,
+                                  float* p_exits, float* p_terminates) {
+  TF_CHECK_ARG(R >= 0 && N >= 1, "bad shape R=%d N=%d", R, N);
+  TF_CHECK_ARG(R == 0 || (sigmas && step_sizes && p_exits && p_terminates), "NULL buffer");
+  return launch_segment_probs((cudaStream_t)s, sigmas, step_sizes, p_exits, p_terminates, R, N);
 }
 
 int64_t tensorf_mlp_workspace_bytes(const tensorf_render_desc* d, int64_t M) {
@@ -265,8 +346,11 @@ int tensorf_render_rgb_fwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   const MlpShape ms = mlp_shape(*d);
   const int64_t M = (int64_t)d->R * d->K;
 
-  TF_RETURN_IF_ERROR(vm_pack(st, p->density_vector, p->density_matrix, w.packed_d, d->cd, d->G));
-  TF_RETURN_IF_ERROR(vm_pack(st, p->appearance_vector, p->appearance_matrix, w.packed_a, d->ca, d->G));
+  {
+    StageTimer t_(st, "pack");
+    TF_RETURN_IF_ERROR(vm_pack(st, p->density_vector, p->density_matrix, w.packed_d, d->cd, d->G));
+    TF_RETURN_IF_ERROR(vm_pack(st, p->appearance_vector, p->appearance_matrix, w.packed_a, d->ca, d->G));
+  }
 
   DensityArgs a{};
   fill_scene(a, *d, *in);
@@ -278,7 +362,10 @@ int tensorf_render_rgb_fwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   a.idx_out = w.idx;
   a.pt_sel_out = w.pt_sel;
   a.stats_out = w.stats;
-  TF_RETURN_IF_ERROR(launch_density_select(st, a));
+  {
+    StageTimer t_(st, "density_select");
+    TF_RETURN_IF_ERROR(launch_density_select(st, a));
+  }
 
   AppearanceArgs ap{};
   fill_scene(ap, *d, *in);
@@ -288,12 +375,18 @@ int tensorf_render_rgb_fwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   ap.Cp = packed_cp(d->ca);
   ap.M = M;
   ap.feat = w.feat;
-  TF_RETURN_IF_ERROR(launch_appearance(st, ap, false));
+  {
+    StageTimer t_(st, "appearance_gather");
+    TF_RETURN_IF_ERROR(launch_appearance(st, ap, false));
+  }
 
   MlpWs mws = mlp_ws_carve(ms, M, w.mlp_base);
-  TF_RETURN_IF_ERROR(
-      mlp_simt_fwd(st, ms, mlp_params(*p), w.feat, in->directions, in->camera_indices, M, d->K, mws, w.rgb_sel));
-
+  {
+    StageTimer t_(st, "mlp_fwd");
+    TF_RETURN_IF_ERROR(
+        mlp_simt_fwd(st, ms, mlp_params(*p), w.feat, in->directions, in->camera_indices, M, d->K, mws, w.rgb_sel));
+  }
+  StageTimer t_(st, "composite");
   if (in->colors) TF_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
   CompositeArgs c{};
   c.rgb_sel = w.rgb_sel;
@@ -336,10 +429,15 @@ int tensorf_render_rgb_bwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   rb.go = d_rgb ? d_rgb : w.go;
   rb.d_rgb_sel = w.d_rgb_sel;
   rb.dz = w.dz;
-  TF_RETURN_IF_ERROR(launch_ray_bwd(st, rb));
-
-  TF_CHECK_CUDA(cudaMemsetAsync(w.gpacked_d, 0, sizeof(float) * packed_floats(d->cd, d->G), st));
-  TF_CHECK_CUDA(cudaMemsetAsync(w.gpacked_a, 0, sizeof(float) * packed_floats(d->ca, d->G), st));
+  {
+    StageTimer t_(st, "ray_bwd");
+    TF_RETURN_IF_ERROR(launch_ray_bwd(st, rb));
+  }
+  {
+    StageTimer t_(st, "zero_grads");
+    TF_CHECK_CUDA(cudaMemsetAsync(w.gpacked_d, 0, sizeof(float) * packed_floats(d->cd, d->G), st));
+    TF_CHECK_CUDA(cudaMemsetAsync(w.gpacked_a, 0, sizeof(float) * packed_floats(d->ca, d->G), st));
+  }
 
   DensityBwdArgs db{};
   fill_scene(db, *d, *in);
@@ -347,11 +445,17 @@ int tensorf_render_rgb_bwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   db.dz = w.dz;
   db.d_packed = w.gpacked_d;
   db.Cp = packed_cp(d->cd);
-  TF_RETURN_IF_ERROR(launch_density_scatter(st, db));
+  {
+    StageTimer t_(st, "density_scatter");
+    TF_RETURN_IF_ERROR(launch_density_scatter(st, db));
+  }
 
   MlpWs mws = mlp_ws_carve(ms, M, w.mlp_base);
-  TF_RETURN_IF_ERROR(mlp_simt_bwd(st, ms, mlp_params(*p), w.feat, in->directions, in->camera_indices, M, d->K, mws,
-                                  w.rgb_sel, w.d_rgb_sel, w.d_feat, mlp_grads(*grads)));
+  {
+    StageTimer t_(st, "mlp_bwd");
+    TF_RETURN_IF_ERROR(mlp_simt_bwd(st, ms, mlp_params(*p), w.feat, in->directions, in->camera_indices, M, d->K, mws,
+                                    w.rgb_sel, w.d_rgb_sel, w.d_feat, mlp_grads(*grads)));
+  }
 
   AppearanceArgs ap{};
   fill_scene(ap, *d, *in);
@@ -362,8 +466,11 @@ int tensorf_render_rgb_bwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   ap.M = M;
   ap.d_feat = w.d_feat;
   ap.d_packed = w.gpacked_a;
-  TF_RETURN_IF_ERROR(launch_appearance(st, ap, true));
-
+  {
+    StageTimer t_(st, "appearance_scatter");
+    TF_RETURN_IF_ERROR(launch_appearance(st, ap, true));
+  }
+  StageTimer t_(st, "unpack");
   TF_RETURN_IF_ERROR(vm_unpack(st, w.gpacked_d, grads->density_vector, grads->density_matrix, d->cd, d->G));
   TF_RETURN_IF_ERROR(vm_unpack(st, w.gpacked_a, grads->appearance_vector, grads->appearance_matrix, d->ca, d->G));
   return 0;

@@ -28,7 +28,21 @@ void set_error(const char* fmt, ...);  // thread-local message, api.cu
   } while (0)
 
 // Launch errors are collected right after enqueue; no device synchronisation.
-#define TF_CHECK_LAUNCH() TF_CHECK_CUDA(cudaGetLastError())
+void count_launch();  // thread-local kernel-launch counter (tensorf_launch_count), api.cu
+#define TF_CHECK_LAUNCH()               \
+  do {                                  \
+    tf::count_launch();                 \
+    TF_CHECK_CUDA(cudaGetLastError());  \
+  } while (0)
+
+// Optional per-stage timing: when enabled (tensorf_profile_enable) every launcher brackets its
+// stages with cudaEventRecord on the launch stream. Off by default (graph-capture safe).
+struct StageTimer {
+  StageTimer(cudaStream_t st, const char* name);
+  ~StageTimer();
+  cudaStream_t st_;
+  int rec_;
+};
 
 #define TF_RETURN_IF_ERROR(expr) \
   do {                           \

@@ -89,10 +89,9 @@ __device__ __forceinline__ void warp_emit_selected(const uint32_t* keys, int N, 
 struct SegTile {
   float a, E, pt;
 };
-__device__ __forceinline__ SegTile seg_tile(float z, float delta, bool valid, int lane, float& carry_c, float& carry_E) {
+__device__ __forceinline__ SegTile seg_tile_a(float a, int lane, float& carry_c, float& carry_E) {
   SegTile o;
-  float sigma = softplus_f(z);
-  o.a = valid ? __fmul_rn(-sigma, delta) : 0.0f;  // neg_scaled_sigmas = -sigmas * step_sizes
+  o.a = a;
   float c = __fadd_rn(carry_c, warp_incl_scan(o.a, lane));
   o.E = expf(c);  // p_exits
   float Eprev = __shfl_up_sync(0xffffffffu, o.E, 1);
@@ -101,6 +100,38 @@ __device__ __forceinline__ SegTile seg_tile(float z, float delta, bool valid, in
   carry_c = __shfl_sync(0xffffffffu, c, 31);
   carry_E = __shfl_sync(0xffffffffu, o.E, 31);
   return o;
+}
+__device__ __forceinline__ SegTile seg_tile(float z, float delta, bool valid, int lane, float& carry_c, float& carry_E) {
+  float sigma = softplus_f(z);
+  // neg_scaled_sigmas = -sigmas * step_sizes
+  return seg_tile_a(valid ? __fmul_rn(-sigma, delta) : 0.0f, lane, carry_c, carry_E);
+}
+
+// render.py:300-347 compute_segment_probabilities as a standalone op: one warp per row.
+__global__ void __launch_bounds__(128) k_segment_probs(const float* __restrict__ sigmas, const float* __restrict__ steps,
+                                                       float* __restrict__ p_exits, float* __restrict__ p_term, int R, int N) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= R) return;
+  float carry_c = 0.f, carry_E = 1.f;
+  for (int base = 0; base < N; base += 32) {
+    int s = base + lane;
+    bool valid = s < N;
+    float a = valid ? __fmul_rn(-sigmas[(int64_t)r * N + s], steps[(int64_t)r * N + s]) : 0.0f;
+    SegTile sg = seg_tile_a(a, lane, carry_c, carry_E);
+    if (valid) {
+      p_exits[(int64_t)r * N + s] = sg.E;
+      p_term[(int64_t)r * N + s] = sg.pt;
+    }
+  }
+}
+
+int launch_segment_probs(cudaStream_t st, const float* sigmas, const float* steps, float* p_exits, float* p_term, int R,
+                         int N) {
+  if (R == 0) return 0;
+  k_segment_probs<<<(R + 3) / 4, 128, 0, st>>>(sigmas, steps, p_exits, p_term, R, N);
+  TF_CHECK_LAUNCH();
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------

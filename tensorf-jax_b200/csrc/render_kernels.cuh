@@ -67,6 +67,7 @@ struct DensityBwdArgs : SceneArgs {
 };
 
 int launch_density_select(cudaStream_t st, const DensityArgs& A);
+int launch_segment_probs(cudaStream_t st, const float* sigmas, const float* steps, float* p_exits, float* p_term, int R, int N);
 int launch_topk_select(cudaStream_t st, const float* g, int R, int N, int K, int32_t* idx);
 int launch_appearance(cudaStream_t st, const AppearanceArgs& A, bool bwd);
 int launch_composite_fwd(cudaStream_t st, const CompositeArgs& A);

@@ -68,12 +68,16 @@ _pd, _pp, _pi = C.POINTER(RenderDesc), C.POINTER(Params), C.POINTER(RenderInputs
 SIGNATURES = {
     "tensorf_last_error": (C.c_char_p, []),
     "tensorf_version": (_i, []),
+    "tensorf_launch_count": (_i64, []),
+    "tensorf_profile_enable": (_i, [_i]),
+    "tensorf_profile_read": (_i, [_i, C.c_char_p, C.POINTER(C.c_float), C.POINTER(_i), C.POINTER(_i)]),
     "tensorf_vm_packed_floats": (_i64, [_i, _i]),
     "tensorf_vm_pack": (_i, [_vp, _vp, _vp, _vp, _i, _i]),
     "tensorf_vm_unpack": (_i, [_vp, _vp, _vp, _vp, _i, _i]),
     "tensorf_vm_interp_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i64, _i]),
     "tensorf_vm_interp_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _i]),
     "tensorf_topk_select": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "tensorf_segment_probabilities": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "tensorf_mlp_workspace_bytes": (_i64, [_pd, _i64]),
     "tensorf_mlp_fwd": (_i, [_vp, _pd, _pp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
     "tensorf_mlp_bwd": (_i, [_vp, _pd, _pp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _pp]),

@@ -137,6 +137,17 @@ def topk_select(g: torch.Tensor, K: int) -> torch.Tensor:
     return idx
 
 
+def segment_probabilities(sigmas: torch.Tensor, step_sizes: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """render.py:300-347: (R,N),(R,N) -> p_exits, p_terminates."""
+    if sigmas.dim() != 2 or sigmas.shape != step_sizes.shape:
+        raise ValueError("sigmas and step_sizes must both be (R,N)")
+    R, N = sigmas.shape
+    pe, pt = torch.empty_like(sigmas), torch.empty_like(sigmas)
+    check(_lib.load().tensorf_segment_probabilities(_stream(), _ptr(sigmas, name="sigmas"), _ptr(step_sizes, name="step_sizes"),
+                                                    R, N, _ptr(pe), _ptr(pt)))
+    return pe, pt
+
+
 # ---------------------------------------------------------------------------------------------
 # FeatureMlp
 # ---------------------------------------------------------------------------------------------
@@ -274,3 +285,29 @@ class RenderCall:
         off = (ptr.value - self.workspace.data_ptr()) // 4
         t = self.workspace[off:off + cnt.value]
         return t.view(torch.int32).clone() if name == "idx" else t.clone()
+
+
+# ---------------------------------------------------------------------------------------------
+# measurement hooks
+# ---------------------------------------------------------------------------------------------
+def launch_count() -> int:
+    """Kernels this thread has enqueued through the library so far."""
+    return int(_lib.load().tensorf_launch_count())
+
+
+def profile_enable(enable: bool = True) -> None:
+    check(_lib.load().tensorf_profile_enable(int(enable)))
+
+
+def profile_read(max_entries: int = 64) -> Dict[str, Tuple[float, int]]:
+    """{stage: (total_ms, calls)} measured with CUDA events the library recorded on the launch
+    stream since profile_enable()/the last read. Blocks until those events completed."""
+    names = C.create_string_buffer(32 * max_entries)
+    ms = (C.c_float * max_entries)()
+    calls = (C.c_int * max_entries)()
+    n = C.c_int(0)
+    check(_lib.load().tensorf_profile_read(max_entries, names, ms, calls, C.byref(n)))
+    out = {}
+    for i in range(n.value):
+        out[names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode()] = (float(ms[i]), int(calls[i]))
+    return out

@@ -1,0 +1,167 @@
+"""The host-side mirror of the reference interface (tensor_vm / networks / render / training)
+run through the CUDA library, checked against the CPU oracle — these read like tests the
+reference would have had."""
+import numpy as np
+import pytest
+import torch
+
+import tensorf_oracle as O
+from helpers import T, assert_close_grad, assert_close_out, oracle_cfgs
+from tensorf_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _learnable(w, inp, cuda):
+    from tensorf_b200 import render
+    flat = {k: T(v, device=cuda).requires_grad_(True) for k, v in inp["params"].items()}
+    return render.LearnableParams.from_flat(flat, w.contracted), flat
+
+
+def test_tensor_vm_interpolate_autograd(cuda):
+    from tensorf_b200 import tensor_vm
+    rng = np.random.default_rng(0)
+    v = rng.normal(0, 0.1, (3, 6, 11)).astype(np.float32)
+    m = rng.normal(0, 0.1, (3, 6, 11, 11)).astype(np.float32)
+    ijk = rng.uniform(-1, 1, (3, 5, 17)).astype(np.float32)          # two batch axes, like (3,R,N)
+    vm = tensor_vm.TensorVM(tensor_vm.TensorVMSingle(T(v, device=cuda).requires_grad_(True), T(m, device=cuda).requires_grad_(True)))
+    assert vm.grid_dim() == 11 and vm.channel_dim() == 18
+    out = vm.interpolate(T(ijk, device=cuda))
+    assert tuple(out.shape) == (18, 5, 17)
+    w = rng.normal(size=(18, 5, 17)).astype(np.float32)
+    (out * T(w, device=cuda)).sum().backward()
+    v64, m64 = T(v, torch.float64).requires_grad_(True), T(m, torch.float64).requires_grad_(True)
+    ref = O.vm_interpolate(v64, m64, T(ijk, torch.float64))
+    (ref * T(w, torch.float64)).sum().backward()
+    assert_close_out(out.detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-5, what="interpolate")
+    assert_close_grad(vm.stacked_single_vm.vector.grad.cpu().numpy(), v64.grad.numpy(), what="d vector")
+    assert_close_grad(vm.stacked_single_vm.matrix.grad.cpu().numpy(), m64.grad.numpy(), what="d matrix")
+    with pytest.raises(ValueError):
+        vm.interpolate(torch.zeros(2, 4, device=cuda))
+    with pytest.raises(NotImplementedError):
+        vm.resize(20)
+
+
+def test_feature_mlp_apply(cuda):
+    from tensorf_b200 import networks
+    mlp = networks.FeatureMlp(feature_n_freqs=2, viewdir_n_freqs=2, num_cameras=5)
+    assert mlp.encoded_dim() == 150
+    gen = torch.Generator(device=cuda).manual_seed(0)
+    variables = mlp.init(gen, torch.zeros(1, 144, device=cuda))
+    assert tuple(variables["params"]["Dense_1"]["kernel"].shape) == (150, 128)
+    rng = np.random.default_rng(1)
+    feat = T(rng.normal(0, 0.3, (4, 9, 144)).astype(np.float32), device=cuda).requires_grad_(True)
+    vd = T(rng.normal(size=(4, 9, 3)).astype(np.float32), device=cuda)
+    cams = T(rng.integers(0, 5, (4, 9)).astype(np.int32), device=cuda)
+    rgb = mlp.apply(variables, feat, vd, cams)
+    assert tuple(rgb.shape) == (4, 9, 3)
+    rgb.sum().backward()
+    flat = {k: v.detach().cpu().double().requires_grad_(True) for k, v in networks.flatten_mlp_params(variables).items()}
+    f64 = feat.detach().cpu().double().requires_grad_(True)
+    ref = O.feature_mlp(O.MlpConfig(27, 128, 2, 2, 5), flat, f64.reshape(36, 144), vd.cpu().double().reshape(36, 3),
+                        cams.cpu().long().reshape(36))
+    ref.sum().backward()
+    assert_close_out(rgb.detach().cpu().numpy().reshape(36, 3), ref.detach().numpy(), what="mlp apply")
+    assert_close_grad(feat.grad.cpu().numpy(), f64.grad.numpy(), what="d features")
+    with pytest.raises(ValueError):
+        mlp.apply(variables, feat, vd[:, :4], cams)
+
+
+@pytest.mark.parametrize("contracted", [False, True])
+def test_render_rays_modes_and_autograd(cuda, contracted):
+    from tensorf_b200 import cameras, networks, prng, render
+    w = S.Workload("api", 96, 12, 4, 8, 45, 7, 2, 2, contracted=contracted, num_cameras=4 if contracted else None)
+    inp = S.make_inputs(w, bias_std=0.05)
+    lp, flat = _learnable(w, inp, cuda)
+    mlp = networks.FeatureMlp(feature_n_freqs=2, viewdir_n_freqs=2, num_cameras=w.num_cameras)
+    rays = cameras.Rays3D(T(inp["origins"], device=cuda), T(inp["directions"], device=cuda), T(inp["camera_indices"], device=cuda))
+    aabb = T(inp["aabb"], device=cuda)
+    key = prng.Key.from_seed(3)
+    noise = prng.render_noise(key, w.R, w.N, contracted)
+    cfg = render.RenderConfig(near=w.near, far=w.far, mode=render.RenderMode.RGB, density_samples_per_ray=w.N,
+                              appearance_samples_per_ray=w.K)
+    rgb = render.render_rays(mlp, lp, aabb, rays, key, cfg)
+    assert tuple(rgb.shape) == (w.R, 3)
+    colors = T(inp["colors"], device=cuda)
+    loss = torch.mean((rgb - colors) ** 2)           # training.py:140, through torch.autograd
+    loss.backward()
+
+    ocfg, mc = oracle_cfgs(w)
+    P64 = {k: T(v, torch.float64) for k, v in inp["params"].items()}
+    args = (T(inp["aabb"], torch.float64), T(inp["origins"], torch.float64), T(inp["directions"], torch.float64),
+            torch.from_numpy(inp["camera_indices"].astype(np.int64)))
+    jit64, gum64 = T(noise.jitter, torch.float64), T(noise.gumbel, torch.float64)
+    out64, aux = O.render_rays(ocfg, mc, P64, contracted, *args, jit64, gum64, return_aux=True)
+    loss64, rgb64, g64 = O.loss_and_grads(ocfg, mc, P64, contracted, *args, T(inp["colors"], torch.float64), jit64, gum64)
+    # (fp64 and fp32 selections agree except for near-ties; tolerate a couple of rays)
+    bad = np.abs(rgb.detach().cpu().numpy() - rgb64.numpy()).max(axis=-1) > 1e-4
+    assert bad.sum() <= 2, f"{bad.sum()} rays differ"
+    if bad.sum() == 0:
+        for k, ref in g64.items():
+            assert_close_grad(flat[k].grad.cpu().numpy(), ref.numpy(), what=f"autograd grad {k}")
+
+    for mode, omode in ((render.RenderMode.DIST_MEAN, O.DIST_MEAN), (render.RenderMode.DIST_MEDIAN, O.DIST_MEDIAN)):
+        cfg_d = render.RenderConfig(near=w.near, far=w.far, mode=mode, density_samples_per_ray=w.N, appearance_samples_per_ray=w.K)
+        d = render.render_rays(mlp, lp, aabb, rays, key, cfg_d)
+        assert tuple(d.shape) == (w.R,)
+        ref = O.render_rays(O.RenderConfig(w.near, w.far, omode, w.N, w.K), mc, P64, contracted, *args, jit64, None).numpy()
+        ok = np.isclose(d.cpu().numpy(), ref, rtol=1e-4, atol=1e-6) | (np.isinf(ref) & np.isinf(d.cpu().numpy()))
+        assert ok.mean() >= 0.97
+
+
+def test_render_rays_batched_ragged(cuda):
+    from tensorf_b200 import cameras, networks, prng, render
+    w = S.Workload("batched", 100, 12, 4, 8, 40, 6, 2, 2)
+    inp = S.make_inputs(w)
+    lp, _ = _learnable(w, inp, cuda)
+    mlp = networks.FeatureMlp(feature_n_freqs=2, viewdir_n_freqs=2)
+    o, d, c = S.frame_rays(10, 10)                                    # (H*W,) raster rays
+    rays = cameras.Rays3D(T(o, device=cuda).reshape(10, 10, 3), T(d, device=cuda).reshape(10, 10, 3), T(c, device=cuda).reshape(10, 10))
+    aabb = T(inp["aabb"], device=cuda)
+    cfg = render.RenderConfig(0.05, 200.0, render.RenderMode.RGB, w.N, w.K)
+    key = prng.Key.from_seed(0)
+    full = render.render_rays_batched(mlp, lp, aabb, rays, key, cfg, batch_size=100)
+    ragged = render.render_rays_batched(mlp, lp, aabb, rays, key, cfg, batch_size=32)   # last chunk of 4 rays
+    assert full.shape == (10, 10, 3) and isinstance(full, np.ndarray)
+    np.testing.assert_allclose(full, ragged, atol=1e-6)
+    depth = render.render_rays_batched(mlp, lp, aabb, rays, key, dataclass_replace(cfg, render.RenderMode.DIST_MEAN), batch_size=64)
+    assert depth.shape == (10, 10)
+
+
+def dataclass_replace(cfg, mode):
+    import dataclasses
+    return dataclasses.replace(cfg, mode=mode)
+
+
+def test_compute_segment_probabilities(cuda):
+    from tensorf_b200 import render
+    rng = np.random.default_rng(0)
+    sig = rng.uniform(0, 12, (3, 7, 221)).astype(np.float32)
+    st = rng.uniform(0.001, 0.02, (3, 7, 221)).astype(np.float32)
+    out = render.compute_segment_probabilities(T(sig, device=cuda), T(st, device=cuda))
+    pe, pt = O.compute_segment_probabilities(T(sig, torch.float64), T(st, torch.float64))
+    assert out.get_batch_axes() == (3, 7, 221)
+    # fp32 `1 - exp(a)` cancels for small |a| (the reference's own formula, render.py:327), so an
+    # elementwise relative bound is ill-posed: 1e-4 relative + 3e-7 absolute (a few ulp of exp ~ 1).
+    np.testing.assert_allclose(out.p_exits.cpu().numpy(), pe.numpy(), rtol=1e-4, atol=3e-7)
+    np.testing.assert_allclose(out.p_terminates.cpu().numpy(), pt.numpy(), rtol=1e-4, atol=3e-7)
+
+
+def test_training_step(cuda):
+    from tensorf_b200 import cameras, train_config, training
+    cfg = train_config.lego_config(grid_dim_init=16, minibatch_size=256, appearance_feat_dim=8, density_feat_dim=4)
+    state = training.TrainState.initialize(cfg, grid_dim=16, prng_key=0, num_cameras=10, device=cuda)
+    assert state.sample_counts() == (27, 4)
+    o, d, c = S.lego_rays(256, seed=5)
+    mb = training.RenderedRays(colors=T(S.make_colors(256), device=cuda),
+                               rays_wrt_world=cameras.Rays3D(T(o, device=cuda), T(d, device=cuda), T(c, device=cuda)))
+    before = {k: v.clone() for k, v in state.learnable_params.flat().items()}
+    losses = []
+    for _ in range(25):
+        state, log = state.training_step(mb)
+        losses.append(log["train/mse"])
+    assert state.step == 25 and set(log) == {"train/mse", "train/psnr", "train/lr_tensor", "train/lr_mlp", "train/grad_norm"}
+    assert losses[-1] < losses[0], losses
+    after = state.learnable_params.flat()
+    assert all(not torch.equal(before[k], after[k]) for k in ("w1", "appearance_matrix"))
+    assert abs(log["train/lr_tensor"] - 0.02 * 0.1 ** (24 / 30000)) < 1e-7
