@@ -468,7 +468,7 @@ int tensorf_render_rgb_bwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   ap.d_packed = w.gpacked_a;
   {
     StageTimer t_(st, "appearance_scatter");
-    TF_RETURN_IF_ERROR(launch_appearance(st, ap, true));
+    TF_RETURN_IF_ERROR(launch_appearance_scatter(st, ap));
   }
   StageTimer t_(st, "unpack");
   TF_RETURN_IF_ERROR(vm_unpack(st, w.gpacked_d, grads->density_vector, grads->density_matrix, d->cd, d->G));

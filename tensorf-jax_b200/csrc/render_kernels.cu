@@ -541,64 +541,246 @@ int launch_ray_bwd(cudaStream_t st, const RayBwdArgs& A) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// density scatter: every density channel of a sample receives the same upstream scalar dz.
+// Sliding-window scatter-add (reverse of the VM gather) for samples that are ordered along a ray.
+//
+// Work item = (ray, segment of consecutive samples, VM pair P, block of LPS float4 channel
+// groups); LPS lanes per item, one float4 of channels per lane.  Consecutive samples of a ray
+// move less than a texel per step, so instead of 6 REDs per sample the lane keeps the current
+// 2-texel line window and 2x2 plane window of gradient sums in registers and issues a vector
+// RED only when a texel leaves the window: one RED per (ray segment, texel visit).
+//   APP=false: density   — walks s in [seg), upstream = scalar dz[r,s] for every channel
+//   APP=true : appearance — walks the ascending selected samples idx[r,k], upstream = d_feat row
 // ---------------------------------------------------------------------------------------------
-template <int LPS>
-__global__ void __launch_bounds__(256) k_density_scatter(DensityBwdArgs A) {
+struct WalkArgs : SceneArgs {
+  const float* packed;
+  float* d_packed;
+  const float* dz;      // density
+  const int32_t* idx;   // appearance
+  const float* d_feat;  // appearance (M, 3C)
+  int C, Cp, seg_len, segs, count;  // count = N (density) or K (appearance)
+};
+
+template <int LPS, bool APP>
+__global__ void __launch_bounds__(256) k_scatter_walk(WalkArgs A) {
   const int nvec = A.Cp >> 2;
-  constexpr int SPB = 256 / LPS;
+  const int vblocks = (nvec + LPS - 1) / LPS;
   const int sub = threadIdx.x % LPS;
-  int64_t i = (int64_t)blockIdx.x * SPB + threadIdx.x / LPS;
-  if (i >= (int64_t)A.R * A.N) return;
-  const float g = A.dz[i];
-  if (g == 0.0f) return;
-  int r = (int)(i / A.N), s = (int)(i % A.N);
+  const int per_ray = A.segs * 3 * vblocks;
+  int64_t item = (int64_t)blockIdx.x * (256 / LPS) + threadIdx.x / LPS;
+  if (item >= (int64_t)A.R * per_ray) return;
+  const int r = (int)(item / per_ray);
+  int rem = (int)(item % per_ray);
+  const int seg = rem / (3 * vblocks);
+  rem -= seg * 3 * vblocks;
+  const int P = rem / vblocks;
+  const int v = (rem % vblocks) * LPS + sub;
+  if (v >= nvec) return;
+  const int j_begin = seg * A.seg_len, j_end = min(A.count, j_begin + A.seg_len);
+
   SceneParams sc;
   load_scene(sc, A.aabb, A.N, A.G, A.contracted, A.jitter, A.base_ts, A.deltas);
   RayParams ray;
   load_ray(ray, sc, A.origins, A.directions, A.aabb, r);
-  float delta;
-  float t = sample_t(ray, sc, r, s, delta);
-  float x[3];
-  sample_grid_coords(ray, sc, t, x);
-  VmTaps taps;
-  make_vm_taps(taps, x, A.G);
-  for (int v = sub; v < nvec; v += LPS) {
-#pragma unroll
-    for (int P = 0; P < 3; ++P) {
-      PairAddr pa = pair_addr(taps, P, A.G, A.Cp, v);
-      float4 lin, bil;
-      pair_values(A.packed_d, pa, lin, bil);
-      float4 gl = f4_scale(bil, g), gb = f4_scale(lin, g);
-      red_add_v4(A.d_packed + pa.l0, f4_scale(gl, pa.wl0));
-      red_add_v4(A.d_packed + pa.l1, f4_scale(gl, pa.wl1));
-      red_add_v4(A.d_packed + pa.m00, f4_scale(gb, pa.w00));
-      red_add_v4(A.d_packed + pa.m01, f4_scale(gb, pa.w01));
-      red_add_v4(A.d_packed + pa.m10, f4_scale(gb, pa.w10));
-      red_add_v4(A.d_packed + pa.m11, f4_scale(gb, pa.w11));
+
+  const int G = A.G, Cp = A.Cp;
+  const int64_t lbase = (int64_t)P * G * Cp + 4 * v;
+  const int64_t mbase = (int64_t)3 * G * Cp + (int64_t)P * G * G * Cp + 4 * v;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr int EMPTY = INT_MIN;
+  int lw = EMPTY;           // line window covers texels lw, lw+1
+  float4 la0 = zero4, la1 = zero4;
+  int pa = EMPTY, pb = 0;   // plane window covers rows pa, pa+1 x cols pb, pb+1
+  float4 m00 = zero4, m01 = zero4, m10 = zero4, m11 = zero4;
+  auto flush_l = [&](int i, const float4& acc) { red_add_v4(A.d_packed + lbase + (int64_t)i * Cp, acc); };
+  auto flush_m = [&](int a, int b, const float4& acc) { red_add_v4(A.d_packed + mbase + ((int64_t)a * G + b) * Cp, acc); };
+
+  for (int j = j_begin; j < j_end; ++j) {
+    int s;
+    float4 g;
+    if (APP) {
+      const int64_t m = (int64_t)r * A.K + j;
+      s = A.idx[m];
+      const float* src = A.d_feat + m * (3 * A.C) + P * A.C + 4 * v;
+      if ((A.C & 3) == 0) {
+        g = *reinterpret_cast<const float4*>(src);
+      } else {
+        float gv[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int q = 0; q < 4; ++q)
+          if (4 * v + q < A.C) gv[q] = src[q];
+        g = make_float4(gv[0], gv[1], gv[2], gv[3]);
+      }
+    } else {
+      s = j;
+      float gz = A.dz[(int64_t)r * A.N + s];
+      g = make_float4(gz, gz, gz, gz);
     }
+    float delta;
+    float t = sample_t(ray, sc, r, s, delta);
+    float x[3];
+    sample_grid_coords(ray, sc, t, x);
+    // axis roles of pair P (tensor_vm.py:50-52), selected without indexing local arrays
+    const float xl = P == 0 ? x[0] : (P == 1 ? x[2] : x[1]);
+    const float xa = P == 0 ? x[1] : (P == 1 ? x[0] : x[2]);
+    const float xb = P == 0 ? x[2] : (P == 1 ? x[1] : x[0]);
+    const Tap L = make_tap(xl, G), Ta = make_tap(xa, G), Tb = make_tap(xb, G);
+
+    // re-gather (bit-identical to the forward)
+    const float4 l0 = ld4(A.packed + lbase + (int64_t)L.i0 * Cp), l1 = ld4(A.packed + lbase + (int64_t)L.i1 * Cp);
+    const float4 v00 = ld4(A.packed + mbase + ((int64_t)Ta.i0 * G + Tb.i0) * Cp);
+    const float4 v01 = ld4(A.packed + mbase + ((int64_t)Ta.i0 * G + Tb.i1) * Cp);
+    const float4 v10 = ld4(A.packed + mbase + ((int64_t)Ta.i1 * G + Tb.i0) * Cp);
+    const float4 v11 = ld4(A.packed + mbase + ((int64_t)Ta.i1 * G + Tb.i1) * Cp);
+    float4 lin = f4_fma(l1, L.w1, f4_scale(l0, L.w0));
+    float4 bil = f4_scale(v00, __fmul_rn(Ta.w0, Tb.w0));
+    bil = f4_fma(v01, __fmul_rn(Ta.w0, Tb.w1), bil);
+    bil = f4_fma(v10, __fmul_rn(Ta.w1, Tb.w0), bil);
+    bil = f4_fma(v11, __fmul_rn(Ta.w1, Tb.w1), bil);
+    const float4 gl = f4_mul(g, bil), gb = f4_mul(g, lin);
+
+    // ---- line window ----
+    const int wb = min(L.i0, G - 2);
+    if (wb != lw) {
+      if (lw != EMPTY) {
+        const int d = wb - lw;
+        if (d == 1) {
+          flush_l(lw, la0);
+          la0 = la1;
+          la1 = zero4;
+        } else if (d == -1) {
+          flush_l(lw + 1, la1);
+          la1 = la0;
+          la0 = zero4;
+        } else {
+          flush_l(lw, la0);
+          flush_l(lw + 1, la1);
+          la0 = la1 = zero4;
+        }
+      }
+      lw = wb;
+    }
+    {
+      const float s0 = (L.i0 == wb ? L.w0 : 0.f) + (L.i1 == wb ? L.w1 : 0.f);
+      const float s1 = (L.i0 == wb + 1 ? L.w0 : 0.f) + (L.i1 == wb + 1 ? L.w1 : 0.f);
+      la0 = f4_fma(gl, s0, la0);
+      la1 = f4_fma(gl, s1, la1);
+    }
+    // ---- plane window ----
+    const int ab = min(Ta.i0, G - 2), bb = min(Tb.i0, G - 2);
+    if (ab != pa || bb != pb) {
+      if (pa != EMPTY) {
+        const int da = ab - pa, db = bb - pb;
+        if (da > 1 || da < -1 || db > 1 || db < -1) {
+          flush_m(pa, pb, m00);
+          flush_m(pa, pb + 1, m01);
+          flush_m(pa + 1, pb, m10);
+          flush_m(pa + 1, pb + 1, m11);
+          m00 = m01 = m10 = m11 = zero4;
+        } else {
+          if (da == 1) {
+            flush_m(pa, pb, m00);
+            flush_m(pa, pb + 1, m01);
+            m00 = m10;
+            m01 = m11;
+            m10 = m11 = zero4;
+          } else if (da == -1) {
+            flush_m(pa + 1, pb, m10);
+            flush_m(pa + 1, pb + 1, m11);
+            m10 = m00;
+            m11 = m01;
+            m00 = m01 = zero4;
+          }
+          // rows now are ab, ab+1; the row that just entered the window is still all zero
+          if (db == 1) {
+            if (da != -1) flush_m(ab, pb, m00);
+            if (da != 1) flush_m(ab + 1, pb, m10);
+            m00 = m01;
+            m10 = m11;
+            m01 = m11 = zero4;
+          } else if (db == -1) {
+            if (da != -1) flush_m(ab, pb + 1, m01);
+            if (da != 1) flush_m(ab + 1, pb + 1, m11);
+            m01 = m00;
+            m11 = m10;
+            m00 = m10 = zero4;
+          }
+        }
+      }
+      pa = ab;
+      pb = bb;
+    }
+    {
+      const float r0 = (Ta.i0 == ab ? Ta.w0 : 0.f) + (Ta.i1 == ab ? Ta.w1 : 0.f);
+      const float r1 = (Ta.i0 == ab + 1 ? Ta.w0 : 0.f) + (Ta.i1 == ab + 1 ? Ta.w1 : 0.f);
+      const float c0 = (Tb.i0 == bb ? Tb.w0 : 0.f) + (Tb.i1 == bb ? Tb.w1 : 0.f);
+      const float c1 = (Tb.i0 == bb + 1 ? Tb.w0 : 0.f) + (Tb.i1 == bb + 1 ? Tb.w1 : 0.f);
+      m00 = f4_fma(gb, r0 * c0, m00);
+      m01 = f4_fma(gb, r0 * c1, m01);
+      m10 = f4_fma(gb, r1 * c0, m10);
+      m11 = f4_fma(gb, r1 * c1, m11);
+    }
+  }
+  if (lw != EMPTY) {
+    flush_l(lw, la0);
+    flush_l(lw + 1, la1);
+  }
+  if (pa != EMPTY) {
+    flush_m(pa, pb, m00);
+    flush_m(pa, pb + 1, m01);
+    flush_m(pa + 1, pb, m10);
+    flush_m(pa + 1, pb + 1, m11);
   }
 }
 
-int launch_density_scatter(cudaStream_t st, const DensityBwdArgs& A) {
-  int64_t samples = (int64_t)A.R * A.N;
-  if (samples == 0) return 0;
-  const int nvec = A.Cp / 4;
-  int lps = 1;
+static int pick_lps(int nvec) {
   for (int p = 8; p >= 1; p >>= 1)
-    if (nvec % p == 0) {
-      lps = p;
-      break;
-    }
-  if (lps == 1 && nvec > 2) lps = nvec >= 8 ? 8 : 4;
+    if (nvec % p == 0) return p;
+  return 1;
+}
+
+template <bool APP>
+static int launch_walk(cudaStream_t st, WalkArgs A) {
+  if (A.R == 0 || A.count == 0) return 0;
+  const int nvec = A.Cp / 4;
+  int lps = pick_lps(nvec);
+  if (lps == 1 && nvec > 2) lps = 4;  // odd channel counts: round the block up, idle lanes exit
+  lps = min(lps, 4);                  // 64-byte texel fragments per item keep more items in flight
+  A.seg_len = APP ? 64 : 64;
+  A.segs = (A.count + A.seg_len - 1) / A.seg_len;
+  const int vblocks = (nvec + lps - 1) / lps;
+  int64_t items = (int64_t)A.R * A.segs * 3 * vblocks;
+  unsigned grid = (unsigned)ceil_div64(items, 256 / lps);
   switch (lps) {
-    case 8: k_density_scatter<8><<<(unsigned)ceil_div64(samples, 32), 256, 0, st>>>(A); break;
-    case 4: k_density_scatter<4><<<(unsigned)ceil_div64(samples, 64), 256, 0, st>>>(A); break;
-    case 2: k_density_scatter<2><<<(unsigned)ceil_div64(samples, 128), 256, 0, st>>>(A); break;
-    default: k_density_scatter<1><<<(unsigned)ceil_div64(samples, 256), 256, 0, st>>>(A); break;
+    case 4: k_scatter_walk<4, APP><<<grid, 256, 0, st>>>(A); break;
+    case 2: k_scatter_walk<2, APP><<<grid, 256, 0, st>>>(A); break;
+    default: k_scatter_walk<1, APP><<<grid, 256, 0, st>>>(A); break;
   }
   TF_CHECK_LAUNCH();
   return 0;
+}
+
+int launch_density_scatter(cudaStream_t st, const DensityBwdArgs& D) {
+  WalkArgs A{};
+  static_cast<SceneArgs&>(A) = static_cast<const SceneArgs&>(D);
+  A.packed = D.packed_d;
+  A.d_packed = D.d_packed;
+  A.dz = D.dz;
+  A.C = D.Cp;
+  A.Cp = D.Cp;
+  A.count = D.N;
+  return launch_walk<false>(st, A);
+}
+
+int launch_appearance_scatter(cudaStream_t st, const AppearanceArgs& D) {
+  WalkArgs A{};
+  static_cast<SceneArgs&>(A) = static_cast<const SceneArgs&>(D);
+  A.packed = D.packed_a;
+  A.d_packed = D.d_packed;
+  A.idx = D.idx;
+  A.d_feat = D.d_feat;
+  A.C = D.C;
+  A.Cp = D.Cp;
+  A.count = D.K;
+  return launch_walk<true>(st, A);
 }
 
 }  // namespace tf

@@ -73,6 +73,7 @@ int launch_appearance(cudaStream_t st, const AppearanceArgs& A, bool bwd);
 int launch_composite_fwd(cudaStream_t st, const CompositeArgs& A);
 int launch_ray_bwd(cudaStream_t st, const RayBwdArgs& A);
 int launch_density_scatter(cudaStream_t st, const DensityBwdArgs& A);
+int launch_appearance_scatter(cudaStream_t st, const AppearanceArgs& A);
 
 int vm_pack(cudaStream_t st, const float* vector, const float* matrix, float* packed, int C, int G);
 int vm_unpack(cudaStream_t st, const float* packed, float* vector, float* matrix, int C, int G);
