@@ -139,6 +139,14 @@ int tensorf_topk_select(tensorf_stream_t s, const float* g, int R, int N, int K,
 int tensorf_segment_probabilities(tensorf_stream_t s, const float* sigmas, const float* step_sizes, int R, int N,
                                   float* p_exits, float* p_terminates);
 
+/* ---- tensor-core GEMM building blocks of the MLP (test entry points) ------------------------ */
+/* C (M,N) = [mask>0] relu?(A (M,K) @ W (K,N) + bias), split-bf16 operands on tcgen05, fp32
+ * accumulation. N <= 256. scratch >= 4*ceil64(K)*ceil16(N)*... bytes (64 KiB * ceil(K/64) suffices). */
+int tensorf_tc_rowgemm_test(tensorf_stream_t s, const float* A, int64_t M, int K, const float* W, int N, const float* bias,
+                            int relu, const float* mask, float* C, void* scratch, int64_t scratch_bytes);
+/* out (Nx, Mg) += X^T (Nx,rows) @ G (rows,Mg): the weight-gradient contraction over rows. Mg <= 128, Nx <= 512. */
+int tensorf_tc_redgemm_test(tensorf_stream_t s, const float* G, int Mg, const float* X, int Nx, int64_t rows, float* out);
+
 /* ---- networks.py:46-121 FeatureMlp.__call__ ----------------------------------------------- */
 /* features (M, 3*ca); viewdirs (M/rows_per_ray, 3); camera_indices (M/rows_per_ray); rgb (M,3).
  * workspace: tensorf_mlp_workspace_bytes. */

@@ -149,6 +149,10 @@ static int check_mlp_params(const tensorf_render_desc& d, const tensorf_params* 
   return 0;
 }
 
+int tc_rowgemm_test(cudaStream_t st, const float* A, int64_t M, int K, const float* W, int N, const float* bias, int relu,
+                    const float* mask, float* C, void* scratch, size_t scratch_bytes);
+int tc_redgemm_test(cudaStream_t st, const float* G, int Mg, const float* X, int Nx, int64_t rows, float* out);
+
 }  // namespace tf
 
 using namespace tf;
@@ -231,6 +235,16 @@ int tensorf_segment_probabilities(tensorf_stream_t s, const float* sigmas, const
   TF_CHECK_ARG(R >= 0 && N >= 1, "bad shape R=%d N=%d", R, N);
   TF_CHECK_ARG(R == 0 || (sigmas && step_sizes && p_exits && p_terminates), "NULL buffer");
   return launch_segment_probs((cudaStream_t)s, sigmas, step_sizes, p_exits, p_terminates, R, N);
+}
+
+int tensorf_tc_rowgemm_test(tensorf_stream_t s, const float* A, int64_t M, int K, const float* W, int N, const float* bias,
+                            int relu, const float* mask, float* C, void* scratch, int64_t scratch_bytes) {
+  TF_CHECK_ARG(A && W && C && scratch && M >= 0 && K >= 1 && N >= 1 && N <= 256, "bad argument");
+  return tc_rowgemm_test((cudaStream_t)s, A, M, K, W, N, bias, relu, mask, C, scratch, (size_t)scratch_bytes);
+}
+int tensorf_tc_redgemm_test(tensorf_stream_t s, const float* G, int Mg, const float* X, int Nx, int64_t rows, float* out) {
+  TF_CHECK_ARG(G && X && out && Mg >= 1 && Mg <= 128 && Nx >= 1 && Nx <= 512 && rows >= 0, "bad argument");
+  return tc_redgemm_test((cudaStream_t)s, G, Mg, X, Nx, rows, out);
 }
 
 int64_t tensorf_mlp_workspace_bytes(const tensorf_render_desc* d, int64_t M) {
