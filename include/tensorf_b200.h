@@ -140,10 +140,11 @@ int tensorf_segment_probabilities(tensorf_stream_t s, const float* sigmas, const
                                   float* p_exits, float* p_terminates);
 
 /* ---- tensor-core GEMM building blocks of the MLP (test entry points) ------------------------ */
-/* C (M,N) = [mask>0] relu?(A (M,K) @ W (K,N) + bias), split-bf16 operands on tcgen05, fp32
- * accumulation. N <= 256. scratch >= 4*ceil64(K)*ceil16(N)*... bytes (64 KiB * ceil(K/64) suffices). */
+/* C (M,N) = [mask>0] relu?(A (M,K) @ W (K,N) + bias), split-bf16 operands on tcgen05 (nsplit = 2:
+ * hi+lo, 3 products, ~2^-16; nsplit = 3: hi+mid+lo, 6 products, fp32-exact operands), fp32
+ * accumulation in TMEM. scratch: 6*ceil16(N)*ceil64(K)+ bytes (128 KiB * ceil(K/64) * ceil(N/256) suffices). */
 int tensorf_tc_rowgemm_test(tensorf_stream_t s, const float* A, int64_t M, int K, const float* W, int N, const float* bias,
-                            int relu, const float* mask, float* C, void* scratch, int64_t scratch_bytes);
+                            int relu, const float* mask, float* C, void* scratch, int64_t scratch_bytes, int nsplit);
 /* out (Nx, Mg) += X^T (Nx,rows) @ G (rows,Mg): the weight-gradient contraction over rows. Mg <= 128, Nx <= 512. */
 int tensorf_tc_redgemm_test(tensorf_stream_t s, const float* G, int Mg, const float* X, int Nx, int64_t rows, float* out);
 

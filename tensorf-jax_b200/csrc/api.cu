@@ -150,7 +150,7 @@ static int check_mlp_params(const tensorf_render_desc& d, const tensorf_params* 
 }
 
 int tc_rowgemm_test(cudaStream_t st, const float* A, int64_t M, int K, const float* W, int N, const float* bias, int relu,
-                    const float* mask, float* C, void* scratch, size_t scratch_bytes);
+                    const float* mask, float* C, void* scratch, size_t scratch_bytes, int nsplit);
 int tc_redgemm_test(cudaStream_t st, const float* G, int Mg, const float* X, int Nx, int64_t rows, float* out);
 
 }  // namespace tf
@@ -238,9 +238,10 @@ int tensorf_segment_probabilities(tensorf_stream_t s, const float* sigmas, const
 }
 
 int tensorf_tc_rowgemm_test(tensorf_stream_t s, const float* A, int64_t M, int K, const float* W, int N, const float* bias,
-                            int relu, const float* mask, float* C, void* scratch, int64_t scratch_bytes) {
-  TF_CHECK_ARG(A && W && C && scratch && M >= 0 && K >= 1 && N >= 1 && N <= 256, "bad argument");
-  return tc_rowgemm_test((cudaStream_t)s, A, M, K, W, N, bias, relu, mask, C, scratch, (size_t)scratch_bytes);
+                            int relu, const float* mask, float* C, void* scratch, int64_t scratch_bytes, int nsplit) {
+  TF_CHECK_ARG(A && W && C && scratch && M >= 0 && K >= 1 && N >= 1, "bad argument");
+  TF_CHECK_ARG(nsplit == 2 || nsplit == 3, "nsplit must be 2 or 3");
+  return tc_rowgemm_test((cudaStream_t)s, A, M, K, W, N, bias, relu, mask, C, scratch, (size_t)scratch_bytes, nsplit);
 }
 int tensorf_tc_redgemm_test(tensorf_stream_t s, const float* G, int Mg, const float* X, int Nx, int64_t rows, float* out) {
   TF_CHECK_ARG(G && X && out && Mg >= 1 && Mg <= 128 && Nx >= 1 && Nx <= 512 && rows >= 0, "bad argument");
@@ -268,7 +269,8 @@ int tensorf_mlp_fwd(tensorf_stream_t s, const tensorf_render_desc* d, const tens
   if (d->num_cameras > 0) TF_CHECK_ARG(M == 0 || camera_indices, "camera embeddings need camera_indices");
   MlpShape ms = mlp_shape(*d);
   MlpWs ws = mlp_ws_carve(ms, M, (float*)workspace);
-  return mlp_simt_fwd((cudaStream_t)s, ms, mlp_params(*p), features, viewdirs, camera_indices, M, rows_per_ray, ws, rgb);
+  return (mlp_use_tc(d->mlp_impl) ? mlp_tc_fwd : mlp_simt_fwd)((cudaStream_t)s, ms, mlp_params(*p), features, viewdirs,
+                                                                camera_indices, M, rows_per_ray, ws, rgb);
 }
 
 int tensorf_mlp_bwd(tensorf_stream_t s, const tensorf_render_desc* d, const tensorf_params* p, const float* features,
@@ -286,8 +288,9 @@ int tensorf_mlp_bwd(tensorf_stream_t s, const tensorf_render_desc* d, const tens
   TF_CHECK_ARG(M == 0 || (features && viewdirs && workspace && rgb && d_rgb && d_features), "NULL buffer");
   MlpShape ms = mlp_shape(*d);
   MlpWs ws = mlp_ws_carve(ms, M, (float*)workspace);
-  return mlp_simt_bwd((cudaStream_t)s, ms, mlp_params(*p), features, viewdirs, camera_indices, M, rows_per_ray, ws, rgb,
-                      d_rgb, d_features, mlp_grads(*grads));
+  return (mlp_use_tc(d->mlp_impl) ? mlp_tc_bwd : mlp_simt_bwd)((cudaStream_t)s, ms, mlp_params(*p), features, viewdirs,
+                                                                camera_indices, M, rows_per_ray, ws, rgb, d_rgb, d_features,
+                                                                mlp_grads(*grads));
 }
 
 int tensorf_render_workspace_bytes(const tensorf_render_desc* d, int64_t* bytes) {
@@ -397,8 +400,8 @@ int tensorf_render_rgb_fwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   MlpWs mws = mlp_ws_carve(ms, M, w.mlp_base);
   {
     StageTimer t_(st, "mlp_fwd");
-    TF_RETURN_IF_ERROR(
-        mlp_simt_fwd(st, ms, mlp_params(*p), w.feat, in->directions, in->camera_indices, M, d->K, mws, w.rgb_sel));
+    TF_RETURN_IF_ERROR((mlp_use_tc(d->mlp_impl) ? mlp_tc_fwd : mlp_simt_fwd)(st, ms, mlp_params(*p), w.feat, in->directions,
+                                                                              in->camera_indices, M, d->K, mws, w.rgb_sel));
   }
   StageTimer t_(st, "composite");
   if (in->colors) TF_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
@@ -467,8 +470,9 @@ int tensorf_render_rgb_bwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   MlpWs mws = mlp_ws_carve(ms, M, w.mlp_base);
   {
     StageTimer t_(st, "mlp_bwd");
-    TF_RETURN_IF_ERROR(mlp_simt_bwd(st, ms, mlp_params(*p), w.feat, in->directions, in->camera_indices, M, d->K, mws,
-                                    w.rgb_sel, w.d_rgb_sel, w.d_feat, mlp_grads(*grads)));
+    TF_RETURN_IF_ERROR((mlp_use_tc(d->mlp_impl) ? mlp_tc_bwd : mlp_simt_bwd)(st, ms, mlp_params(*p), w.feat, in->directions,
+                                                                              in->camera_indices, M, d->K, mws, w.rgb_sel,
+                                                                              w.d_rgb_sel, w.d_feat, mlp_grads(*grads)));
   }
 
   AppearanceArgs ap{};

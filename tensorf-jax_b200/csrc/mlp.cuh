@@ -27,8 +27,11 @@ inline MlpShape mlp_shape(const tensorf_render_desc& d) {
 
 // Activation workspace of one MLP call (all fp32, row-major).
 struct MlpWs {
-  float* f;    // (M, squash)   Dense_0 output
-  float* x;    // (M, enc)      encoded input of Dense_1
+  int ldf, ldx;  // row strides of f/df and x/dx: squash and enc rounded up to 16
+  unsigned char* wpack;  // split-bf16 packed weights of the tensor-core path
+  size_t wpack_bytes;
+  float* f;    // (M, ldf)      Dense_0 output
+  float* x;    // (M, ldx)      encoded input of Dense_1
   float* h1;   // (M, units)    relu(Dense_1)
   float* h2;   // (M, units)    relu(Dense_2), before FiLM
   float* dp2;  // (M, units)    d pre-activation of Dense_2
@@ -52,5 +55,24 @@ int mlp_simt_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const f
 int mlp_simt_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs,
                  const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, const float* rgb, const float* d_rgb,
                  float* d_feat, const MlpGrads& g);
+// tcgen05 tensor-core path (split-bf16 operands, fp32 accumulate), same contract.
+int mlp_tc_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs,
+               const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, float* rgb);
+int mlp_tc_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs,
+               const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, const float* rgb, const float* d_rgb,
+               float* d_feat, const MlpGrads& g);
+size_t mlp_tc_wpack_bytes(const MlpShape& s);
+
+// pieces shared by both implementations (mlp_simt.cu)
+int mlp_encode_fwd(cudaStream_t st, const MlpShape& s, const MlpWs& ws, const float* viewdirs, int64_t M, int rows_per_ray);
+int mlp_encode_bwd(cudaStream_t st, const MlpShape& s, const MlpWs& ws, int64_t M);
+int mlp_out_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const MlpWs& ws, const uint32_t* cams, int64_t M,
+                int rows_per_ray, float* rgb);
+int mlp_out_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const MlpWs& ws, const uint32_t* cams, int64_t M,
+                int rows_per_ray, const float* rgb, const float* d_rgb, const MlpGrads& g);
+int mlp_colsum128(cudaStream_t st, const float* G, float* out, int64_t M);
+int mlp_zero_grads(cudaStream_t st, const MlpShape& s, const MlpGrads& g);
+
+inline bool mlp_use_tc(int mlp_impl) { return mlp_impl != TENSORF_MLP_SIMT_FP32; }
 
 }  // namespace tf

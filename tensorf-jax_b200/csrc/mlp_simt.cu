@@ -8,16 +8,22 @@ namespace tf {
 
 int64_t mlp_ws_floats(const MlpShape& s, int64_t M) {
   int64_t Mp = round_up64(M, 128);
-  return Mp * ((int64_t)2 * round_up(s.squash, 4) + 2 * round_up(s.enc, 4) + 4 * s.units);
+  return Mp * ((int64_t)2 * round_up(s.squash, 16) + 2 * round_up(s.enc, 16) + 4 * s.units) +
+         (int64_t)round_up64((int64_t)mlp_tc_wpack_bytes(s), 256) / 4;
 }
 MlpWs mlp_ws_carve(const MlpShape& s, int64_t M, float* base) {
   int64_t Mp = round_up64(M, 128);
   MlpWs w;
+  w.ldf = round_up(s.squash, 16);
+  w.ldx = round_up(s.enc, 16);
   float* p = base;
-  w.f = p;   p += Mp * round_up(s.squash, 4);
-  w.df = p;  p += Mp * round_up(s.squash, 4);
-  w.x = p;   p += Mp * round_up(s.enc, 4);
-  w.dx = p;  p += Mp * round_up(s.enc, 4);
+  w.wpack = reinterpret_cast<unsigned char*>(p);
+  w.wpack_bytes = mlp_tc_wpack_bytes(s);
+  p += round_up64((int64_t)w.wpack_bytes, 256) / 4;
+  w.f = p;   p += Mp * w.ldf;
+  w.df = p;  p += Mp * w.ldf;
+  w.x = p;   p += Mp * w.ldx;
+  w.dx = p;  p += Mp * w.ldx;
   w.h1 = p;  p += Mp * s.units;
   w.h2 = p;  p += Mp * s.units;
   w.dp2 = p; p += Mp * s.units;
@@ -150,17 +156,20 @@ static int launch_sgemm(cudaStream_t st, GemmArgs g, int splits) {
 // Fourier encoding (networks.py:13-35, :68-76)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_encode_fwd(const float* __restrict__ f, const float* __restrict__ viewdirs,
-                                                    float* __restrict__ x, int64_t M, int rows_per_ray, MlpShape s) {
+                                                    float* __restrict__ x, int64_t M, int rows_per_ray, MlpShape s, int ldf,
+                                                    int ldx) {
   const int D = s.squash + 3;
   int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= M * D) return;
   int64_t m = item / D;
   int d = (int)(item % D);
-  float* row = x + m * s.enc;
+  float* row = x + m * ldx;
   float val;
   int F, off;
+  if (d == 0)
+    for (int q = s.enc; q < ldx; ++q) row[q] = 0.f;  // padding columns stay finite
   if (d < s.squash) {
-    val = f[m * s.squash + d];
+    val = f[m * ldf + d];
     F = s.Ff;
     off = D + d * 2 * s.Ff;
   } else {
@@ -180,13 +189,13 @@ __global__ void __launch_bounds__(256) k_encode_fwd(const float* __restrict__ f,
 }
 
 __global__ void __launch_bounds__(256) k_encode_bwd(const float* __restrict__ f, const float* __restrict__ dx,
-                                                    float* __restrict__ df, int64_t M, MlpShape s) {
+                                                    float* __restrict__ df, int64_t M, MlpShape s, int ldf, int ldx) {
   int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= M * s.squash) return;
   int64_t m = item / s.squash;
   int d = (int)(item % s.squash);
-  const float* row = dx + m * s.enc;
-  float val = f[m * s.squash + d];
+  const float* row = dx + m * ldx;
+  float val = f[m * ldf + d];
   float g = row[d];
   int off = s.squash + 3 + d * 2 * s.Ff;
   const float half_pi = 1.57079632679489661923f;
@@ -196,7 +205,7 @@ __global__ void __launch_bounds__(256) k_encode_bwd(const float* __restrict__ f,
     g += scale * (row[off + j] * cosf(in) + row[off + s.Ff + j] * cosf(__fadd_rn(in, half_pi)));
     scale *= 2.0f;
   }
-  df[item] = g;
+  df[m * ldf + d] = g;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -243,18 +252,20 @@ __global__ void __launch_bounds__(256) k_out_fwd(const float* __restrict__ h2, c
   }
 }
 
-// Reverse of the output layer. Each warp walks a contiguous chunk of rows, keeps the dW3 / db3 /
-// dEmbed partial sums in registers and flushes them with atomics (embedding rows are flushed
-// whenever the camera index changes: consecutive rows of one ray share the camera).
+// Reverse of the output layer. Each warp walks a contiguous chunk of rows (two rows in flight),
+// keeps the dW3 / db3 / dEmbed partial sums in registers; dW3/db3 are reduced across the block in
+// shared memory so only one set of atomics per block reaches L2 (the 387 addresses are a hot
+// spot otherwise). Embedding rows are flushed whenever the camera index changes: consecutive
+// rows of one ray share the camera.
 __global__ void __launch_bounds__(256) k_out_bwd(const float* __restrict__ h2, const float* __restrict__ w3,
                                                  const float* __restrict__ embed, const uint32_t* __restrict__ cams,
                                                  const float* __restrict__ rgb, const float* __restrict__ d_rgb,
                                                  float* __restrict__ dp2, float* __restrict__ dw3, float* __restrict__ db3,
                                                  float* __restrict__ dembed, int64_t M, int rows_per_ray, int64_t chunk) {
-  const int lane = threadIdx.x & 31;
-  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  __shared__ float red[8][388];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  int64_t warp = (int64_t)blockIdx.x * 8 + wib;
   int64_t mbeg = warp * chunk, mend = min(M, mbeg + chunk);
-  if (mbeg >= M) return;
   float w[4][3], gw[4][3];
 #pragma unroll
   for (int j = 0; j < 4; ++j)
@@ -279,8 +290,7 @@ __global__ void __launch_bounds__(256) k_out_bwd(const float* __restrict__ h2, c
       }
     }
   };
-  for (int64_t m = mbeg; m < mend; ++m) {
-    float4 h = *reinterpret_cast<const float4*>(h2 + m * 128 + 4 * lane);
+  auto process = [&](int64_t m, const float4& h, const float* y3, const float* dy3) {
     float hv[4] = {h.x, h.y, h.z, h.w};   // pre-FiLM (post-relu)
     float hf[4] = {h.x, h.y, h.z, h.w};   // post-FiLM
     float sc[4] = {1.f, 1.f, 1.f, 1.f};
@@ -304,8 +314,7 @@ __global__ void __launch_bounds__(256) k_out_bwd(const float* __restrict__ h2, c
     float dy[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      float y = rgb[3 * m + c];
-      dy[c] = d_rgb[3 * m + c] * y * (1.0f - y);
+      dy[c] = dy3[c] * y3[c] * (1.0f - y3[c]);
       gb[c] += dy[c];
     }
     float dh[4];
@@ -329,16 +338,51 @@ __global__ void __launch_bounds__(256) k_out_bwd(const float* __restrict__ h2, c
     o.z = hv[2] > 0.f ? dh[2] : 0.f;
     o.w = hv[3] > 0.f ? dh[3] : 0.f;
     *reinterpret_cast<float4*>(dp2 + m * 128 + 4 * lane) = o;
+  };
+  int64_t m = mbeg;
+  for (; m + 1 < mend; m += 2) {  // two independent rows in flight
+    float4 ha = *reinterpret_cast<const float4*>(h2 + m * 128 + 4 * lane);
+    float4 hb = *reinterpret_cast<const float4*>(h2 + (m + 1) * 128 + 4 * lane);
+    float ya[3], da[3], yb[3], dbv[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      ya[c] = rgb[3 * m + c];
+      da[c] = d_rgb[3 * m + c];
+      yb[c] = rgb[3 * (m + 1) + c];
+      dbv[c] = d_rgb[3 * (m + 1) + c];
+    }
+    process(m, ha, ya, da);
+    process(m + 1, hb, yb, dbv);
+  }
+  if (m < mend) {
+    float4 ha = *reinterpret_cast<const float4*>(h2 + m * 128 + 4 * lane);
+    float ya[3], da[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      ya[c] = rgb[3 * m + c];
+      da[c] = d_rgb[3 * m + c];
+    }
+    process(m, ha, ya, da);
   }
   flush_embed();
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) atomicAdd(&dw3[(4 * lane + j) * 3 + c], gw[j][c]);
+    for (int c = 0; c < 3; ++c) red[wib][(4 * lane + j) * 3 + c] = gw[j][c];
   if (lane == 0) {
-    atomicAdd(&db3[0], gb[0]);
-    atomicAdd(&db3[1], gb[1]);
-    atomicAdd(&db3[2], gb[2]);
+    red[wib][384] = gb[0];
+    red[wib][385] = gb[1];
+    red[wib][386] = gb[2];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 387; i += 256) {
+    float a = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a += red[q][i];
+    if (i < 384)
+      atomicAdd(&dw3[i], a);
+    else
+      atomicAdd(&db3[i - 384], a);
   }
 }
 
@@ -356,31 +400,42 @@ __global__ void __launch_bounds__(256) k_colsum128(const float* __restrict__ G, 
 }
 
 // ---------------------------------------------------------------------------------------------
-int mlp_simt_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs,
-                 const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, float* rgb) {
-  if (M == 0) return 0;
-  GemmArgs g{};
-  // Dense_0: f = feat @ W0 (no bias)
-  g = GemmArgs{feat, s.Ca, 1, p.w0, s.squash, 1, ws.f, s.squash, nullptr, nullptr, 0, M, s.squash, s.Ca, 0, 0};
-  TF_RETURN_IF_ERROR((launch_sgemm<128, 32, 4, 4>(st, g, 1)));
-  k_encode_fwd<<<(unsigned)ceil_div64(M * (s.squash + 3), 256), 256, 0, st>>>(ws.f, viewdirs, ws.x, M, rows_per_ray, s);
+int mlp_encode_fwd(cudaStream_t st, const MlpShape& s, const MlpWs& ws, const float* viewdirs, int64_t M, int rows_per_ray) {
+  k_encode_fwd<<<(unsigned)ceil_div64(M * (s.squash + 3), 256), 256, 0, st>>>(ws.f, viewdirs, ws.x, M, rows_per_ray, s, ws.ldf,
+                                                                            ws.ldx);
   TF_CHECK_LAUNCH();
-  // Dense_1 + relu
-  g = GemmArgs{ws.x, s.enc, 1, p.w1, s.units, 1, ws.h1, s.units, p.b1, nullptr, 0, M, s.units, s.enc, 0, 1};
-  TF_RETURN_IF_ERROR((launch_sgemm<128, 128, 8, 8>(st, g, 1)));
-  // Dense_2 + relu
-  g = GemmArgs{ws.h1, s.units, 1, p.w2, s.units, 1, ws.h2, s.units, p.b2, nullptr, 0, M, s.units, s.units, 0, 1};
-  TF_RETURN_IF_ERROR((launch_sgemm<128, 128, 8, 8>(st, g, 1)));
+  return 0;
+}
+int mlp_encode_bwd(cudaStream_t st, const MlpShape& s, const MlpWs& ws, int64_t M) {
+  k_encode_bwd<<<(unsigned)ceil_div64(M * s.squash, 256), 256, 0, st>>>(ws.f, ws.dx, ws.df, M, s, ws.ldf, ws.ldx);
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+int mlp_out_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const MlpWs& ws, const uint32_t* cams, int64_t M,
+                int rows_per_ray, float* rgb) {
   int64_t warps = std::min<int64_t>(M, (int64_t)kSMs * 64);
   k_out_fwd<<<(unsigned)ceil_div64(warps * 32, 256), 256, 0, st>>>(ws.h2, p.w3, p.b3, s.ncam ? p.embed : nullptr, cams, rgb, M,
                                                                     rows_per_ray);
   TF_CHECK_LAUNCH();
   return 0;
 }
-
-int mlp_simt_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs,
-                 const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, const float* rgb, const float* d_rgb,
-                 float* d_feat, const MlpGrads& gr) {
+int mlp_out_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const MlpWs& ws, const uint32_t* cams, int64_t M,
+                int rows_per_ray, const float* rgb, const float* d_rgb, const MlpGrads& gr) {
+  // chunk = whole rays (one embedding flush per ray), ~64 rows per warp, 8 warps per block
+  int64_t chunk = ceil_div64(std::max<int64_t>(64, rows_per_ray), rows_per_ray) * rows_per_ray;
+  int64_t warps = ceil_div64(M, chunk);
+  k_out_bwd<<<(unsigned)ceil_div64(warps, 8), 256, 0, st>>>(ws.h2, p.w3, s.ncam ? p.embed : nullptr, cams, rgb, d_rgb,
+                                                                    ws.dp2, gr.w3, gr.b3, gr.embed, M, rows_per_ray, chunk);
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+int mlp_colsum128(cudaStream_t st, const float* G, float* out, int64_t M) {
+  const int64_t cs_chunk = std::max<int64_t>(256, ceil_div64(M, 4 * kSMs));
+  k_colsum128<<<(unsigned)ceil_div64(M, cs_chunk), 256, 0, st>>>(G, out, M, cs_chunk);
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+int mlp_zero_grads(cudaStream_t st, const MlpShape& s, const MlpGrads& gr) {
   const int U = s.units;
   TF_CHECK_CUDA(cudaMemsetAsync(gr.w0, 0, sizeof(float) * s.Ca * s.squash, st));
   TF_CHECK_CUDA(cudaMemsetAsync(gr.w1, 0, sizeof(float) * s.enc * U, st));
@@ -390,44 +445,57 @@ int mlp_simt_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const f
   TF_CHECK_CUDA(cudaMemsetAsync(gr.w3, 0, sizeof(float) * U * 3, st));
   TF_CHECK_CUDA(cudaMemsetAsync(gr.b3, 0, sizeof(float) * 3, st));
   if (s.ncam) TF_CHECK_CUDA(cudaMemsetAsync(gr.embed, 0, sizeof(float) * (int64_t)s.ncam * U, st));
+  return 0;
+}
+
+int mlp_simt_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs,
+                 const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, float* rgb) {
+  if (M == 0) return 0;
+  GemmArgs g{};
+  // Dense_0: f = feat @ W0 (no bias)
+  g = GemmArgs{feat, s.Ca, 1, p.w0, s.squash, 1, ws.f, ws.ldf, nullptr, nullptr, 0, M, s.squash, s.Ca, 0, 0};
+  TF_RETURN_IF_ERROR((launch_sgemm<128, 32, 4, 4>(st, g, 1)));
+  TF_RETURN_IF_ERROR(mlp_encode_fwd(st, s, ws, viewdirs, M, rows_per_ray));
+  // Dense_1 + relu
+  g = GemmArgs{ws.x, ws.ldx, 1, p.w1, s.units, 1, ws.h1, s.units, p.b1, nullptr, 0, M, s.units, s.enc, 0, 1};
+  TF_RETURN_IF_ERROR((launch_sgemm<128, 128, 8, 8>(st, g, 1)));
+  // Dense_2 + relu
+  g = GemmArgs{ws.h1, s.units, 1, p.w2, s.units, 1, ws.h2, s.units, p.b2, nullptr, 0, M, s.units, s.units, 0, 1};
+  TF_RETURN_IF_ERROR((launch_sgemm<128, 128, 8, 8>(st, g, 1)));
+  return mlp_out_fwd(st, s, p, ws, cams, M, rows_per_ray, rgb);
+}
+
+int mlp_simt_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs,
+                 const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, const float* rgb, const float* d_rgb,
+                 float* d_feat, const MlpGrads& gr) {
+  const int U = s.units;
+  TF_RETURN_IF_ERROR(mlp_zero_grads(st, s, gr));
   if (M == 0) return 0;
   (void)viewdirs;
-
-  // output layer reverse: chunk = whole rays so the embedding flush is per ray group
-  int64_t chunk = std::max<int64_t>(rows_per_ray, 32);
-  chunk = ceil_div64(chunk, rows_per_ray) * rows_per_ray;
-  int64_t warps = ceil_div64(M, chunk);
-  k_out_bwd<<<(unsigned)ceil_div64(warps * 32, 256), 256, 0, st>>>(ws.h2, p.w3, s.ncam ? p.embed : nullptr, cams, rgb, d_rgb,
-                                                                    ws.dp2, gr.w3, gr.b3, gr.embed, M, rows_per_ray, chunk);
-  TF_CHECK_LAUNCH();
-
+  TF_RETURN_IF_ERROR(mlp_out_bwd(st, s, p, ws, cams, M, rows_per_ray, rgb, d_rgb, gr));
   const int splits = (int)std::min<int64_t>(2 * kSMs, std::max<int64_t>(1, M / 256));
-  const int64_t cs_chunk = std::max<int64_t>(256, ceil_div64(M, 4 * kSMs));
   GemmArgs g{};
   // dW2 = h1^T dp2 ; db2
   g = GemmArgs{ws.h1, 1, U, ws.dp2, U, 1, gr.w2, U, nullptr, nullptr, 0, U, U, M, 0, 0};
   TF_RETURN_IF_ERROR((launch_sgemm<128, 128, 8, 8>(st, g, splits)));
-  k_colsum128<<<(unsigned)ceil_div64(M, cs_chunk), 256, 0, st>>>(ws.dp2, gr.b2, M, cs_chunk);
-  TF_CHECK_LAUNCH();
+  TF_RETURN_IF_ERROR(mlp_colsum128(st, ws.dp2, gr.b2, M));
   // dp1 = (dp2 @ W2^T) * (h1 > 0)
   g = GemmArgs{ws.dp2, U, 1, p.w2, 1, U, ws.dp1, U, nullptr, ws.h1, U, M, U, U, 0, 0};
   TF_RETURN_IF_ERROR((launch_sgemm<128, 128, 8, 8>(st, g, 1)));
   // dW1 = x^T dp1 ; db1
-  g = GemmArgs{ws.x, 1, s.enc, ws.dp1, U, 1, gr.w1, U, nullptr, nullptr, 0, s.enc, U, M, 0, 0};
+  g = GemmArgs{ws.x, 1, ws.ldx, ws.dp1, U, 1, gr.w1, U, nullptr, nullptr, 0, s.enc, U, M, 0, 0};
   TF_RETURN_IF_ERROR((launch_sgemm<128, 128, 8, 8>(st, g, splits)));
-  k_colsum128<<<(unsigned)ceil_div64(M, cs_chunk), 256, 0, st>>>(ws.dp1, gr.b1, M, cs_chunk);
-  TF_CHECK_LAUNCH();
+  TF_RETURN_IF_ERROR(mlp_colsum128(st, ws.dp1, gr.b1, M));
   // dx = dp1 @ W1^T
-  g = GemmArgs{ws.dp1, U, 1, p.w1, 1, U, ws.dx, s.enc, nullptr, nullptr, 0, M, s.enc, U, 0, 0};
+  g = GemmArgs{ws.dp1, U, 1, p.w1, 1, U, ws.dx, ws.ldx, nullptr, nullptr, 0, M, s.enc, U, 0, 0};
   TF_RETURN_IF_ERROR((launch_sgemm<128, 128, 8, 8>(st, g, 1)));
   // df through the Fourier features
-  k_encode_bwd<<<(unsigned)ceil_div64(M * s.squash, 256), 256, 0, st>>>(ws.f, ws.dx, ws.df, M, s);
-  TF_CHECK_LAUNCH();
+  TF_RETURN_IF_ERROR(mlp_encode_bwd(st, s, ws, M));
   // dW0 = feat^T df
-  g = GemmArgs{feat, 1, s.Ca, ws.df, s.squash, 1, gr.w0, s.squash, nullptr, nullptr, 0, s.Ca, s.squash, M, 0, 0};
+  g = GemmArgs{feat, 1, s.Ca, ws.df, ws.ldf, 1, gr.w0, s.squash, nullptr, nullptr, 0, s.Ca, s.squash, M, 0, 0};
   TF_RETURN_IF_ERROR((launch_sgemm<128, 32, 4, 4>(st, g, splits)));
   // d_feat = df @ W0^T
-  g = GemmArgs{ws.df, s.squash, 1, p.w0, 1, s.squash, d_feat, s.Ca, nullptr, nullptr, 0, M, s.Ca, s.squash, 0, 0};
+  g = GemmArgs{ws.df, ws.ldf, 1, p.w0, 1, s.squash, d_feat, s.Ca, nullptr, nullptr, 0, M, s.Ca, s.squash, 0, 0};
   TF_RETURN_IF_ERROR((launch_sgemm<128, 128, 8, 8>(st, g, 1)));
   return 0;
 }

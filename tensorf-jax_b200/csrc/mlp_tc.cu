@@ -21,10 +21,56 @@ namespace tf {
 using namespace tc;
 
 // ---------------------------------------------------------------------------------------------
-// weight packing: W (fp32, any strides) -> per 64-wide K chunk [hi tile N_pad x 64][lo tile]
+// Operand splitting. NSPLIT=2: x ~ hi+lo (16 mantissa bits), products hi*hi + hi*lo + lo*hi.
+// NSPLIT=3: x = hi+mid+lo (24 bits, fp32-exact operands), six products down to 2^-24.
 // ---------------------------------------------------------------------------------------------
-constexpr int kKC = 64;   // K chunk of the row GEMM
-constexpr int kRC = 32;   // row chunk of the reduction GEMM
+template <int NSPLIT>
+__device__ __forceinline__ void split_store(const float* x, unsigned char* tile0, uint32_t tile_stride, uint32_t off) {
+  uint32_t h[4], m[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+    float r0 = x[2 * i] - __low2float(hh), r1 = x[2 * i + 1] - __high2float(hh);
+    __nv_bfloat162 mm = __floats2bfloat162_rn(r0, r1);
+    h[i] = *reinterpret_cast<uint32_t*>(&hh);
+    m[i] = *reinterpret_cast<uint32_t*>(&mm);
+    if (NSPLIT == 3) {
+      r0 -= __low2float(mm);
+      r1 -= __high2float(mm);
+      __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
+      l[i] = *reinterpret_cast<uint32_t*>(&ll);
+    }
+  }
+  *reinterpret_cast<uint4*>(tile0 + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(tile0 + tile_stride + off) = make_uint4(m[0], m[1], m[2], m[3]);
+  if (NSPLIT == 3) *reinterpret_cast<uint4*>(tile0 + 2 * tile_stride + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// Issue the split products of one k-step, smallest terms first. a[i], b[i]: descriptors of split i.
+template <int NSPLIT>
+__device__ __forceinline__ void umma_split(uint32_t d, const uint64_t* a, const uint64_t* b, uint32_t idesc, bool first) {
+  if (NSPLIT == 2) {
+    umma_bf16(d, a[1], b[0], idesc, !first);
+    umma_bf16(d, a[0], b[1], idesc, 1);
+    umma_bf16(d, a[0], b[0], idesc, 1);
+  } else {
+    umma_bf16(d, a[2], b[0], idesc, !first);
+    umma_bf16(d, a[0], b[2], idesc, 1);
+    umma_bf16(d, a[1], b[1], idesc, 1);
+    umma_bf16(d, a[1], b[0], idesc, 1);
+    umma_bf16(d, a[0], b[1], idesc, 1);
+    umma_bf16(d, a[0], b[0], idesc, 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: W (fp32, any strides) -> per KC-wide K chunk NSPLIT tiles [N_pad x KC]
+// ---------------------------------------------------------------------------------------------
+constexpr int kRC = 32;  // row chunk of the reduction GEMM
+template <int NSPLIT>
+struct RowCfg {
+  static constexpr int KC = 32;  // K chunk per pipeline stage
+};
 
 struct PackArgs {
   const float* W;
@@ -33,32 +79,29 @@ struct PackArgs {
   unsigned char* out;
 };
 
+template <int NSPLIT>
 __global__ void __launch_bounds__(256) k_pack_weights(PackArgs a) {
-  const int k8s = (a.K_pad + 7) / 8;
+  constexpr int KC = RowCfg<NSPLIT>::KC;
   int item = blockIdx.x * blockDim.x + threadIdx.x;  // (n, k8)
-  const int nchunks = (a.K_pad + kKC - 1) / kKC;
-  if (item >= a.N_pad * nchunks * (kKC / 8)) return;
-  (void)k8s;
+  const int nchunks = (a.K_pad + KC - 1) / KC;
+  if (item >= a.N_pad * nchunks * (KC / 8)) return;
   const int n = item % a.N_pad;
-  const int k8g = item / a.N_pad;  // global k8 index over padded chunks
-  const int c = k8g / (kKC / 8), j = k8g % (kKC / 8);
+  const int k8g = item / a.N_pad;  // k8 index over padded chunks
+  const int c = k8g / (KC / 8), j = k8g % (KC / 8);
   float x[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    int k = c * kKC + j * 8 + q;
+    int k = c * KC + j * 8 + q;
     x[q] = (k < a.K_valid && n < a.N_valid) ? a.W[k * a.sk + n * a.sn] : 0.f;
   }
-  uint4 hi, lo;
-  split8(x, hi, lo);
-  const uint32_t tb = tile_bytes(a.N_pad, kKC);
-  unsigned char* chunk = a.out + (size_t)c * 2 * tb;
-  const uint32_t off = tile_offset(n, j * 8, kKC);
-  *reinterpret_cast<uint4*>(chunk + off) = hi;
-  *reinterpret_cast<uint4*>(chunk + tb + off) = lo;
+  const uint32_t tb = tile_bytes(a.N_pad, KC);
+  split_store<NSPLIT>(x, a.out + (size_t)c * NSPLIT * tb, tb, tile_offset(n, j * 8, KC));
 }
 
+template <int NSPLIT>
 static size_t packed_weight_bytes(int K_pad, int N_pad) {
-  return (size_t)((K_pad + kKC - 1) / kKC) * 2 * tile_bytes(N_pad, kKC);
+  constexpr int KC = RowCfg<NSPLIT>::KC;
+  return (size_t)((K_pad + KC - 1) / KC) * NSPLIT * tile_bytes(N_pad, KC);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -81,9 +124,18 @@ struct RowGemmArgs {
   uint32_t tmem_cols;         // power of two >= 2*N_pad
 };
 
-constexpr int kRowThreads = 320;  // warps 0-3 epilogue, 4 MMA, 5 weight loader, 6-9 producers
+// warps 0-3 epilogue, 4 MMA issuer, 5 weight loader, then kGroups producer groups of 4 warps.
+// fence.proxy.async drains the issuing thread's outstanding loads, so one thread cannot overlap
+// its own global loads with publishing a stage; instead every producer group owns whole chunks
+// (chunk seq -> group seq % kGroups) and kGroups chunks are in flight per SM.
+constexpr int kGroups = 4;
+constexpr int kGroupThreads = 128;
+constexpr int kRowThreads = 192 + kGroups * kGroupThreads;
 
+template <int NSPLIT>
 __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
+  constexpr int KC = RowCfg<NSPLIT>::KC;
+  constexpr int ITEMS = 128 * (KC / 8) / kGroupThreads;  // 16-byte k-chunks per producer thread and stage
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = g.stages;
@@ -92,14 +144,15 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
   uint64_t* tfull = empty + S;                          // [2]
   uint64_t* tempty = tfull + 2;                         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  const uint32_t a_tile = tile_bytes(128, kKC), b_tile = tile_bytes(g.N_pad, kKC);
-  const uint32_t stage_bytes = 2 * a_tile + 2 * b_tile;
-  unsigned char* stage0 = smem + 1024;
+  float* s_bias = reinterpret_cast<float*>(smem + 512);  // [<=256] bias staged once per CTA... (first 128 here)
+  const uint32_t a_tile = tile_bytes(128, KC), b_tile = tile_bytes(g.N_pad, KC);
+  const uint32_t stage_bytes = NSPLIT * (a_tile + b_tile);
+  unsigned char* stage0 = smem + 2048;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(&full[s], 128 + 1);  // 128 producer threads + the weight loader's expect_tx arrive
-      mbar_init(&empty[s], 1);       // tcgen05.commit
+      mbar_init(&full[s], kGroupThreads + 1);  // one producer group + the weight loader's expect_tx arrive
+      mbar_init(&empty[s], 1);                 // tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);       // tcgen05.commit
@@ -107,6 +160,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
     }
     fence_barrier_init();
   }
+  for (int n = tid; n < 256; n += kRowThreads) s_bias[n] = (g.bias && n < g.N_store) ? g.bias[n] : 0.f;
   if (warp == 4) tmem_alloc(tmem_slot, g.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -114,94 +168,95 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
   const uint32_t tmem_base = *tmem_slot;
 
   const int64_t ntiles = (g.M + 127) / 128;
-  const int nchunks = (g.K_pad + kKC - 1) / kKC;
+  const int nchunks = (g.K_pad + KC - 1) / KC;
+  const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const int64_t total = my_tiles * nchunks;  // chunks this CTA processes, in (tile, k-chunk) order
 
   if (warp >= 6) {
-    // ================= A producers: fp32 rows -> hi/lo bf16 core matrices =================
-    const int pt = tid - 192, pw = pt >> 5;
+    // ================= A producers: fp32 rows -> split bf16 core matrices =================
+    // 8 consecutive lanes fill one 128-byte core matrix (8 rows x 16 B).
+    const int grp = (warp - 6) >> 2, pw = (warp - 6) & 3;
     const bool vec_ok = (g.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
-    uint32_t it_s = 0, ph = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      const int64_t m0 = t * 128;
-      for (int c = 0; c < nchunks; ++c) {
-        mbar_wait(&empty[it_s], ph ^ 1);
-        unsigned char* sA = stage0 + (size_t)it_s * stage_bytes;
-        const int k0 = c * kKC;
-#pragma unroll 2
-        for (int it = 0; it < 8; ++it) {
-          const int rb = pw + 4 * (it >> 1);
-          const int k8 = (lane >> 3) + 4 * (it & 1);
-          const int row = rb * 8 + (lane & 7);
-          const int k = k0 + k8 * 8;
-          if (k >= g.K_pad) continue;
-          float x[8];
-          const int64_t m = m0 + row;
-          if (m < g.M) {
-            const float* src = g.A + m * g.lda + k;
-            if (vec_ok && k + 8 <= g.K_valid) {
-              float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
-              x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
-              x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-            } else {
+    for (int64_t seq = grp; seq < total; seq += kGroups) {
+      const int64_t t = blockIdx.x + (seq / nchunks) * gridDim.x;
+      const int k0 = (int)(seq % nchunks) * KC;
+      const uint32_t st = (uint32_t)(seq % S), ph = (uint32_t)((seq / S) & 1);
+      float x[ITEMS][8];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) x[q] = (k + q < g.K_valid) ? src[q] : 0.f;
-            }
+      for (int it = 0; it < ITEMS; ++it) {
+        const int q = it * 4 + pw;                         // 32-lane group: (row block, k8 quad)
+        const int rb = q / (KC / 32), kh = q % (KC / 32);
+        const int row = rb * 8 + (lane & 7);
+        const int k = k0 + (kh * 4 + (lane >> 3)) * 8;
+        const int64_t m = t * 128 + row;
+        if (m < g.M && k < g.K_pad) {
+          const float* src = g.A + m * g.lda + k;
+          if (vec_ok && k + 8 <= g.K_valid) {
+            float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+            x[it][0] = v0.x; x[it][1] = v0.y; x[it][2] = v0.z; x[it][3] = v0.w;
+            x[it][4] = v1.x; x[it][5] = v1.y; x[it][6] = v1.z; x[it][7] = v1.w;
           } else {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) x[q] = 0.f;
+            for (int e = 0; e < 8; ++e) x[it][e] = (k + e < g.K_valid) ? src[e] : 0.f;
           }
-          uint4 hi, lo;
-          split8(x, hi, lo);
-          const uint32_t off = tile_offset(row, k8 * 8, kKC);
-          *reinterpret_cast<uint4*>(sA + off) = hi;
-          *reinterpret_cast<uint4*>(sA + a_tile + off) = lo;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[it][e] = 0.f;
         }
-        fence_proxy_async();
-        mbar_arrive(&full[it_s]);
-        if (++it_s == (uint32_t)S) { it_s = 0; ph ^= 1; }
       }
+      mbar_wait(&empty[st], ph ^ 1);
+      unsigned char* sA = stage0 + (size_t)st * stage_bytes;
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it) {
+        const int q = it * 4 + pw;
+        const int rb = q / (KC / 32), kh = q % (KC / 32);
+        const int row = rb * 8 + (lane & 7);
+        const int k8 = kh * 4 + (lane >> 3);
+        split_store<NSPLIT>(x[it], sA, a_tile, tile_offset(row, k8 * 8, KC));
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[st]);
     }
   } else if (warp == 5) {
     // ================= weight loader: one bulk copy per chunk =================
     if (lane == 0) {
-      uint32_t it_s = 0, ph = 0;
-      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        for (int c = 0; c < nchunks; ++c) {
-          mbar_wait(&empty[it_s], ph ^ 1);
-          unsigned char* sB = stage0 + (size_t)it_s * stage_bytes + 2 * a_tile;
-          mbar_arrive_expect_tx(&full[it_s], 2 * b_tile);
-          bulk_copy_g2s(sB, g.Bp + (size_t)c * 2 * b_tile, 2 * b_tile, &full[it_s]);
-          if (++it_s == (uint32_t)S) { it_s = 0; ph ^= 1; }
-        }
+      for (int64_t seq = 0; seq < total; ++seq) {
+        const uint32_t st = (uint32_t)(seq % S), ph = (uint32_t)((seq / S) & 1);
+        const int c = (int)(seq % nchunks);
+        mbar_wait(&empty[st], ph ^ 1);
+        unsigned char* sB = stage0 + (size_t)st * stage_bytes + NSPLIT * a_tile;
+        mbar_arrive_expect_tx(&full[st], NSPLIT * b_tile);
+        bulk_copy_g2s(sB, g.Bp + (size_t)c * NSPLIT * b_tile, NSPLIT * b_tile, &full[st]);
       }
     }
   } else if (warp == 4) {
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, g.N_pad);
-      const uint32_t sbo = kKC * 16;  // next 8 rows
-      uint32_t it_s = 0, ph = 0, acc = 0, acc_ph = 0;
-      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const uint32_t sbo = KC * 16;  // next 8 rows
+      uint32_t acc = 0, acc_ph = 0;
+      int64_t seq = 0;
+      for (int64_t ti = 0; ti < my_tiles; ++ti) {
         mbar_wait(&tempty[acc], acc_ph ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * (uint32_t)g.N_pad;
-        for (int c = 0; c < nchunks; ++c) {
-          mbar_wait(&full[it_s], ph);
+        for (int c = 0; c < nchunks; ++c, ++seq) {
+          const uint32_t st = (uint32_t)(seq % S), ph = (uint32_t)((seq / S) & 1);
+          mbar_wait(&full[st], ph);
           tc_fence_after();
-          const uint32_t sA = smem_u32(stage0 + (size_t)it_s * stage_bytes);
-          const uint32_t sB = sA + 2 * a_tile;
-          const int nks = min(kKC / 16, (g.K_pad - c * kKC) / 16);
+          const uint32_t sA = smem_u32(stage0 + (size_t)st * stage_bytes);
+          const uint32_t sB = sA + NSPLIT * a_tile;
+          const int nks = min(KC / 16, (g.K_pad - c * KC) / 16);
           for (int ks = 0; ks < nks; ++ks) {
-            const uint64_t a_hi = make_smem_desc(sA + ks * 256, 128, sbo);
-            const uint64_t a_lo = make_smem_desc(sA + a_tile + ks * 256, 128, sbo);
-            const uint64_t b_hi = make_smem_desc(sB + ks * 256, 128, sbo);
-            const uint64_t b_lo = make_smem_desc(sB + b_tile + ks * 256, 128, sbo);
-            umma_bf16(d, a_lo, b_hi, idesc, (c | ks) != 0);
-            umma_bf16(d, a_hi, b_lo, idesc, 1);
-            umma_bf16(d, a_hi, b_hi, idesc, 1);
+            uint64_t da[NSPLIT], db[NSPLIT];
+#pragma unroll
+            for (int i = 0; i < NSPLIT; ++i) {
+              da[i] = make_smem_desc(sA + i * a_tile + ks * 256, 128, sbo);
+              db[i] = make_smem_desc(sB + i * b_tile + ks * 256, 128, sbo);
+            }
+            umma_split<NSPLIT>(d, da, db, idesc, (c | ks) == 0);
           }
-          umma_commit(&empty[it_s]);  // smem stage free once these MMAs have read it
-          if (++it_s == (uint32_t)S) { it_s = 0; ph ^= 1; }
+          umma_commit(&empty[st]);  // smem stage free once these MMAs have read it
         }
         umma_commit(&tfull[acc]);  // accumulator complete
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
@@ -211,25 +266,44 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
     // ================= epilogue: TMEM -> registers -> bias / relu / mask -> global =================
     uint32_t acc = 0, acc_ph = 0;
     const bool vec_st = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+    const bool vec_mk = g.mask && (g.ldmask % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.mask) & 15) == 0);
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int64_t m = t * 128 + warp * 32 + lane;
+      const bool row_ok = m < g.M;
+      // the mask row (forward activations) does not depend on the accumulator: fetch the first
+      // block before waiting, then always one block ahead
+      float mk[16], mk_next[16];
+      auto load_mask = [&](int n0, float* dst) {
+        if (!g.mask) return;
+        const float* src = g.mask + m * g.ldmask + n0;
+        if (row_ok && vec_mk && n0 + 16 <= g.N_store) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(src) + q);
+            dst[4 * q] = v.x; dst[4 * q + 1] = v.y; dst[4 * q + 2] = v.z; dst[4 * q + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) dst[q] = (row_ok && n0 + q < g.N_store) ? src[q] : 0.f;
+        }
+      };
+      load_mask(0, mk_next);
       mbar_wait(&tfull[acc], acc_ph);
       tc_fence_after();
-      const int64_t m = t * 128 + warp * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (uint32_t)g.N_pad;
       for (int n0 = 0; n0 < g.N_pad; n0 += 16) {
         float v[16];
         tmem_ld16(trow + n0, v);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) mk[q] = mk_next[q];
+        if (n0 + 16 < g.N_pad) load_mask(n0 + 16, mk_next);
         tmem_ld_wait();
-        if (m < g.M && n0 < g.N_store) {
+        if (row_ok && n0 < g.N_store) {
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
-            const int n = n0 + q;
-            float y = v[q];
-            if (n < g.N_store) {
-              if (g.bias) y += g.bias[n];
-              if (g.relu) y = fmaxf(y, 0.f);
-              if (g.mask && !(g.mask[m * g.ldmask + n] > 0.f)) y = 0.f;
-            }
+            float y = v[q] + s_bias[n0 + q];
+            if (g.relu) y = fmaxf(y, 0.f);
+            if (g.mask && !(mk[q] > 0.f)) y = 0.f;
             v[q] = y;
           }
           float* dst = g.C + m * g.ldc + n0;
@@ -263,20 +337,22 @@ static uint32_t pow2_cols(int n) {
   return c;
 }
 
+template <int NSPLIT>
 static int launch_rowgemm(cudaStream_t st, RowGemmArgs g) {
+  constexpr int KC = RowCfg<NSPLIT>::KC;
   if (g.M == 0) return 0;
   TF_CHECK_ARG(g.N_pad % 16 == 0 && g.N_pad >= 16 && g.N_pad <= 256, "tc rowgemm: N_pad=%d unsupported", g.N_pad);
   TF_CHECK_ARG(g.K_pad % 16 == 0 && g.K_pad >= 16, "tc rowgemm: K_pad=%d unsupported", g.K_pad);
-  const size_t stage = 2 * (size_t)tile_bytes(128, kKC) + 2 * (size_t)tile_bytes(g.N_pad, kKC);
-  int stages = (int)std::min<size_t>(6, (227 * 1024 - 1024) / stage);
+  const size_t stage = (size_t)NSPLIT * (tile_bytes(128, KC) + tile_bytes(g.N_pad, KC));
+  int stages = (int)std::min<size_t>(8, (227 * 1024 - 2048) / stage);
   TF_CHECK_ARG(stages >= 2, "tc rowgemm: tile too large for shared memory");
   g.stages = stages;
   g.tmem_cols = pow2_cols(2 * g.N_pad);
-  const size_t smem = 1024 + stages * stage;
-  TF_CHECK_CUDA(cudaFuncSetAttribute(k_tc_rowgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = 2048 + stages * stage;
+  TF_CHECK_CUDA(cudaFuncSetAttribute(k_tc_rowgemm<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ntiles = (g.M + 127) / 128;
   const unsigned grid = (unsigned)std::min<int64_t>(ntiles, kSMs);
-  k_tc_rowgemm<<<grid, kRowThreads, smem, st>>>(g);
+  k_tc_rowgemm<NSPLIT><<<grid, kRowThreads, smem, st>>>(g);
   TF_CHECK_LAUNCH();
   return 0;
 }
@@ -299,7 +375,8 @@ struct RedGemmArgs {
   uint32_t tmem_cols;
 };
 
-constexpr int kRedThreads = 128 + 32 + 256;  // warps 0-3 epilogue, 4 MMA, 5-12 producers
+// warps 0-3 epilogue, 4 MMA issuer, then kGroups producer groups of 4 warps (chunk c -> group c % kGroups)
+constexpr int kRedThreads = 160 + kGroups * kGroupThreads;
 
 __global__ void __launch_bounds__(kRedThreads, 1) k_tc_redgemm(RedGemmArgs g) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -315,7 +392,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) k_tc_redgemm(RedGemmArgs g) {
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(&full[s], 256);
+      mbar_init(&full[s], kGroupThreads);
       mbar_init(&empty[s], 1);
     }
     mbar_init(tfull, 1);
@@ -332,68 +409,97 @@ __global__ void __launch_bounds__(kRedThreads, 1) k_tc_redgemm(RedGemmArgs g) {
   const int nchunks = (int)((r_end - r_begin + kRC - 1) / kRC);
 
   if (warp >= 5) {
-    // ===== producers: transposing loads, 8 consecutive rows -> one 16-byte k-chunk =====
-    const int pt = tid - 160;
-    const int a_items = 128 * (kRC / 8), b_items = g.N_pad * (kRC / 8);
-    uint32_t it_s = 0, ph = 0;
-    for (int c = 0; c < nchunks; ++c) {
-      mbar_wait(&empty[it_s], ph ^ 1);
-      unsigned char* sA = stage0 + (size_t)it_s * stage_bytes;
+    // ===== producers: item = 8 rows x 4 columns (8 coalesced float4 loads), transposed in
+    // registers into four 16-byte k-chunks (one per column) =====
+    const int grp = (warp - 5) >> 2, pt = (tid - 160) & (kGroupThreads - 1);
+    const bool vecA = (g.ldg % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.G) & 15) == 0);
+    const bool vecB = (g.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.X) & 15) == 0);
+    const int a_items = 32 * (kRC / 8), b_items = (g.N_pad / 4) * (kRC / 8);
+    for (int c = grp; c < nchunks; c += kGroups) {
+      const uint32_t st = (uint32_t)(c % S), ph = (uint32_t)((c / S) & 1);
+      unsigned char* sA = stage0 + (size_t)st * stage_bytes;
       unsigned char* sB = sA + 2 * a_tile;
       const int64_t r0 = r_begin + (int64_t)c * kRC;
-      for (int item = pt; item < a_items + b_items; item += 256) {
-        const bool isA = item < a_items;
-        const int e = isA ? item : item - a_items;
-        const int ncols = isA ? 128 : g.N_pad;
-        const int col = e % ncols, j = e / ncols;  // j = row group of 8
-        const float* src = isA ? g.G : g.X;
-        const int64_t ld = isA ? g.ldg : g.ldx;
-        const int valid = isA ? g.Mg : g.Nx;
-        float x[8];
+      bool waited = false;
+      for (int base = 0; base < a_items + b_items; base += 2 * kGroupThreads) {
+        float x[2][8][4];
+        int col4[2], jj[2];
+        bool isA[2], live[2];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int64_t r = r0 + j * 8 + q;
-          x[q] = (col < valid && r < r_end) ? src[r * ld + col] : 0.f;
+        for (int u = 0; u < 2; ++u) {
+          const int item = base + u * kGroupThreads + pt;
+          live[u] = item < a_items + b_items;
+          isA[u] = item < a_items;
+          const int e = isA[u] ? item : item - a_items;
+          const int nc4 = isA[u] ? 32 : g.N_pad / 4;
+          col4[u] = e % nc4;
+          jj[u] = e / nc4;
+          const float* src = isA[u] ? g.G : g.X;
+          const int64_t ld = isA[u] ? g.ldg : g.ldx;
+          const int valid = isA[u] ? g.Mg : g.Nx;
+          const bool vec = isA[u] ? vecA : vecB;
+          const int c0 = col4[u] * 4;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int64_t r = r0 + jj[u] * 8 + q;
+            if (live[u] && r < r_end && c0 < valid) {
+              if (vec && c0 + 4 <= valid) {
+                float4 v = __ldg(reinterpret_cast<const float4*>(src + r * ld + c0));
+                x[u][q][0] = v.x; x[u][q][1] = v.y; x[u][q][2] = v.z; x[u][q][3] = v.w;
+              } else {
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4) x[u][q][e4] = (c0 + e4 < valid) ? src[r * ld + c0 + e4] : 0.f;
+              }
+            } else {
+              x[u][q][0] = x[u][q][1] = x[u][q][2] = x[u][q][3] = 0.f;
+            }
+          }
         }
-        uint4 hi, lo;
-        split8(x, hi, lo);
-        const uint32_t off = tile_offset(col, j * 8, kRC);
-        unsigned char* base = isA ? sA : sB;
-        const uint32_t tb = isA ? a_tile : b_tile;
-        *reinterpret_cast<uint4*>(base + off) = hi;
-        *reinterpret_cast<uint4*>(base + tb + off) = lo;
+        if (!waited) {
+          mbar_wait(&empty[st], ph ^ 1);
+          waited = true;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (!live[u]) continue;
+          unsigned char* tile = isA[u] ? sA : sB;
+          const uint32_t tb = isA[u] ? a_tile : b_tile;
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            float col[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) col[q] = x[u][q][e4];
+            split_store<2>(col, tile, tb, tile_offset(col4[u] * 4 + e4, jj[u] * 8, kRC));
+          }
+        }
       }
       fence_proxy_async();
-      mbar_arrive(&full[it_s]);
-      if (++it_s == (uint32_t)S) { it_s = 0; ph ^= 1; }
+      mbar_arrive(&full[st]);
     }
   } else if (warp == 4) {
     if (lane == 0) {
       const uint32_t sbo = kRC * 16;
-      uint32_t it_s = 0, ph = 0;
       for (int c = 0; c < nchunks; ++c) {
-        mbar_wait(&full[it_s], ph);
+        const uint32_t st = (uint32_t)(c % S), ph = (uint32_t)((c / S) & 1);
+        mbar_wait(&full[st], ph);
         tc_fence_after();
-        const uint32_t sA = smem_u32(stage0 + (size_t)it_s * stage_bytes);
+        const uint32_t sA = smem_u32(stage0 + (size_t)st * stage_bytes);
         const uint32_t sB = sA + 2 * a_tile;
         for (int ks = 0; ks < kRC / 16; ++ks) {
-          const uint64_t a_hi = make_smem_desc(sA + ks * 256, 128, sbo);
-          const uint64_t a_lo = make_smem_desc(sA + a_tile + ks * 256, 128, sbo);
+          uint64_t da[2], db[2];
+          da[0] = make_smem_desc(sA + ks * 256, 128, sbo);
+          da[1] = make_smem_desc(sA + a_tile + ks * 256, 128, sbo);
           for (int n0 = 0; n0 < g.N_pad; n0 += 256) {
             const int nn = min(256, g.N_pad - n0);
             const uint32_t idesc = make_idesc_bf16(128, nn);
             // rows n0.. of the B tile start (n0/8) core-matrix rows further
             const uint32_t boff = (uint32_t)(n0 >> 3) * sbo + ks * 256;
-            const uint64_t b_hi = make_smem_desc(sB + boff, 128, sbo);
-            const uint64_t b_lo = make_smem_desc(sB + b_tile + boff, 128, sbo);
-            const uint32_t d = tmem_base + n0;
-            umma_bf16(d, a_lo, b_hi, idesc, (c | ks) != 0);
-            umma_bf16(d, a_hi, b_lo, idesc, 1);
-            umma_bf16(d, a_hi, b_hi, idesc, 1);
+            db[0] = make_smem_desc(sB + boff, 128, sbo);
+            db[1] = make_smem_desc(sB + b_tile + boff, 128, sbo);
+            umma_split<2>(tmem_base + n0, da, db, idesc, (c | ks) == 0);
           }
         }
-        umma_commit(&empty[it_s]);
-        if (++it_s == (uint32_t)S) { it_s = 0; ph ^= 1; }
+        umma_commit(&empty[st]);
       }
       umma_commit(tfull);
     }
@@ -428,7 +534,7 @@ static int launch_redgemm(cudaStream_t st, RedGemmArgs g) {
   if (g.rows == 0) return 0;
   TF_CHECK_ARG(g.N_pad % 16 == 0 && g.N_pad <= 512 && g.Mg <= 128, "tc redgemm: shape unsupported (Mg=%d N_pad=%d)", g.Mg, g.N_pad);
   const size_t stage = 2 * (size_t)tile_bytes(128, kRC) + 2 * (size_t)tile_bytes(g.N_pad, kRC);
-  int stages = (int)std::min<size_t>(6, (227 * 1024 - 1024) / stage);
+  int stages = (int)std::min<size_t>(8, (227 * 1024 - 1024) / stage);
   TF_CHECK_ARG(stages >= 2, "tc redgemm: tile too large for shared memory");
   g.stages = stages;
   g.tmem_cols = pow2_cols(g.N_pad);
@@ -443,20 +549,125 @@ static int launch_redgemm(cudaStream_t st, RedGemmArgs g) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// FeatureMlp forward / reverse on the tensor-core GEMMs
+// ---------------------------------------------------------------------------------------------
+template <int NSPLIT>
+static int pack_weights(cudaStream_t st, const float* W, int64_t sk, int64_t sn, int K_valid, int N_valid, int K_pad, int N_pad,
+                        unsigned char* out) {
+  constexpr int KC = RowCfg<NSPLIT>::KC;
+  PackArgs p{W, sk, sn, K_valid, N_valid, K_pad, N_pad, out};
+  const int items = N_pad * ((K_pad + KC - 1) / KC) * (KC / 8);
+  k_pack_weights<NSPLIT><<<(items + 255) / 256, 256, 0, st>>>(p);
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+
+// C[:, n0:n0+nn] = epilogue(A @ W[:, n0:n0+nn]) for column tiles of at most 256 (UMMA N limit).
+template <int NSPLIT>
+static int rowgemm_tiled(cudaStream_t st, const float* A, int64_t lda, int64_t M, int K_valid, const float* W, int64_t sk,
+                         int64_t sn, int N_valid, float* C, int64_t ldc, int N_store_total, const float* bias, int relu,
+                         const float* mask, int64_t ldmask, unsigned char* scratch) {
+  const int K_pad = round_up(K_valid, 16);
+  const int N_total = round_up(N_store_total, 16);
+  for (int n0 = 0; n0 < N_total; n0 += 256) {
+    const int nn = std::min(256, N_total - n0);
+    TF_RETURN_IF_ERROR(pack_weights<NSPLIT>(st, W + n0 * sn, sk, sn, K_valid, std::max(0, N_valid - n0), K_pad, nn, scratch));
+    RowGemmArgs g{};
+    g.A = A; g.lda = lda; g.M = M; g.K_valid = K_valid; g.K_pad = K_pad; g.Bp = scratch; g.N_pad = nn;
+    g.C = C + n0; g.ldc = ldc; g.N_store = std::min(nn, N_store_total - n0);
+    g.bias = bias ? bias + n0 : nullptr; g.relu = relu; g.mask = mask ? mask + n0 : nullptr; g.ldmask = ldmask;
+    TF_RETURN_IF_ERROR(launch_rowgemm<NSPLIT>(st, g));
+    scratch += packed_weight_bytes<NSPLIT>(K_pad, nn);
+  }
+  return 0;
+}
+
+// sized for the larger (3-way) split so either precision fits
+static size_t rowgemm_scratch(int K_valid, int N_total) {
+  const int K_pad = round_up(K_valid, 16);
+  N_total = round_up(N_total, 16);
+  size_t b = 0;
+  for (int n0 = 0; n0 < N_total; n0 += 256)
+    b += std::max(packed_weight_bytes<2>(K_pad, std::min(256, N_total - n0)), packed_weight_bytes<3>(K_pad, std::min(256, N_total - n0)));
+  return b;
+}
+
+size_t mlp_tc_wpack_bytes(const MlpShape& s) {
+  const int ldf = round_up(s.squash, 16), ldx = round_up(s.enc, 16), U = s.units;
+  return rowgemm_scratch(s.Ca, ldf) + rowgemm_scratch(s.enc, U) + rowgemm_scratch(U, U)      // forward
+         + rowgemm_scratch(U, U) + rowgemm_scratch(U, ldx) + rowgemm_scratch(s.squash, s.Ca);  // reverse (dX)
+}
+
+// The forward feeds the composite reverse, which cancels (u*c_k - W*A/B^2): it needs fp32-exact
+// operands (3-way split). The reverse GEMMs feed gradients directly: the 2-way split suffices.
+constexpr int kFwdSplit = 3, kBwdSplit = 2;
+
+int mlp_tc_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs,
+               const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, float* rgb) {
+  if (M == 0) return 0;
+  const int U = s.units;
+  unsigned char* sc = ws.wpack;
+  // Dense_0: f = feat @ W0 (no bias); the padding columns of f come out as exact zeros
+  TF_RETURN_IF_ERROR(rowgemm_tiled<kFwdSplit>(st, feat, s.Ca, M, s.Ca, p.w0, s.squash, 1, s.squash, ws.f, ws.ldf, ws.ldf, nullptr, 0,
+                                   nullptr, 0, sc));
+  sc += rowgemm_scratch(s.Ca, ws.ldf);
+  TF_RETURN_IF_ERROR(mlp_encode_fwd(st, s, ws, viewdirs, M, rows_per_ray));
+  // Dense_1 + relu
+  TF_RETURN_IF_ERROR(rowgemm_tiled<kFwdSplit>(st, ws.x, ws.ldx, M, s.enc, p.w1, U, 1, U, ws.h1, U, U, p.b1, 1, nullptr, 0, sc));
+  sc += rowgemm_scratch(s.enc, U);
+  // Dense_2 + relu
+  TF_RETURN_IF_ERROR(rowgemm_tiled<kFwdSplit>(st, ws.h1, U, M, U, p.w2, U, 1, U, ws.h2, U, U, p.b2, 1, nullptr, 0, sc));
+  return mlp_out_fwd(st, s, p, ws, cams, M, rows_per_ray, rgb);
+}
+
+int mlp_tc_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs,
+               const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, const float* rgb, const float* d_rgb,
+               float* d_feat, const MlpGrads& gr) {
+  const int U = s.units;
+  (void)viewdirs;
+  TF_RETURN_IF_ERROR(mlp_zero_grads(st, s, gr));
+  if (M == 0) return 0;
+  unsigned char* sc = ws.wpack + rowgemm_scratch(s.Ca, ws.ldf) + rowgemm_scratch(s.enc, U) + rowgemm_scratch(U, U);
+  TF_RETURN_IF_ERROR(mlp_out_bwd(st, s, p, ws, cams, M, rows_per_ray, rgb, d_rgb, gr));
+  RedGemmArgs r{};
+  // dW2[k][n] = sum_rows h1[row][k] * dp2[row][n] ; db2
+  r = RedGemmArgs{};
+  r.G = ws.dp2; r.ldg = U; r.Mg = U; r.X = ws.h1; r.ldx = U; r.Nx = U; r.N_pad = U; r.rows = M; r.out = gr.w2; r.ldo = U;
+  TF_RETURN_IF_ERROR(launch_redgemm(st, r));
+  TF_RETURN_IF_ERROR(mlp_colsum128(st, ws.dp2, gr.b2, M));
+  // dp1 = (dp2 @ W2^T) * (h1 > 0)
+  TF_RETURN_IF_ERROR(rowgemm_tiled<kBwdSplit>(st, ws.dp2, U, M, U, p.w2, 1, U, U, ws.dp1, U, U, nullptr, 0, ws.h1, U, sc));
+  sc += rowgemm_scratch(U, U);
+  // dW1[k][n] = sum_rows x[row][k] * dp1[row][n] ; db1
+  r = RedGemmArgs{};
+  r.G = ws.dp1; r.ldg = U; r.Mg = U; r.X = ws.x; r.ldx = ws.ldx; r.Nx = s.enc; r.N_pad = ws.ldx; r.rows = M; r.out = gr.w1;
+  r.ldo = U;
+  TF_RETURN_IF_ERROR(launch_redgemm(st, r));
+  TF_RETURN_IF_ERROR(mlp_colsum128(st, ws.dp1, gr.b1, M));
+  // dx = dp1 @ W1^T   (W1^T(k, n) = W1[n][k])
+  TF_RETURN_IF_ERROR(rowgemm_tiled<kBwdSplit>(st, ws.dp1, U, M, U, p.w1, 1, U, s.enc, ws.dx, ws.ldx, ws.ldx, nullptr, 0, nullptr, 0, sc));
+  sc += rowgemm_scratch(U, ws.ldx);
+  TF_RETURN_IF_ERROR(mlp_encode_bwd(st, s, ws, M));
+  // dW0[k][n] = sum_rows feat[row][k] * df[row][n]
+  r = RedGemmArgs{};
+  r.G = ws.df; r.ldg = ws.ldf; r.Mg = s.squash; r.X = feat; r.ldx = s.Ca; r.Nx = s.Ca; r.N_pad = round_up(s.Ca, 16); r.rows = M;
+  r.out = gr.w0; r.ldo = s.squash;
+  TF_RETURN_IF_ERROR(launch_redgemm(st, r));
+  // d_feat = df @ W0^T
+  TF_RETURN_IF_ERROR(rowgemm_tiled<kBwdSplit>(st, ws.df, ws.ldf, M, s.squash, p.w0, 1, s.squash, s.Ca, d_feat, s.Ca, s.Ca, nullptr, 0,
+                                   nullptr, 0, sc));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // test entry points (tests/test_gpu_tc.py): plain GEMMs through the tensor-core kernels
 // ---------------------------------------------------------------------------------------------
 int tc_rowgemm_test(cudaStream_t st, const float* A, int64_t M, int K, const float* W, int N, const float* bias, int relu,
-                    const float* mask, float* C, void* scratch, size_t scratch_bytes) {
-  const int K_pad = round_up(K, 16), N_pad = round_up(N, 16);
-  TF_CHECK_ARG(packed_weight_bytes(K_pad, N_pad) <= scratch_bytes, "scratch too small");
-  PackArgs p{W, N, 1, K, N, K_pad, N_pad, (unsigned char*)scratch};
-  const int items = N_pad * ((K_pad + kKC - 1) / kKC) * (kKC / 8);
-  k_pack_weights<<<(items + 255) / 256, 256, 0, st>>>(p);
-  TF_CHECK_LAUNCH();
-  RowGemmArgs g{};
-  g.A = A; g.lda = K; g.M = M; g.K_valid = K; g.K_pad = K_pad; g.Bp = (const unsigned char*)scratch; g.N_pad = N_pad;
-  g.C = C; g.ldc = N; g.N_store = N; g.bias = bias; g.mask = mask; g.ldmask = N; g.relu = relu;
-  return launch_rowgemm(st, g);
+                    const float* mask, float* C, void* scratch, size_t scratch_bytes, int nsplit) {
+  TF_CHECK_ARG(rowgemm_scratch(K, N) <= scratch_bytes, "scratch too small");
+  if (nsplit == 3)
+    return rowgemm_tiled<3>(st, A, K, M, K, W, N, 1, N, C, N, N, bias, relu, mask, N, (unsigned char*)scratch);
+  return rowgemm_tiled<2>(st, A, K, M, K, W, N, 1, N, C, N, N, bias, relu, mask, N, (unsigned char*)scratch);
 }
 
 int tc_redgemm_test(cudaStream_t st, const float* G, int Mg, const float* X, int Nx, int64_t rows, float* out) {

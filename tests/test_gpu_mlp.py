@@ -14,7 +14,8 @@ MLP_LEAVES = ("w0", "w1", "b1", "w2", "b2", "w3", "b3", "embed")
 
 @pytest.mark.parametrize("ca,F,V,ncam,rays,rpr", [(3, 2, 2, None, 70, 5), (48, 2, 2, None, 300, 33), (48, 6, 6, 7, 64, 9),
                                                   (5, 0, 1, 3, 130, 1), (24, 6, 6, None, 257, 3)])
-def test_mlp_fwd_bwd(cuda, ca, F, V, ncam, rays, rpr):
+@pytest.mark.parametrize("impl", [1, 2], ids=["simt_fp32", "tcgen05"])
+def test_mlp_fwd_bwd(cuda, ca, F, V, ncam, rays, rpr, impl):
     from tensorf_b200 import ops
     M = rays * rpr
     p_np = S.make_params(4, 1, ca, F, V, ncam, seed=11, bias_std=0.1)
@@ -33,7 +34,7 @@ def test_mlp_fwd_bwd(cuda, ca, F, V, ncam, rays, rpr):
     ref = O.feature_mlp(mc, P64, f64, vd64, cams64)
     (ref * T(d_rgb, torch.float64)).sum().backward()
 
-    desc = ops.make_desc(R=rays, N=rpr, K=rpr, G=4, cd=1, ca=ca, feat_freqs=F, view_freqs=V, num_cameras=ncam)
+    desc = ops.make_desc(R=rays, N=rpr, K=rpr, G=4, cd=1, ca=ca, feat_freqs=F, view_freqs=V, num_cameras=ncam, mlp_impl=impl)
     call = ops.MlpCall(desc, M, cuda)
     params = {k: T(v, device=cuda) for k, v in p_np.items()}
     rgb = call.forward(params, T(feat, device=cuda), T(vd, device=cuda), T(cams, device=cuda), rpr)

@@ -22,10 +22,10 @@ DOZER_S = S.Workload("dozer_s", 48, 16, 32, 48, 90, 13, 6, 6, contracted=True, n
 DOZER_T = S.Workload("dozer_t", 40, 9, 4, 3, 41, 6, 2, 2, contracted=True, num_cameras=None)
 
 
-def run_cuda(w, inp, cuda, with_colors=True):
+def run_cuda(w, inp, cuda, with_colors=True, mlp_impl=0):
     from tensorf_b200 import ops
     desc = ops.make_desc(R=w.R, N=w.N, K=w.K, G=w.G, cd=w.cd, ca=w.ca, contracted=w.contracted, feat_freqs=w.feat_freqs,
-                         view_freqs=w.view_freqs, num_cameras=w.num_cameras, loss_scale=1.0 / (3 * w.R))
+                         view_freqs=w.view_freqs, num_cameras=w.num_cameras, loss_scale=1.0 / (3 * w.R), mlp_impl=mlp_impl)
     call = ops.RenderCall(desc, cuda)
     params, dins = device_inputs(w, inp, cuda, with_colors)
     rgb, loss = call.forward(params, dins)
@@ -47,10 +47,11 @@ def audit_selection(idx_cuda, aux, K):
     return len(bad_rows)
 
 
+@pytest.mark.parametrize("mlp_impl", [2, 1], ids=["tcgen05", "simt_fp32"])
 @pytest.mark.parametrize("w", [SMALL, SMALL6, MID, ODD, DOZER_S, DOZER_T], ids=lambda w: w.name)
-def test_render_rgb_forward_and_grads(cuda, w):
+def test_render_rgb_forward_and_grads(cuda, w, mlp_impl):
     inp = S.make_inputs(w, bias_std=0.05)
-    call, params, dins, rgb, loss = run_cuda(w, inp, cuda)
+    call, params, dins, rgb, loss = run_cuda(w, inp, cuda, mlp_impl=mlp_impl)
     idx = call.view("idx").cpu().numpy().reshape(w.R, w.K)
     assert (np.diff(idx, axis=-1) > 0).all() or w.K == 1
 
