@@ -140,11 +140,13 @@ int tensorf_segment_probabilities(tensorf_stream_t s, const float* sigmas, const
                                   float* p_exits, float* p_terminates);
 
 /* ---- tensor-core GEMM building blocks of the MLP (test entry points) ------------------------ */
-/* C (M,N) = [mask>0] relu?(A (M,K) @ W (K,N) + bias), split-bf16 operands on tcgen05 (nsplit = 2:
+/* C (M,N) = [mask bit] relu?(A (M,K) @ W (K,N) + bias); mask_bits / bits_out: ceil16(N)/32 (rounded up)
+ * uint32 words per row, bit n of row m (bits_out = C > 0); split-bf16 operands on tcgen05 (nsplit = 2:
  * hi+lo, 3 products, ~2^-16; nsplit = 3: hi+mid+lo, 6 products, fp32-exact operands), fp32
  * accumulation in TMEM. scratch: 6*ceil16(N)*ceil64(K)+ bytes (128 KiB * ceil(K/64) * ceil(N/256) suffices). */
 int tensorf_tc_rowgemm_test(tensorf_stream_t s, const float* A, int64_t M, int K, const float* W, int N, const float* bias,
-                            int relu, const float* mask, float* C, void* scratch, int64_t scratch_bytes, int nsplit);
+                            int relu, const uint32_t* mask_bits, uint32_t* bits_out, float* C, void* scratch,
+                            int64_t scratch_bytes, int nsplit);
 /* out (Nx, Mg) += X^T (Nx,rows) @ G (rows,Mg): the weight-gradient contraction over rows. Mg <= 128, Nx <= 512. */
 int tensorf_tc_redgemm_test(tensorf_stream_t s, const float* G, int Mg, const float* X, int Nx, int64_t rows, float* out);
 

@@ -150,7 +150,7 @@ static int check_mlp_params(const tensorf_render_desc& d, const tensorf_params* 
 }
 
 int tc_rowgemm_test(cudaStream_t st, const float* A, int64_t M, int K, const float* W, int N, const float* bias, int relu,
-                    const float* mask, float* C, void* scratch, size_t scratch_bytes, int nsplit);
+                    const uint32_t* mask_bits, uint32_t* bits_out, float* C, void* scratch, size_t scratch_bytes, int nsplit);
 int tc_redgemm_test(cudaStream_t st, const float* G, int Mg, const float* X, int Nx, int64_t rows, float* out);
 
 }  // namespace tf
@@ -238,10 +238,12 @@ int tensorf_segment_probabilities(tensorf_stream_t s, const float* sigmas, const
 }
 
 int tensorf_tc_rowgemm_test(tensorf_stream_t s, const float* A, int64_t M, int K, const float* W, int N, const float* bias,
-                            int relu, const float* mask, float* C, void* scratch, int64_t scratch_bytes, int nsplit) {
+                            int relu, const uint32_t* mask_bits, uint32_t* bits_out, float* C, void* scratch,
+                            int64_t scratch_bytes, int nsplit) {
   TF_CHECK_ARG(A && W && C && scratch && M >= 0 && K >= 1 && N >= 1, "bad argument");
   TF_CHECK_ARG(nsplit == 2 || nsplit == 3, "nsplit must be 2 or 3");
-  return tc_rowgemm_test((cudaStream_t)s, A, M, K, W, N, bias, relu, mask, C, scratch, (size_t)scratch_bytes, nsplit);
+  TF_CHECK_ARG(!(mask_bits || bits_out) || N <= 256, "bit masks need N <= 256");
+  return tc_rowgemm_test((cudaStream_t)s, A, M, K, W, N, bias, relu, mask_bits, bits_out, C, scratch, (size_t)scratch_bytes, nsplit);
 }
 int tensorf_tc_redgemm_test(tensorf_stream_t s, const float* G, int Mg, const float* X, int Nx, int64_t rows, float* out) {
   TF_CHECK_ARG(G && X && out && Mg >= 1 && Mg <= 128 && Nx >= 1 && Nx <= 512 && rows >= 0, "bad argument");

@@ -38,6 +38,7 @@ struct MlpWs {
   float* dp1;  // (M, units)
   float* dx;   // (M, enc)
   float* df;   // (M, squash)
+  uint32_t* bits1;  // (M, units/32) ReLU mask of layer 1, one bit per unit (tensor-core path)
 };
 int64_t mlp_ws_floats(const MlpShape& s, int64_t M);
 MlpWs mlp_ws_carve(const MlpShape& s, int64_t M, float* base);

@@ -11,6 +11,8 @@
 //       -> global). smem stage ring + double-buffered TMEM accumulators.
 //   k_tc_redgemm : dW^T[128 x N] += G^T[128 x rows] * X[rows x N]   weight gradients (split over
 //       rows across CTAs, RED-add epilogue).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "mlp.cuh"
@@ -117,10 +119,12 @@ struct RowGemmArgs {
   int64_t ldc;
   int N_store;                // columns written (<= N_pad)
   const float* bias;          // [N_store] or null
-  const float* mask;          // keep where mask(m,n) > 0, or null
-  int64_t ldmask;
+  const uint32_t* bits_in;    // keep C(m,n) only where bit n of row m is set (ceil(N_pad/32) words per row), or null
+  uint32_t* bits_out;         // receives bit(m,n) = C(m,n) > 0 (the ReLU mask for the reverse pass), or null
   int relu;
   int stages;
+  int no_bulk;                // debug: force the direct-store epilogue
+  int groups;                 // active producer groups; stages % groups == 0 (see launch_rowgemm)
   uint32_t tmem_cols;         // power of two >= 2*N_pad
 };
 
@@ -131,6 +135,8 @@ struct RowGemmArgs {
 constexpr int kGroups = 4;
 constexpr int kGroupThreads = 128;
 constexpr int kRowThreads = 192 + kGroups * kGroupThreads;
+constexpr int kOutBlock = 64;  // columns per epilogue staging block
+constexpr int kRowHeader = 2048 + 2 * 128 * (kOutBlock + 4) * 4;  // barriers, bias, two staging tiles (71680 B)
 
 template <int NSPLIT>
 __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
@@ -144,10 +150,11 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
   uint64_t* tfull = empty + S;                          // [2]
   uint64_t* tempty = tfull + 2;                         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* s_bias = reinterpret_cast<float*>(smem + 512);  // [<=256] bias staged once per CTA... (first 128 here)
+  float* s_bias = reinterpret_cast<float*>(smem + 1024);   // [256] bias staged once per CTA
+  float* s_out = reinterpret_cast<float*>(smem + 2048);    // [2][128][kOutBlock+4] epilogue staging tiles
   const uint32_t a_tile = tile_bytes(128, KC), b_tile = tile_bytes(g.N_pad, KC);
   const uint32_t stage_bytes = NSPLIT * (a_tile + b_tile);
-  unsigned char* stage0 = smem + 2048;
+  unsigned char* stage0 = smem + kRowHeader;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
@@ -177,7 +184,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
     // 8 consecutive lanes fill one 128-byte core matrix (8 rows x 16 B).
     const int grp = (warp - 6) >> 2, pw = (warp - 6) & 3;
     const bool vec_ok = (g.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
-    for (int64_t seq = grp; seq < total; seq += kGroups) {
+    for (int64_t seq = grp; seq < total && grp < g.groups; seq += g.groups) {
       const int64_t t = blockIdx.x + (seq / nchunks) * gridDim.x;
       const int k0 = (int)(seq % nchunks) * KC;
       const uint32_t st = (uint32_t)(seq % S), ph = (uint32_t)((seq / S) & 1);
@@ -204,7 +211,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
           for (int e = 0; e < 8; ++e) x[it][e] = 0.f;
         }
       }
-      mbar_wait(&empty[st], ph ^ 1);
+      mbar_wait(&empty[st], ph ^ 1, 100 + (int)seq);
       unsigned char* sA = stage0 + (size_t)st * stage_bytes;
 #pragma unroll
       for (int it = 0; it < ITEMS; ++it) {
@@ -223,7 +230,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
       for (int64_t seq = 0; seq < total; ++seq) {
         const uint32_t st = (uint32_t)(seq % S), ph = (uint32_t)((seq / S) & 1);
         const int c = (int)(seq % nchunks);
-        mbar_wait(&empty[st], ph ^ 1);
+        mbar_wait(&empty[st], ph ^ 1, 200 + (int)seq);
         unsigned char* sB = stage0 + (size_t)st * stage_bytes + NSPLIT * a_tile;
         mbar_arrive_expect_tx(&full[st], NSPLIT * b_tile);
         bulk_copy_g2s(sB, g.Bp + (size_t)c * NSPLIT * b_tile, NSPLIT * b_tile, &full[st]);
@@ -237,12 +244,12 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
       uint32_t acc = 0, acc_ph = 0;
       int64_t seq = 0;
       for (int64_t ti = 0; ti < my_tiles; ++ti) {
-        mbar_wait(&tempty[acc], acc_ph ^ 1);
+        mbar_wait(&tempty[acc], acc_ph ^ 1, 300);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * (uint32_t)g.N_pad;
         for (int c = 0; c < nchunks; ++c, ++seq) {
           const uint32_t st = (uint32_t)(seq % S), ph = (uint32_t)((seq / S) & 1);
-          mbar_wait(&full[st], ph);
+          mbar_wait(&full[st], ph, 400 + (int)seq);
           tc_fence_after();
           const uint32_t sA = smem_u32(stage0 + (size_t)st * stage_bytes);
           const uint32_t sB = sA + NSPLIT * a_tile;
@@ -263,64 +270,79 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
       }
     }
   } else {
-    // ================= epilogue: TMEM -> registers -> bias / relu / mask -> global =================
+    // ================= epilogue: TMEM -> registers -> bias / relu / mask -> smem row -> bulk store ====
+    // tcgen05.ld gives lane <-> row. Each thread stages 64-column blocks of ITS OWN row in a padded
+    // smem tile (conflict-free STS.128) and ships them with its own asynchronous bulk copy
+    // (cp.async.bulk shared -> global): coalesced 256-byte row segments, no LSU store wavefronts.
+    // ReLU masks travel as one bit per element (bits_out / bits_in), not as fp32 activations.
     uint32_t acc = 0, acc_ph = 0;
-    const bool vec_st = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
-    const bool vec_mk = g.mask && (g.ldmask % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.mask) & 15) == 0);
+    const int row = warp * 32 + lane;
+    const int rs = kOutBlock + 4;  // padded row stride (floats) of the staging tiles
+    float* my0 = s_out + (size_t)row * rs;
+    float* my1 = my0 + (size_t)128 * rs;
+    const bool bulk_ok = !g.no_bulk && (g.ldc % 4 == 0) && (g.N_store % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+    const int words = (g.N_pad + 31) / 32;
+    int buf = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      const int64_t m = t * 128 + warp * 32 + lane;
+      const int64_t m = t * 128 + row;
       const bool row_ok = m < g.M;
-      // the mask row (forward activations) does not depend on the accumulator: fetch the first
-      // block before waiting, then always one block ahead
-      float mk[16], mk_next[16];
-      auto load_mask = [&](int n0, float* dst) {
-        if (!g.mask) return;
-        const float* src = g.mask + m * g.ldmask + n0;
-        if (row_ok && vec_mk && n0 + 16 <= g.N_store) {
+      uint32_t mbits[8];
+      if (g.bits_in) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 v = __ldg(reinterpret_cast<const float4*>(src) + q);
-            dst[4 * q] = v.x; dst[4 * q + 1] = v.y; dst[4 * q + 2] = v.z; dst[4 * q + 3] = v.w;
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 16; ++q) dst[q] = (row_ok && n0 + q < g.N_store) ? src[q] : 0.f;
-        }
-      };
-      load_mask(0, mk_next);
-      mbar_wait(&tfull[acc], acc_ph);
+        for (int w = 0; w < 8; ++w) mbits[w] = (row_ok && w < words) ? __ldg(g.bits_in + m * words + w) : 0u;
+      }
+      mbar_wait(&tfull[acc], acc_ph, 500);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (uint32_t)g.N_pad;
-      for (int n0 = 0; n0 < g.N_pad; n0 += 16) {
-        float v[16];
-        tmem_ld16(trow + n0, v);
+      for (int b0 = 0; b0 < g.N_pad; b0 += kOutBlock) {
+        const int bcols = min(kOutBlock, g.N_pad - b0);
+        float* mine = buf ? my1 : my0;
+        const uint32_t mw[2] = {mbits[(b0 >> 5) & 7], mbits[((b0 >> 5) + 1) & 7]};  // kOutBlock = 64 = two words
+        uint32_t ow[2] = {0u, 0u};
+        if (bulk_ok) bulk_wait_read<1>();  // the group that last read this buffer has drained
 #pragma unroll
-        for (int q = 0; q < 16; ++q) mk[q] = mk_next[q];
-        if (n0 + 16 < g.N_pad) load_mask(n0 + 16, mk_next);
-        tmem_ld_wait();
-        if (row_ok && n0 < g.N_store) {
+        for (int j = 0; j < kOutBlock / 16; ++j) {
+          const int n0 = b0 + j * 16;
+          if (j * 16 < bcols) {
+            float v[16];
+            tmem_ld16(trow + n0, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            float y = v[q] + s_bias[n0 + q];
-            if (g.relu) y = fmaxf(y, 0.f);
-            if (g.mask && !(mk[q] > 0.f)) y = 0.f;
-            v[q] = y;
+            for (int q = 0; q < 16; ++q) {
+              const int n = n0 + q;
+              float y = v[q] + s_bias[n];
+              if (g.relu) y = fmaxf(y, 0.f);
+              if (g.bits_in && !((mw[j >> 1] >> ((j & 1) * 16 + q)) & 1u)) y = 0.f;
+              if (y > 0.f) ow[j >> 1] |= 1u << ((j & 1) * 16 + q);
+              v[q] = y;
+            }
+            if (bulk_ok) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(mine + j * 16 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            } else if (row_ok) {
+              for (int q = 0; q < 16; ++q)
+                if (n0 + q < g.N_store) g.C[m * g.ldc + n0 + q] = v[q];
+            }
           }
-          float* dst = g.C + m * g.ldc + n0;
-          if (vec_st && n0 + 16 <= g.N_store) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          } else {
-            for (int q = 0; q < 16; ++q)
-              if (n0 + q < g.N_store) dst[q] = v[q];
-          }
+        }
+        if (g.bits_out && row_ok) {
+          g.bits_out[m * words + (b0 >> 5)] = ow[0];
+          if ((b0 >> 5) + 1 < words) g.bits_out[m * words + (b0 >> 5) + 1] = ow[1];
+        }
+        if (bulk_ok) {
+          const int ncopy = min(bcols, g.N_store - b0);
+          fence_proxy_async();
+          if (row_ok && ncopy > 0) bulk_store_s2g(g.C + m * g.ldc + b0, mine, (uint32_t)ncopy * 4);
+          bulk_commit();
+          buf ^= 1;
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
+    if (bulk_ok) bulk_wait<0>();  // all stores of this thread are globally complete before exit
   }
 
   tc_fence_before();
@@ -344,11 +366,18 @@ static int launch_rowgemm(cudaStream_t st, RowGemmArgs g) {
   TF_CHECK_ARG(g.N_pad % 16 == 0 && g.N_pad >= 16 && g.N_pad <= 256, "tc rowgemm: N_pad=%d unsupported", g.N_pad);
   TF_CHECK_ARG(g.K_pad % 16 == 0 && g.K_pad >= 16, "tc rowgemm: K_pad=%d unsupported", g.K_pad);
   const size_t stage = (size_t)NSPLIT * (tile_bytes(128, KC) + tile_bytes(g.N_pad, KC));
-  int stages = (int)std::min<size_t>(8, (227 * 1024 - 2048) / stage);
+  int stages = (int)std::min<size_t>(8, (227 * 1024 - kRowHeader) / stage);
   TF_CHECK_ARG(stages >= 2, "tc rowgemm: tile too large for shared memory");
+  if (const char* e = getenv("TENSORF_TC_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));
+  g.no_bulk = getenv("TENSORF_TC_NOBULK") != nullptr;
+  // A stage must always be filled by the same producer group, in order: mbarrier parity waits
+  // cannot tell "two phases ahead" from "not yet", so the stage count is a multiple of the
+  // number of active groups (chunk seq -> group seq % groups, stage seq % stages).
+  g.groups = std::min(kGroups, stages);
+  stages = stages / g.groups * g.groups;
   g.stages = stages;
   g.tmem_cols = pow2_cols(2 * g.N_pad);
-  const size_t smem = 2048 + stages * stage;
+  const size_t smem = kRowHeader + stages * stage;
   TF_CHECK_CUDA(cudaFuncSetAttribute(k_tc_rowgemm<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ntiles = (g.M + 127) / 128;
   const unsigned grid = (unsigned)std::min<int64_t>(ntiles, kSMs);
@@ -371,12 +400,13 @@ struct RedGemmArgs {
   int64_t rows_per_cta;  // multiple of kRC
   float* out;
   int64_t ldo;
-  int stages;
+  int stages, groups;
   uint32_t tmem_cols;
 };
 
 // warps 0-3 epilogue, 4 MMA issuer, then kGroups producer groups of 4 warps (chunk c -> group c % kGroups)
-constexpr int kRedThreads = 160 + kGroups * kGroupThreads;
+constexpr int kRedGroupThreads = 96;
+constexpr int kRedThreads = 160 + kGroups * kRedGroupThreads;
 
 __global__ void __launch_bounds__(kRedThreads, 1) k_tc_redgemm(RedGemmArgs g) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -392,7 +422,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) k_tc_redgemm(RedGemmArgs g) {
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(&full[s], kGroupThreads);
+      mbar_init(&full[s], kRedGroupThreads);
       mbar_init(&empty[s], 1);
     }
     mbar_init(tfull, 1);
@@ -411,23 +441,23 @@ __global__ void __launch_bounds__(kRedThreads, 1) k_tc_redgemm(RedGemmArgs g) {
   if (warp >= 5) {
     // ===== producers: item = 8 rows x 4 columns (8 coalesced float4 loads), transposed in
     // registers into four 16-byte k-chunks (one per column) =====
-    const int grp = (warp - 5) >> 2, pt = (tid - 160) & (kGroupThreads - 1);
+    const int grp = (warp - 5) / 3, pt = (tid - 160) % kRedGroupThreads;
     const bool vecA = (g.ldg % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.G) & 15) == 0);
     const bool vecB = (g.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.X) & 15) == 0);
     const int a_items = 32 * (kRC / 8), b_items = (g.N_pad / 4) * (kRC / 8);
-    for (int c = grp; c < nchunks; c += kGroups) {
+    for (int c = grp; c < nchunks && grp < g.groups; c += g.groups) {
       const uint32_t st = (uint32_t)(c % S), ph = (uint32_t)((c / S) & 1);
       unsigned char* sA = stage0 + (size_t)st * stage_bytes;
       unsigned char* sB = sA + 2 * a_tile;
       const int64_t r0 = r_begin + (int64_t)c * kRC;
       bool waited = false;
-      for (int base = 0; base < a_items + b_items; base += 2 * kGroupThreads) {
+      for (int base = 0; base < a_items + b_items; base += 2 * kRedGroupThreads) {
         float x[2][8][4];
         int col4[2], jj[2];
         bool isA[2], live[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const int item = base + u * kGroupThreads + pt;
+          const int item = base + u * kRedGroupThreads + pt;
           live[u] = item < a_items + b_items;
           isA[u] = item < a_items;
           const int e = isA[u] ? item : item - a_items;
@@ -510,7 +540,9 @@ __global__ void __launch_bounds__(kRedThreads, 1) k_tc_redgemm(RedGemmArgs g) {
       tc_fence_after();
       const int m = warp * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-      for (int n0 = 0; n0 < g.N_pad; n0 += 16) {
+      const int nblk = g.N_pad / 16;
+      for (int i = 0; i < nblk; ++i) {
+        const int n0 = ((i + (int)blockIdx.x) % nblk) * 16;  // CTAs start at different columns
         float v[16];
         tmem_ld16(trow + n0, v);
         tmem_ld_wait();
@@ -536,6 +568,8 @@ static int launch_redgemm(cudaStream_t st, RedGemmArgs g) {
   const size_t stage = 2 * (size_t)tile_bytes(128, kRC) + 2 * (size_t)tile_bytes(g.N_pad, kRC);
   int stages = (int)std::min<size_t>(8, (227 * 1024 - 1024) / stage);
   TF_CHECK_ARG(stages >= 2, "tc redgemm: tile too large for shared memory");
+  g.groups = std::min(kGroups, stages);
+  stages = stages / g.groups * g.groups;  // same-group-per-stage rule, see launch_rowgemm
   g.stages = stages;
   g.tmem_cols = pow2_cols(g.N_pad);
   int64_t ctas = std::min<int64_t>(kSMs, std::max<int64_t>(1, g.rows / 256));
@@ -566,7 +600,7 @@ static int pack_weights(cudaStream_t st, const float* W, int64_t sk, int64_t sn,
 template <int NSPLIT>
 static int rowgemm_tiled(cudaStream_t st, const float* A, int64_t lda, int64_t M, int K_valid, const float* W, int64_t sk,
                          int64_t sn, int N_valid, float* C, int64_t ldc, int N_store_total, const float* bias, int relu,
-                         const float* mask, int64_t ldmask, unsigned char* scratch) {
+                         const uint32_t* bits_in, uint32_t* bits_out, unsigned char* scratch) {
   const int K_pad = round_up(K_valid, 16);
   const int N_total = round_up(N_store_total, 16);
   for (int n0 = 0; n0 < N_total; n0 += 256) {
@@ -575,7 +609,9 @@ static int rowgemm_tiled(cudaStream_t st, const float* A, int64_t lda, int64_t M
     RowGemmArgs g{};
     g.A = A; g.lda = lda; g.M = M; g.K_valid = K_valid; g.K_pad = K_pad; g.Bp = scratch; g.N_pad = nn;
     g.C = C + n0; g.ldc = ldc; g.N_store = std::min(nn, N_store_total - n0);
-    g.bias = bias ? bias + n0 : nullptr; g.relu = relu; g.mask = mask ? mask + n0 : nullptr; g.ldmask = ldmask;
+    g.bias = bias ? bias + n0 : nullptr; g.relu = relu;
+    TF_CHECK_ARG(!(bits_in || bits_out) || N_total <= 256, "relu bit masks need a single column tile");
+    g.bits_in = bits_in; g.bits_out = bits_out;
     TF_RETURN_IF_ERROR(launch_rowgemm<NSPLIT>(st, g));
     scratch += packed_weight_bytes<NSPLIT>(K_pad, nn);
   }
@@ -609,14 +645,14 @@ int mlp_tc_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const flo
   unsigned char* sc = ws.wpack;
   // Dense_0: f = feat @ W0 (no bias); the padding columns of f come out as exact zeros
   TF_RETURN_IF_ERROR(rowgemm_tiled<kFwdSplit>(st, feat, s.Ca, M, s.Ca, p.w0, s.squash, 1, s.squash, ws.f, ws.ldf, ws.ldf, nullptr, 0,
-                                   nullptr, 0, sc));
+                                              nullptr, nullptr, sc));
   sc += rowgemm_scratch(s.Ca, ws.ldf);
   TF_RETURN_IF_ERROR(mlp_encode_fwd(st, s, ws, viewdirs, M, rows_per_ray));
   // Dense_1 + relu
-  TF_RETURN_IF_ERROR(rowgemm_tiled<kFwdSplit>(st, ws.x, ws.ldx, M, s.enc, p.w1, U, 1, U, ws.h1, U, U, p.b1, 1, nullptr, 0, sc));
+  TF_RETURN_IF_ERROR(rowgemm_tiled<kFwdSplit>(st, ws.x, ws.ldx, M, s.enc, p.w1, U, 1, U, ws.h1, U, U, p.b1, 1, nullptr, ws.bits1, sc));
   sc += rowgemm_scratch(s.enc, U);
   // Dense_2 + relu
-  TF_RETURN_IF_ERROR(rowgemm_tiled<kFwdSplit>(st, ws.h1, U, M, U, p.w2, U, 1, U, ws.h2, U, U, p.b2, 1, nullptr, 0, sc));
+  TF_RETURN_IF_ERROR(rowgemm_tiled<kFwdSplit>(st, ws.h1, U, M, U, p.w2, U, 1, U, ws.h2, U, U, p.b2, 1, nullptr, nullptr, sc));
   return mlp_out_fwd(st, s, p, ws, cams, M, rows_per_ray, rgb);
 }
 
@@ -636,7 +672,7 @@ int mlp_tc_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const flo
   TF_RETURN_IF_ERROR(launch_redgemm(st, r));
   TF_RETURN_IF_ERROR(mlp_colsum128(st, ws.dp2, gr.b2, M));
   // dp1 = (dp2 @ W2^T) * (h1 > 0)
-  TF_RETURN_IF_ERROR(rowgemm_tiled<kBwdSplit>(st, ws.dp2, U, M, U, p.w2, 1, U, U, ws.dp1, U, U, nullptr, 0, ws.h1, U, sc));
+  TF_RETURN_IF_ERROR(rowgemm_tiled<kBwdSplit>(st, ws.dp2, U, M, U, p.w2, 1, U, U, ws.dp1, U, U, nullptr, 0, ws.bits1, nullptr, sc));
   sc += rowgemm_scratch(U, U);
   // dW1[k][n] = sum_rows x[row][k] * dp1[row][n] ; db1
   r = RedGemmArgs{};
@@ -645,7 +681,7 @@ int mlp_tc_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const flo
   TF_RETURN_IF_ERROR(launch_redgemm(st, r));
   TF_RETURN_IF_ERROR(mlp_colsum128(st, ws.dp1, gr.b1, M));
   // dx = dp1 @ W1^T   (W1^T(k, n) = W1[n][k])
-  TF_RETURN_IF_ERROR(rowgemm_tiled<kBwdSplit>(st, ws.dp1, U, M, U, p.w1, 1, U, s.enc, ws.dx, ws.ldx, ws.ldx, nullptr, 0, nullptr, 0, sc));
+  TF_RETURN_IF_ERROR(rowgemm_tiled<kBwdSplit>(st, ws.dp1, U, M, U, p.w1, 1, U, s.enc, ws.dx, ws.ldx, ws.ldx, nullptr, 0, nullptr, nullptr, sc));
   sc += rowgemm_scratch(U, ws.ldx);
   TF_RETURN_IF_ERROR(mlp_encode_bwd(st, s, ws, M));
   // dW0[k][n] = sum_rows feat[row][k] * df[row][n]
@@ -655,7 +691,7 @@ int mlp_tc_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const flo
   TF_RETURN_IF_ERROR(launch_redgemm(st, r));
   // d_feat = df @ W0^T
   TF_RETURN_IF_ERROR(rowgemm_tiled<kBwdSplit>(st, ws.df, ws.ldf, M, s.squash, p.w0, 1, s.squash, s.Ca, d_feat, s.Ca, s.Ca, nullptr, 0,
-                                   nullptr, 0, sc));
+                                              nullptr, nullptr, sc));
   return 0;
 }
 
@@ -663,11 +699,11 @@ int mlp_tc_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const flo
 // test entry points (tests/test_gpu_tc.py): plain GEMMs through the tensor-core kernels
 // ---------------------------------------------------------------------------------------------
 int tc_rowgemm_test(cudaStream_t st, const float* A, int64_t M, int K, const float* W, int N, const float* bias, int relu,
-                    const float* mask, float* C, void* scratch, size_t scratch_bytes, int nsplit) {
+                    const uint32_t* mask_bits, uint32_t* bits_out, float* C, void* scratch, size_t scratch_bytes, int nsplit) {
   TF_CHECK_ARG(rowgemm_scratch(K, N) <= scratch_bytes, "scratch too small");
   if (nsplit == 3)
-    return rowgemm_tiled<3>(st, A, K, M, K, W, N, 1, N, C, N, N, bias, relu, mask, N, (unsigned char*)scratch);
-  return rowgemm_tiled<2>(st, A, K, M, K, W, N, 1, N, C, N, N, bias, relu, mask, N, (unsigned char*)scratch);
+    return rowgemm_tiled<3>(st, A, K, M, K, W, N, 1, N, C, N, N, bias, relu, mask_bits, bits_out, (unsigned char*)scratch);
+  return rowgemm_tiled<2>(st, A, K, M, K, W, N, 1, N, C, N, N, bias, relu, mask_bits, bits_out, (unsigned char*)scratch);
 }
 
 int tc_redgemm_test(cudaStream_t st, const float* G, int Mg, const float* X, int Nx, int64_t rows, float* out) {

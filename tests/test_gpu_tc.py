@@ -21,21 +21,32 @@ def test_rowgemm(cuda, M, K, N, nsplit, tol):
     A = torch.from_numpy(rng.normal(size=(M, K)).astype(np.float32)).to(cuda)
     W = torch.from_numpy((rng.normal(size=(K, N)) / np.sqrt(K)).astype(np.float32)).to(cuda)
     bias = torch.from_numpy(rng.normal(size=(N,)).astype(np.float32)).to(cuda)
-    mask = torch.from_numpy(rng.normal(size=(M, N)).astype(np.float32)).to(cuda)
+    mask_np = rng.normal(size=(M, N)).astype(np.float32) > 0
+    words = (((N + 15) // 16 * 16) + 31) // 32
+    bits_np = np.zeros((M, words * 32), dtype=bool)
+    bits_np[:, :N] = mask_np
+    bits = torch.from_numpy(np.packbits(bits_np.reshape(M, words, 32), axis=-1, bitorder="little").view(np.uint32).reshape(M, words).view(np.int32)).to(cuda)
+    bits_out = torch.zeros((M, words), dtype=torch.int32, device=cuda)
     out = torch.full((M, N), float("nan"), dtype=torch.float32, device=cuda)
     scratch = torch.empty(128 * 1024 * ((K + 63) // 64 + 1) * ((N + 255) // 256), dtype=torch.uint8, device=cuda)
     lib = _lib.load()
     for relu, use_mask in ((0, False), (1, True)):
         _lib.check(lib.tensorf_tc_rowgemm_test(ops._stream(), A.data_ptr(), M, K, W.data_ptr(), N, bias.data_ptr(), relu,
-                                               mask.data_ptr() if use_mask else None, out.data_ptr(), scratch.data_ptr(),
-                                               scratch.numel(), nsplit))
+                                               bits.data_ptr() if use_mask and N <= 256 else None,
+                                               bits_out.data_ptr() if N <= 256 else None, out.data_ptr(),
+                                               scratch.data_ptr(), scratch.numel(), nsplit))
         ref = A.double().cpu() @ W.double().cpu() + bias.double().cpu()
         if relu:
             ref = torch.relu(ref)
-        if use_mask:
-            ref = ref * (mask.cpu() > 0)
+        if use_mask and N <= 256:
+            ref = ref * torch.from_numpy(mask_np)
         err = _rel(out.cpu().numpy(), ref.numpy())
         assert err < tol, f"rowgemm M={M} K={K} N={N} relu={relu} nsplit={nsplit}: rel err {err:.3e}"
+        if N <= 256:  # bits_out = (C > 0), up to sign flips of values within rounding of zero
+            got = np.unpackbits(bits_out.cpu().numpy().view(np.uint32).reshape(M, words, 1).view(np.uint8), axis=-1, bitorder="little").reshape(M, words * 32)[:, :N].astype(bool)
+            exp = ref.numpy() > 0
+            diff = got != exp
+            assert (np.abs(ref.numpy()[diff]) < 1e-4).all() and diff.mean() < 1e-3
 
 
 @pytest.mark.parametrize("rows,Mg,Nx", [(256, 128, 128), (5000, 128, 150), (3001, 27, 144), (40000, 128, 128), (999, 128, 390)])
