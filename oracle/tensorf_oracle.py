@@ -129,7 +129,7 @@ class MlpConfig:
         )
 
 
-def feature_mlp(cfg: MlpConfig, mlp: Dict[str, torch.Tensor], features, viewdirs, camera_indices):
+def feature_mlp(cfg: MlpConfig, mlp: Dict[str, torch.Tensor], features, viewdirs, camera_indices, aux: Optional[dict] = None):
     """networks.py:46-121 (FeatureMlp.__call__). `mlp` holds flax leaves:
     w0 (Ca,27); w1 (enc,128), b1; w2 (128,128), b2; w3 (128,3), b3; embed (ncam,128)."""
     f = features @ mlp["w0"]  # :57-61 (no bias)
@@ -137,8 +137,12 @@ def feature_mlp(cfg: MlpConfig, mlp: Dict[str, torch.Tensor], features, viewdirs
         [f, viewdirs, fourier_encode(f, cfg.feature_n_freqs), fourier_encode(viewdirs, cfg.viewdir_n_freqs)], dim=-1
     )  # :68-76
     assert x.shape[-1] == cfg.encoded_dim()
-    x = torch.relu(x @ mlp["w1"] + mlp["b1"])  # :86-90
-    x = torch.relu(x @ mlp["w2"] + mlp["b2"])  # :94-98
+    z1 = x @ mlp["w1"] + mlp["b1"]
+    x = torch.relu(z1)  # :86-90
+    z2 = x @ mlp["w2"] + mlp["b2"]
+    x = torch.relu(z2)  # :94-98
+    if aux is not None:  # pre-activations: lets tests find rows that sit on a ReLU kink
+        aux["z1"], aux["z2"] = z1.detach(), z2.detach()
     if cfg.num_cameras is not None:  # :103-111
         h = cfg.units // 2
         cond = mlp["embed"][camera_indices.to(torch.int64)]
@@ -298,7 +302,7 @@ def render_rays(
         app_feat = app_feat.permute(1, 2, 0).reshape(R * K, Ca)  # :484-486
         viewdirs = directions[:, None, :].expand(R, K, 3).reshape(-1, 3)  # :487-490
         cams = camera_indices[:, None].expand(R, K).reshape(-1)  # :494-496
-        visible_rgb = feature_mlp(mlp_cfg, params, app_feat, viewdirs, cams).reshape(R, K, 3)  # :499-509
+        visible_rgb = feature_mlp(mlp_cfg, params, app_feat, viewdirs, cams, aux=aux).reshape(R, K, 3)  # :499-509
         rgb = torch.zeros(R, N, 3, dtype=visible_rgb.dtype)
         rgb = rgb.index_put((rows, idx), visible_rgb)  # :511-515
         sampled_pt = p_terminates[rows, idx]  # :529-531

@@ -73,3 +73,15 @@ def grad_errors(g, ref):
 def assert_close_grad(g, ref, rtol=RTOL_GRAD, what=""):
     einf, el2 = grad_errors(g, ref)
     assert einf <= rtol and el2 <= rtol, f"{what}: rel-inf {einf:.3e}, rel-L2 {el2:.3e} > {rtol}"
+
+
+KINK_TAU = 5e-6
+
+
+def kink_rows(aux, tau=KINK_TAU):
+    """Rows of the MLP batch with a hidden pre-activation within rounding of zero. d relu/dz is
+    discontinuous there: two correct fp32 implementations may legitimately pick different
+    sides, so such rows get a zero cotangent in BOTH the kernel and the oracle (the same
+    treatment the selection stage gets for near-ties)."""
+    bad = (aux["z1"].abs() < tau).any(dim=-1) | (aux["z2"].abs() < tau).any(dim=-1)
+    return torch.where(bad)[0].numpy()

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import tensorf_oracle as O
-from helpers import T, assert_close_grad, assert_close_out, oracle_cfgs
+from helpers import T, assert_close_grad, assert_close_out, kink_rows, oracle_cfgs
 from tensorf_b200 import synthetic as S
 
 pytestmark = pytest.mark.gpu
@@ -96,7 +96,9 @@ def test_render_rays_modes_and_autograd(cuda, contracted):
     # (fp64 and fp32 selections agree except for near-ties; tolerate a couple of rays)
     bad = np.abs(rgb.detach().cpu().numpy() - rgb64.numpy()).max(axis=-1) > 1e-4
     assert bad.sum() <= 2, f"{bad.sum()} rays differ"
-    if bad.sum() == 0:
+    # strict gradient parity lives in test_gpu_render.py (forced selection + ReLU-kink audit); here the
+    # autograd plumbing is checked whenever this instance has no near-tie and no kink row
+    if bad.sum() == 0 and len(kink_rows(aux)) == 0:
         for k, ref in g64.items():
             assert_close_grad(flat[k].grad.cpu().numpy(), ref.numpy(), what=f"autograd grad {k}")
 
