@@ -144,6 +144,49 @@ def run_reference_arm(args, w):
 # ---------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------
+def bench_render(ops, dev, world, rank, dist, chunks=6, warm=2):
+    """Forward rendering at the render_360 shapes (render_360.py:43-51 with the BASELINE sizes: 800x800
+    frames, N=512, K=128, 300^3 lego model, chunks of 16384 rays). Frames are split into row bands
+    across ranks (no collective); every rank renders `chunks` raster-ordered chunks of its band.
+    Reports whole-job Mpix/s for RGB and for the two distance modes."""
+    from tensorf_b200 import dist as tdist
+    w = S.render360_workload()
+    params = {k: torch.from_numpy(v).to(dev) for k, v in S.make_params(w.G, w.cd, w.ca, w.feat_freqs, w.view_freqs, None, 0).items()}
+    r0, r1 = tdist.tile_rows(800, rank, world)
+    o, d, c = S.frame_rays(800, 800, rows=(r0, r1))
+    jitter, gumbel = S.make_noise(w.N, w.R, False, 2)
+    shared = {"aabb": torch.from_numpy(w.aabb()).to(dev), "jitter": torch.from_numpy(jitter).to(dev),
+              "gumbel": torch.from_numpy(gumbel).to(dev)}
+    nrays = o.shape[0]
+    starts = [(i * w.R) % max(1, nrays - w.R + 1) for i in range(chunks + warm)]
+    O_, D_, C_ = (torch.from_numpy(x).to(dev) for x in (o, d, c.view(np.int32)))
+    out = {"workload": w.name, "rays_per_chunk": w.R, "chunks_timed": chunks}
+    for label, mode in (("rgb", ops.MODE_RGB), ("dist_median", ops.MODE_DIST_MEDIAN), ("dist_mean", ops.MODE_DIST_MEAN)):
+        desc = ops.make_desc(R=w.R, N=w.N, K=w.K, G=w.G, cd=w.cd, ca=w.ca, mode=mode, feat_freqs=w.feat_freqs,
+                             view_freqs=w.view_freqs)
+        call = ops.RenderCall(desc, dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i, st in enumerate(starts):
+            if i == warm:
+                torch.cuda.synchronize()
+                ev0.record()
+            ins = dict(shared, origins=O_[st:st + w.R].contiguous(), directions=D_[st:st + w.R].contiguous(),
+                       camera_indices=C_[st:st + w.R].contiguous())
+            if mode == ops.MODE_RGB:
+                call.forward(params, ins)
+            else:
+                call.depth(params, ins)
+        ev1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item()) / chunks
+        out[label] = {"mpix_per_s": world * w.R / (ms * 1e-3) / 1e6, "ms_per_chunk": ms}
+        del call
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,6 +196,7 @@ def main():
     ap.add_argument("--workload", default="lego_256")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")
+    ap.add_argument("--no-render", action="store_true")
     args = ap.parse_args()
     w = workload_from_name(args.workload)
     if args.impl == "reference":
@@ -200,14 +244,9 @@ def main():
         dins["base_ts"], dins["deltas"] = dv(base), dv(delta)
 
     # all gradient leaves live in ONE flat buffer -> one NCCL allreduce per step
-    shapes = ops.param_shapes(desc)
-    total = sum(int(np.prod(s)) for s in shapes.values())
-    flat = torch.empty(total, dtype=torch.float32, device=dev)
-    grads, off = {}, 0
-    for k, s in shapes.items():
-        n = int(np.prod(s))
-        grads[k] = flat[off:off + n].view(s)
-        off += n
+    from tensorf_b200 import dist as tdist
+    fg = tdist.FlatGrads(ops.param_shapes(desc), dev)
+    grads, flat = fg.leaves, fg.flat
 
     flush = None if args.no_l2_flush else torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
@@ -224,12 +263,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks are sampled from the warm-up through the timed and end-to-end loops (the timed region
+    # alone is only tens of milliseconds, shorter than nvidia-smi's sampling period)
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(warmup):
         step()
     barrier()
 
     # ---- timed region: exactly `steps` steps, CUDA events per step, L2 flushed between steps ----
-    sampler = ClockSampler(local) if rank == 0 else None
     ops.profile_enable(True)
     launches0 = ops.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
@@ -244,7 +285,6 @@ def main():
     launches = ops.launch_count() - launches0
     prof = ops.profile_read()
     ops.profile_enable(False)
-    clocks = sampler.stop() if sampler else None
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -270,6 +310,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item()) / steps
     e2e_value = R_global / (e2e_ms * 1e-3)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- render_360-style forward rendering (BASELINE configs[4] shapes), this rank's image tiles ----
+    render = None
+    if not args.no_render:
+        render = bench_render(ops, dev, world, rank, dist if world > 1 else None)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -309,6 +355,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if render is not None:
+            out["render"] = render
         if world == 1 and not args.no_cpu_baseline:
             v, ms, cores = cpu_reference_rays_per_s(w, 512, 6, 1)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

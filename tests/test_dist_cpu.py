@@ -1,0 +1,67 @@
+"""Host-side multi-GPU logic on CPU: world_size-2 gloo process group (the N>1 path of bench.py /
+TrainState.training_step) and the sharding arithmetic."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tensorf_b200 import dist as tdist
+from tensorf_b200 import synthetic as S
+
+
+def test_shard_ranges_cover_and_balance():
+    for total in (0, 1, 7, 4096, 16385):
+        for world in (1, 2, 3, 8):
+            spans = [tdist.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        tdist.shard_range(10, 2, 2)
+    assert tdist.tile_rows(800, 3, 8) == (300, 400)
+
+
+def test_shard_rays_slices_only_per_ray_arrays():
+    w = S.dozer_workload(R=10, G=8)
+    inp = S.make_inputs(w)
+    flat = {k: inp[k] for k in ("origins", "directions", "camera_indices", "colors", "jitter", "gumbel", "aabb")}
+    parts = [tdist.shard_rays(flat, r, 3, per_ray=("origins", "directions", "camera_indices", "colors", "jitter")) for r in range(3)]
+    assert [p["origins"].shape[0] for p in parts] == [4, 3, 3]
+    assert np.array_equal(np.concatenate([p["jitter"] for p in parts]), inp["jitter"])   # contracted: (R,N) rows
+    assert all(p["gumbel"] is inp["gumbel"] and p["aabb"] is inp["aabb"] for p in parts)  # shared by all ranks
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        shapes = {"density_vector": (3, 2, 5), "w1": (7, 4), "b3": (3,)}
+        fg = tdist.FlatGrads(shapes, "cpu")
+        assert fg.total == 30 + 28 + 3 and fg.leaves["w1"].data_ptr() == fg.flat[30:].data_ptr()
+        # rank-local "gradients": a deterministic function of the rank's ray shard
+        a, b = tdist.shard_range(10, rank, world)
+        for i, (k, t) in enumerate(fg.leaves.items()):
+            t.copy_(torch.full(t.shape, float(sum(range(a, b)) + i)))
+        fg.allreduce()
+        expect = {k: float(sum(range(10)) + world * i) for i, k in enumerate(shapes)}
+        ok = all(torch.all(fg.leaves[k] == expect[k]).item() for k in shapes)
+        scale = tdist.global_loss_scale(b - a, world)
+        out[rank] = (ok, scale)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_grads_allreduce_gloo_world2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0][0] and out[1][0]
+    assert out[0][1] == pytest.approx(1.0 / 30.0)   # 1/(3*R_global) with R_global = 10

@@ -1,0 +1,71 @@
+"""Golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py from the fp64 oracle):
+the fp32 oracle must reproduce them on CPU, the CUDA path must reproduce them on the GPU."""
+import pathlib
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import tensorf_oracle as O
+from helpers import T, assert_close_grad, assert_close_out, device_inputs, kink_rows, oracle_cfgs, oracle_inputs
+from tensorf_b200 import synthetic as S
+
+sys.path.insert(0, str(pathlib.Path(__file__).parent / "golden"))
+from make_golden import CASES  # noqa: E402
+
+GOLD = pathlib.Path(__file__).parent / "golden"
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_fp32_reproduces_golden(name):
+    w = CASES[name]
+    g = np.load(GOLD / f"{name}.npz")
+    inp = S.make_inputs(w, bias_std=0.05)
+    cfg, mc = oracle_cfgs(w)
+    oi = oracle_inputs(inp, torch.float32)
+    forced = torch.from_numpy(g["indices"].astype(np.int64))
+    loss, rgb, grads = O.loss_and_grads(cfg, mc, oi["params"], w.contracted, oi["aabb"], oi["origins"], oi["directions"],
+                                        oi["camera_indices"], oi["colors"], oi["jitter"], oi["gumbel"], forced_indices=forced)
+    assert_close_out(rgb.numpy(), g["rgb"], what="rgb")
+    assert_close_out(loss.numpy(), g["loss"], what="loss")
+    for k, v in grads.items():
+        assert_close_grad(v.numpy(), g["grad_" + k], what=k)
+    _, aux = O.render_rays(cfg, mc, oi["params"], w.contracted, oi["aabb"], oi["origins"], oi["directions"],
+                           oi["camera_indices"], oi["jitter"], oi["gumbel"], return_aux=True)
+    same = (np.sort(aux["indices"].numpy(), -1) == g["indices"]).all(axis=-1)
+    assert same.mean() >= 0.95          # fp32 vs fp64 selections differ only at near-ties
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CASES))
+def test_cuda_reproduces_golden(cuda, name):
+    from tensorf_b200 import ops
+    w = CASES[name]
+    g = np.load(GOLD / f"{name}.npz")
+    inp = S.make_inputs(w, bias_std=0.05)
+    desc = ops.make_desc(R=w.R, N=w.N, K=w.K, G=w.G, cd=w.cd, ca=w.ca, contracted=w.contracted, feat_freqs=w.feat_freqs,
+                         view_freqs=w.view_freqs, num_cameras=w.num_cameras, loss_scale=1.0 / (3 * w.R))
+    call = ops.RenderCall(desc, cuda)
+    params, dins = device_inputs(w, inp, cuda)
+    rgb, loss = call.forward(params, dins)
+    idx = call.view("idx").cpu().numpy().reshape(w.R, w.K)
+    same = (idx == g["indices"]).all(axis=-1)
+    assert same.mean() >= 0.95
+    assert_close_out(call.view("z").cpu().numpy().reshape(w.R, w.N), g["z"], what="z")
+    assert_close_out(rgb.cpu().numpy()[same], g["rgb"][same], what="rgb")
+    if same.all():
+        assert_close_out(loss.cpu().numpy(), g["loss"], what="loss")
+        cfg, mc = oracle_cfgs(w)
+        o64 = oracle_inputs(inp, torch.float64)
+        _, aux = O.render_rays(cfg, mc, o64["params"], w.contracted, o64["aabb"], o64["origins"], o64["directions"],
+                               o64["camera_indices"], o64["jitter"], o64["gumbel"], return_aux=True)
+        if len(kink_rows(aux)) == 0:
+            grads = call.backward()
+            for k in grads:
+                assert_close_grad(grads[k].cpu().numpy(), g["grad_" + k], what=k)
+    for mode, key in ((O.DIST_MEDIAN, "depth_median"), (O.DIST_MEAN, "depth_mean")):
+        d = ops.make_desc(R=w.R, N=w.N, K=w.K, G=w.G, cd=w.cd, ca=w.ca, mode=mode, contracted=w.contracted)
+        depth = ops.RenderCall(d, cuda).depth(params, {k: v for k, v in dins.items() if k != "colors"}).cpu().numpy()
+        ok = np.isclose(depth, g[key], rtol=1e-4, atol=1e-6) | (np.isinf(depth) & np.isinf(g[key]))
+        assert ok.mean() >= 0.97, key
