@@ -205,6 +205,12 @@ def main():
     import torch.distributed as dist
     from tensorf_b200 import ops
 
+    # rank 0 prints exactly ONE JSON line on stdout: anything libraries write to fd 1 (e.g. NCCL's
+    # version banner) is sent to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -362,7 +368,7 @@ def main():
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": f"512-ray slice of the same batch, fwd+bwd, 6 timed steps ({ms:.0f} ms each), "
                                              f"PyTorch-CPU fp32 restatement of the reference (JAX not in image)"}
-        print(json.dumps(out))
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
