@@ -147,6 +147,9 @@ int tensorf_segment_probabilities(tensorf_stream_t s, const float* sigmas, const
 int tensorf_tc_rowgemm_test(tensorf_stream_t s, const float* A, int64_t M, int K, const float* W, int N, const float* bias,
                             int relu, const uint32_t* mask_bits, uint32_t* bits_out, float* C, void* scratch,
                             int64_t scratch_bytes, int nsplit);
+/* Debug: with TENSORF_TC_TRACE=1 CTA 0 of the row GEMM records clock64() per role/chunk; copies 8 x 1024
+ * int64 slots to HOST memory (synchronises the device). */
+int tensorf_tc_trace_read(long long* host, int n);
 /* out (Nx, Mg) += X^T (Nx,rows) @ G (rows,Mg): the weight-gradient contraction over rows. Mg <= 128, Nx <= 512. */
 int tensorf_tc_redgemm_test(tensorf_stream_t s, const float* G, int Mg, const float* X, int Nx, int64_t rows, float* out);
 

@@ -152,6 +152,7 @@ static int check_mlp_params(const tensorf_render_desc& d, const tensorf_params* 
 int tc_rowgemm_test(cudaStream_t st, const float* A, int64_t M, int K, const float* W, int N, const float* bias, int relu,
                     const uint32_t* mask_bits, uint32_t* bits_out, float* C, void* scratch, size_t scratch_bytes, int nsplit);
 int tc_redgemm_test(cudaStream_t st, const float* G, int Mg, const float* X, int Nx, int64_t rows, float* out);
+int tc_trace_read(long long* host, int n);
 
 }  // namespace tf
 
@@ -249,6 +250,8 @@ int tensorf_tc_redgemm_test(tensorf_stream_t s, const float* G, int Mg, const fl
   TF_CHECK_ARG(G && X && out && Mg >= 1 && Mg <= 128 && Nx >= 1 && Nx <= 512 && rows >= 0, "bad argument");
   return tc_redgemm_test((cudaStream_t)s, G, Mg, X, Nx, rows, out);
 }
+
+int tensorf_tc_trace_read(long long* host, int n) { return tc_trace_read(host, n); }
 
 int64_t tensorf_mlp_workspace_bytes(const tensorf_render_desc* d, int64_t M) {
   if (!d || M < 0) return -1;

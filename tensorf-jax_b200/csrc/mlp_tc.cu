@@ -106,6 +106,10 @@ static size_t packed_weight_bytes(int K_pad, int N_pad) {
   return (size_t)((K_pad + KC - 1) / KC) * NSPLIT * tile_bytes(N_pad, KC);
 }
 
+// Debug timeline (TENSORF_TC_TRACE=1): CTA 0 records clock64() per role and chunk.
+__device__ long long g_trace[8192];
+#define TF_TRACE(slot, idx) do { if (g.trace && blockIdx.x == 0 && (idx) < 1024) g_trace[(slot) * 1024 + (idx)] = clock64(); } while (0)
+
 // ---------------------------------------------------------------------------------------------
 // k_tc_rowgemm
 // ---------------------------------------------------------------------------------------------
@@ -124,21 +128,34 @@ struct RowGemmArgs {
   int relu;
   int stages;
   int no_bulk;                // debug: force the direct-store epilogue
+  int trace;                  // debug: record the CTA-0 timeline into g_trace
+  int out_stride;             // floats per epilogue staging row (columns per half tile + 4), 0 = no staging
+  int header_bytes;           // kRowFixed + staging
+  // fused output layer (networks.py:103-120): FiLM + Dense(3) + sigmoid on the epilogue's rows (N_pad == 128)
+  const float* w3;            // (128,3) or null
+  const float* b3;            // (3)
+  const float* embed;         // (ncam,128) or null
+  const uint32_t* cams;       // camera index per ray
+  int rows_per_ray;
+  float* rgb_out;             // (M,3)
   int groups;                 // active producer groups; stages % groups == 0 (see launch_rowgemm)
   uint32_t tmem_cols;         // power of two >= 2*N_pad
 };
 
-// warps 0-3 epilogue, 4 MMA issuer, 5 weight loader, then kGroups producer groups of 4 warps.
+// warps 0-7 epilogue (two per TMEM lane quadrant, each takes half of the columns), 8 MMA issuer,
+// 9 weight loader, then kGroups producer groups of 4 warps.
 // fence.proxy.async drains the issuing thread's outstanding loads, so one thread cannot overlap
 // its own global loads with publishing a stage; instead every producer group owns whole chunks
-// (chunk seq -> group seq % kGroups) and kGroups chunks are in flight per SM.
-constexpr int kGroups = 4;
+// (chunk seq -> group seq % groups) and several chunks are in flight per SM.
+constexpr int kGroups = 3;
 constexpr int kGroupThreads = 128;
-constexpr int kRowThreads = 192 + kGroups * kGroupThreads;
-constexpr int kOutBlock = 64;  // columns per epilogue staging block
-constexpr int kRowHeader = 2048 + 2 * 128 * (kOutBlock + 4) * 4;  // barriers, bias, two staging tiles (71680 B)
+constexpr int kEpiWarps = 8;
+constexpr int kMmaWarp = kEpiWarps, kLoadWarp = kEpiWarps + 1, kProdWarp0 = kEpiWarps + 2;
+constexpr int kRowThreads = 32 * kProdWarp0 + kGroups * kGroupThreads;
+constexpr int kRowFixed = 6144;  // barriers [0,1K), bias [1K,2K), W3/b3 [2K,4K), out3 exchange [4K,6K)
+enum : int { EPI_BITS_IN = 1, EPI_BITS_OUT = 2, EPI_OUT3 = 4 };
 
-template <int NSPLIT>
+template <int NSPLIT, int EPI>
 __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
   constexpr int KC = RowCfg<NSPLIT>::KC;
   constexpr int ITEMS = 128 * (KC / 8) / kGroupThreads;  // 16-byte k-chunks per producer thread and stage
@@ -151,10 +168,12 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
   uint64_t* tempty = tfull + 2;                         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* s_bias = reinterpret_cast<float*>(smem + 1024);   // [256] bias staged once per CTA
-  float* s_out = reinterpret_cast<float*>(smem + 2048);    // [2][128][kOutBlock+4] epilogue staging tiles
+  float* s_w3 = reinterpret_cast<float*>(smem + 2048);     // [128*3 + 3] output layer weights + bias
+  float* s_xch = reinterpret_cast<float*>(smem + 4096);    // [128][3] partial outputs of the second column half
+  float* s_out = reinterpret_cast<float*>(smem + kRowFixed);  // [2][128][out_stride] epilogue staging rows
   const uint32_t a_tile = tile_bytes(128, KC), b_tile = tile_bytes(g.N_pad, KC);
   const uint32_t stage_bytes = NSPLIT * (a_tile + b_tile);
-  unsigned char* stage0 = smem + kRowHeader;
+  unsigned char* stage0 = smem + g.header_bytes;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
@@ -162,13 +181,15 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
       mbar_init(&empty[s], 1);                 // tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&tfull[a], 1);       // tcgen05.commit
-      mbar_init(&tempty[a], 128);    // epilogue threads
+      mbar_init(&tfull[a], 1);                // tcgen05.commit
+      mbar_init(&tempty[a], 32 * kEpiWarps);  // epilogue threads
     }
     fence_barrier_init();
   }
   for (int n = tid; n < 256; n += kRowThreads) s_bias[n] = (g.bias && n < g.N_store) ? g.bias[n] : 0.f;
-  if (warp == 4) tmem_alloc(tmem_slot, g.tmem_cols);
+  if (EPI & EPI_OUT3)
+    for (int n = tid; n < 387; n += kRowThreads) s_w3[n] = n < 384 ? g.w3[n] : g.b3[n - 384];
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, g.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -179,15 +200,16 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
   const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
   const int64_t total = my_tiles * nchunks;  // chunks this CTA processes, in (tile, k-chunk) order
 
-  if (warp >= 6) {
+  if (warp >= kProdWarp0) {
     // ================= A producers: fp32 rows -> split bf16 core matrices =================
     // 8 consecutive lanes fill one 128-byte core matrix (8 rows x 16 B).
-    const int grp = (warp - 6) >> 2, pw = (warp - 6) & 3;
+    const int grp = (warp - kProdWarp0) >> 2, pw = (warp - kProdWarp0) & 3;
     const bool vec_ok = (g.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
     for (int64_t seq = grp; seq < total && grp < g.groups; seq += g.groups) {
       const int64_t t = blockIdx.x + (seq / nchunks) * gridDim.x;
       const int k0 = (int)(seq % nchunks) * KC;
       const uint32_t st = (uint32_t)(seq % S), ph = (uint32_t)((seq / S) & 1);
+      if (pw == 0 && lane == 0) TF_TRACE(0, seq);
       float x[ITEMS][8];
 #pragma unroll
       for (int it = 0; it < ITEMS; ++it) {
@@ -211,7 +233,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
           for (int e = 0; e < 8; ++e) x[it][e] = 0.f;
         }
       }
-      mbar_wait(&empty[st], ph ^ 1, 100 + (int)seq);
+      mbar_wait_backoff(&empty[st], ph ^ 1, 100 + (int)seq);
+      if (pw == 0 && lane == 0) TF_TRACE(1, seq);
       unsigned char* sA = stage0 + (size_t)st * stage_bytes;
 #pragma unroll
       for (int it = 0; it < ITEMS; ++it) {
@@ -221,22 +244,24 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
         const int k8 = kh * 4 + (lane >> 3);
         split_store<NSPLIT>(x[it], sA, a_tile, tile_offset(row, k8 * 8, KC));
       }
+      if (pw == 0 && lane == 0) TF_TRACE(2, seq);
       fence_proxy_async();
       mbar_arrive(&full[st]);
+      if (pw == 0 && lane == 0) TF_TRACE(3, seq);
     }
-  } else if (warp == 5) {
+  } else if (warp == kLoadWarp) {
     // ================= weight loader: one bulk copy per chunk =================
     if (lane == 0) {
       for (int64_t seq = 0; seq < total; ++seq) {
         const uint32_t st = (uint32_t)(seq % S), ph = (uint32_t)((seq / S) & 1);
         const int c = (int)(seq % nchunks);
-        mbar_wait(&empty[st], ph ^ 1, 200 + (int)seq);
+        mbar_wait_backoff(&empty[st], ph ^ 1, 200 + (int)seq);
         unsigned char* sB = stage0 + (size_t)st * stage_bytes + NSPLIT * a_tile;
         mbar_arrive_expect_tx(&full[st], NSPLIT * b_tile);
         bulk_copy_g2s(sB, g.Bp + (size_t)c * NSPLIT * b_tile, NSPLIT * b_tile, &full[st]);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kMmaWarp) {
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, g.N_pad);
@@ -250,6 +275,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
         for (int c = 0; c < nchunks; ++c, ++seq) {
           const uint32_t st = (uint32_t)(seq % S), ph = (uint32_t)((seq / S) & 1);
           mbar_wait(&full[st], ph, 400 + (int)seq);
+          TF_TRACE(4, seq);
           tc_fence_after();
           const uint32_t sA = smem_u32(stage0 + (size_t)st * stage_bytes);
           const uint32_t sB = sA + NSPLIT * a_tile;
@@ -264,6 +290,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
             umma_split<NSPLIT>(d, da, db, idesc, (c | ks) == 0);
           }
           umma_commit(&empty[st]);  // smem stage free once these MMAs have read it
+          TF_TRACE(5, seq);
         }
         umma_commit(&tfull[acc]);  // accumulator complete
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
@@ -271,73 +298,97 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
     }
   } else {
     // ================= epilogue: TMEM -> registers -> bias / relu / mask -> smem row -> bulk store ====
-    // tcgen05.ld gives lane <-> row. Each thread stages 64-column blocks of ITS OWN row in a padded
-    // smem tile (conflict-free STS.128) and ships them with its own asynchronous bulk copy
-    // (cp.async.bulk shared -> global): coalesced 256-byte row segments, no LSU store wavefronts.
+    // tcgen05.ld gives lane <-> row. Two warps share a TMEM lane quadrant and split the columns.
+    // Each thread stages ITS OWN row segment in padded smem (conflict-free STS.128) and ships it
+    // with ONE asynchronous bulk copy per tile (cp.async.bulk shared -> global).
     // ReLU masks travel as one bit per element (bits_out / bits_in), not as fp32 activations.
     uint32_t acc = 0, acc_ph = 0;
-    const int row = warp * 32 + lane;
-    const int rs = kOutBlock + 4;  // padded row stride (floats) of the staging tiles
-    float* my0 = s_out + (size_t)row * rs;
-    float* my1 = my0 + (size_t)128 * rs;
-    const bool bulk_ok = !g.no_bulk && (g.ldc % 4 == 0) && (g.N_store % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;
+    const int nch = g.N_pad / 16;                               // 16-column chunks of the tile
+    const int ch_begin = half ? (nch + 1) / 2 : 0, ch_end = half ? nch : (nch + 1) / 2;
+    const int c_begin = ch_begin * 16, c_cols = (ch_end - ch_begin) * 16;
+    float* mine = s_out + ((size_t)half * 128 + row) * g.out_stride;
+    const bool bulk_ok = g.out_stride > 0 && (g.ldc % 4 == 0) && (g.N_store % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
     const int words = (g.N_pad + 31) / 32;
-    int buf = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const int64_t m = t * 128 + row;
       const bool row_ok = m < g.M;
       uint32_t mbits[8];
-      if (g.bits_in) {
+      if (EPI & EPI_BITS_IN) {
 #pragma unroll
         for (int w = 0; w < 8; ++w) mbits[w] = (row_ok && w < words) ? __ldg(g.bits_in + m * words + w) : 0u;
       }
+      const float* em = nullptr;  // FiLM conditioner of this row's camera (networks.py:103-111)
+      if ((EPI & EPI_OUT3) && g.embed && row_ok) em = g.embed + (int64_t)g.cams[m / g.rows_per_ray] * 128;
+      float o3[3] = {0.f, 0.f, 0.f};
+      if (bulk_ok) bulk_wait_read<0>();  // last tile's store has finished reading my staging row
       mbar_wait(&tfull[acc], acc_ph, 500);
+      if (tid == 0) TF_TRACE(6, (t - blockIdx.x) / gridDim.x);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (uint32_t)g.N_pad;
-      for (int b0 = 0; b0 < g.N_pad; b0 += kOutBlock) {
-        const int bcols = min(kOutBlock, g.N_pad - b0);
-        float* mine = buf ? my1 : my0;
-        const uint32_t mw[2] = {mbits[(b0 >> 5) & 7], mbits[((b0 >> 5) + 1) & 7]};  // kOutBlock = 64 = two words
-        uint32_t ow[2] = {0u, 0u};
-        if (bulk_ok) bulk_wait_read<1>();  // the group that last read this buffer has drained
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)g.N_pad;
+      for (int j = 0; j * 16 < c_cols; ++j) {
+        const int n0 = c_begin + j * 16;
+        float v[16];
+        tmem_ld16(trow + n0, v);
+        tmem_ld_wait();
+        const uint32_t mw = (EPI & EPI_BITS_IN) ? (mbits[(n0 >> 5) & 7] >> (n0 & 16)) : 0u;
+        uint32_t ow = 0u;
 #pragma unroll
-        for (int j = 0; j < kOutBlock / 16; ++j) {
-          const int n0 = b0 + j * 16;
-          if (j * 16 < bcols) {
-            float v[16];
-            tmem_ld16(trow + n0, v);
-            tmem_ld_wait();
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const float4 bb = *reinterpret_cast<const float4*>(s_bias + n0 + 4 * q4);
+          const float bq[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
+          for (int e = 0; e < 4; ++e) {
+            const int q = 4 * q4 + e;
+            float y = v[q] + bq[e];
+            if (g.relu) y = fmaxf(y, 0.f);
+            if ((EPI & EPI_BITS_IN) && !((mw >> q) & 1u)) y = 0.f;
+            if ((EPI & EPI_BITS_OUT) && y > 0.f) ow |= 1u << q;
+            v[q] = y;
+            if (EPI & EPI_OUT3) {
               const int n = n0 + q;
-              float y = v[q] + s_bias[n];
-              if (g.relu) y = fmaxf(y, 0.f);
-              if (g.bits_in && !((mw[j >> 1] >> ((j & 1) * 16 + q)) & 1u)) y = 0.f;
-              if (y > 0.f) ow[j >> 1] |= 1u << ((j & 1) * 16 + q);
-              v[q] = y;
-            }
-            if (bulk_ok) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<float4*>(mine + j * 16 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            } else if (row_ok) {
-              for (int q = 0; q < 16; ++q)
-                if (n0 + q < g.N_store) g.C[m * g.ldc + n0 + q] = v[q];
+              float yf = y;
+              if (em && n >= 64) yf = __fadd_rn(__fmul_rn(__ldg(em + n - 64), y), __ldg(em + n));
+              o3[0] = fmaf(yf, s_w3[3 * n + 0], o3[0]);
+              o3[1] = fmaf(yf, s_w3[3 * n + 1], o3[1]);
+              o3[2] = fmaf(yf, s_w3[3 * n + 2], o3[2]);
             }
           }
         }
-        if (g.bits_out && row_ok) {
-          g.bits_out[m * words + (b0 >> 5)] = ow[0];
-          if ((b0 >> 5) + 1 < words) g.bits_out[m * words + (b0 >> 5) + 1] = ow[1];
+        if ((EPI & EPI_BITS_OUT) && row_ok) {  // two 16-bit halves per word, written by the owning thread
+          reinterpret_cast<uint16_t*>(g.bits_out + m * words)[n0 >> 4] = (uint16_t)ow;
         }
         if (bulk_ok) {
-          const int ncopy = min(bcols, g.N_store - b0);
-          fence_proxy_async();
-          if (row_ok && ncopy > 0) bulk_store_s2g(g.C + m * g.ldc + b0, mine, (uint32_t)ncopy * 4);
-          bulk_commit();
-          buf ^= 1;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(mine + j * 16 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else if (row_ok) {
+          for (int q = 0; q < 16; ++q)
+            if (n0 + q < g.N_store) g.C[m * g.ldc + n0 + q] = v[q];
         }
       }
+      if (bulk_ok) {
+        const int ncopy = min(c_cols, g.N_store - c_begin);
+        fence_proxy_async();
+        if (row_ok && ncopy > 0) bulk_store_s2g(g.C + m * g.ldc + c_begin, mine, (uint32_t)ncopy * 4);
+        bulk_commit();
+      }
+      if (EPI & EPI_OUT3) {
+        // both halves of a row contribute to the three outputs: combine through the staging header
+        // (s_w3 + 400 .. : [128 rows][3]) — half 1 publishes, half 0 adds, applies the sigmoid, stores
+        float* xch = s_xch + row * 3;
+        if (half == 1) {
+          xch[0] = o3[0]; xch[1] = o3[1]; xch[2] = o3[2];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
+        if (half == 0 && row_ok) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) g.rgb_out[3 * m + c] = 1.0f / (1.0f + expf(-(o3[c] + xch[c] + s_w3[384 + c])));
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      if (tid == 0) TF_TRACE(7, (t - blockIdx.x) / gridDim.x);
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
@@ -347,7 +398,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, g.tmem_cols);
   }
@@ -359,6 +410,14 @@ static uint32_t pow2_cols(int n) {
   return c;
 }
 
+template <int NSPLIT, int EPI>
+static int launch_rowgemm_epi(cudaStream_t st, const RowGemmArgs& g, unsigned grid, size_t smem) {
+  TF_CHECK_CUDA(cudaFuncSetAttribute(k_tc_rowgemm<NSPLIT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_tc_rowgemm<NSPLIT, EPI><<<grid, kRowThreads, smem, st>>>(g);
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+
 template <int NSPLIT>
 static int launch_rowgemm(cudaStream_t st, RowGemmArgs g) {
   constexpr int KC = RowCfg<NSPLIT>::KC;
@@ -366,10 +425,20 @@ static int launch_rowgemm(cudaStream_t st, RowGemmArgs g) {
   TF_CHECK_ARG(g.N_pad % 16 == 0 && g.N_pad >= 16 && g.N_pad <= 256, "tc rowgemm: N_pad=%d unsupported", g.N_pad);
   TF_CHECK_ARG(g.K_pad % 16 == 0 && g.K_pad >= 16, "tc rowgemm: K_pad=%d unsupported", g.K_pad);
   const size_t stage = (size_t)NSPLIT * (tile_bytes(128, KC) + tile_bytes(g.N_pad, KC));
-  int stages = (int)std::min<size_t>(8, (227 * 1024 - kRowHeader) / stage);
+  // epilogue staging: [2 column halves][128 rows][cols per half + 4]; dropped (direct stores) when it
+  // would leave fewer than 3 pipeline stages
+  g.no_bulk = getenv("TENSORF_TC_NOBULK") != nullptr;
+  g.out_stride = ((g.N_pad / 16 + 1) / 2) * 16 + 4;
+  size_t staging = (size_t)2 * 128 * g.out_stride * 4;
+  if (g.no_bulk || (227 * 1024 - kRowFixed - staging) / stage < 3) {
+    g.out_stride = 0;
+    staging = 0;
+  }
+  g.header_bytes = kRowFixed + (int)staging;
+  int stages = (int)std::min<size_t>(8, (227 * 1024 - g.header_bytes) / stage);
   TF_CHECK_ARG(stages >= 2, "tc rowgemm: tile too large for shared memory");
   if (const char* e = getenv("TENSORF_TC_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));
-  g.no_bulk = getenv("TENSORF_TC_NOBULK") != nullptr;
+  g.trace = getenv("TENSORF_TC_TRACE") != nullptr;
   // A stage must always be filled by the same producer group, in order: mbarrier parity waits
   // cannot tell "two phases ahead" from "not yet", so the stage count is a multiple of the
   // number of active groups (chunk seq -> group seq % groups, stage seq % stages).
@@ -377,13 +446,18 @@ static int launch_rowgemm(cudaStream_t st, RowGemmArgs g) {
   stages = stages / g.groups * g.groups;
   g.stages = stages;
   g.tmem_cols = pow2_cols(2 * g.N_pad);
-  const size_t smem = kRowHeader + stages * stage;
-  TF_CHECK_CUDA(cudaFuncSetAttribute(k_tc_rowgemm<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = g.header_bytes + stages * stage;
   const int64_t ntiles = (g.M + 127) / 128;
   const unsigned grid = (unsigned)std::min<int64_t>(ntiles, kSMs);
-  k_tc_rowgemm<NSPLIT><<<grid, kRowThreads, smem, st>>>(g);
-  TF_CHECK_LAUNCH();
-  return 0;
+  const int epi = (g.bits_in ? EPI_BITS_IN : 0) | (g.bits_out ? EPI_BITS_OUT : 0) | (g.rgb_out ? EPI_OUT3 : 0);
+  switch (epi) {
+    case 0: return launch_rowgemm_epi<NSPLIT, 0>(st, g, grid, smem);
+    case EPI_BITS_IN: return launch_rowgemm_epi<NSPLIT, EPI_BITS_IN>(st, g, grid, smem);
+    case EPI_BITS_OUT: return launch_rowgemm_epi<NSPLIT, EPI_BITS_OUT>(st, g, grid, smem);
+    case EPI_BITS_IN | EPI_BITS_OUT: return launch_rowgemm_epi<NSPLIT, EPI_BITS_IN | EPI_BITS_OUT>(st, g, grid, smem);
+    case EPI_OUT3: return launch_rowgemm_epi<NSPLIT, EPI_OUT3>(st, g, grid, smem);
+    default: set_error("tc rowgemm: unsupported epilogue combination %d", epi); return TENSORF_ERR_UNSUPPORTED;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -400,13 +474,15 @@ struct RedGemmArgs {
   int64_t rows_per_cta;  // multiple of kRC
   float* out;
   int64_t ldo;
+  float* colsum;   // optional: colsum[m] += sum_rows G[row][m] via a virtual all-ones column n == Nx of X (N_pad > Nx)
   int stages, groups;
   uint32_t tmem_cols;
 };
 
 // warps 0-3 epilogue, 4 MMA issuer, then kGroups producer groups of 4 warps (chunk c -> group c % kGroups)
+constexpr int kRedGroups = 4;
 constexpr int kRedGroupThreads = 96;
-constexpr int kRedThreads = 160 + kGroups * kRedGroupThreads;
+constexpr int kRedThreads = 160 + kRedGroups * kRedGroupThreads;
 
 __global__ void __launch_bounds__(kRedThreads, 1) k_tc_redgemm(RedGemmArgs g) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -478,8 +554,12 @@ __global__ void __launch_bounds__(kRedThreads, 1) k_tc_redgemm(RedGemmArgs g) {
                 x[u][q][0] = v.x; x[u][q][1] = v.y; x[u][q][2] = v.z; x[u][q][3] = v.w;
               } else {
 #pragma unroll
-                for (int e4 = 0; e4 < 4; ++e4) x[u][q][e4] = (c0 + e4 < valid) ? src[r * ld + c0 + e4] : 0.f;
+                for (int e4 = 0; e4 < 4; ++e4)
+                  x[u][q][e4] = (c0 + e4 < valid) ? src[r * ld + c0 + e4] : ((!isA[u] && g.colsum && c0 + e4 == g.Nx) ? 1.0f : 0.f);
               }
+            } else if (live[u] && r < r_end && !isA[u] && g.colsum && c0 <= g.Nx && g.Nx < c0 + 4) {
+#pragma unroll
+              for (int e4 = 0; e4 < 4; ++e4) x[u][q][e4] = (c0 + e4 == g.Nx) ? 1.0f : 0.f;  // ones column -> bias gradient
             } else {
               x[u][q][0] = x[u][q][1] = x[u][q][2] = x[u][q][3] = 0.f;
             }
@@ -548,8 +628,10 @@ __global__ void __launch_bounds__(kRedThreads, 1) k_tc_redgemm(RedGemmArgs g) {
         tmem_ld_wait();
         if (m < g.Mg) {
 #pragma unroll
-          for (int q = 0; q < 16; ++q)
+          for (int q = 0; q < 16; ++q) {
             if (n0 + q < g.Nx) atomicAdd(g.out + (int64_t)(n0 + q) * g.ldo + m, v[q]);
+            else if (g.colsum && n0 + q == g.Nx) atomicAdd(g.colsum + m, v[q]);
+          }
         }
       }
     }
@@ -568,7 +650,7 @@ static int launch_redgemm(cudaStream_t st, RedGemmArgs g) {
   const size_t stage = 2 * (size_t)tile_bytes(128, kRC) + 2 * (size_t)tile_bytes(g.N_pad, kRC);
   int stages = (int)std::min<size_t>(8, (227 * 1024 - 1024) / stage);
   TF_CHECK_ARG(stages >= 2, "tc redgemm: tile too large for shared memory");
-  g.groups = std::min(kGroups, stages);
+  g.groups = std::min(kRedGroups, stages);
   stages = stages / g.groups * g.groups;  // same-group-per-stage rule, see launch_rowgemm
   g.stages = stages;
   g.tmem_cols = pow2_cols(g.N_pad);
@@ -585,34 +667,80 @@ static int launch_redgemm(cudaStream_t st, RedGemmArgs g) {
 // ---------------------------------------------------------------------------------------------
 // FeatureMlp forward / reverse on the tensor-core GEMMs
 // ---------------------------------------------------------------------------------------------
-template <int NSPLIT>
-static int pack_weights(cudaStream_t st, const float* W, int64_t sk, int64_t sn, int K_valid, int N_valid, int K_pad, int N_pad,
-                        unsigned char* out) {
-  constexpr int KC = RowCfg<NSPLIT>::KC;
-  PackArgs p{W, sk, sn, K_valid, N_valid, K_pad, N_pad, out};
-  const int items = N_pad * ((K_pad + KC - 1) / KC) * (KC / 8);
-  k_pack_weights<NSPLIT><<<(items + 255) / 256, 256, 0, st>>>(p);
+// All weight packings of one MLP call go out in ONE launch (blockIdx.y = job).
+struct PackJobs {
+  PackArgs a[8];
+  int nsplit[8];
+  int n;
+};
+__global__ void __launch_bounds__(256) k_pack_all(PackJobs jobs) {
+  const PackArgs a = jobs.a[blockIdx.y];
+  const int nsplit = jobs.nsplit[blockIdx.y];
+  constexpr int KC = RowCfg<2>::KC;
+  int item = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nchunks = (a.K_pad + KC - 1) / KC;
+  if (item >= a.N_pad * nchunks * (KC / 8)) return;
+  const int n = item % a.N_pad;
+  const int k8g = item / a.N_pad;
+  const int c = k8g / (KC / 8), j = k8g % (KC / 8);
+  float x[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    int k = c * KC + j * 8 + q;
+    x[q] = (k < a.K_valid && n < a.N_valid) ? a.W[k * a.sk + n * a.sn] : 0.f;
+  }
+  const uint32_t tb = tile_bytes(a.N_pad, KC);
+  if (nsplit == 3)
+    split_store<3>(x, a.out + (size_t)c * 3 * tb, tb, tile_offset(n, j * 8, KC));
+  else
+    split_store<2>(x, a.out + (size_t)c * 2 * tb, tb, tile_offset(n, j * 8, KC));
+}
+static int launch_pack_jobs(cudaStream_t st, const PackJobs& jobs) {
+  if (jobs.n == 0) return 0;
+  constexpr int KC = RowCfg<2>::KC;
+  int max_items = 0;
+  for (int i = 0; i < jobs.n; ++i)
+    max_items = std::max(max_items, jobs.a[i].N_pad * ((jobs.a[i].K_pad + KC - 1) / KC) * (KC / 8));
+  k_pack_all<<<dim3((max_items + 255) / 256, jobs.n), 256, 0, st>>>(jobs);
   TF_CHECK_LAUNCH();
   return 0;
 }
 
+struct RowEpilogue {  // optional fused pieces of a row GEMM
+  const uint32_t* bits_in = nullptr;
+  uint32_t* bits_out = nullptr;
+  const float *w3 = nullptr, *b3 = nullptr, *embed = nullptr;
+  const uint32_t* cams = nullptr;
+  int rows_per_ray = 1;
+  float* rgb_out = nullptr;
+};
+
 // C[:, n0:n0+nn] = epilogue(A @ W[:, n0:n0+nn]) for column tiles of at most 256 (UMMA N limit).
+// `collect` != null: only record the weight-packing jobs; else: only launch the GEMMs (weights
+// already packed into `scratch`).
 template <int NSPLIT>
 static int rowgemm_tiled(cudaStream_t st, const float* A, int64_t lda, int64_t M, int K_valid, const float* W, int64_t sk,
                          int64_t sn, int N_valid, float* C, int64_t ldc, int N_store_total, const float* bias, int relu,
-                         const uint32_t* bits_in, uint32_t* bits_out, unsigned char* scratch) {
+                         const RowEpilogue& ep, unsigned char* scratch, PackJobs* collect) {
   const int K_pad = round_up(K_valid, 16);
   const int N_total = round_up(N_store_total, 16);
   for (int n0 = 0; n0 < N_total; n0 += 256) {
     const int nn = std::min(256, N_total - n0);
-    TF_RETURN_IF_ERROR(pack_weights<NSPLIT>(st, W + n0 * sn, sk, sn, K_valid, std::max(0, N_valid - n0), K_pad, nn, scratch));
-    RowGemmArgs g{};
-    g.A = A; g.lda = lda; g.M = M; g.K_valid = K_valid; g.K_pad = K_pad; g.Bp = scratch; g.N_pad = nn;
-    g.C = C + n0; g.ldc = ldc; g.N_store = std::min(nn, N_store_total - n0);
-    g.bias = bias ? bias + n0 : nullptr; g.relu = relu;
-    TF_CHECK_ARG(!(bits_in || bits_out) || N_total <= 256, "relu bit masks need a single column tile");
-    g.bits_in = bits_in; g.bits_out = bits_out;
-    TF_RETURN_IF_ERROR(launch_rowgemm<NSPLIT>(st, g));
+    if (collect) {
+      TF_CHECK_ARG(collect->n < 8, "too many weight tiles");
+      collect->a[collect->n] = PackArgs{W + n0 * sn, sk, sn, K_valid, std::max(0, N_valid - n0), K_pad, nn, scratch};
+      collect->nsplit[collect->n++] = NSPLIT;
+    } else {
+      RowGemmArgs g{};
+      g.A = A; g.lda = lda; g.M = M; g.K_valid = K_valid; g.K_pad = K_pad; g.Bp = scratch; g.N_pad = nn;
+      g.C = C + n0; g.ldc = ldc; g.N_store = std::min(nn, N_store_total - n0);
+      g.bias = bias ? bias + n0 : nullptr; g.relu = relu;
+      TF_CHECK_ARG(!(ep.bits_in || ep.bits_out || ep.rgb_out) || N_total <= 256, "fused epilogues need a single column tile");
+      TF_CHECK_ARG(!ep.rgb_out || nn == 128, "fused output layer needs N == 128");
+      g.bits_in = ep.bits_in; g.bits_out = ep.bits_out;
+      g.w3 = ep.w3; g.b3 = ep.b3; g.embed = ep.embed; g.cams = ep.cams; g.rows_per_ray = ep.rows_per_ray; g.rgb_out = ep.rgb_out;
+      TF_RETURN_IF_ERROR(launch_rowgemm<NSPLIT>(st, g));
+    }
     scratch += packed_weight_bytes<NSPLIT>(K_pad, nn);
   }
   return 0;
@@ -638,22 +766,66 @@ size_t mlp_tc_wpack_bytes(const MlpShape& s) {
 // operands (3-way split). The reverse GEMMs feed gradients directly: the 2-way split suffices.
 constexpr int kFwdSplit = 3, kBwdSplit = 2;
 
+// The six row GEMMs of one MLP call. pass 0 = record weight packing jobs, 1 = forward GEMMs,
+// 2 = reverse GEMMs (interleaved with the other reverse kernels by the caller through `stage`).
+struct TcPlan {
+  const MlpShape& s;
+  const MlpParams& p;
+  const MlpWs& ws;
+  const float* feat;
+  int64_t M;
+  unsigned char* sc[6];
+  TcPlan(const MlpShape& s_, const MlpParams& p_, const MlpWs& ws_, const float* feat_, int64_t M_)
+      : s(s_), p(p_), ws(ws_), feat(feat_), M(M_) {
+    const int U = s.units;
+    size_t off[6] = {rowgemm_scratch(s.Ca, ws.ldf), rowgemm_scratch(s.enc, U), rowgemm_scratch(U, U),
+                     rowgemm_scratch(U, U), rowgemm_scratch(U, ws.ldx), rowgemm_scratch(s.squash, s.Ca)};
+    unsigned char* q = ws.wpack;
+    for (int i = 0; i < 6; ++i) {
+      sc[i] = q;
+      q += off[i];
+    }
+  }
+  int gemm(cudaStream_t st, int i, PackJobs* collect, const RowEpilogue& ep, float* d_feat) const {
+    const int U = s.units;
+    switch (i) {
+      case 0:  // Dense_0: f = feat @ W0 (no bias); padding columns of f come out as exact zeros
+        return rowgemm_tiled<kFwdSplit>(st, feat, s.Ca, M, s.Ca, p.w0, s.squash, 1, s.squash, ws.f, ws.ldf, ws.ldf, nullptr, 0,
+                                        ep, sc[0], collect);
+      case 1:  // Dense_1 + relu (+ ReLU bitmask for the reverse pass)
+        return rowgemm_tiled<kFwdSplit>(st, ws.x, ws.ldx, M, s.enc, p.w1, U, 1, U, ws.h1, U, U, p.b1, 1, ep, sc[1], collect);
+      case 2:  // Dense_2 + relu (+ fused FiLM / Dense_3 / sigmoid)
+        return rowgemm_tiled<kFwdSplit>(st, ws.h1, U, M, U, p.w2, U, 1, U, ws.h2, U, U, p.b2, 1, ep, sc[2], collect);
+      case 3:  // dp1 = (dp2 @ W2^T) * relu'(h1)
+        return rowgemm_tiled<kBwdSplit>(st, ws.dp2, U, M, U, p.w2, 1, U, U, ws.dp1, U, U, nullptr, 0, ep, sc[3], collect);
+      case 4:  // dx = dp1 @ W1^T
+        return rowgemm_tiled<kBwdSplit>(st, ws.dp1, U, M, U, p.w1, 1, U, s.enc, ws.dx, ws.ldx, ws.ldx, nullptr, 0, ep, sc[4],
+                                        collect);
+      default:  // d_feat = df @ W0^T
+        return rowgemm_tiled<kBwdSplit>(st, ws.df, ws.ldf, M, s.squash, p.w0, 1, s.squash, s.Ca, d_feat, s.Ca, s.Ca, nullptr, 0,
+                                        ep, sc[5], collect);
+    }
+  }
+};
+
 int mlp_tc_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs,
                const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, float* rgb) {
   if (M == 0) return 0;
-  const int U = s.units;
-  unsigned char* sc = ws.wpack;
-  // Dense_0: f = feat @ W0 (no bias); the padding columns of f come out as exact zeros
-  TF_RETURN_IF_ERROR(rowgemm_tiled<kFwdSplit>(st, feat, s.Ca, M, s.Ca, p.w0, s.squash, 1, s.squash, ws.f, ws.ldf, ws.ldf, nullptr, 0,
-                                              nullptr, nullptr, sc));
-  sc += rowgemm_scratch(s.Ca, ws.ldf);
+  TcPlan plan(s, p, ws, feat, M);
+  // pack the weights of all six GEMMs (forward and reverse) in one launch
+  PackJobs jobs{};
+  RowEpilogue none;
+  for (int i = 0; i < 6; ++i) TF_RETURN_IF_ERROR(plan.gemm(st, i, &jobs, none, nullptr));
+  TF_RETURN_IF_ERROR(launch_pack_jobs(st, jobs));
+  TF_RETURN_IF_ERROR(plan.gemm(st, 0, nullptr, none, nullptr));
   TF_RETURN_IF_ERROR(mlp_encode_fwd(st, s, ws, viewdirs, M, rows_per_ray));
-  // Dense_1 + relu
-  TF_RETURN_IF_ERROR(rowgemm_tiled<kFwdSplit>(st, ws.x, ws.ldx, M, s.enc, p.w1, U, 1, U, ws.h1, U, U, p.b1, 1, nullptr, ws.bits1, sc));
-  sc += rowgemm_scratch(s.enc, U);
-  // Dense_2 + relu
-  TF_RETURN_IF_ERROR(rowgemm_tiled<kFwdSplit>(st, ws.h1, U, M, U, p.w2, U, 1, U, ws.h2, U, U, p.b2, 1, nullptr, nullptr, sc));
-  return mlp_out_fwd(st, s, p, ws, cams, M, rows_per_ray, rgb);
+  RowEpilogue e1;
+  e1.bits_out = ws.bits1;
+  TF_RETURN_IF_ERROR(plan.gemm(st, 1, nullptr, e1, nullptr));
+  RowEpilogue e2;
+  e2.w3 = p.w3; e2.b3 = p.b3; e2.embed = s.ncam ? p.embed : nullptr; e2.cams = cams; e2.rows_per_ray = rows_per_ray;
+  e2.rgb_out = rgb;
+  return plan.gemm(st, 2, nullptr, e2, nullptr);
 }
 
 int mlp_tc_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs,
@@ -663,35 +835,36 @@ int mlp_tc_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const flo
   (void)viewdirs;
   TF_RETURN_IF_ERROR(mlp_zero_grads(st, s, gr));
   if (M == 0) return 0;
-  unsigned char* sc = ws.wpack + rowgemm_scratch(s.Ca, ws.ldf) + rowgemm_scratch(s.enc, U) + rowgemm_scratch(U, U);
+  TcPlan plan(s, p, ws, feat, M);  // weights were packed by mlp_tc_fwd on the same workspace
+  RowEpilogue none;
   TF_RETURN_IF_ERROR(mlp_out_bwd(st, s, p, ws, cams, M, rows_per_ray, rgb, d_rgb, gr));
   RedGemmArgs r{};
-  // dW2[k][n] = sum_rows h1[row][k] * dp2[row][n] ; db2
+  // dW2[k][n] = sum_rows h1[row][k] * dp2[row][n] ; db2 through the ones column
   r = RedGemmArgs{};
-  r.G = ws.dp2; r.ldg = U; r.Mg = U; r.X = ws.h1; r.ldx = U; r.Nx = U; r.N_pad = U; r.rows = M; r.out = gr.w2; r.ldo = U;
+  r.G = ws.dp2; r.ldg = U; r.Mg = U; r.X = ws.h1; r.ldx = U; r.Nx = U; r.N_pad = round_up(U + 1, 16); r.rows = M; r.out = gr.w2;
+  r.ldo = U; r.colsum = gr.b2;
   TF_RETURN_IF_ERROR(launch_redgemm(st, r));
-  TF_RETURN_IF_ERROR(mlp_colsum128(st, ws.dp2, gr.b2, M));
-  // dp1 = (dp2 @ W2^T) * (h1 > 0)
-  TF_RETURN_IF_ERROR(rowgemm_tiled<kBwdSplit>(st, ws.dp2, U, M, U, p.w2, 1, U, U, ws.dp1, U, U, nullptr, 0, ws.bits1, nullptr, sc));
-  sc += rowgemm_scratch(U, U);
+  RowEpilogue e3;
+  e3.bits_in = ws.bits1;
+  TF_RETURN_IF_ERROR(plan.gemm(st, 3, nullptr, e3, nullptr));
   // dW1[k][n] = sum_rows x[row][k] * dp1[row][n] ; db1
   r = RedGemmArgs{};
-  r.G = ws.dp1; r.ldg = U; r.Mg = U; r.X = ws.x; r.ldx = ws.ldx; r.Nx = s.enc; r.N_pad = ws.ldx; r.rows = M; r.out = gr.w1;
-  r.ldo = U;
+  r.G = ws.dp1; r.ldg = U; r.Mg = U; r.X = ws.x; r.ldx = ws.ldx; r.Nx = s.enc; r.N_pad = round_up(s.enc + 1, 16); r.rows = M;
+  r.out = gr.w1; r.ldo = U; r.colsum = gr.b1;
   TF_RETURN_IF_ERROR(launch_redgemm(st, r));
-  TF_RETURN_IF_ERROR(mlp_colsum128(st, ws.dp1, gr.b1, M));
-  // dx = dp1 @ W1^T   (W1^T(k, n) = W1[n][k])
-  TF_RETURN_IF_ERROR(rowgemm_tiled<kBwdSplit>(st, ws.dp1, U, M, U, p.w1, 1, U, s.enc, ws.dx, ws.ldx, ws.ldx, nullptr, 0, nullptr, nullptr, sc));
-  sc += rowgemm_scratch(U, ws.ldx);
+  TF_RETURN_IF_ERROR(plan.gemm(st, 4, nullptr, none, nullptr));
   TF_RETURN_IF_ERROR(mlp_encode_bwd(st, s, ws, M));
   // dW0[k][n] = sum_rows feat[row][k] * df[row][n]
   r = RedGemmArgs{};
   r.G = ws.df; r.ldg = ws.ldf; r.Mg = s.squash; r.X = feat; r.ldx = s.Ca; r.Nx = s.Ca; r.N_pad = round_up(s.Ca, 16); r.rows = M;
   r.out = gr.w0; r.ldo = s.squash;
   TF_RETURN_IF_ERROR(launch_redgemm(st, r));
-  // d_feat = df @ W0^T
-  TF_RETURN_IF_ERROR(rowgemm_tiled<kBwdSplit>(st, ws.df, ws.ldf, M, s.squash, p.w0, 1, s.squash, s.Ca, d_feat, s.Ca, s.Ca, nullptr, 0,
-                                              nullptr, nullptr, sc));
+  return plan.gemm(st, 5, nullptr, none, d_feat);
+}
+
+int tc_trace_read(long long* host, int n) {
+  TF_CHECK_CUDA(cudaDeviceSynchronize());
+  TF_CHECK_CUDA(cudaMemcpyFromSymbol(host, g_trace, sizeof(long long) * (size_t)std::min(n, 8192)));
   return 0;
 }
 
@@ -701,9 +874,18 @@ int mlp_tc_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const flo
 int tc_rowgemm_test(cudaStream_t st, const float* A, int64_t M, int K, const float* W, int N, const float* bias, int relu,
                     const uint32_t* mask_bits, uint32_t* bits_out, float* C, void* scratch, size_t scratch_bytes, int nsplit) {
   TF_CHECK_ARG(rowgemm_scratch(K, N) <= scratch_bytes, "scratch too small");
-  if (nsplit == 3)
-    return rowgemm_tiled<3>(st, A, K, M, K, W, N, 1, N, C, N, N, bias, relu, mask_bits, bits_out, (unsigned char*)scratch);
-  return rowgemm_tiled<2>(st, A, K, M, K, W, N, 1, N, C, N, N, bias, relu, mask_bits, bits_out, (unsigned char*)scratch);
+  RowEpilogue ep;
+  ep.bits_in = mask_bits;
+  ep.bits_out = bits_out;
+  PackJobs jobs{};
+  if (nsplit == 3) {
+    TF_RETURN_IF_ERROR(rowgemm_tiled<3>(st, A, K, M, K, W, N, 1, N, C, N, N, bias, relu, ep, (unsigned char*)scratch, &jobs));
+    TF_RETURN_IF_ERROR(launch_pack_jobs(st, jobs));
+    return rowgemm_tiled<3>(st, A, K, M, K, W, N, 1, N, C, N, N, bias, relu, ep, (unsigned char*)scratch, nullptr);
+  }
+  TF_RETURN_IF_ERROR(rowgemm_tiled<2>(st, A, K, M, K, W, N, 1, N, C, N, N, bias, relu, ep, (unsigned char*)scratch, &jobs));
+  TF_RETURN_IF_ERROR(launch_pack_jobs(st, jobs));
+  return rowgemm_tiled<2>(st, A, K, M, K, W, N, 1, N, C, N, N, bias, relu, ep, (unsigned char*)scratch, nullptr);
 }
 
 int tc_redgemm_test(cudaStream_t st, const float* G, int Mg, const float* X, int Nx, int64_t rows, float* out) {

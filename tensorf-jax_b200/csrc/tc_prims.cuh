@@ -32,6 +32,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps instead of hanging the GPU.
+// Polite variant for warps that are off the critical path (producers): back off between polls so
+// the spinning warps do not take issue slots from the epilogue / MMA warps.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, int tag = 0) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (++spins > 20000000u) {
+      printf("tensorf_b200: mbarrier wait timed out (block %d thread %d tag %d parity %u)\n", blockIdx.x, threadIdx.x, tag,
+             parity);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
