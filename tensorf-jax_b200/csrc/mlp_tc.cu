@@ -130,6 +130,7 @@ struct RowGemmArgs {
   int no_bulk;                // debug: force the direct-store epilogue
   int trace;                  // debug: record the CTA-0 timeline into g_trace
   int out_stride;             // floats per epilogue staging row (columns per half tile + 4), 0 = no staging
+  int resident;               // 1: all weight chunks live in smem for the whole kernel (loaded once)
   int header_bytes;           // kRowFixed + staging
   // fused output layer (networks.py:103-120): FiLM + Dense(3) + sigmoid on the epilogue's rows (N_pad == 128)
   const float* w3;            // (128,3) or null
@@ -172,14 +173,19 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
   float* s_xch = reinterpret_cast<float*>(smem + 4096);    // [128][3] partial outputs of the second column half
   float* s_out = reinterpret_cast<float*>(smem + kRowFixed);  // [2][128][out_stride] epilogue staging rows
   const uint32_t a_tile = tile_bytes(128, KC), b_tile = tile_bytes(g.N_pad, KC);
-  const uint32_t stage_bytes = NSPLIT * (a_tile + b_tile);
-  unsigned char* stage0 = smem + g.header_bytes;
+  const int nchunks_w = (g.K_pad + KC - 1) / KC;
+  // resident weights: [header][all weight chunks][A stages]; streamed: [header][stages of A+B]
+  const uint32_t stage_bytes = g.resident ? NSPLIT * a_tile : NSPLIT * (a_tile + b_tile);
+  unsigned char* wres = smem + g.header_bytes;
+  unsigned char* stage0 = wres + (g.resident ? (size_t)nchunks_w * NSPLIT * b_tile : 0);
+  uint64_t* wfull = tempty + 2 + 1;  // after tmem_slot (8-byte aligned slot)
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(&full[s], kGroupThreads + 1);  // one producer group + the weight loader's expect_tx arrive
-      mbar_init(&empty[s], 1);                 // tcgen05.commit
+      mbar_init(&full[s], kGroupThreads + (g.resident ? 0 : 1));  // producer group (+ the weight loader's expect_tx arrive)
+      mbar_init(&empty[s], 1);                                    // tcgen05.commit
     }
+    mbar_init(wfull, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);                // tcgen05.commit
       mbar_init(&tempty[a], 32 * kEpiWarps);  // epilogue threads
@@ -251,7 +257,12 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
     }
   } else if (warp == kLoadWarp) {
     // ================= weight loader: one bulk copy per chunk =================
-    if (lane == 0) {
+    if (lane == 0 && g.resident) {
+      // the weights are the same for every tile: load all chunks once
+      mbar_arrive_expect_tx(wfull, (uint32_t)nchunks * NSPLIT * b_tile);
+      for (int c = 0; c < nchunks; ++c)
+        bulk_copy_g2s(wres + (size_t)c * NSPLIT * b_tile, g.Bp + (size_t)c * NSPLIT * b_tile, NSPLIT * b_tile, wfull);
+    } else if (lane == 0) {
       for (int64_t seq = 0; seq < total; ++seq) {
         const uint32_t st = (uint32_t)(seq % S), ph = (uint32_t)((seq / S) & 1);
         const int c = (int)(seq % nchunks);
@@ -268,6 +279,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
       const uint32_t sbo = KC * 16;  // next 8 rows
       uint32_t acc = 0, acc_ph = 0;
       int64_t seq = 0;
+      if (g.resident) mbar_wait(wfull, 0, 250);
       for (int64_t ti = 0; ti < my_tiles; ++ti) {
         mbar_wait(&tempty[acc], acc_ph ^ 1, 300);
         tc_fence_after();
@@ -278,7 +290,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
           TF_TRACE(4, seq);
           tc_fence_after();
           const uint32_t sA = smem_u32(stage0 + (size_t)st * stage_bytes);
-          const uint32_t sB = sA + NSPLIT * a_tile;
+          const uint32_t sB = g.resident ? smem_u32(wres + (size_t)c * NSPLIT * b_tile) : sA + NSPLIT * a_tile;
           const int nks = min(KC / 16, (g.K_pad - c * KC) / 16);
           for (int ks = 0; ks < nks; ++ks) {
             uint64_t da[NSPLIT], db[NSPLIT];
@@ -435,7 +447,17 @@ static int launch_rowgemm(cudaStream_t st, RowGemmArgs g) {
     staging = 0;
   }
   g.header_bytes = kRowFixed + (int)staging;
-  int stages = (int)std::min<size_t>(8, (227 * 1024 - g.header_bytes) / stage);
+  // weights resident in smem for the whole kernel when they fit next to >= 2 A-only stages
+  const size_t wres = (size_t)((g.K_pad + KC - 1) / KC) * NSPLIT * tile_bytes(g.N_pad, KC);
+  const size_t a_stage = (size_t)NSPLIT * tile_bytes(128, KC);
+  g.resident = 0;
+  size_t stage_sz = stage, base = g.header_bytes;
+  if (!getenv("TENSORF_TC_STREAM_W") && g.header_bytes + wres + 2 * a_stage <= 227 * 1024) {
+    g.resident = 1;
+    stage_sz = a_stage;
+    base += wres;
+  }
+  int stages = (int)std::min<size_t>(8, (227 * 1024 - base) / stage_sz);
   TF_CHECK_ARG(stages >= 2, "tc rowgemm: tile too large for shared memory");
   if (const char* e = getenv("TENSORF_TC_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));
   g.trace = getenv("TENSORF_TC_TRACE") != nullptr;
@@ -446,7 +468,7 @@ static int launch_rowgemm(cudaStream_t st, RowGemmArgs g) {
   stages = stages / g.groups * g.groups;
   g.stages = stages;
   g.tmem_cols = pow2_cols(2 * g.N_pad);
-  const size_t smem = g.header_bytes + stages * stage;
+  const size_t smem = base + stages * stage_sz;
   const int64_t ntiles = (g.M + 127) / 128;
   const unsigned grid = (unsigned)std::min<int64_t>(ntiles, kSMs);
   const int epi = (g.bits_in ? EPI_BITS_IN : 0) | (g.bits_out ? EPI_BITS_OUT : 0) | (g.rgb_out ? EPI_OUT3 : 0);
@@ -474,6 +496,7 @@ struct RedGemmArgs {
   int64_t rows_per_cta;  // multiple of kRC
   float* out;
   int64_t ldo;
+  int trace;
   float* colsum;   // optional: colsum[m] += sum_rows G[row][m] via a virtual all-ones column n == Nx of X (N_pad > Nx)
   int stages, groups;
   uint32_t tmem_cols;
@@ -527,6 +550,7 @@ __global__ void __launch_bounds__(kRedThreads, 1) k_tc_redgemm(RedGemmArgs g) {
       unsigned char* sB = sA + 2 * a_tile;
       const int64_t r0 = r_begin + (int64_t)c * kRC;
       bool waited = false;
+      if (pt == 0) TF_TRACE(0, c);
       for (int base = 0; base < a_items + b_items; base += 2 * kRedGroupThreads) {
         float x[2][8][4];
         int col4[2], jj[2];
@@ -566,8 +590,10 @@ __global__ void __launch_bounds__(kRedThreads, 1) k_tc_redgemm(RedGemmArgs g) {
           }
         }
         if (!waited) {
-          mbar_wait(&empty[st], ph ^ 1);
+          if (pt == 0) TF_TRACE(1, c);
+          mbar_wait_backoff(&empty[st], ph ^ 1);
           waited = true;
+          if (pt == 0) TF_TRACE(2, c);
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -585,6 +611,175 @@ __global__ void __launch_bounds__(kRedThreads, 1) k_tc_redgemm(RedGemmArgs g) {
       }
       fence_proxy_async();
       mbar_arrive(&full[st]);
+      if (pt == 0) TF_TRACE(3, c);
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t sbo = kRC * 16;
+      for (int c = 0; c < nchunks; ++c) {
+        const uint32_t st = (uint32_t)(c % S), ph = (uint32_t)((c / S) & 1);
+        mbar_wait(&full[st], ph);
+        TF_TRACE(4, c);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(stage0 + (size_t)st * stage_bytes);
+        const uint32_t sB = sA + 2 * a_tile;
+        for (int ks = 0; ks < kRC / 16; ++ks) {
+          uint64_t da[2], db[2];
+          da[0] = make_smem_desc(sA + ks * 256, 128, sbo);
+          da[1] = make_smem_desc(sA + a_tile + ks * 256, 128, sbo);
+          for (int n0 = 0; n0 < g.N_pad; n0 += 256) {
+            const int nn = min(256, g.N_pad - n0);
+            const uint32_t idesc = make_idesc_bf16(128, nn);
+            // rows n0.. of the B tile start (n0/8) core-matrix rows further
+            const uint32_t boff = (uint32_t)(n0 >> 3) * sbo + ks * 256;
+            db[0] = make_smem_desc(sB + boff, 128, sbo);
+            db[1] = make_smem_desc(sB + b_tile + boff, 128, sbo);
+            umma_split<2>(tmem_base + n0, da, db, idesc, (c | ks) == 0);
+          }
+        }
+        umma_commit(&empty[st]);
+        TF_TRACE(5, c);
+      }
+      umma_commit(tfull);
+    }
+  } else {
+    // ===== epilogue: RED-add the 128 x N tile into out[n*ldo + m] =====
+    if (nchunks > 0) {
+      mbar_wait(tfull, 0);
+      if (tid == 0) TF_TRACE(6, 0);
+      tc_fence_after();
+      const int m = warp * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+      const int nblk = g.N_pad / 16;
+      for (int i = 0; i < nblk; ++i) {
+        const int n0 = ((i + (int)blockIdx.x) % nblk) * 16;  // CTAs start at different columns
+        float v[16];
+        tmem_ld16(trow + n0, v);
+        tmem_ld_wait();
+        if (m < g.Mg) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            if (n0 + q < g.Nx) atomicAdd(g.out + (int64_t)(n0 + q) * g.ldo + m, v[q]);
+            else if (g.colsum && n0 + q == g.Nx) atomicAdd(g.colsum + m, v[q]);
+          }
+        }
+      }
+    }
+  }
+  if (tid == 0) TF_TRACE(7, 0);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, g.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_tc_redgemm2: same contraction, asynchronous loads. A 32-row chunk of G and of X is one
+// contiguous block in global memory (ld % 4 == 0), so ONE thread streams raw fp32 chunks into a
+// shared-memory staging ring with cp.async.bulk (deep prefetch, no registers, no LSU), and the
+// converter warps transpose + split them smem -> smem into the UMMA operand tiles.
+//   warps 0-3 epilogue, 4 MMA issuer, 5 loader, 6.. converters
+// ---------------------------------------------------------------------------------------------
+constexpr int kConvWarps = 12;
+constexpr int kRed2Threads = 192 + 32 * kConvWarps;
+
+__global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, int T /*staging slots*/) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = g.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [S] operand stage converted
+  uint64_t* empty = full + S;                           // [S] operand stage consumed (tcgen05.commit)
+  uint64_t* sfull = empty + S;                          // [T] staging slot loaded (tx bytes)
+  uint64_t* sempty = sfull + T;                         // [T] staging slot read by all converter warps
+  uint64_t* tfull = sempty + T;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+  const uint32_t a_tile = tile_bytes(128, kRC), b_tile = tile_bytes(g.N_pad, kRC);
+  const uint32_t stage_bytes = 2 * a_tile + 2 * b_tile;
+  const uint32_t slot_floats = (uint32_t)kRC * (uint32_t)(g.ldg + g.ldx);
+  unsigned char* stage0 = smem + 1024;
+  float* slot0 = reinterpret_cast<float*>(stage0 + (size_t)S * stage_bytes);
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], kConvWarps);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < T; ++s) {
+      mbar_init(&sfull[s], 1);
+      mbar_init(&sempty[s], kConvWarps);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, g.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t r_begin = (int64_t)blockIdx.x * g.rows_per_cta;
+  const int64_t r_end = min(g.rows, r_begin + g.rows_per_cta);
+  const int nchunks = (int)((r_end - r_begin + kRC - 1) / kRC);
+
+  if (warp == 5) {
+    // ===== loader: two bulk copies per chunk (raw fp32 rows of G and X) =====
+    if (lane == 0) {
+      for (int c = 0; c < nchunks; ++c) {
+        const uint32_t sl = (uint32_t)(c % T), ph = (uint32_t)((c / T) & 1);
+        mbar_wait_backoff(&sempty[sl], ph ^ 1);
+        const int64_t r0 = r_begin + (int64_t)c * kRC;
+        const uint32_t nrows = (uint32_t)min((int64_t)kRC, r_end - r0);
+        float* dst = slot0 + (size_t)sl * slot_floats;
+        const uint32_t bg = nrows * (uint32_t)g.ldg * 4, bx = nrows * (uint32_t)g.ldx * 4;
+        mbar_arrive_expect_tx(&sfull[sl], bg + bx);
+        bulk_copy_g2s(dst, g.G + r0 * g.ldg, bg, &sfull[sl]);
+        bulk_copy_g2s(dst + (size_t)kRC * g.ldg, g.X + r0 * g.ldx, bx, &sfull[sl]);
+      }
+    }
+  } else if (warp >= 6) {
+    // ===== converters: item = (operand, column, group of 8 rows) -> one 16-byte k-chunk per split =====
+    const int ct = tid - 192;
+    const int a_items = 128 * (kRC / 8), b_items = g.N_pad * (kRC / 8);
+    for (int c = 0; c < nchunks; ++c) {
+      const uint32_t sl = (uint32_t)(c % T), sph = (uint32_t)((c / T) & 1);
+      const uint32_t st = (uint32_t)(c % S), ph = (uint32_t)((c / S) & 1);
+      const int64_t r0 = r_begin + (int64_t)c * kRC;
+      const int nrows = (int)min((int64_t)kRC, r_end - r0);
+      const float* sG = slot0 + (size_t)sl * slot_floats;
+      const float* sX = sG + (size_t)kRC * g.ldg;
+      unsigned char* sA = stage0 + (size_t)st * stage_bytes;
+      unsigned char* sB = sA + 2 * a_tile;
+      mbar_wait(&sfull[sl], sph);
+      mbar_wait(&empty[st], ph ^ 1);
+      for (int item = ct; item < a_items + b_items; item += 32 * kConvWarps) {
+        const bool isA = item < a_items;
+        const int e = isA ? item : item - a_items;
+        const int ncols = isA ? 128 : g.N_pad;
+        const int col = e % ncols, j = e / ncols;
+        const float* src = isA ? sG : sX;
+        const int ld = isA ? (int)g.ldg : (int)g.ldx;
+        const int valid = isA ? g.Mg : g.Nx;
+        float x[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int r = j * 8 + q;
+          float v = 0.f;
+          if (r < nrows) {
+            if (col < valid) v = src[r * ld + col];
+            else if (!isA && g.colsum && col == g.Nx) v = 1.0f;  // ones column -> bias gradient
+          }
+          x[q] = v;
+        }
+        split_store<2>(x, isA ? sA : sB, isA ? a_tile : b_tile, tile_offset(col, j * 8, kRC));
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&full[st]);     // operand stage ready for the tensor core
+        mbar_arrive(&sempty[sl]);   // staging slot may be overwritten
+      }
     }
   } else if (warp == 4) {
     if (lane == 0) {
@@ -602,7 +797,6 @@ __global__ void __launch_bounds__(kRedThreads, 1) k_tc_redgemm(RedGemmArgs g) {
           for (int n0 = 0; n0 < g.N_pad; n0 += 256) {
             const int nn = min(256, g.N_pad - n0);
             const uint32_t idesc = make_idesc_bf16(128, nn);
-            // rows n0.. of the B tile start (n0/8) core-matrix rows further
             const uint32_t boff = (uint32_t)(n0 >> 3) * sbo + ks * 256;
             db[0] = make_smem_desc(sB + boff, 128, sbo);
             db[1] = make_smem_desc(sB + b_tile + boff, 128, sbo);
@@ -647,16 +841,36 @@ __global__ void __launch_bounds__(kRedThreads, 1) k_tc_redgemm(RedGemmArgs g) {
 static int launch_redgemm(cudaStream_t st, RedGemmArgs g) {
   if (g.rows == 0) return 0;
   TF_CHECK_ARG(g.N_pad % 16 == 0 && g.N_pad <= 512 && g.Mg <= 128, "tc redgemm: shape unsupported (Mg=%d N_pad=%d)", g.Mg, g.N_pad);
+  g.tmem_cols = pow2_cols(g.N_pad);
+  g.trace = getenv("TENSORF_TC_TRACE") != nullptr;
+  int64_t ctas = std::min<int64_t>(kSMs, std::max<int64_t>(1, g.rows / 256));
+  g.rows_per_cta = round_up64(ceil_div64(g.rows, ctas), kRC);
+  ctas = ceil_div64(g.rows, g.rows_per_cta);
   const size_t stage = 2 * (size_t)tile_bytes(128, kRC) + 2 * (size_t)tile_bytes(g.N_pad, kRC);
+  // asynchronous-load variant: rows of G and X must be 16-byte multiples, and 2 operand stages plus
+  // >= 2 staging slots must fit in shared memory
+  const size_t slot = (size_t)kRC * (size_t)(g.ldg + g.ldx) * 4;
+  const bool aligned = g.ldg % 4 == 0 && g.ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(g.G) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(g.X) & 15) == 0;
+  if (aligned && !getenv("TENSORF_TC_RED_REGS") && 1024 + 2 * stage + 2 * slot <= 227 * 1024) {
+    g.stages = 2;
+    g.groups = 1;
+    int T = (int)std::min<size_t>(6, (227 * 1024 - 1024 - 2 * stage) / slot);
+    if (T >= 4 && 1024 + 3 * stage + 3 * slot <= 227 * 1024) {  // prefer a third operand stage when there is room
+      g.stages = 3;
+      T = (int)std::min<size_t>(6, (227 * 1024 - 1024 - 3 * stage) / slot);
+    }
+    const size_t smem = 1024 + g.stages * stage + (size_t)T * slot;
+    TF_CHECK_CUDA(cudaFuncSetAttribute(k_tc_redgemm2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tc_redgemm2<<<(unsigned)ctas, kRed2Threads, smem, st>>>(g, T);
+    TF_CHECK_LAUNCH();
+    return 0;
+  }
   int stages = (int)std::min<size_t>(8, (227 * 1024 - 1024) / stage);
   TF_CHECK_ARG(stages >= 2, "tc redgemm: tile too large for shared memory");
   g.groups = std::min(kRedGroups, stages);
   stages = stages / g.groups * g.groups;  // same-group-per-stage rule, see launch_rowgemm
   g.stages = stages;
-  g.tmem_cols = pow2_cols(g.N_pad);
-  int64_t ctas = std::min<int64_t>(kSMs, std::max<int64_t>(1, g.rows / 256));
-  g.rows_per_cta = round_up64(ceil_div64(g.rows, ctas), kRC);
-  ctas = ceil_div64(g.rows, g.rows_per_cta);
   const size_t smem = 1024 + stages * stage;
   TF_CHECK_CUDA(cudaFuncSetAttribute(k_tc_redgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_tc_redgemm<<<(unsigned)ctas, kRedThreads, smem, st>>>(g);
