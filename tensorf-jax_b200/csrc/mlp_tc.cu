@@ -276,7 +276,15 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, g.N_pad);
-      const uint32_t sbo = KC * 16;  // next 8 rows
+      // Descriptors differ only in the 14-bit start-address field: build the constant words once
+      // and add the (16-byte unit) offset per MMA, so the single issuing thread stays cheap.
+      const uint32_t desc_hi = ((KC * 16) >> 4) | (1u << 14);          // SBO = KC*16 B, version 1
+      const uint32_t lo_const = (128u >> 4) << 16;                       // LBO = 128 B
+      const uint32_t a_lo0 = (smem_u32(stage0) >> 4) | lo_const;
+      const uint32_t b_lo0 = g.resident ? ((smem_u32(wres) >> 4) | lo_const) : a_lo0 + ((NSPLIT * a_tile) >> 4);
+      const uint32_t a_split = a_tile >> 4, b_split = b_tile >> 4, st_units = stage_bytes >> 4;
+      const uint32_t w_chunk = (NSPLIT * b_tile) >> 4;
+      auto mk = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
       uint32_t acc = 0, acc_ph = 0;
       int64_t seq = 0;
       if (g.resident) mbar_wait(wfull, 0, 250);
@@ -289,17 +297,20 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
           mbar_wait(&full[st], ph, 400 + (int)seq);
           TF_TRACE(4, seq);
           tc_fence_after();
-          const uint32_t sA = smem_u32(stage0 + (size_t)st * stage_bytes);
-          const uint32_t sB = g.resident ? smem_u32(wres + (size_t)c * NSPLIT * b_tile) : sA + NSPLIT * a_tile;
+          const uint32_t a_st = a_lo0 + st * st_units;
+          const uint32_t b_st = g.resident ? b_lo0 + (uint32_t)c * w_chunk : b_lo0 + st * st_units;
           const int nks = min(KC / 16, (g.K_pad - c * KC) / 16);
-          for (int ks = 0; ks < nks; ++ks) {
-            uint64_t da[NSPLIT], db[NSPLIT];
 #pragma unroll
-            for (int i = 0; i < NSPLIT; ++i) {
-              da[i] = make_smem_desc(sA + i * a_tile + ks * 256, 128, sbo);
-              db[i] = make_smem_desc(sB + i * b_tile + ks * 256, 128, sbo);
+          for (int ks = 0; ks < KC / 16; ++ks) {
+            if (ks < nks) {
+              uint64_t da[NSPLIT], db[NSPLIT];
+#pragma unroll
+              for (int i = 0; i < NSPLIT; ++i) {
+                da[i] = mk(a_st + i * a_split + ks * 16);  // 256 B per k-step
+                db[i] = mk(b_st + i * b_split + ks * 16);
+              }
+              umma_split<NSPLIT>(d, da, db, idesc, (c | ks) == 0);
             }
-            umma_split<NSPLIT>(d, da, db, idesc, (c | ks) == 0);
           }
           umma_commit(&empty[st]);  // smem stage free once these MMAs have read it
           TF_TRACE(5, seq);

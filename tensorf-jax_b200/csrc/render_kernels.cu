@@ -7,8 +7,16 @@
 //   k_composite_fwd    weighted RGB sum x unbias + white background (+ fused MSE loss)
 //   k_ray_bwd          reverse of composite + unbias + segment probabilities (suffix scan)
 //   k_density_scatter / k_appearance_scatter  re-gather + vector RED into packed gradients
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "render_kernels.cuh"
 #include "vm.cuh"
+
+#ifndef TF_DS_MINB
+#define TF_DS_MINB 8  // measured on B200: 8 CTAs/SM (64 regs) 0.113 ms; 6: 0.119; default: 0.125; 1: 0.156
+#endif
 
 namespace tf {
 
@@ -158,7 +166,7 @@ __device__ __forceinline__ float density_sample_sum(const float* __restrict__ pa
 }
 
 template <int LPS>
-__global__ void __launch_bounds__(128) k_density_select(DensityArgs A) {
+__global__ void __launch_bounds__(128, TF_DS_MINB) k_density_select(DensityArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Npad = round_up(A.N, 32);
@@ -560,8 +568,11 @@ struct WalkArgs : SceneArgs {
   int C, Cp, seg_len, segs, count;  // count = N (density) or K (appearance)
 };
 
+#ifndef TF_SW_MINB
+#define TF_SW_MINB 2  // measured on B200: 2 -> step 1.318 ms; 1: 1.409; 3: 1.354; 4: 1.393
+#endif
 template <int LPS, bool APP>
-__global__ void __launch_bounds__(256) k_scatter_walk(WalkArgs A) {
+__global__ void __launch_bounds__(256, TF_SW_MINB) k_scatter_walk(WalkArgs A) {
   const int nvec = A.Cp >> 2;
   const int vblocks = (nvec + LPS - 1) / LPS;
   const int sub = threadIdx.x % LPS;
@@ -744,7 +755,8 @@ static int launch_walk(cudaStream_t st, WalkArgs A) {
   int lps = pick_lps(nvec);
   if (lps == 1 && nvec > 2) lps = 4;  // odd channel counts: round the block up, idle lanes exit
   lps = min(lps, 4);                  // 64-byte texel fragments per item keep more items in flight
-  A.seg_len = APP ? 64 : 64;
+  A.seg_len = APP ? 64 : 16;  // measured on B200 (A'): density 16: 0.218 ms (32: 0.232, 64: 0.259); appearance 64
+  if (const char* e = getenv(APP ? "TENSORF_SEG_LEN_APP" : "TENSORF_SEG_LEN")) A.seg_len = std::max(8, atoi(e));
   A.segs = (A.count + A.seg_len - 1) / A.seg_len;
   const int vblocks = (nvec + lps - 1) / lps;
   int64_t items = (int64_t)A.R * A.segs * 3 * vblocks;
