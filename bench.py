@@ -42,8 +42,12 @@ def workload_from_name(name: str) -> S.Workload:
         return S.lego_workload(R=4096, G=128, N=256, K=38, name="lego_G128_R4096_N256_K38 (BASELINE configs[1])")
     if name == "lego_221":  # what the reference would execute at G=128 (training.py:115-118)
         return S.lego_workload(R=4096, G=128)
-    if name == "lego_300":  # configs[2] per-GPU shard at 8 GPUs
+    if name == "lego_300":  # configs[2] per-GPU shard at 8 GPUs (16384 global rays)
         return S.lego_workload(R=2048, G=300)
+    if name == "lego_300_4096":
+        return S.lego_workload(R=4096, G=300)
+    if name == "dozer_300":
+        return S.dozer_workload(R=2048, G=300)
     if name == "dozer_128":
         return S.dozer_workload(R=2048, G=128)
     raise SystemExit(f"unknown workload {name}")
