@@ -150,6 +150,9 @@ int tensorf_tc_rowgemm_test(tensorf_stream_t s, const float* A, int64_t M, int K
 /* Debug: with TENSORF_TC_TRACE=1 CTA 0 of the row GEMM records clock64() per role/chunk; copies 8 x 1024
  * int64 slots to HOST memory (synchronises the device). */
 int tensorf_tc_trace_read(long long* host, int n);
+/* Microbenchmark: SM cycles for `count` back-to-back tcgen05.mma (M=128, K=16, bf16, given N) with the given
+ * shared-memory descriptor layout type / LBO / SBO; result in out_dev[0] (device int64). */
+int tensorf_tc_umma_bench(tensorf_stream_t s, int N, int layout_type, int lbo, int sbo, int count, long long* out_dev);
 /* out (Nx, Mg) += X^T (Nx,rows) @ G (rows,Mg): the weight-gradient contraction over rows. Mg <= 128, Nx <= 512. */
 int tensorf_tc_redgemm_test(tensorf_stream_t s, const float* G, int Mg, const float* X, int Nx, int64_t rows, float* out);
 

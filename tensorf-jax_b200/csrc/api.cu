@@ -153,6 +153,7 @@ int tc_rowgemm_test(cudaStream_t st, const float* A, int64_t M, int K, const flo
                     const uint32_t* mask_bits, uint32_t* bits_out, float* C, void* scratch, size_t scratch_bytes, int nsplit);
 int tc_redgemm_test(cudaStream_t st, const float* G, int Mg, const float* X, int Nx, int64_t rows, float* out);
 int tc_trace_read(long long* host, int n);
+int tc_umma_bench(cudaStream_t st, int N, int layout_type, int lbo, int sbo, int count, long long* out_dev);
 
 }  // namespace tf
 
@@ -252,6 +253,10 @@ int tensorf_tc_redgemm_test(tensorf_stream_t s, const float* G, int Mg, const fl
 }
 
 int tensorf_tc_trace_read(long long* host, int n) { return tc_trace_read(host, n); }
+int tensorf_tc_umma_bench(tensorf_stream_t s, int N, int layout_type, int lbo, int sbo, int count, long long* out_dev) {
+  TF_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && count > 0 && out_dev, "bad argument");
+  return tc_umma_bench((cudaStream_t)s, N, layout_type, lbo, sbo, count, out_dev);
+}
 
 int64_t tensorf_mlp_workspace_bytes(const tensorf_render_desc* d, int64_t M) {
   if (!d || M < 0) return -1;

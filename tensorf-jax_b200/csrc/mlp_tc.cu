@@ -65,6 +65,23 @@ __device__ __forceinline__ void umma_split(uint32_t d, const uint64_t* a, const 
   }
 }
 
+template <int NSPLIT>
+__device__ __forceinline__ void umma_split_lo(uint32_t d, uint32_t a0, uint32_t a_split, uint32_t b0, uint32_t b_split,
+                                              uint32_t desc_hi, uint32_t idesc, bool first) {
+  if (NSPLIT == 2) {
+    umma_bf16_lo(d, a0 + a_split, b0, desc_hi, idesc, !first);
+    umma_bf16_lo(d, a0, b0 + b_split, desc_hi, idesc, 1);
+    umma_bf16_lo(d, a0, b0, desc_hi, idesc, 1);
+  } else {
+    umma_bf16_lo(d, a0 + 2 * a_split, b0, desc_hi, idesc, !first);
+    umma_bf16_lo(d, a0, b0 + 2 * b_split, desc_hi, idesc, 1);
+    umma_bf16_lo(d, a0 + a_split, b0 + b_split, desc_hi, idesc, 1);
+    umma_bf16_lo(d, a0 + a_split, b0, desc_hi, idesc, 1);
+    umma_bf16_lo(d, a0, b0 + b_split, desc_hi, idesc, 1);
+    umma_bf16_lo(d, a0, b0, desc_hi, idesc, 1);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // weight packing: W (fp32, any strides) -> per KC-wide K chunk NSPLIT tiles [N_pad x KC]
 // ---------------------------------------------------------------------------------------------
@@ -274,48 +291,43 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
     }
   } else if (warp == kMmaWarp) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    // The whole warp runs this loop (warp-uniform control flow, values derived from kernel
+    // parameters and loop counters only) so the compiler keeps descriptors in uniform registers;
+    // just the tcgen05 instructions themselves are predicated to one elected lane.
+    {
       const uint32_t idesc = make_idesc_bf16(128, g.N_pad);
-      // Descriptors differ only in the 14-bit start-address field: build the constant words once
-      // and add the (16-byte unit) offset per MMA, so the single issuing thread stays cheap.
       const uint32_t desc_hi = ((KC * 16) >> 4) | (1u << 14);          // SBO = KC*16 B, version 1
       const uint32_t lo_const = (128u >> 4) << 16;                       // LBO = 128 B
-      const uint32_t a_lo0 = (smem_u32(stage0) >> 4) | lo_const;
-      const uint32_t b_lo0 = g.resident ? ((smem_u32(wres) >> 4) | lo_const) : a_lo0 + ((NSPLIT * a_tile) >> 4);
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t a_lo0 = ((smem_base + (uint32_t)g.header_bytes + (g.resident ? (uint32_t)nchunks_w * NSPLIT * b_tile : 0u)) >> 4) | lo_const;
+      const uint32_t b_lo0 = g.resident ? (((smem_base + (uint32_t)g.header_bytes) >> 4) | lo_const) : a_lo0 + ((NSPLIT * a_tile) >> 4);
       const uint32_t a_split = a_tile >> 4, b_split = b_tile >> 4, st_units = stage_bytes >> 4;
       const uint32_t w_chunk = (NSPLIT * b_tile) >> 4;
-      auto mk = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t acc = 0, acc_ph = 0;
-      int64_t seq = 0;
+      uint32_t st = 0, ph = 0;
       if (g.resident) mbar_wait(wfull, 0, 250);
       for (int64_t ti = 0; ti < my_tiles; ++ti) {
         mbar_wait(&tempty[acc], acc_ph ^ 1, 300);
         tc_fence_after();
-        const uint32_t d = tmem_base + acc * (uint32_t)g.N_pad;
-        for (int c = 0; c < nchunks; ++c, ++seq) {
-          const uint32_t st = (uint32_t)(seq % S), ph = (uint32_t)((seq / S) & 1);
-          mbar_wait(&full[st], ph, 400 + (int)seq);
-          TF_TRACE(4, seq);
+        const uint32_t d = tmem_u + acc * (uint32_t)g.N_pad;
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait(&full[st], ph, 400);
           tc_fence_after();
           const uint32_t a_st = a_lo0 + st * st_units;
           const uint32_t b_st = g.resident ? b_lo0 + (uint32_t)c * w_chunk : b_lo0 + st * st_units;
           const int nks = min(KC / 16, (g.K_pad - c * KC) / 16);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < KC / 16; ++ks) {
-            if (ks < nks) {
-              uint64_t da[NSPLIT], db[NSPLIT];
-#pragma unroll
-              for (int i = 0; i < NSPLIT; ++i) {
-                da[i] = mk(a_st + i * a_split + ks * 16);  // 256 B per k-step
-                db[i] = mk(b_st + i * b_split + ks * 16);
-              }
-              umma_split<NSPLIT>(d, da, db, idesc, (c | ks) == 0);
-            }
+            for (int ks = 0; ks < KC / 16; ++ks)
+              if (ks < nks) umma_split_lo<NSPLIT>(d, a_st + ks * 16, a_split, b_st + ks * 16, b_split, desc_hi, idesc, (c | ks) == 0);
+            umma_commit(&empty[st]);  // smem stage free once these MMAs have read it
           }
-          umma_commit(&empty[st]);  // smem stage free once these MMAs have read it
-          TF_TRACE(5, seq);
+          __syncwarp();
+          if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[acc]);  // accumulator complete
+        if (elect_one()) umma_commit(&tfull[acc]);  // accumulator complete
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
       }
     }
@@ -625,33 +637,36 @@ __global__ void __launch_bounds__(kRedThreads, 1) k_tc_redgemm(RedGemmArgs g) {
       if (pt == 0) TF_TRACE(3, c);
     }
   } else if (warp == 4) {
-    if (lane == 0) {
-      const uint32_t sbo = kRC * 16;
+    {  // warp-uniform issue loop (see k_tc_rowgemm): descriptors stay in uniform registers
+      const uint32_t desc_hi = ((kRC * 16) >> 4) | (1u << 14);
+      const uint32_t lo_const = (128u >> 4) << 16;
+      const uint32_t a_lo0 = ((smem_u32(smem) + 1024u) >> 4) | lo_const;
+      const uint32_t a_split = a_tile >> 4, b_split = b_tile >> 4, st_units = stage_bytes >> 4, sbo_units = (kRC * 16) >> 4;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      uint32_t st = 0, ph = 0;
       for (int c = 0; c < nchunks; ++c) {
-        const uint32_t st = (uint32_t)(c % S), ph = (uint32_t)((c / S) & 1);
         mbar_wait(&full[st], ph);
-        TF_TRACE(4, c);
         tc_fence_after();
-        const uint32_t sA = smem_u32(stage0 + (size_t)st * stage_bytes);
-        const uint32_t sB = sA + 2 * a_tile;
-        for (int ks = 0; ks < kRC / 16; ++ks) {
-          uint64_t da[2], db[2];
-          da[0] = make_smem_desc(sA + ks * 256, 128, sbo);
-          da[1] = make_smem_desc(sA + a_tile + ks * 256, 128, sbo);
-          for (int n0 = 0; n0 < g.N_pad; n0 += 256) {
-            const int nn = min(256, g.N_pad - n0);
-            const uint32_t idesc = make_idesc_bf16(128, nn);
-            // rows n0.. of the B tile start (n0/8) core-matrix rows further
-            const uint32_t boff = (uint32_t)(n0 >> 3) * sbo + ks * 256;
-            db[0] = make_smem_desc(sB + boff, 128, sbo);
-            db[1] = make_smem_desc(sB + b_tile + boff, 128, sbo);
-            umma_split<2>(tmem_base + n0, da, db, idesc, (c | ks) == 0);
+        const uint32_t a_st = a_lo0 + st * st_units;
+        const uint32_t b_st = a_st + 2 * a_split;
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < kRC / 16; ++ks) {
+            for (int n0 = 0; n0 < g.N_pad; n0 += 256) {
+              const int nn = min(256, g.N_pad - n0);
+              const uint32_t idesc = make_idesc_bf16(128, nn);
+              // rows n0.. of the B tile start (n0/8) core-matrix rows further
+              umma_split_lo<2>(tmem_u + n0, a_st + ks * 16, a_split, b_st + (uint32_t)(n0 >> 3) * sbo_units + ks * 16, b_split,
+                               desc_hi, idesc, (c | ks) == 0);
+            }
           }
+          umma_commit(&empty[st]);
         }
-        umma_commit(&empty[st]);
-        TF_TRACE(5, c);
+        __syncwarp();
+        if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
       }
-      umma_commit(tfull);
+      if (elect_one()) umma_commit(tfull);
+      __syncwarp();
     }
   } else {
     // ===== epilogue: RED-add the 128 x N tile into out[n*ldo + m] =====
@@ -793,30 +808,36 @@ __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, 
       }
     }
   } else if (warp == 4) {
-    if (lane == 0) {
-      const uint32_t sbo = kRC * 16;
+    {  // warp-uniform issue loop (see k_tc_rowgemm): descriptors stay in uniform registers
+      const uint32_t desc_hi = ((kRC * 16) >> 4) | (1u << 14);
+      const uint32_t lo_const = (128u >> 4) << 16;
+      const uint32_t a_lo0 = ((smem_u32(smem) + 1024u) >> 4) | lo_const;
+      const uint32_t a_split = a_tile >> 4, b_split = b_tile >> 4, st_units = stage_bytes >> 4, sbo_units = (kRC * 16) >> 4;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      uint32_t st = 0, ph = 0;
       for (int c = 0; c < nchunks; ++c) {
-        const uint32_t st = (uint32_t)(c % S), ph = (uint32_t)((c / S) & 1);
         mbar_wait(&full[st], ph);
         tc_fence_after();
-        const uint32_t sA = smem_u32(stage0 + (size_t)st * stage_bytes);
-        const uint32_t sB = sA + 2 * a_tile;
-        for (int ks = 0; ks < kRC / 16; ++ks) {
-          uint64_t da[2], db[2];
-          da[0] = make_smem_desc(sA + ks * 256, 128, sbo);
-          da[1] = make_smem_desc(sA + a_tile + ks * 256, 128, sbo);
-          for (int n0 = 0; n0 < g.N_pad; n0 += 256) {
-            const int nn = min(256, g.N_pad - n0);
-            const uint32_t idesc = make_idesc_bf16(128, nn);
-            const uint32_t boff = (uint32_t)(n0 >> 3) * sbo + ks * 256;
-            db[0] = make_smem_desc(sB + boff, 128, sbo);
-            db[1] = make_smem_desc(sB + b_tile + boff, 128, sbo);
-            umma_split<2>(tmem_base + n0, da, db, idesc, (c | ks) == 0);
+        const uint32_t a_st = a_lo0 + st * st_units;
+        const uint32_t b_st = a_st + 2 * a_split;
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < kRC / 16; ++ks) {
+            for (int n0 = 0; n0 < g.N_pad; n0 += 256) {
+              const int nn = min(256, g.N_pad - n0);
+              const uint32_t idesc = make_idesc_bf16(128, nn);
+              // rows n0.. of the B tile start (n0/8) core-matrix rows further
+              umma_split_lo<2>(tmem_u + n0, a_st + ks * 16, a_split, b_st + (uint32_t)(n0 >> 3) * sbo_units + ks * 16, b_split,
+                               desc_hi, idesc, (c | ks) == 0);
+            }
           }
+          umma_commit(&empty[st]);
         }
-        umma_commit(&empty[st]);
+        __syncwarp();
+        if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
       }
-      umma_commit(tfull);
+      if (elect_one()) umma_commit(tfull);
+      __syncwarp();
     }
   } else {
     // ===== epilogue: RED-add the 128 x N tile into out[n*ldo + m] =====
@@ -1085,6 +1106,74 @@ int mlp_tc_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const flo
   r.out = gr.w0; r.ldo = s.squash;
   TF_RETURN_IF_ERROR(launch_redgemm(st, r));
   return plan.gemm(st, 5, nullptr, none, d_feat);
+}
+
+// ---------------------------------------------------------------------------------------------
+// microbenchmark: cycles per tcgen05.mma (M=128, K=16, bf16) for a given N and smem layout type
+// (operand contents are irrelevant). out[0] = cycles for `count` MMAs on one SM.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) k_umma_bench(int N, int layout_type, uint32_t lbo, uint32_t sbo, int count, int distinct,
+                                                      long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem + 64);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 32) tmem_alloc(slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *slot;
+  if (distinct < 0 && threadIdx.x < 32) {  // warp-uniform issue loop, MMA predicated by elect.sync
+    distinct = -distinct;
+    const uint32_t base = smem_u32(smem + 1024);
+    const uint32_t idesc = make_idesc_bf16(128, N);
+    long long t0 = clock64();
+    for (int i = 0; i < count; ++i) {
+      const uint32_t off = (uint32_t)(i % distinct) * 4096;
+      uint64_t da = (uint64_t)(((base + off) >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+                    ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)layout_type << 61);
+      uint64_t db = (uint64_t)(((base + 65536 + off) >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+                    ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)layout_type << 61);
+      if (elect_one()) umma_bf16(tm, da, db, idesc, i != 0);
+    }
+    if (elect_one()) umma_commit(bar);
+    __syncwarp();
+    mbar_wait(bar, 0);
+    if (threadIdx.x == 0) out[0] = clock64() - t0;
+  } else if (distinct > 0 && threadIdx.x == 0) {
+    const uint32_t base = smem_u32(smem + 1024);
+    const uint32_t idesc = make_idesc_bf16(128, N);
+    long long t0 = clock64();
+    for (int i = 0; i < count; ++i) {
+      const uint32_t off = (uint32_t)(i % distinct) * 4096;  // different operand tiles, like a K loop
+      uint64_t da = (uint64_t)(((base + off) >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+                    ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)layout_type << 61);
+      uint64_t db = (uint64_t)(((base + 65536 + off) >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+                    ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)layout_type << 61);
+      umma_bf16(tm, da, db, idesc, i != 0);
+    }
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    out[0] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    tc_fence_after();
+    tmem_dealloc(tm, 256);
+  }
+}
+
+int tc_umma_bench(cudaStream_t st, int N, int layout_type, int lbo, int sbo, int count, long long* out_dev) {
+  const int distinct = getenv("TENSORF_UMMA_UNIFORM") ? -8 : 8;
+  const size_t smem = 1024 + 2 * 65536 + 16384;
+  TF_CHECK_CUDA(cudaFuncSetAttribute(k_umma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_umma_bench<<<1, 128, smem, st>>>(N, layout_type, (uint32_t)lbo, (uint32_t)sbo, count, distinct, out_dev);
+  TF_CHECK_LAUNCH();
+  return 0;
 }
 
 int tc_trace_read(long long* host, int n) {
