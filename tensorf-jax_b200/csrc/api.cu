@@ -58,7 +58,7 @@ static inline int64_t al(int64_t floats) { return round_up64(floats, 64); }  // 
 
 struct RenderWs {
   float *packed_d, *packed_a, *gpacked_d, *gpacked_a;
-  float *z, *dz, *pt_sel, *stats, *feat, *d_feat, *rgb_sel, *d_rgb_sel, *go;
+  float *z, *dz, *xs, *pt_sel, *stats, *feat, *d_feat, *rgb_sel, *d_rgb_sel, *go;
   int32_t* idx;
   float* mlp_base;
   int64_t total_floats;
@@ -80,6 +80,7 @@ static RenderWs carve(const tensorf_render_desc& d, float* base) {
   w.gpacked_a = take(packed_floats(d.ca, d.G));
   w.z = take(R * N);
   w.dz = take(R * N);
+  w.xs = take(R * N * 3);
   w.idx = reinterpret_cast<int32_t*>(take(M));
   w.pt_sel = take(M);
   w.stats = take(R * 8);
@@ -386,6 +387,7 @@ int tensorf_render_rgb_fwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   a.Cp = packed_cp(d->cd);
   a.mode = d->mode;
   a.z_out = w.z;
+  a.xs_out = w.xs;
   a.idx_out = w.idx;
   a.pt_sel_out = w.pt_sel;
   a.stats_out = w.stats;
@@ -398,6 +400,7 @@ int tensorf_render_rgb_fwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   fill_scene(ap, *d, *in);
   ap.packed_a = w.packed_a;
   ap.idx = w.idx;
+  ap.xs = w.xs;
   ap.C = d->ca;
   ap.Cp = packed_cp(d->ca);
   ap.M = M;
@@ -470,6 +473,7 @@ int tensorf_render_rgb_bwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   fill_scene(db, *d, *in);
   db.packed_d = w.packed_d;
   db.dz = w.dz;
+  db.xs = w.xs;
   db.d_packed = w.gpacked_d;
   db.Cp = packed_cp(d->cd);
   {
@@ -489,6 +493,7 @@ int tensorf_render_rgb_bwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   fill_scene(ap, *d, *in);
   ap.packed_a = w.packed_a;
   ap.idx = w.idx;
+  ap.xs = w.xs;
   ap.C = d->ca;
   ap.Cp = packed_cp(d->ca);
   ap.M = M;

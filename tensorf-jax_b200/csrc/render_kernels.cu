@@ -195,6 +195,12 @@ __global__ void __launch_bounds__(128, TF_DS_MINB) k_density_select(DensityArgs 
       float t = sample_t(ray, sc, r, s, delta);
       float x[3];
       sample_grid_coords(ray, sc, t, x);
+      if (sub == 0 && A.xs_out) {
+        float* xo = A.xs_out + ((int64_t)r * A.N + s) * 3;
+        xo[0] = x[0];
+        xo[1] = x[1];
+        xo[2] = x[2];
+      }
       VmTaps taps;
       make_vm_taps(taps, x, A.G);
       acc = density_sample_sum<LPS>(A.packed_d, taps, A.G, A.Cp, sub);
@@ -341,14 +347,8 @@ __global__ void __launch_bounds__(256) k_appearance(AppearanceArgs A) {
   int v = (int)(item % nvec);
   int r = (int)(m / A.K);
   int s = A.idx[m];
-  SceneParams sc;
-  load_scene(sc, A.aabb, A.N, A.G, A.contracted, A.jitter, A.base_ts, A.deltas);
-  RayParams ray;
-  load_ray(ray, sc, A.origins, A.directions, A.aabb, r);
-  float delta;
-  float t = sample_t(ray, sc, r, s, delta);
-  float x[3];
-  sample_grid_coords(ray, sc, t, x);
+  const float* xp = A.xs + ((int64_t)r * A.N + s) * 3;  // coordinates computed once by k_density_select
+  float x[3] = {xp[0], xp[1], xp[2]};
   VmTaps taps;
   make_vm_taps(taps, x, A.G);
   const int Ca = 3 * A.C;
@@ -563,6 +563,7 @@ struct WalkArgs : SceneArgs {
   const float* packed;
   float* d_packed;
   const float* dz;      // density
+  const float* xs;      // (R,N,3) grid coordinates
   const int32_t* idx;   // appearance
   const float* d_feat;  // appearance (M, 3C)
   int C, Cp, seg_len, segs, count;  // count = N (density) or K (appearance)
@@ -587,11 +588,6 @@ __global__ void __launch_bounds__(256, TF_SW_MINB) k_scatter_walk(WalkArgs A) {
   const int v = (rem % vblocks) * LPS + sub;
   if (v >= nvec) return;
   const int j_begin = seg * A.seg_len, j_end = min(A.count, j_begin + A.seg_len);
-
-  SceneParams sc;
-  load_scene(sc, A.aabb, A.N, A.G, A.contracted, A.jitter, A.base_ts, A.deltas);
-  RayParams ray;
-  load_ray(ray, sc, A.origins, A.directions, A.aabb, r);
 
   const int G = A.G, Cp = A.Cp;
   const int64_t lbase = (int64_t)P * G * Cp + 4 * v;
@@ -625,10 +621,8 @@ __global__ void __launch_bounds__(256, TF_SW_MINB) k_scatter_walk(WalkArgs A) {
       float gz = A.dz[(int64_t)r * A.N + s];
       g = make_float4(gz, gz, gz, gz);
     }
-    float delta;
-    float t = sample_t(ray, sc, r, s, delta);
-    float x[3];
-    sample_grid_coords(ray, sc, t, x);
+    const float* xp = A.xs + ((int64_t)r * A.N + s) * 3;  // coordinates saved by the forward gather
+    const float x[3] = {xp[0], xp[1], xp[2]};
     // axis roles of pair P (tensor_vm.py:50-52), selected without indexing local arrays
     const float xl = P == 0 ? x[0] : (P == 1 ? x[2] : x[1]);
     const float xa = P == 0 ? x[1] : (P == 1 ? x[0] : x[2]);
@@ -776,6 +770,7 @@ int launch_density_scatter(cudaStream_t st, const DensityBwdArgs& D) {
   A.packed = D.packed_d;
   A.d_packed = D.d_packed;
   A.dz = D.dz;
+  A.xs = D.xs;
   A.C = D.Cp;
   A.Cp = D.Cp;
   A.count = D.N;
@@ -788,6 +783,7 @@ int launch_appearance_scatter(cudaStream_t st, const AppearanceArgs& D) {
   A.packed = D.packed_a;
   A.d_packed = D.d_packed;
   A.idx = D.idx;
+  A.xs = D.xs;
   A.d_feat = D.d_feat;
   A.C = D.C;
   A.Cp = D.Cp;

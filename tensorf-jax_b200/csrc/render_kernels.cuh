@@ -20,6 +20,7 @@ struct DensityArgs : SceneArgs {
   const float* gumbel;  // (N,)
   int Cp, mode;
   float* z_out;        // (R,N)
+  float* xs_out;       // (R,N,3) continuous grid coordinates of every sample (reused by the reverse kernels)
   int32_t* idx_out;    // (R,K) ascending
   float* pt_sel_out;   // (R,K)
   float* stats_out;    // (R,8): E_last, S, u, -, W0, W1, W2, -
@@ -29,6 +30,7 @@ struct DensityArgs : SceneArgs {
 struct AppearanceArgs : SceneArgs {
   const float* packed_a;
   const int32_t* idx;  // (M,)
+  const float* xs;     // (R,N,3) grid coordinates saved by the forward gather
   int C, Cp;
   int64_t M;
   float* feat;           // fwd: (M,3C)
@@ -62,6 +64,7 @@ struct RayBwdArgs : SceneArgs {
 struct DensityBwdArgs : SceneArgs {
   const float* packed_d;
   const float* dz;  // (R,N)
+  const float* xs;  // (R,N,3)
   float* d_packed;  // (+=)
   int Cp;
 };
