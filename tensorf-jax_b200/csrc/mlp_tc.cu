@@ -357,7 +357,9 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
       const float* em = nullptr;  // FiLM conditioner of this row's camera (networks.py:103-111)
       if ((EPI & EPI_OUT3) && g.embed && row_ok) em = g.embed + (int64_t)g.cams[m / g.rows_per_ray] * 128;
       float o3[3] = {0.f, 0.f, 0.f};
+      if (tid == 0) TF_TRACE(4, (t - blockIdx.x) / gridDim.x);
       if (bulk_ok) bulk_wait_read<0>();  // last tile's store has finished reading my staging row
+      if (tid == 0) TF_TRACE(4, 512 + (t - blockIdx.x) / gridDim.x);
       mbar_wait(&tfull[acc], acc_ph, 500);
       if (tid == 0) TF_TRACE(6, (t - blockIdx.x) / gridDim.x);
       tc_fence_after();
@@ -403,12 +405,14 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
             if (n0 + q < g.N_store) g.C[m * g.ldc + n0 + q] = v[q];
         }
       }
+      if (tid == 0) TF_TRACE(5, (t - blockIdx.x) / gridDim.x);
       if (bulk_ok) {
         const int ncopy = min(c_cols, g.N_store - c_begin);
         fence_proxy_async();
         if (row_ok && ncopy > 0) bulk_store_s2g(g.C + m * g.ldc + c_begin, mine, (uint32_t)ncopy * 4);
         bulk_commit();
       }
+      if (tid == 0) TF_TRACE(5, 512 + (t - blockIdx.x) / gridDim.x);
       if (EPI & EPI_OUT3) {
         // both halves of a row contribute to the three outputs: combine through the staging header
         // (s_w3 + 400 .. : [128 rows][3]) — half 1 publishes, half 0 adds, applies the sigmoid, stores

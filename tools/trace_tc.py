@@ -32,8 +32,8 @@ print("chunks per tile", nch, "tiles for CTA0", mine)
 print("seq  " + "  ".join(f"{n:>16s}" for n in names[:6]))
 for q in range(min(nseq, 24)):
     print(f"{q:3d}  " + "  ".join(f"{int(t[s, q] - base):16d}" for s in range(6)))
-print("tile  E.tfullWaitDone  E.tileDone")
+print("tile  E.start  E.bulkReadDone  E.tfullWaitDone  E.loopDone  E.bulkIssued  E.tileDone")
 for i in range(mine):
-    print(i, int(t[6, i] - base), int(t[7, i] - base))
+    print(i, *(int(x - base) for x in (t[4, i], t[4, 512 + i], t[6, i], t[5, i], t[5, 512 + i], t[7, i])))
 print("total cycles (last tile done)", int(t[7, mine - 1] - base))
 
