@@ -191,6 +191,58 @@ def bench_render(ops, dev, world, rank, dist, chunks=6, warm=2):
     return out
 
 
+def bench_optimizer(ops, dev, params, grads, peak_gbs, reps=10):
+    """The two callers right after the reverse pass, timed on their own (NOT part of the
+    headline step): one `tensorf_adam_step` over every leaf (training.py:183-201; 16 B read + 12 B written per
+    parameter) and one `tensorf_vm_resize` of both factor sets to the next grid of the lego schedule
+    (training.py:245-276; bytes = read old + write new)."""
+    names = list(params.keys())
+    p = [params[k].clone() for k in names]
+    mu = [torch.zeros_like(x) for x in p]
+    nu = [torch.zeros_like(x) for x in p]
+    g = [grads[k] for k in names]
+    call = ops.AdamCall(p, mu, nu, [-(0.02 if k.startswith(("density_", "appearance_")) else 1e-3) for k in names])
+    n = sum(x.numel() for x in p)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(3):
+        call.step(g, count=i)
+    torch.cuda.synchronize()
+    # the kernel is ~15 us at 128^3: replay `reps` captured steps so host launch overhead is not what is timed
+    graph, side = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for i in range(reps):
+                call.step(g, count=3 + i)
+    graph.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    adam_ms = e0.elapsed_time(e1) / reps
+    out = {"adam": {"ms": adam_ms, "parameters": n, "GB/s": 28 * n / (adam_ms * 1e-3) / 1e9,
+                    "frac_of_hbm_peak": 28 * n / (adam_ms * 1e-3) / 1e9 / peak_gbs, "launches_per_step": 2}}
+    G = params["density_vector"].shape[-1]
+    G2 = int(round(G * 1.27))
+    moved = 0
+    for which in ("density", "appearance"):
+        v, m = params[f"{which}_vector"], params[f"{which}_matrix"]
+        moved += 4 * (v.numel() + m.numel()) * (1 + (G2 / G) ** 2)
+    for i in range(2):
+        ops.vm_resize(params["density_vector"], params["density_matrix"], G2)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(reps):
+        for which in ("density", "appearance"):
+            ops.vm_resize(params[f"{which}_vector"], params[f"{which}_matrix"], G2)
+    e1.record()
+    torch.cuda.synchronize()
+    rs_ms = e0.elapsed_time(e1) / reps
+    out["resize"] = {"ms": rs_ms, "from": G, "to": G2, "GB/s": moved / (rs_ms * 1e-3) / 1e9,
+                     "note": "includes torch.empty of outputs/scratch per call"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -367,6 +419,8 @@ def main():
         }
         if render is not None:
             out["render"] = render
+        if not args.no_render:
+            out["optimizer"] = bench_optimizer(ops, dev, params, grads, peak)
         if world == 1 and not args.no_cpu_baseline:
             v, ms, cores = cpu_reference_rays_per_s(w, 512, 6, 1)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

@@ -192,6 +192,38 @@ int tensorf_render_depth(tensorf_stream_t s, const tensorf_render_desc* d, const
 int tensorf_render_workspace_view(const tensorf_render_desc* d, void* workspace, const char* name, void** ptr,
                                   int64_t* count);
 
+/* ---- training.py:158-243 optimiser step ------------------------------------ */
+/* optax.chain(scale_by_adam(b1, b2, eps, eps_root), masked(scale(-lr_mlp)), masked(scale(-lr_tensor)))
+ * (training.py:213-243), the learning-rate decay factor of training.py:176-186 and
+ * optax.apply_updates (training.py:199-201), over all leaves in one launch; optax.global_norm(grads)
+ * (training.py:194) comes out of the same pass.  The step count stays on the host: the caller passes
+ * the bias corrections 1 - b^t (t = count + 1) and lr_decay = exponential_decay(...)(resetted_step). */
+#define TENSORF_ADAM_MAX_LEAVES 16
+typedef struct tensorf_adam_desc {
+  int32_t n_leaves;
+  int32_t reserved;
+  float b1, b2, eps, eps_root;
+  float bias_correction1; /* 1 - b1^t */
+  float bias_correction2; /* 1 - b2^t */
+  float lr_decay;         /* lr_decay_coeff, training.py:176-181 */
+  float reserved2;
+} tensorf_adam_desc;
+/* HOST arrays of length n_leaves: sizes (elements), params/grads/mu/nu (device pointers), neg_lrs (-lr of
+ * the leaf's group).  params, mu, nu are updated in place (training_step donates its state, training.py:101).
+ * grad_norm: device scalar (overwritten) or NULL.  scratch: tensorf_adam_scratch_bytes. */
+int64_t tensorf_adam_scratch_bytes(const int64_t* sizes, int n_leaves);
+int tensorf_adam_step(tensorf_stream_t s, const tensorf_adam_desc* d, const int64_t* sizes, float* const* params,
+                      const float* const* grads, float* const* mu, float* const* nu, const float* neg_lrs,
+                      float* grad_norm, void* scratch, int64_t scratch_bytes);
+
+/* ---- tensor_vm.py:183-223 TensorVMSingle.resize ------------------------------ */
+/* vector (3,C,G_in) -> (3,C,G_out), matrix (3,C,G_in,G_in) -> (3,C,G_out,G_out): jax.image.scale_and_translate,
+ * "linear" kernel, scale (G_out-1)/(G_in-1), translation -(scale/2 - 0.5) (align corners), antialiased when
+ * shrinking.  Applied to parameters and to both Adam moments by training.py:245-276. */
+int64_t tensorf_vm_resize_scratch_bytes(int C, int G_in, int G_out);
+int tensorf_vm_resize(tensorf_stream_t s, const float* vector_in, const float* matrix_in, int C, int G_in, int G_out,
+                      float* vector_out, float* matrix_out, void* scratch, int64_t scratch_bytes);
+
 #ifdef __cplusplus
 }
 #endif

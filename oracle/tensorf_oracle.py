@@ -352,3 +352,91 @@ def loss_and_grads(cfg, mlp_cfg, params, scene_contraction, aabb, origins, direc
     loss.backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
     return loss.detach(), rendered.detach(), grads
+
+
+# --------------------------------------------------------------------------------------
+# training.py:158-243 — optimiser (optax 0.2.6, restated from its published algorithm)
+# --------------------------------------------------------------------------------------
+def lr_decay_coeff(step: int, upsamp_iters, n_iters: int, lr_decay_iters, target_ratio: float, upsample_reset: bool) -> float:
+    """training.py:158-181.  optax.exponential_decay(init_value=1, transition_steps=T, decay_rate=r,
+    end_value=r)(count) = clip(r ** (count / T), min=r) (decay_rate < 1 → end_value is a lower bound)."""
+    if upsample_reset:
+        deltas = [step - u for u in (0,) + tuple(upsamp_iters)]
+        resetted = min(d for d in deltas if d >= 0)  # training.py:161-168
+    else:
+        resetted = step
+    T = lr_decay_iters if lr_decay_iters is not None else n_iters  # :171-173
+    return max(target_ratio ** (resetted / T), target_ratio)
+
+
+def global_norm(grads) -> float:
+    """optax.global_norm (training.py:194): sqrt(sum over leaves of sum(g^2)); fp64 arbiter."""
+    return math.sqrt(sum(float((np.asarray(g, dtype=np.float64) ** 2).sum()) for g in grads))
+
+
+def adam_step(params, grads, mu, nu, count: int, neg_lrs, lr_decay: float, b1=0.9, b2=0.99, eps=1e-8, eps_root=0.0,
+              dtype=np.float32):
+    """training.py:183-201 with the optimiser of :213-243, per leaf, every operation rounded in `dtype`
+    in optax's order:
+      scale_by_adam:  mu' = (1-b1)*g + b1*mu ; nu' = (1-b2)*g**2 + b2*nu          (update_moment[_per_elem_norm])
+                      mu_hat = mu' / (1 - b1**t) ; nu_hat = nu' / (1 - b2**t), t = count+1   (bias_correction)
+                      u = mu_hat / (sqrt(nu_hat + eps_root) + eps)
+      masked scale:   u = neg_lr * u      (neg_lr = -lr_init_mlp | -lr_init_tensor, :225-243)
+      decay:          u = lr_decay * u    (:186)
+      apply_updates:  p' = p + u          (:199-201)
+    Returns (new_params, new_mu, new_nu) as lists of numpy arrays."""
+    f = dtype
+    t = f(count + 1)
+    bc1 = f(1) - np.power(f(b1), t)
+    bc2 = f(1) - np.power(f(b2), t)
+    omb1, omb2 = f(1) - f(b1), f(1) - f(b2)
+    out_p, out_m, out_v = [], [], []
+    for p, g, m, v, nlr in zip(params, grads, mu, nu, neg_lrs):
+        p, g, m, v = (np.asarray(a, dtype=f) for a in (p, g, m, v))
+        m2 = omb1 * g + f(b1) * m
+        v2 = omb2 * (g * g) + f(b2) * v
+        u = (m2 / bc1) / (np.sqrt(v2 / bc2 + f(eps_root)) + f(eps))
+        out_p.append(p + f(lr_decay) * (f(nlr) * u))
+        out_m.append(m2)
+        out_v.append(v2)
+    return out_p, out_m, out_v
+
+
+# --------------------------------------------------------------------------------------
+# tensor_vm.py:183-223 — resize (jax.image.scale_and_translate, jax 0.9.0.1, restated)
+# --------------------------------------------------------------------------------------
+def resize_weight_matrix(input_size: int, output_size: int, dtype=np.float32) -> np.ndarray:
+    """jax/_src/image/scale.py compute_weight_mat for the triangle ("linear") kernel with antialias=True and
+    the align-corners scale/translation of tensor_vm.py:204-213:
+      scale = (out-1)/(in-1) ; translation = -(scale/2 - 0.5)
+      inv_scale = 1/scale ; kernel_scale = max(inv_scale, 1)
+      sample_f = (arange(out)+0.5)*inv_scale - translation*inv_scale - 0.5
+      x = |sample_f[None,:] - arange(in)[:,None]| / kernel_scale ; w = max(0, 1-x)
+      w /= sum_in(w) where |sum| > 1000*eps32 (else 0) ; w = 0 where sample_f outside [-0.5, in-0.5]
+    Returns (in, out)."""
+    f = dtype
+    scale = f(f(output_size - 1.0) / f(input_size - 1.0))
+    translation = f(-(scale / f(2.0) - f(0.5)))
+    inv_scale = f(f(1.0) / scale)
+    kernel_scale = max(inv_scale, f(1.0))
+    sample_f = (np.arange(output_size, dtype=f) + f(0.5)) * inv_scale - translation * inv_scale - f(0.5)
+    x = np.abs(sample_f[None, :] - np.arange(input_size, dtype=f)[:, None]) / kernel_scale
+    w = np.maximum(f(0), f(1) - np.abs(x)).astype(f)
+    total = w.sum(axis=0, keepdims=True, dtype=f)
+    w = np.where(np.abs(total) > 1000.0 * float(np.finfo(np.float32).eps), w / np.where(total != 0, total, 1), 0).astype(f)
+    inside = np.logical_and(sample_f >= -0.5, sample_f <= input_size - 0.5)
+    return np.where(inside[None, :], w, 0).astype(f)
+
+
+def vm_resize(vector: np.ndarray, matrix: np.ndarray, grid_dim: int, dtype=np.float32):
+    """TensorVM.resize (tensor_vm.py:91-100) → TensorVMSingle.resize (:183-199) →
+    resize_with_aligned_corners (:202-223): vector (3,C,G) → (3,C,g'), matrix (3,C,G,G) → (3,C,g',g').
+    Spatial dims are those whose size changes (:208-210); none → identity."""
+    G = vector.shape[-1]
+    v, m = np.asarray(vector, dtype=dtype), np.asarray(matrix, dtype=dtype)
+    if G == grid_dim:
+        return v.copy(), m.copy()
+    w = resize_weight_matrix(G, grid_dim, dtype)
+    vo = np.einsum("pci,io->pco", v, w).astype(dtype)
+    mo = np.einsum("pcij,ia,jb->pcab", m, w, w, optimize=True).astype(dtype)
+    return vo, mo

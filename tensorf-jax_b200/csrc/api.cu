@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "mlp.cuh"
+#include "optim.cuh"
 #include "render_kernels.cuh"
 
 namespace tf {
@@ -507,6 +508,25 @@ int tensorf_render_rgb_bwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   TF_RETURN_IF_ERROR(vm_unpack(st, w.gpacked_d, grads->density_vector, grads->density_matrix, d->cd, d->G));
   TF_RETURN_IF_ERROR(vm_unpack(st, w.gpacked_a, grads->appearance_vector, grads->appearance_matrix, d->ca, d->G));
   return 0;
+}
+
+int64_t tensorf_adam_scratch_bytes(const int64_t* sizes, int n_leaves) {
+  if (!sizes || n_leaves < 0) return -1;
+  return adam_scratch_bytes(sizes, n_leaves);
+}
+int tensorf_adam_step(tensorf_stream_t s, const tensorf_adam_desc* d, const int64_t* sizes, float* const* params,
+                      const float* const* grads, float* const* mu, float* const* nu, const float* neg_lrs,
+                      float* grad_norm, void* scratch, int64_t scratch_bytes) {
+  return adam_step((cudaStream_t)s, d, sizes, params, grads, mu, nu, neg_lrs, grad_norm, scratch, scratch_bytes);
+}
+
+int64_t tensorf_vm_resize_scratch_bytes(int C, int G_in, int G_out) {
+  if (C < 1 || G_in < 2 || G_out < 2) return -1;
+  return vm_resize_scratch_bytes(C, G_in, G_out);
+}
+int tensorf_vm_resize(tensorf_stream_t s, const float* vector_in, const float* matrix_in, int C, int G_in, int G_out,
+                      float* vector_out, float* matrix_out, void* scratch, int64_t scratch_bytes) {
+  return vm_resize((cudaStream_t)s, vector_in, matrix_in, C, G_in, G_out, vector_out, matrix_out, scratch, scratch_bytes);
 }
 
 }  // extern "C"

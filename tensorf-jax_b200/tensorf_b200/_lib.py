@@ -61,6 +61,18 @@ class RenderInputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in INPUT_FIELDS]
 
 
+class AdamDesc(C.Structure):
+    """struct tensorf_adam_desc"""
+
+    _fields_ = [
+        ("n_leaves", C.c_int32), ("reserved", C.c_int32),
+        ("b1", C.c_float), ("b2", C.c_float), ("eps", C.c_float), ("eps_root", C.c_float),
+        ("bias_correction1", C.c_float), ("bias_correction2", C.c_float), ("lr_decay", C.c_float), ("reserved2", C.c_float),
+    ]
+
+
+ADAM_MAX_LEAVES = 16
+
 _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
 _pd, _pp, _pi = C.POINTER(RenderDesc), C.POINTER(Params), C.POINTER(RenderInputs)
 
@@ -90,6 +102,11 @@ SIGNATURES = {
     "tensorf_render_rgb_bwd": (_i, [_vp, _pd, _pp, _pi, _vp, _vp, _pp]),
     "tensorf_render_depth": (_i, [_vp, _pd, _pp, _pi, _vp, _vp]),
     "tensorf_render_workspace_view": (_i, [_pd, _vp, C.c_char_p, C.POINTER(_vp), C.POINTER(_i64)]),
+    "tensorf_adam_scratch_bytes": (_i64, [C.POINTER(_i64), _i]),
+    "tensorf_adam_step": (_i, [_vp, C.POINTER(AdamDesc), C.POINTER(_i64), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
+                               C.POINTER(_vp), C.POINTER(C.c_float), _vp, _vp, _i64]),
+    "tensorf_vm_resize_scratch_bytes": (_i64, [_i, _i, _i]),
+    "tensorf_vm_resize": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i64]),
 }
 
 _lock = threading.Lock()

@@ -12,7 +12,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import PARAM_FIELDS, Params, RenderDesc, RenderInputs, check
+from ._lib import PARAM_FIELDS, AdamDesc, Params, RenderDesc, RenderInputs, check
 
 MODE_RGB, MODE_DIST_MEDIAN, MODE_DIST_MEAN = 0, 1, 2
 MLP_AUTO, MLP_SIMT_FP32, MLP_TCGEN05 = 0, 1, 2
@@ -290,6 +290,74 @@ class RenderCall:
 # ---------------------------------------------------------------------------------------------
 # measurement hooks
 # ---------------------------------------------------------------------------------------------
+class AdamCall:
+    """`tensorf_adam_step` over a fixed list of leaves (training.py:158-243): the pointer tables and the
+    scratch buffer are built once, every step is one kernel launch.  `neg_lrs[i]` = -(group learning rate)."""
+
+    def __init__(self, params, mu, nu, neg_lrs, b1: float = 0.9, b2: float = 0.99, eps: float = 1e-8, eps_root: float = 0.0):
+        self.lib = _lib.load()
+        n = len(params)
+        if not (n == len(mu) == len(nu) == len(neg_lrs)) or n > _lib.ADAM_MAX_LEAVES:
+            raise ValueError(f"adam: {n} leaves (max {_lib.ADAM_MAX_LEAVES}) with mismatched state lists")
+        self.params, self.mu, self.nu = list(params), list(mu), list(nu)
+        for i, (p, m, v) in enumerate(zip(self.params, self.mu, self.nu)):
+            if m.shape != p.shape or v.shape != p.shape:
+                raise ValueError(f"adam: leaf {i} state shape mismatch")
+        self.n = n
+        self.b1, self.b2, self.eps, self.eps_root = b1, b2, eps, eps_root
+        self.sizes = (C.c_int64 * n)(*[p.numel() for p in self.params])
+        self.neg_lrs = (C.c_float * n)(*[float(x) for x in neg_lrs])
+        self._p = (C.c_void_p * n)(*[_ptr(t, name="param") for t in self.params])
+        self._m = (C.c_void_p * n)(*[_ptr(t, name="mu") for t in self.mu])
+        self._v = (C.c_void_p * n)(*[_ptr(t, name="nu") for t in self.nu])
+        nbytes = self.lib.tensorf_adam_scratch_bytes(self.sizes, n)
+        dev = self.params[0].device
+        self.scratch = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+        self.grad_norm = torch.zeros((), dtype=torch.float32, device=dev)
+        self._g_key, self._g_ptrs = None, None
+
+    def step(self, grads, count: int, lr_decay: float = 1.0) -> torch.Tensor:
+        """One optimiser step; `count` = steps taken so far (optax's count before increment).  Returns the
+        device scalar global_norm(grads)."""
+        import numpy as np
+        if len(grads) != self.n:
+            raise ValueError("adam: gradient list does not match the leaves")
+        for g, p in zip(grads, self.params):
+            if g.shape != p.shape:
+                raise ValueError("adam: gradient shape mismatch")
+        key = tuple(t.data_ptr() for t in grads)
+        if self._g_key != key:  # pointer table rebuilt only when the gradient buffers change
+            self._g_ptrs = (C.c_void_p * self.n)(*[_ptr(t, name="grad") for t in grads])
+            self._g_key = key
+        g_ptrs = self._g_ptrs
+        t = np.float32(count + 1)
+        # optax bias_correction: 1 - decay**count in fp32
+        bc1 = np.float32(1) - np.power(np.float32(self.b1), t)
+        bc2 = np.float32(1) - np.power(np.float32(self.b2), t)
+        d = AdamDesc(n_leaves=self.n, reserved=0, b1=self.b1, b2=self.b2, eps=self.eps, eps_root=self.eps_root,
+                     bias_correction1=float(bc1), bias_correction2=float(bc2), lr_decay=float(lr_decay), reserved2=0.0)
+        check(self.lib.tensorf_adam_step(_stream(), C.byref(d), self.sizes, self._p, g_ptrs, self._m, self._v, self.neg_lrs,
+                                         self.grad_norm.data_ptr(), self.scratch.data_ptr(), self.scratch.numel()))
+        return self.grad_norm
+
+
+def vm_resize(vector: torch.Tensor, matrix: torch.Tensor, grid_dim: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """tensor_vm.py:183-223: (3,C,G) / (3,C,G,G) -> (3,C,grid_dim) / (3,C,grid_dim,grid_dim)."""
+    lib = _lib.load()
+    three, C_, G = vector.shape
+    if three != 3 or tuple(matrix.shape) != (3, C_, G, G):
+        raise ValueError(f"vm_resize: vector {tuple(vector.shape)} / matrix {tuple(matrix.shape)} are not a TensorVM")
+    vo = torch.empty((3, C_, grid_dim), dtype=torch.float32, device=vector.device)
+    mo = torch.empty((3, C_, grid_dim, grid_dim), dtype=torch.float32, device=vector.device)
+    nbytes = lib.tensorf_vm_resize_scratch_bytes(C_, G, grid_dim)
+    if nbytes < 0:
+        raise ValueError(f"vm_resize: unsupported shape C={C_} G={G} -> {grid_dim}")
+    scratch = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=vector.device)
+    check(lib.tensorf_vm_resize(_stream(), _ptr(vector, name="vector"), _ptr(matrix, name="matrix"), C_, G, grid_dim,
+                                vo.data_ptr(), mo.data_ptr(), scratch.data_ptr(), scratch.numel()))
+    return vo, mo
+
+
 def launch_count() -> int:
     """Kernels this thread has enqueued through the library so far."""
     return int(_lib.load().tensorf_launch_count())

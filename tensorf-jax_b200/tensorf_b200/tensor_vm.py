@@ -87,6 +87,11 @@ class TensorVM:
         return self.stacked_single_vm.channel_dim() * 3
 
     def resize(self, grid_dim: int) -> "TensorVM":
-        """tensor_vm.py:91-100 — grid upsampling is a 'next' row, not on the
-        per-ray hot path; not built yet."""
-        raise NotImplementedError("TensorVM.resize is outside the hot path built so far (SURVEY.md §8f)")
+        """tensor_vm.py:91-100 / :183-223: align-corners linear resampling of all three pairs
+        (`tensorf_vm_resize`)."""
+        sv = self.stacked_single_vm
+        with torch.no_grad():
+            v, m = ops.vm_resize(sv.vector.detach().contiguous(), sv.matrix.detach().contiguous(), int(grid_dim))
+        v.requires_grad_(sv.vector.requires_grad)
+        m.requires_grad_(sv.matrix.requires_grad)
+        return TensorVM(stacked_single_vm=TensorVMSingle(vector=v, matrix=m))

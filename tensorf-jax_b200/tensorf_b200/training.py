@@ -1,8 +1,9 @@
 """Mirror of tensorf/training.py:19-243 (TrainState.initialize / training_step) over the CUDA
 library.  The forward + reverse (training.py:108-156) is the hot path and runs entirely in
-libtensorf_b200.so (fused MSE, no autograd graph); Adam + LR decay + apply
-(training.py:158-204, optax scale_by_adam b1=.9 b2=.99 eps=1e-8, masked group LRs) is a "next"
-row and is plain torch elementwise math here.
+libtensorf_b200.so (fused MSE, no autograd graph); Adam + LR decay + apply + grad_norm
+(training.py:158-204, optax scale_by_adam b1=.9 b2=.99 eps=1e-8, masked group LRs) is ONE launch of
+`tensorf_adam_step` over all leaves; `resize_grid` (training.py:245-276) resamples parameters and
+both Adam moments with `tensorf_vm_resize`.
 """
 from __future__ import annotations
 
@@ -39,6 +40,8 @@ class TrainState:
     prng_key: prng.Key
     step: int = 0
     world_size: int = 1  # rays sharded over ranks; gradients sum-allreduced
+    _adam: Optional[ops.AdamCall] = dataclasses.field(default=None, repr=False, compare=False)
+    _adam_names: Optional[list] = dataclasses.field(default=None, repr=False, compare=False)
 
     @staticmethod
     def initialize(config: train_config.TensorfConfig, grid_dim: int, prng_key, num_cameras: int,
@@ -107,32 +110,47 @@ class TrainState:
             for g in grads.values():
                 dist.all_reduce(g)
             dist.all_reduce(loss)
-        cfg, oc = self.config, self.config.optimizer
-        # LR decay with reset after upsampling (training.py:161-181)
-        step = self.step
-        if oc.lr_upsample_reset:
-            deltas = [step - u for u in (0,) + tuple(cfg.upsamp_iters) if step - u >= 0]
-            resetted = min(deltas)
-        else:
-            resetted = step
-        decay_iters = oc.lr_decay_iters if oc.lr_decay_iters is not None else cfg.n_iters
-        coeff = max(oc.lr_decay_target_ratio ** (resetted / decay_iters), oc.lr_decay_target_ratio)
-        # optax.scale_by_adam(b1=0.9, b2=0.99, eps=1e-8) + masked group learning rates (:213-243)
-        b1, b2, eps, t = 0.9, 0.99, 1e-8, step + 1
+        coeff = self.lr_decay_coeff()
+        oc = self.config.optimizer
+        # optax.scale_by_adam(b1=0.9, b2=0.99, eps=1e-8) + masked group learning rates (:213-243), one launch
         flat = self.learnable_params.flat()
-        gnorm_sq = torch.zeros((), device=loss.device)
-        for k, p in flat.items():
-            g = grads[k]
-            gnorm_sq += (g * g).sum()
-            mu, nu = self.optimizer_state["mu"][k], self.optimizer_state["nu"][k]
-            mu.mul_(b1).add_(g, alpha=1 - b1)
-            nu.mul_(b2).addcmul_(g, g, value=1 - b2)
-            lr = oc.lr_init_tensor if k.startswith(("density_", "appearance_")) else oc.lr_init_mlp
-            upd = (mu / (1 - b1**t)) / (torch.sqrt(nu / (1 - b2**t)) + eps)
-            p.add_(upd, alpha=-lr * coeff)
+        names = list(flat.keys())
+        if self._adam is None or self._adam_names != names or any(
+                a.data_ptr() != flat[k].data_ptr() for a, k in zip(self._adam.params, names)):
+            neg_lrs = [-(oc.lr_init_tensor if k.startswith(("density_", "appearance_")) else oc.lr_init_mlp) for k in names]
+            self._adam = ops.AdamCall([flat[k] for k in names], [self.optimizer_state["mu"][k] for k in names],
+                                      [self.optimizer_state["nu"][k] for k in names], neg_lrs, b1=0.9, b2=0.99, eps=1e-8)
+            self._adam_names = names
+        gnorm = self._adam.step([grads[k] for k in names], count=self.step, lr_decay=coeff)
+        step = self.step
         self.prng_key = new_key
         self.step = step + 1
         mse = float(loss.item())  # the blocking read the reference does at training.py:342
         log = {"train/mse": mse, "train/psnr": psnr_from_mse(mse), "train/lr_tensor": coeff * oc.lr_init_tensor,
-               "train/lr_mlp": coeff * oc.lr_init_mlp, "train/grad_norm": float(torch.sqrt(gnorm_sq).item())}
+               "train/lr_mlp": coeff * oc.lr_init_mlp, "train/grad_norm": float(gnorm.item())}
         return self, log
+
+    def lr_decay_coeff(self) -> float:
+        """training.py:158-181: optax.exponential_decay(1.0, decay_iters, ratio, end_value=ratio) at the step
+        count since the last upsampling (when `lr_upsample_reset`)."""
+        cfg, oc = self.config, self.config.optimizer
+        step = self.step
+        if oc.lr_upsample_reset:
+            resetted = min(step - u for u in (0,) + tuple(cfg.upsamp_iters) if step - u >= 0)
+        else:
+            resetted = step
+        decay_iters = oc.lr_decay_iters if oc.lr_decay_iters is not None else cfg.n_iters
+        return max(oc.lr_decay_target_ratio ** (resetted / decay_iters), oc.lr_decay_target_ratio)
+
+    def resize_grid(self, new_grid_dim: int) -> "TrainState":
+        """training.py:245-276: resample the factor grids and their Adam moments (mu, nu)."""
+        lp = self.learnable_params
+        lp.density_tensor = lp.density_tensor.resize(new_grid_dim)
+        lp.appearance_tensor = lp.appearance_tensor.resize(new_grid_dim)
+        for mom in ("mu", "nu"):
+            st = self.optimizer_state[mom]
+            for which in ("density", "appearance"):
+                v, m = ops.vm_resize(st[f"{which}_vector"], st[f"{which}_matrix"], int(new_grid_dim))
+                st[f"{which}_vector"], st[f"{which}_matrix"] = v, m
+        self._adam = None  # leaf buffers changed: rebuild the pointer tables
+        return self

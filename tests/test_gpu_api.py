@@ -38,8 +38,8 @@ def test_tensor_vm_interpolate_autograd(cuda):
     assert_close_grad(vm.stacked_single_vm.matrix.grad.cpu().numpy(), m64.grad.numpy(), what="d matrix")
     with pytest.raises(ValueError):
         vm.interpolate(torch.zeros(2, 4, device=cuda))
-    with pytest.raises(NotImplementedError):
-        vm.resize(20)
+    big = vm.resize(20)
+    assert big.grid_dim() == 20 and big.channel_dim() == vm.channel_dim()
 
 
 def test_feature_mlp_apply(cuda):
