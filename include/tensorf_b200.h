@@ -224,6 +224,21 @@ int64_t tensorf_vm_resize_scratch_bytes(int C, int G_in, int G_out);
 int tensorf_vm_resize(tensorf_stream_t s, const float* vector_in, const float* matrix_in, int C, int G_in, int G_out,
                       float* vector_out, float* matrix_out, void* scratch, int64_t scratch_bytes);
 
+/* ---- jax.random on the device + pixel rays ------------------------------------ */
+/* Threefry-2x32 (20 rounds), HOST function: out2 = cipher(key (k0,k1), counter (x0,x1)); the Random123
+ * known-answer vectors check it (tests/test_prng.py). */
+void tensorf_threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t* out2);
+/* jax.random.uniform(key, (n,), float32, minval, maxval) / jax.random.gumbel(key, (n,)) for a raw threefry key
+ * (render.py:158-161, :375-379, :462-468): element i uses counter (hi32(i), lo32(i)), bits = out0 ^ out1
+ * (jax_threefry_partitionable layout), so any (R,N) array is the flat array reshaped. */
+int tensorf_prng_uniform(tensorf_stream_t s, uint32_t k0, uint32_t k1, int64_t n, float minval, float maxval, float* out);
+int tensorf_prng_gumbel(tensorf_stream_t s, uint32_t k0, uint32_t k1, int64_t n, float* out);
+/* cameras.py:100-143 pixel_rays_wrt_world for image rows [row0,row1): M (HOST, 3x3 row-major) =
+ * R_world_camera @ K^-1, origin (HOST, 3) = T_world_camera.translation(); direction = M @ [u,v,1] / (norm + 1e-8).
+ * origins, directions ((row1-row0)*W, 3); camera_indices ((row1-row0)*W) or NULL. */
+int tensorf_pixel_rays(tensorf_stream_t s, const float* M, const float* origin, int W, int row0, int row1,
+                       uint32_t camera_index, float* origins, float* directions, uint32_t* camera_indices);
+
 #ifdef __cplusplus
 }
 #endif

@@ -440,3 +440,23 @@ def vm_resize(vector: np.ndarray, matrix: np.ndarray, grid_dim: int, dtype=np.fl
     vo = np.einsum("pci,io->pco", v, w).astype(dtype)
     mo = np.einsum("pcij,ia,jb->pcab", m, w, w, optimize=True).astype(dtype)
     return vo, mo
+
+
+# --------------------------------------------------------------------------------------
+# cameras.py:100-143 — per-pixel rays
+# --------------------------------------------------------------------------------------
+def pixel_rays(K: np.ndarray, T_camera_world: np.ndarray, width: int, height: int, camera_index: int, dtype=np.float32):
+    """Camera.pixel_rays_wrt_world (cameras.py:124-143) over ray_wrt_world_from_uv (:100-121):
+    direction = R_world_camera @ K^-1 @ [u, v, 1] (left to right), / (norm + 1e-8); origin =
+    T_world_camera.translation() = -R^T t; u = column, v = row (onp.mgrid[:H, :W], :134).
+    T_camera_world is a 4x4 homogeneous matrix. Returns origins (H,W,3), directions (H,W,3), camera_indices (H,W)."""
+    f = dtype
+    T = np.asarray(T_camera_world, dtype=f)
+    R_wc = T[:3, :3].T
+    origin = (-(R_wc @ T[:3, 3])).astype(f)
+    M = (R_wc @ np.linalg.inv(np.asarray(K, dtype=f))).astype(f)
+    v, u = np.mgrid[:height, :width]
+    uv1 = np.stack([u, v, np.ones_like(u)], axis=-1).astype(f)
+    d = np.einsum("ij,hwj->hwi", M, uv1).astype(f)
+    d = (d / (np.linalg.norm(d, axis=-1, keepdims=True).astype(f) + f(1e-8))).astype(f)
+    return np.broadcast_to(origin, d.shape).copy(), d, np.full((height, width), camera_index, dtype=np.uint32)

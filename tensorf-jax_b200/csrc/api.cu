@@ -6,6 +6,7 @@
 
 #include "mlp.cuh"
 #include "optim.cuh"
+#include "prng.cuh"
 #include "render_kernels.cuh"
 
 namespace tf {
@@ -527,6 +528,20 @@ int64_t tensorf_vm_resize_scratch_bytes(int C, int G_in, int G_out) {
 int tensorf_vm_resize(tensorf_stream_t s, const float* vector_in, const float* matrix_in, int C, int G_in, int G_out,
                       float* vector_out, float* matrix_out, void* scratch, int64_t scratch_bytes) {
   return vm_resize((cudaStream_t)s, vector_in, matrix_in, C, G_in, G_out, vector_out, matrix_out, scratch, scratch_bytes);
+}
+
+void tensorf_threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t* out2) {
+  if (out2) threefry2x32_host(k0, k1, x0, x1, out2);
+}
+int tensorf_prng_uniform(tensorf_stream_t s, uint32_t k0, uint32_t k1, int64_t n, float minval, float maxval, float* out) {
+  return prng_uniform((cudaStream_t)s, k0, k1, n, minval, maxval, out);
+}
+int tensorf_prng_gumbel(tensorf_stream_t s, uint32_t k0, uint32_t k1, int64_t n, float* out) {
+  return prng_gumbel((cudaStream_t)s, k0, k1, n, out);
+}
+int tensorf_pixel_rays(tensorf_stream_t s, const float* M, const float* origin, int W, int row0, int row1,
+                       uint32_t camera_index, float* origins, float* directions, uint32_t* camera_indices) {
+  return pixel_rays((cudaStream_t)s, M, origin, W, row0, row1, camera_index, origins, directions, camera_indices);
 }
 
 }  // extern "C"

@@ -107,6 +107,10 @@ SIGNATURES = {
                                C.POINTER(_vp), C.POINTER(C.c_float), _vp, _vp, _i64]),
     "tensorf_vm_resize_scratch_bytes": (_i64, [_i, _i, _i]),
     "tensorf_vm_resize": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i64]),
+    "tensorf_threefry2x32": (None, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "tensorf_prng_uniform": (_i, [_vp, C.c_uint32, C.c_uint32, _i64, C.c_float, C.c_float, _vp]),
+    "tensorf_prng_gumbel": (_i, [_vp, C.c_uint32, C.c_uint32, _i64, _vp]),
+    "tensorf_pixel_rays": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _i, _i, _i, C.c_uint32, _vp, _vp, _vp]),
 }
 
 _lock = threading.Lock()

@@ -358,6 +358,41 @@ def vm_resize(vector: torch.Tensor, matrix: torch.Tensor, grid_dim: int) -> Tupl
     return vo, mo
 
 
+def threefry2x32(k0: int, k1: int, x0: int, x1: int) -> Tuple[int, int]:
+    """The library's host threefry block (for known-answer checks)."""
+    out = (C.c_uint32 * 2)()
+    _lib.load().tensorf_threefry2x32(k0, k1, x0, x1, out)
+    return int(out[0]), int(out[1])
+
+
+def prng_uniform(k0: int, k1: int, shape, device, minval: float = 0.0, maxval: float = 1.0) -> torch.Tensor:
+    """jax.random.uniform(key, shape, float32, minval, maxval) drawn on the device (`tensorf_prng_uniform`)."""
+    out = torch.empty(tuple(shape), dtype=torch.float32, device=device)
+    check(_lib.load().tensorf_prng_uniform(_stream(), k0, k1, out.numel(), minval, maxval, out.data_ptr()))
+    return out
+
+
+def prng_gumbel(k0: int, k1: int, shape, device) -> torch.Tensor:
+    """jax.random.gumbel(key, shape) drawn on the device (`tensorf_prng_gumbel`)."""
+    out = torch.empty(tuple(shape), dtype=torch.float32, device=device)
+    check(_lib.load().tensorf_prng_gumbel(_stream(), k0, k1, out.numel(), out.data_ptr()))
+    return out
+
+
+def pixel_rays(M, origin, width: int, rows: Tuple[int, int], camera_index: int, device):
+    """cameras.py:124-143 for image rows [rows[0], rows[1]): M = R_world_camera @ K^-1 (3x3), origin (3,), host
+    values. Returns (origins (n,3), directions (n,3), camera_indices (n,) int32 with uint32 bits)."""
+    r0, r1 = rows
+    n = (r1 - r0) * width
+    o = torch.empty((n, 3), dtype=torch.float32, device=device)
+    d = torch.empty((n, 3), dtype=torch.float32, device=device)
+    c = torch.empty((n,), dtype=torch.int32, device=device)
+    Mh = (C.c_float * 9)(*[float(x) for x in M])
+    oh = (C.c_float * 3)(*[float(x) for x in origin])
+    check(_lib.load().tensorf_pixel_rays(_stream(), Mh, oh, width, r0, r1, camera_index, o.data_ptr(), d.data_ptr(), c.data_ptr()))
+    return o, d, c
+
+
 def launch_count() -> int:
     """Kernels this thread has enqueued through the library so far."""
     return int(_lib.load().tensorf_launch_count())

@@ -129,6 +129,16 @@ def _device_noise(noise: prng.RenderNoise, device) -> Dict[str, torch.Tensor]:
     return out
 
 
+def _noise_inputs(prng_key, ray_count: int, density_samples: int, contracted: bool, need_gumbel: bool, device) -> Dict[str, torch.Tensor]:
+    """The jitter / Gumbel input arrays of the C ABI for a key.  A `prng.Key` is expanded on the device
+    (`tensorf_prng_uniform/gumbel`: no host draw, no H2D copy of the (R,N) jitter); explicit `RenderNoise`
+    arrays and JAX keys take the host route."""
+    if isinstance(prng_key, prng.Key):
+        d = prng.render_noise_device(prng_key, ray_count, density_samples, contracted, device, need_gumbel)
+        return {k: v for k, v in d.items() if v is not None}
+    return _device_noise(prng.render_noise(prng_key, ray_count, density_samples, contracted, need_gumbel=need_gumbel), device)
+
+
 def render_rays(appearance_mlp: networks.FeatureMlp, learnable_params: LearnableParams, aabb: torch.Tensor,
                 rays_wrt_world: cameras.Rays3D, prng_key, config: RenderConfig) -> torch.Tensor:
     """render.py:105-279. Output (ray_count, 3) for RGB, (ray_count,) for the distance modes."""
@@ -148,12 +158,11 @@ def render_rays(appearance_mlp: networks.FeatureMlp, learnable_params: Learnable
                          contracted=contracted, feat_freqs=appearance_mlp.feature_n_freqs,
                          view_freqs=appearance_mlp.viewdir_n_freqs, num_cameras=appearance_mlp.num_cameras,
                          squash=appearance_mlp.feature_squash_dim, units=appearance_mlp.units)
-    noise = prng.render_noise(prng_key, ray_count, N, contracted, need_gumbel=config.mode is RenderMode.RGB)
     inputs = {"origins": rays_wrt_world.origins.to(torch.float32).contiguous(),
               "directions": rays_wrt_world.directions.to(torch.float32).contiguous(),
               "camera_indices": rays_wrt_world.camera_indices.to(torch.int32).contiguous(),
               "aabb": aabb.to(torch.float32).contiguous()}
-    inputs.update(_device_noise(noise, device))
+    inputs.update(_noise_inputs(prng_key, ray_count, N, contracted, config.mode is RenderMode.RGB, device))
     if contracted:
         base, delta = contracted_schedule(config.near, config.far, N)
         inputs["base_ts"] = torch.from_numpy(base).to(device)

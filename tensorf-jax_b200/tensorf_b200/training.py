@@ -85,12 +85,11 @@ class TrainState:
                              view_freqs=mlp.viewdir_n_freqs, num_cameras=mlp.num_cameras, squash=mlp.feature_squash_dim,
                              units=mlp.units, loss_scale=1.0 / (3 * R * self.world_size))
         dev = self.aabb.device
-        noise = prng.render_noise(render_prng_key, R, N, self.config.scene_contraction)
         rays = minibatch.rays_wrt_world
         inputs = {"origins": rays.origins.contiguous(), "directions": rays.directions.contiguous(),
                   "camera_indices": rays.camera_indices.to(torch.int32).contiguous(), "aabb": self.aabb,
                   "colors": minibatch.colors.contiguous()}
-        inputs.update(render._device_noise(noise, dev))
+        inputs.update(render._noise_inputs(render_prng_key, R, N, self.config.scene_contraction, True, dev))
         if self.config.scene_contraction:
             base, delta = render.contracted_schedule(self.config.render_near, self.config.render_far, N)
             inputs["base_ts"], inputs["deltas"] = torch.from_numpy(base).to(dev), torch.from_numpy(delta).to(dev)

@@ -61,3 +61,13 @@ def test_ops_reject_cpu_tensors():
     from tensorf_b200 import ops
     with pytest.raises(ValueError, match="no CPU path"):
         ops._ptr(torch.zeros(3))
+
+
+def test_library_threefry_known_answers():
+    """The host cipher block exported by the library (no GPU needed) against the Random123 vectors."""
+    from tensorf_b200 import ops
+    kat = [((0x00000000, 0x00000000), (0x00000000, 0x00000000), (0x6B200159, 0x99BA4EFE)),
+           ((0xFFFFFFFF, 0xFFFFFFFF), (0xFFFFFFFF, 0xFFFFFFFF), (0x1CB996FC, 0xBB002BE7)),
+           ((0x13198A2E, 0x03707344), (0x243F6A88, 0x85A308D3), (0xC4923A9C, 0x483DF7A0))]
+    for key, ctr, out in kat:
+        assert ops.threefry2x32(key[0], key[1], ctr[0], ctr[1]) == out

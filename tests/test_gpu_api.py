@@ -77,7 +77,11 @@ def test_render_rays_modes_and_autograd(cuda, contracted):
     rays = cameras.Rays3D(T(inp["origins"], device=cuda), T(inp["directions"], device=cuda), T(inp["camera_indices"], device=cuda))
     aabb = T(inp["aabb"], device=cuda)
     key = prng.Key.from_seed(3)
-    noise = prng.render_noise(key, w.R, w.N, contracted)
+    # a prng.Key is expanded on the device; the oracle consumes exactly those arrays (jitter is bit-identical
+    # to the host draw, gumbel within an ulp of logf — checked in test_gpu_prng.py)
+    dn = prng.render_noise_device(key, w.R, w.N, contracted, cuda)
+    noise = prng.RenderNoise(dn["jitter"].cpu().numpy(), dn["gumbel"].cpu().numpy())
+    assert np.array_equal(noise.jitter, prng.render_noise(key, w.R, w.N, contracted).jitter)
     cfg = render.RenderConfig(near=w.near, far=w.far, mode=render.RenderMode.RGB, density_samples_per_ray=w.N,
                               appearance_samples_per_ray=w.K)
     rgb = render.render_rays(mlp, lp, aabb, rays, key, cfg)
