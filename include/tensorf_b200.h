@@ -239,6 +239,17 @@ int tensorf_prng_gumbel(tensorf_stream_t s, uint32_t k0, uint32_t k1, int64_t n,
 int tensorf_pixel_rays(tensorf_stream_t s, const float* M, const float* origin, int W, int row0, int row1,
                        uint32_t camera_index, float* origins, float* directions, uint32_t* camera_indices);
 
+/* ---- training data path -------------------------------------------------------- */
+/* data.py:301-337 keeps every training ray in memory; training.py:318-323 draws shuffled minibatches.  Here the
+ * table (origins, directions (n_table,3); camera_indices (n_table) or NULL; colors (n_table,3) or NULL) lives on
+ * the device and a minibatch is a gather by idx (R,) int64.  Indices outside [0,n_table) read row 0 and are
+ * counted in *bad_count (device int, overwritten; may be NULL). */
+int tensorf_gather_rays(tensorf_stream_t s, const float* origins, const float* directions, const uint32_t* camera_indices,
+                        const float* colors, int64_t n_table, const int64_t* idx, int64_t R, float* out_origins,
+                        float* out_directions, uint32_t* out_camera_indices, float* out_colors, int* bad_count);
+/* data.py:318-320: rgb = rgba[:3]*a + (1-a) (opaque white background); rgba (n,4) 16-byte aligned -> rgb (n,3). */
+int tensorf_rgba_over_white(tensorf_stream_t s, const float* rgba, int64_t n, float* rgb);
+
 #ifdef __cplusplus
 }
 #endif

@@ -544,4 +544,14 @@ int tensorf_pixel_rays(tensorf_stream_t s, const float* M, const float* origin, 
   return pixel_rays((cudaStream_t)s, M, origin, W, row0, row1, camera_index, origins, directions, camera_indices);
 }
 
+int tensorf_gather_rays(tensorf_stream_t s, const float* origins, const float* directions, const uint32_t* camera_indices,
+                        const float* colors, int64_t n_table, const int64_t* idx, int64_t R, float* out_origins,
+                        float* out_directions, uint32_t* out_camera_indices, float* out_colors, int* bad_count) {
+  return gather_rays((cudaStream_t)s, origins, directions, camera_indices, colors, n_table, idx, R, out_origins, out_directions,
+                     out_camera_indices, out_colors, bad_count);
+}
+int tensorf_rgba_over_white(tensorf_stream_t s, const float* rgba, int64_t n, float* rgb) {
+  return rgba_over_white((cudaStream_t)s, rgba, n, rgb);
+}
+
 }  // extern "C"

@@ -110,3 +110,71 @@ int pixel_rays(cudaStream_t st, const float* M_host, const float* origin_host, i
 }
 
 }  // namespace tf
+
+// ---- training data path --------------------------------------------------
+// The ray table (data.py:301-337: every pixel of every training view as origin, direction, camera id,
+// colour = 40 B) stays resident on the device; a minibatch is a gather of R table rows by a shuffled index
+// (training.py:318-323), so a step moves 4*R B of indices instead of 40*R B of rays and never leaves the stream.
+namespace tf {
+
+__global__ void __launch_bounds__(256) k_gather_rays(const float* __restrict__ origins, const float* __restrict__ directions,
+                                                     const uint32_t* __restrict__ cams, const float* __restrict__ colors,
+                                                     const int64_t* __restrict__ idx, int64_t R, int64_t n_table,
+                                                     float* __restrict__ o_out, float* __restrict__ d_out,
+                                                     uint32_t* __restrict__ c_out, float* __restrict__ col_out,
+                                                     int* __restrict__ bad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  int64_t j = idx[i];
+  if (j < 0 || j >= n_table) {  // never read out of the table; the host checks `bad` when it wants to
+    if (bad) atomicAdd(bad, 1);
+    j = 0;
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    o_out[3 * i + a] = __ldg(origins + 3 * j + a);
+    d_out[3 * i + a] = __ldg(directions + 3 * j + a);
+    if (colors) col_out[3 * i + a] = __ldg(colors + 3 * j + a);
+  }
+  if (cams) c_out[i] = __ldg(cams + j);
+}
+
+int gather_rays(cudaStream_t st, const float* origins, const float* directions, const uint32_t* cams, const float* colors,
+                int64_t n_table, const int64_t* idx, int64_t R, float* o_out, float* d_out, uint32_t* c_out, float* col_out,
+                int* bad_count) {
+  TF_CHECK_ARG(R >= 0 && n_table >= 1, "gather_rays: R=%lld n_table=%lld", (long long)R, (long long)n_table);
+  if (bad_count) {
+    TF_CHECK_CUDA(cudaMemsetAsync(bad_count, 0, sizeof(int), st));
+    count_launch();
+  }
+  if (R == 0) return 0;  // empty minibatch: buffers may be null
+  TF_CHECK_ARG(origins && directions && idx && o_out && d_out, "gather_rays: null argument");
+  TF_CHECK_ARG((cams == nullptr) == (c_out == nullptr) && (colors == nullptr) == (col_out == nullptr),
+               "gather_rays: optional table columns and outputs must be given together");
+  k_gather_rays<<<(unsigned)ceil_div64(R, 256), 256, 0, st>>>(origins, directions, cams, colors, idx, R, n_table, o_out, d_out,
+                                                               c_out, col_out, bad_count);
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+
+// rgba (n,4) -> rgb over an opaque white background: rgb*a + (1-a)  (data.py:318-320)
+__global__ void __launch_bounds__(256) k_rgba_over_white(const float* __restrict__ rgba, int64_t n, float* __restrict__ rgb) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = __ldg(reinterpret_cast<const float4*>(rgba) + i);
+  const float bg = __fsub_rn(1.0f, p.w);
+  rgb[3 * i + 0] = __fadd_rn(__fmul_rn(p.x, p.w), bg);
+  rgb[3 * i + 1] = __fadd_rn(__fmul_rn(p.y, p.w), bg);
+  rgb[3 * i + 2] = __fadd_rn(__fmul_rn(p.z, p.w), bg);
+}
+
+int rgba_over_white(cudaStream_t st, const float* rgba, int64_t n, float* rgb) {
+  TF_CHECK_ARG(n >= 0 && (n == 0 || (rgba && rgb)), "rgba_over_white: bad arguments");
+  TF_CHECK_ARG((reinterpret_cast<uintptr_t>(rgba) & 15) == 0, "rgba_over_white: rgba must be 16-byte aligned");
+  if (n == 0) return 0;
+  k_rgba_over_white<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(rgba, n, rgb);
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace tf
