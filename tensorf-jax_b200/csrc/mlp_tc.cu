@@ -783,24 +783,34 @@ __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, 
       unsigned char* sB = sA + 2 * a_tile;
       mbar_wait(&sfull[sl], sph);
       mbar_wait(&empty[st], ph ^ 1);
+      const bool full_chunk = nrows == kRC;
       for (int item = ct; item < a_items + b_items; item += 32 * kConvWarps) {
         const bool isA = item < a_items;
-        const int e = isA ? item : item - a_items;
-        const int ncols = isA ? 128 : g.N_pad;
-        const int col = e % ncols, j = e / ncols;
-        const float* src = isA ? sG : sX;
+        int col, j;
+        if (isA) {  // 128 columns: shifts
+          col = item & 127;
+          j = item >> 7;
+        } else {    // N_pad columns, kRC/8 = 4 row groups: three compares instead of a division
+          const int e = item - a_items;
+          j = (e >= g.N_pad) + (e >= 2 * g.N_pad) + (e >= 3 * g.N_pad);
+          col = e - j * g.N_pad;
+        }
+        const float* src = (isA ? sG : sX) + col;
         const int ld = isA ? (int)g.ldg : (int)g.ldx;
         const int valid = isA ? g.Mg : g.Nx;
         float x[8];
+        if (col < valid) {
+          if (full_chunk) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int r = j * 8 + q;
-          float v = 0.f;
-          if (r < nrows) {
-            if (col < valid) v = src[r * ld + col];
-            else if (!isA && g.colsum && col == g.Nx) v = 1.0f;  // ones column -> bias gradient
+            for (int q = 0; q < 8; ++q) x[q] = src[(j * 8 + q) * ld];
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) x[q] = (j * 8 + q < nrows) ? src[(j * 8 + q) * ld] : 0.f;
           }
-          x[q] = v;
+        } else {
+          const bool ones = !isA && g.colsum && col == g.Nx;  // ones column -> bias gradient
+#pragma unroll
+          for (int q = 0; q < 8; ++q) x[q] = (ones && j * 8 + q < nrows) ? 1.0f : 0.f;
         }
         split_store<2>(x, isA ? sA : sB, isA ? a_tile : b_tile, tile_offset(col, j * 8, kRC));
       }
