@@ -710,9 +710,13 @@ __global__ void __launch_bounds__(kRedThreads, 1) k_tc_redgemm(RedGemmArgs g) {
 // contiguous block in global memory (ld % 4 == 0), so ONE thread streams raw fp32 chunks into a
 // shared-memory staging ring with cp.async.bulk (deep prefetch, no registers, no LSU), and the
 // converter warps transpose + split them smem -> smem into the UMMA operand tiles.
-//   warps 0-3 epilogue, 4 MMA issuer, 5 loader, 6.. converters
+//   warps 0-3 epilogue, 4 MMA issuer, 5 loader, 6.. converters: kConvGroups groups that own alternate
+//   chunks, so one group's barrier/fence latency overlaps the other group's conversion (stage and slot
+//   counts are multiples of the group count: a stage is always filled by the same group, in order).
 // ---------------------------------------------------------------------------------------------
-constexpr int kConvWarps = 12;
+constexpr int kConvGroups = 2;
+constexpr int kConvGroupWarps = 8;
+constexpr int kConvWarps = kConvGroups * kConvGroupWarps;
 constexpr int kRed2Threads = 192 + 32 * kConvWarps;
 
 __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, int T /*staging slots*/) {
@@ -733,12 +737,12 @@ __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, 
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(&full[s], kConvWarps);
+      mbar_init(&full[s], kConvGroupWarps);
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < T; ++s) {
       mbar_init(&sfull[s], 1);
-      mbar_init(&sempty[s], kConvWarps);
+      mbar_init(&sempty[s], kConvGroupWarps);
     }
     mbar_init(tfull, 1);
     fence_barrier_init();
@@ -759,6 +763,7 @@ __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, 
       for (int c = 0; c < nchunks; ++c) {
         const uint32_t sl = (uint32_t)(c % T), ph = (uint32_t)((c / T) & 1);
         mbar_wait_backoff(&sempty[sl], ph ^ 1);
+        TF_TRACE(4, c);
         const int64_t r0 = r_begin + (int64_t)c * kRC;
         const uint32_t nrows = (uint32_t)min((int64_t)kRC, r_end - r0);
         float* dst = slot0 + (size_t)sl * slot_floats;
@@ -770,9 +775,10 @@ __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, 
     }
   } else if (warp >= 6) {
     // ===== converters: item = (operand, column, group of 8 rows) -> one 16-byte k-chunk per split =====
-    const int ct = tid - 192;
+    const int grp = (warp - 6) / kConvGroupWarps;
+    const int ct = tid - 192 - grp * 32 * kConvGroupWarps;
     const int a_items = 128 * (kRC / 8), b_items = g.N_pad * (kRC / 8);
-    for (int c = 0; c < nchunks; ++c) {
+    for (int c = grp; c < nchunks; c += kConvGroups) {
       const uint32_t sl = (uint32_t)(c % T), sph = (uint32_t)((c / T) & 1);
       const uint32_t st = (uint32_t)(c % S), ph = (uint32_t)((c / S) & 1);
       const int64_t r0 = r_begin + (int64_t)c * kRC;
@@ -781,10 +787,13 @@ __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, 
       const float* sX = sG + (size_t)kRC * g.ldg;
       unsigned char* sA = stage0 + (size_t)st * stage_bytes;
       unsigned char* sB = sA + 2 * a_tile;
+      if (ct == 0) TF_TRACE(0, c);
       mbar_wait(&sfull[sl], sph);
+      if (ct == 0) TF_TRACE(1, c);
       mbar_wait(&empty[st], ph ^ 1);
+      if (ct == 0) TF_TRACE(2, c);
       const bool full_chunk = nrows == kRC;
-      for (int item = ct; item < a_items + b_items; item += 32 * kConvWarps) {
+      for (int item = ct; item < a_items + b_items; item += 32 * kConvGroupWarps) {
         const bool isA = item < a_items;
         int col, j;
         if (isA) {  // 128 columns: shifts
@@ -820,6 +829,7 @@ __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, 
         mbar_arrive(&full[st]);     // operand stage ready for the tensor core
         mbar_arrive(&sempty[sl]);   // staging slot may be overwritten
       }
+      if (ct == 0) TF_TRACE(3, c);
     }
   } else if (warp == 4) {
     {  // warp-uniform issue loop (see k_tc_rowgemm): descriptors stay in uniform registers
@@ -831,6 +841,7 @@ __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, 
       uint32_t st = 0, ph = 0;
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(&full[st], ph);
+        if (lane == 0) TF_TRACE(5, c);
         tc_fence_after();
         const uint32_t a_st = a_lo0 + st * st_units;
         const uint32_t b_st = a_st + 2 * a_split;
@@ -857,6 +868,7 @@ __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, 
     // ===== epilogue: RED-add the 128 x N tile into out[n*ldo + m] =====
     if (nchunks > 0) {
       mbar_wait(tfull, 0);
+      if (tid == 0) TF_TRACE(6, 0);
       tc_fence_after();
       const int m = warp * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -876,6 +888,7 @@ __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, 
       }
     }
   }
+  if (tid == 0) TF_TRACE(7, 0);
   tc_fence_before();
   __syncthreads();
   if (warp == 4) {
@@ -899,13 +912,10 @@ static int launch_redgemm(cudaStream_t st, RedGemmArgs g) {
   const bool aligned = g.ldg % 4 == 0 && g.ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(g.G) & 15) == 0 &&
                        (reinterpret_cast<uintptr_t>(g.X) & 15) == 0;
   if (aligned && !getenv("TENSORF_TC_RED_REGS") && 1024 + 2 * stage + 2 * slot <= 227 * 1024) {
-    g.stages = 2;
-    g.groups = 1;
+    g.stages = kConvGroups;
+    g.groups = kConvGroups;
     int T = (int)std::min<size_t>(6, (227 * 1024 - 1024 - 2 * stage) / slot);
-    if (T >= 4 && 1024 + 3 * stage + 3 * slot <= 227 * 1024) {  // prefer a third operand stage when there is room
-      g.stages = 3;
-      T = (int)std::min<size_t>(6, (227 * 1024 - 1024 - 3 * stage) / slot);
-    }
+    T = T / kConvGroups * kConvGroups;
     const size_t smem = 1024 + g.stages * stage + (size_t)T * slot;
     TF_CHECK_CUDA(cudaFuncSetAttribute(k_tc_redgemm2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_tc_redgemm2<<<(unsigned)ctas, kRed2Threads, smem, st>>>(g, T);

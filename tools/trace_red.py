@@ -22,7 +22,7 @@ buf = (ctypes.c_longlong * 8192)()
 _lib.check(lib.tensorf_tc_trace_read(buf, 8192))
 t = np.array(buf[:], dtype=np.int64).reshape(8, 1024)
 base = t[0, 0]
-names = ["P.start", "P.loadsIssued", "P.afterEmpty", "P.arrived", "M.fullDone", "M.committed"]
+names = ["C.start", "C.rawReady", "C.stageFree", "C.arrived", "L.slotFree", "M.fullDone"]
 print("chunk " + " ".join(f"{n:>14s}" for n in names))
 for q in range(34):
     print(f"{q:3d}   " + " ".join(f"{int(t[s, q] - base):14d}" for s in range(6)))
