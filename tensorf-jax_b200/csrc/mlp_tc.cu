@@ -332,98 +332,133 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
       }
     }
   } else {
-    // ================= epilogue: TMEM -> registers -> bias / relu / mask -> smem row -> bulk store ====
-    // tcgen05.ld gives lane <-> row. Two warps share a TMEM lane quadrant and split the columns.
-    // Each thread stages ITS OWN row segment in padded smem (conflict-free STS.128) and ships it
-    // with ONE asynchronous bulk copy per tile (cp.async.bulk shared -> global).
+    // ================= epilogue: TMEM -> registers -> bias / relu / mask -> global ====================
+    // Two warps share a TMEM lane quadrant and split the columns. tcgen05.ld.16x256b hands every group
+    // of 4 lanes 32 contiguous bytes of one row (the mma C-fragment layout), so the registers are stored
+    // straight to global memory as whole 32-byte sectors: no staging rows in shared memory and no
+    // per-thread bulk stores (issuing 256 small cp.async.bulk per tile cost ~3k cycles of an ~8k epilogue).
+    // A thread owns 4 rows of the tile (rr = 2*blk + h -> quad*32 + blk*16 + h*8 + lane/4) and columns
+    // 2*(lane%4) + {0,1} of every 8-column group.  Row-wise results (ReLU bit masks, the fused output
+    // layer) are combined across the 4 lanes of a row with two xor-shuffles.
     // ReLU masks travel as one bit per element (bits_out / bits_in), not as fp32 activations.
     uint32_t acc = 0, acc_ph = 0;
     const int quad = warp & 3, half = warp >> 2;
-    const int row = quad * 32 + lane;
+    const int lrow = lane >> 2, lq = lane & 3, lc = lq * 2;
     const int nch = g.N_pad / 16;                               // 16-column chunks of the tile
     const int ch_begin = half ? (nch + 1) / 2 : 0, ch_end = half ? nch : (nch + 1) / 2;
     const int c_begin = ch_begin * 16, c_cols = (ch_end - ch_begin) * 16;
-    float* mine = s_out + ((size_t)half * 128 + row) * g.out_stride;
-    const bool bulk_ok = g.out_stride > 0 && (g.ldc % 4 == 0) && (g.N_store % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+    const bool vec_ok = (g.ldc % 2 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 7) == 0);
     const int words = (g.N_pad + 31) / 32;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      const int64_t m = t * 128 + row;
-      const bool row_ok = m < g.M;
-      uint32_t mbits[8];
-      if (EPI & EPI_BITS_IN) {
+      const int64_t mbase = t * 128 + quad * 32 + lrow;  // row rr = mbase + roff(rr)
+#define TF_ROFF(rr) ((((rr) >> 1) * 16) + (((rr) & 1) * 8))
+      int em_off[4];  // FiLM conditioner row of each row's camera (networks.py:103-111), -1 = none
 #pragma unroll
-        for (int w = 0; w < 8; ++w) mbits[w] = (row_ok && w < words) ? __ldg(g.bits_in + m * words + w) : 0u;
+      for (int rr = 0; rr < 4; ++rr) {
+        em_off[rr] = -1;
+        if ((EPI & EPI_OUT3) && g.embed && mbase + TF_ROFF(rr) < g.M)
+          em_off[rr] = (int)g.cams[(mbase + TF_ROFF(rr)) / g.rows_per_ray] * 128;
       }
-      const float* em = nullptr;  // FiLM conditioner of this row's camera (networks.py:103-111)
-      if ((EPI & EPI_OUT3) && g.embed && row_ok) em = g.embed + (int64_t)g.cams[m / g.rows_per_ray] * 128;
-      float o3[3] = {0.f, 0.f, 0.f};
+      float o3[4][3];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) o3[rr][0] = o3[rr][1] = o3[rr][2] = 0.f;
       if (tid == 0) TF_TRACE(4, (t - blockIdx.x) / gridDim.x);
-      if (bulk_ok) bulk_wait_read<0>();  // last tile's store has finished reading my staging row
-      if (tid == 0) TF_TRACE(4, 512 + (t - blockIdx.x) / gridDim.x);
       mbar_wait(&tfull[acc], acc_ph, 500);
       if (tid == 0) TF_TRACE(6, (t - blockIdx.x) / gridDim.x);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)g.N_pad;
+      const uint32_t tcol = tmem_base + acc * (uint32_t)g.N_pad;
       for (int j = 0; j * 16 < c_cols; ++j) {
         const int n0 = c_begin + j * 16;
-        float v[16];
-        tmem_ld16(trow + n0, v);
+        float v[2][8];
+        tmem_ld_16x256b_x2(tcol + ((uint32_t)(quad * 32) << 16) + n0, v[0]);
+        tmem_ld_16x256b_x2(tcol + ((uint32_t)(quad * 32 + 16) << 16) + n0, v[1]);
         tmem_ld_wait();
-        const uint32_t mw = (EPI & EPI_BITS_IN) ? (mbits[(n0 >> 5) & 7] >> (n0 & 16)) : 0u;
-        uint32_t ow = 0u;
+        const float2 b0 = *reinterpret_cast<const float2*>(s_bias + n0 + lc);
+        const float2 b1 = *reinterpret_cast<const float2*>(s_bias + n0 + 8 + lc);
+        const float bq[4] = {b0.x, b0.y, b1.x, b1.y};
+        uint32_t ow[4];
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const float4 bb = *reinterpret_cast<const float4*>(s_bias + n0 + 4 * q4);
-          const float bq[4] = {bb.x, bb.y, bb.z, bb.w};
+        for (int rr = 0; rr < 4; ++rr) {
+          const int blk = rr >> 1, h = rr & 1;
+          const int64_t mr = mbase + TF_ROFF(rr);
+          uint32_t mw = 0u;
+          if (EPI & EPI_BITS_IN) mw = mr < g.M ? (__ldg(g.bits_in + mr * words + (n0 >> 5)) >> (n0 & 16)) : 0u;
+          ow[rr] = 0u;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int q = 4 * q4 + e;
-            float y = v[q] + bq[e];
+          for (int e = 0; e < 4; ++e) {               // e = 2*(8-column group) + (column within the pair)
+            const int q = (e >> 1) * 8 + lc + (e & 1);  // column within the 16-column chunk
+            float y = v[blk][(e >> 1) * 4 + h * 2 + (e & 1)] + bq[e];
             if (g.relu) y = fmaxf(y, 0.f);
             if ((EPI & EPI_BITS_IN) && !((mw >> q) & 1u)) y = 0.f;
-            if ((EPI & EPI_BITS_OUT) && y > 0.f) ow |= 1u << q;
-            v[q] = y;
+            if ((EPI & EPI_BITS_OUT) && y > 0.f) ow[rr] |= 1u << q;
+            v[blk][(e >> 1) * 4 + h * 2 + (e & 1)] = y;
             if (EPI & EPI_OUT3) {
               const int n = n0 + q;
               float yf = y;
-              if (em && n >= 64) yf = __fadd_rn(__fmul_rn(__ldg(em + n - 64), y), __ldg(em + n));
-              o3[0] = fmaf(yf, s_w3[3 * n + 0], o3[0]);
-              o3[1] = fmaf(yf, s_w3[3 * n + 1], o3[1]);
-              o3[2] = fmaf(yf, s_w3[3 * n + 2], o3[2]);
+              if (em_off[rr] >= 0 && n >= 64) yf = __fadd_rn(__fmul_rn(__ldg(g.embed + em_off[rr] + n - 64), y), __ldg(g.embed + em_off[rr] + n));
+              o3[rr][0] = fmaf(yf, s_w3[3 * n + 0], o3[rr][0]);
+              o3[rr][1] = fmaf(yf, s_w3[3 * n + 1], o3[rr][1]);
+              o3[rr][2] = fmaf(yf, s_w3[3 * n + 2], o3[rr][2]);
             }
           }
         }
-        if ((EPI & EPI_BITS_OUT) && row_ok) {  // two 16-bit halves per word, written by the owning thread
-          reinterpret_cast<uint16_t*>(g.bits_out + m * words)[n0 >> 4] = (uint16_t)ow;
+        if (EPI & EPI_BITS_OUT) {
+          // 16 mask bits per (row, chunk): OR over the row's 4 lanes (two rows per 32-bit word), then lane
+          // lq writes row rr == lq's half-word
+          uint32_t p01 = ow[0] | (ow[1] << 16), p23 = ow[2] | (ow[3] << 16);
+          p01 |= __shfl_xor_sync(0xffffffffu, p01, 1);
+          p23 |= __shfl_xor_sync(0xffffffffu, p23, 1);
+          p01 |= __shfl_xor_sync(0xffffffffu, p01, 2);
+          p23 |= __shfl_xor_sync(0xffffffffu, p23, 2);
+          const uint32_t mine = (lq & 2) ? p23 : p01;
+          const int64_t mq = mbase + TF_ROFF(lq);
+          if (mq < g.M) reinterpret_cast<uint16_t*>(g.bits_out + mq * words)[n0 >> 4] = (uint16_t)(mine >> ((lq & 1) * 16));
         }
-        if (bulk_ok) {
+        if (g.C != nullptr) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<float4*>(mine + j * 16 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        } else if (row_ok) {
-          for (int q = 0; q < 16; ++q)
-            if (n0 + q < g.N_store) g.C[m * g.ldc + n0 + q] = v[q];
+          for (int rr = 0; rr < 4; ++rr) {
+            const int64_t mr = mbase + TF_ROFF(rr);
+            if (mr >= g.M) continue;
+            const int blk = rr >> 1, h = rr & 1;
+#pragma unroll
+            for (int gq = 0; gq < 2; ++gq) {
+              const int n = n0 + gq * 8 + lc;
+              float* dst = g.C + mr * g.ldc + n;
+              const float y0 = v[blk][gq * 4 + h * 2], y1 = v[blk][gq * 4 + h * 2 + 1];
+              if (vec_ok && n + 1 < g.N_store) {
+                *reinterpret_cast<float2*>(dst) = make_float2(y0, y1);
+              } else {
+                if (n < g.N_store) dst[0] = y0;
+                if (n + 1 < g.N_store) dst[1] = y1;
+              }
+            }
+          }
         }
       }
       if (tid == 0) TF_TRACE(5, (t - blockIdx.x) / gridDim.x);
-      if (bulk_ok) {
-        const int ncopy = min(c_cols, g.N_store - c_begin);
-        fence_proxy_async();
-        if (row_ok && ncopy > 0) bulk_store_s2g(g.C + m * g.ldc + c_begin, mine, (uint32_t)ncopy * 4);
-        bulk_commit();
-      }
-      if (tid == 0) TF_TRACE(5, 512 + (t - blockIdx.x) / gridDim.x);
       if (EPI & EPI_OUT3) {
-        // both halves of a row contribute to the three outputs: combine through the staging header
-        // (s_w3 + 400 .. : [128 rows][3]) — half 1 publishes, half 0 adds, applies the sigmoid, stores
-        float* xch = s_xch + row * 3;
+        // sum the row's partial outputs over its 4 lanes; both column halves contribute: half 1 publishes
+        // through s_xch ([128 rows][3]), half 0 adds, applies the sigmoid, stores
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            o3[rr][c] += __shfl_xor_sync(0xffffffffu, o3[rr][c], 1);
+            o3[rr][c] += __shfl_xor_sync(0xffffffffu, o3[rr][c], 2);
+          }
+        float mine3[3];  // lane lq keeps row rr == lq
+#pragma unroll
+        for (int c = 0; c < 3; ++c) mine3[c] = lq == 0 ? o3[0][c] : lq == 1 ? o3[1][c] : lq == 2 ? o3[2][c] : o3[3][c];
+        const int rloc = quad * 32 + TF_ROFF(lq) + lrow;
+        float* xch = s_xch + rloc * 3;
         if (half == 1) {
-          xch[0] = o3[0]; xch[1] = o3[1]; xch[2] = o3[2];
+          xch[0] = mine3[0]; xch[1] = mine3[1]; xch[2] = mine3[2];
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
-        if (half == 0 && row_ok) {
+        const int64_t mm = t * 128 + rloc;
+        if (half == 0 && mm < g.M) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) g.rgb_out[3 * m + c] = 1.0f / (1.0f + expf(-(o3[c] + xch[c] + s_w3[384 + c])));
+          for (int c = 0; c < 3; ++c) g.rgb_out[3 * mm + c] = 1.0f / (1.0f + expf(-(mine3[c] + xch[c] + s_w3[384 + c])));
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
@@ -432,7 +467,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
       mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
-    if (bulk_ok) bulk_wait<0>();  // all stores of this thread are globally complete before exit
+#undef TF_ROFF
   }
 
   tc_fence_before();
@@ -464,16 +499,9 @@ static int launch_rowgemm(cudaStream_t st, RowGemmArgs g) {
   TF_CHECK_ARG(g.N_pad % 16 == 0 && g.N_pad >= 16 && g.N_pad <= 256, "tc rowgemm: N_pad=%d unsupported", g.N_pad);
   TF_CHECK_ARG(g.K_pad % 16 == 0 && g.K_pad >= 16, "tc rowgemm: K_pad=%d unsupported", g.K_pad);
   const size_t stage = (size_t)NSPLIT * (tile_bytes(128, KC) + tile_bytes(g.N_pad, KC));
-  // epilogue staging: [2 column halves][128 rows][cols per half + 4]; dropped (direct stores) when it
-  // would leave fewer than 3 pipeline stages
-  g.no_bulk = getenv("TENSORF_TC_NOBULK") != nullptr;
-  g.out_stride = ((g.N_pad / 16 + 1) / 2) * 16 + 4;
-  size_t staging = (size_t)2 * 128 * g.out_stride * 4;
-  if (g.no_bulk || (227 * 1024 - kRowFixed - staging) / stage < 3) {
-    g.out_stride = 0;
-    staging = 0;
-  }
-  g.header_bytes = kRowFixed + (int)staging;
+  g.no_bulk = 1;  // the epilogue stores registers straight to global memory (no staging rows)
+  g.out_stride = 0;
+  g.header_bytes = kRowFixed;
   // weights resident in smem for the whole kernel when they fit next to >= 2 A-only stages
   const size_t wres = (size_t)((g.K_pad + KC - 1) / KC) * NSPLIT * tile_bytes(g.N_pad, KC);
   const size_t a_stage = (size_t)NSPLIT * tile_bytes(128, KC);

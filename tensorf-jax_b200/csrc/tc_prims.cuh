@@ -161,6 +161,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
       : "r"(taddr)
       : "memory");
 }
+// 16 lanes x 256 bit pattern, twice (16 columns): thread t of the warp receives, for rows r = t/4 and r + 8 of
+// the 16 lanes at the address's lane offset, columns 2*(t%4) + {0,1} of each 8-column group
+// (cute copy_traits_sm100.hpp, SM100_TMEM_LOAD_16dp256b2x):
+//   v[0],v[1]: (r, c), (r, c+1)   v[2],v[3]: (r+8, c), (r+8, c+1)   v[4..7]: the same for columns c+8, c+9.
+// Four lanes hold 32 contiguous bytes of a row, so registers go to global memory as whole sectors.
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors ----------------------------------------------------------------------------------------
