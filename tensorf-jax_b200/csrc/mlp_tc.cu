@@ -12,8 +12,11 @@
 //   k_tc_redgemm : dW^T[128 x N] += G^T[128 x rows] * X[rows x N]   weight gradients (split over
 //       rows across CTAs, RED-add epilogue).
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
+
+#include <cuda.h>
 
 #include "mlp.cuh"
 #include "tc_prims.cuh"
@@ -157,24 +160,29 @@ struct RowGemmArgs {
   int rows_per_ray;
   float* rgb_out;             // (M,3)
   int groups;                 // active producer groups; stages % groups == 0 (see launch_rowgemm)
+  int raw_slots;              // > 0: A chunks arrive by TMA (tensor map) into a raw fp32 ring of this many slots
   uint32_t tmem_cols;         // power of two >= 2*N_pad
 };
 
 // warps 0-7 epilogue (two per TMEM lane quadrant, each takes half of the columns), 8 MMA issuer,
-// 9 weight loader, then kGroups producer groups of 4 warps.
-// fence.proxy.async drains the issuing thread's outstanding loads, so one thread cannot overlap
-// its own global loads with publishing a stage; instead every producer group owns whole chunks
-// (chunk seq -> group seq % groups) and several chunks are in flight per SM.
+// 9 weight loader, 10 TMA loader of the raw A ring, then kGroups producer groups of 4 warps.
+// A operand path: ONE thread issues a 2-D TMA load (tensor map over the fp32 activation matrix, box =
+// 128 rows x 32 columns, SWIZZLE_128B so the column-wise reads below are bank-conflict free) per K-chunk
+// into a ring of raw fp32 slots; the producer groups only convert shared -> shared (split into bf16
+// core matrices) and never wait on global memory.  Fallback (unaligned A): the groups load through
+// registers; fence.proxy.async then drains the issuing thread's outstanding loads, so overlap only
+// comes from every group owning whole chunks (chunk seq -> group seq % groups).
 constexpr int kGroups = 3;
 constexpr int kGroupThreads = 128;
 constexpr int kEpiWarps = 8;
-constexpr int kMmaWarp = kEpiWarps, kLoadWarp = kEpiWarps + 1, kProdWarp0 = kEpiWarps + 2;
+constexpr int kMmaWarp = kEpiWarps, kLoadWarp = kEpiWarps + 1, kRawWarp = kEpiWarps + 2, kProdWarp0 = kEpiWarps + 3;
 constexpr int kRowThreads = 32 * kProdWarp0 + kGroups * kGroupThreads;
+constexpr int kRawSlotsMax = 8;
 constexpr int kRowFixed = 6144;  // barriers [0,1K), bias [1K,2K), W3/b3 [2K,4K), out3 exchange [4K,6K)
 enum : int { EPI_BITS_IN = 1, EPI_BITS_OUT = 2, EPI_OUT3 = 4 };
 
 template <int NSPLIT, int EPI>
-__global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
+__global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, const __grid_constant__ CUtensorMap tmapA) {
   constexpr int KC = RowCfg<NSPLIT>::KC;
   constexpr int ITEMS = 128 * (KC / 8) / kGroupThreads;  // 16-byte k-chunks per producer thread and stage
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -196,6 +204,12 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
   unsigned char* wres = smem + g.header_bytes;
   unsigned char* stage0 = wres + (g.resident ? (size_t)nchunks_w * NSPLIT * b_tile : 0);
   uint64_t* wfull = tempty + 2 + 1;  // after tmem_slot (8-byte aligned slot)
+  uint64_t* rfull = wfull + 1;             // [raw_slots] raw fp32 chunk landed (TMA tx bytes)
+  uint64_t* rempty = rfull + kRawSlotsMax;  // [raw_slots] raw chunk read by its producer group (4 warps)
+  constexpr uint32_t kRawBytes = 128 * KC * 4;
+  unsigned char* raw0 = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(stage0 + (size_t)S * stage_bytes) + 1023) & ~(uintptr_t)1023);  // swizzle atom alignment
+  const int T = g.raw_slots;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
@@ -203,6 +217,10 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
       mbar_init(&empty[s], 1);                                    // tcgen05.commit
     }
     mbar_init(wfull, 1);
+    for (int r = 0; r < T; ++r) {
+      mbar_init(&rfull[r], 1);
+      mbar_init(&rempty[r], kGroupThreads / 32);
+    }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);                // tcgen05.commit
       mbar_init(&tempty[a], 32 * kEpiWarps);  // epilogue threads
@@ -241,6 +259,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
         const int row = rb * 8 + (lane & 7);
         const int k = k0 + (kh * 4 + (lane >> 3)) * 8;
         const int64_t m = t * 128 + row;
+        if (T > 0) continue;  // TMA path: filled from the raw ring below
         if (m < g.M && k < g.K_pad) {
           const float* src = g.A + m * g.lda + k;
           if (vec_ok && k + 8 <= g.K_valid) {
@@ -255,6 +274,26 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) x[it][e] = 0.f;
         }
+      }
+      if (T > 0) {
+        // raw slot: [128 rows][128 B], 16-byte unit u of row r stored at unit u ^ (r & 7) (SWIZZLE_128B);
+        // 8 consecutive lanes read the same logical unit of 8 consecutive rows -> 8 distinct units
+        const uint32_t sl = (uint32_t)(seq % T), rph = (uint32_t)((seq / T) & 1);
+        const unsigned char* raw = raw0 + (size_t)sl * kRawBytes;
+        mbar_wait_backoff(&rfull[sl], rph, 300 + (int)seq);
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it) {
+          const int q = it * 4 + pw;
+          const int rb = q / (KC / 32), kh = q % (KC / 32);
+          const int row = rb * 8 + (lane & 7);
+          const int u = (kh * 4 + (lane >> 3)) * 2;
+          const float4 v0 = *reinterpret_cast<const float4*>(raw + row * 128 + ((u ^ (row & 7)) << 4));
+          const float4 v1 = *reinterpret_cast<const float4*>(raw + row * 128 + (((u + 1) ^ (row & 7)) << 4));
+          x[it][0] = v0.x; x[it][1] = v0.y; x[it][2] = v0.z; x[it][3] = v0.w;
+          x[it][4] = v1.x; x[it][5] = v1.y; x[it][6] = v1.z; x[it][7] = v1.w;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rempty[sl]);  // values are in registers: the slot may be refilled
       }
       mbar_wait_backoff(&empty[st], ph ^ 1, 100 + (int)seq);
       if (pw == 0 && lane == 0) TF_TRACE(1, seq);
@@ -287,6 +326,18 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g) {
         unsigned char* sB = stage0 + (size_t)st * stage_bytes + NSPLIT * a_tile;
         mbar_arrive_expect_tx(&full[st], NSPLIT * b_tile);
         bulk_copy_g2s(sB, g.Bp + (size_t)c * NSPLIT * b_tile, NSPLIT * b_tile, &full[st]);
+      }
+    }
+  } else if (warp == kRawWarp) {
+    // ================= TMA loader of the raw A ring: one 2-D box (128 rows x KC columns) per chunk ==========
+    if (lane == 0 && T > 0) {
+      for (int64_t seq = 0; seq < total; ++seq) {
+        const uint32_t sl = (uint32_t)(seq % T), ph = (uint32_t)((seq / T) & 1);
+        const int64_t t = blockIdx.x + (seq / nchunks) * gridDim.x;
+        const int k0 = (int)(seq % nchunks) * KC;
+        mbar_wait_backoff(&rempty[sl], ph ^ 1, 400 + (int)seq);
+        mbar_arrive_expect_tx(&rfull[sl], kRawBytes);  // the whole box counts, zero-filled parts included
+        tma_load_2d(raw0 + (size_t)sl * kRawBytes, &tmapA, k0, (int)(t * 128), &rfull[sl]);
       }
     }
   } else if (warp == kMmaWarp) {
@@ -484,10 +535,38 @@ static uint32_t pow2_cols(int n) {
   return c;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// Tensor map over the fp32 activation matrix A (M rows, K_valid columns, row stride lda): box = 128 rows x
+// KC columns (one A chunk), 128-byte swizzle, zero fill outside the matrix (row and column tails).
+static bool make_a_tensor_map(CUtensorMap* tm, const float* A, int64_t M, int K_valid, int64_t lda, int kc) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || (reinterpret_cast<uintptr_t>(A) & 15) != 0 || (lda * 4) % 16 != 0 || K_valid < 1 || M < 1 || kc * 4 != 128) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)K_valid, (cuuint64_t)M};
+  const cuuint64_t strides[1] = {(cuuint64_t)lda * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)kc, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int NSPLIT, int EPI>
-static int launch_rowgemm_epi(cudaStream_t st, const RowGemmArgs& g, unsigned grid, size_t smem) {
+static int launch_rowgemm_epi(cudaStream_t st, const RowGemmArgs& g, const CUtensorMap& tm, unsigned grid, size_t smem) {
   TF_CHECK_CUDA(cudaFuncSetAttribute(k_tc_rowgemm<NSPLIT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_tc_rowgemm<NSPLIT, EPI><<<grid, kRowThreads, smem, st>>>(g);
+  k_tc_rowgemm<NSPLIT, EPI><<<grid, kRowThreads, smem, st>>>(g, tm);
   TF_CHECK_LAUNCH();
   return 0;
 }
@@ -505,14 +584,33 @@ static int launch_rowgemm(cudaStream_t st, RowGemmArgs g) {
   // weights resident in smem for the whole kernel when they fit next to >= 2 A-only stages
   const size_t wres = (size_t)((g.K_pad + KC - 1) / KC) * NSPLIT * tile_bytes(g.N_pad, KC);
   const size_t a_stage = (size_t)NSPLIT * tile_bytes(128, KC);
+  constexpr size_t kRaw = (size_t)128 * KC * 4;
+  // raw A ring by TMA when A is 16-byte aligned with 16-byte row pitch
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  const bool tma = !getenv("TENSORF_TC_NO_TMA") && make_a_tensor_map(&tm, g.A, g.M, g.K_valid, g.lda, KC);
   g.resident = 0;
   size_t stage_sz = stage, base = g.header_bytes;
-  if (!getenv("TENSORF_TC_STREAM_W") && g.header_bytes + wres + 2 * a_stage <= 227 * 1024) {
+  if (!getenv("TENSORF_TC_STREAM_W") && g.header_bytes + wres + (tma ? kGroups * a_stage + 3 * kRaw + 1024 : 2 * a_stage) <= 227 * 1024) {
     g.resident = 1;
     stage_sz = a_stage;
     base += wres;
   }
-  int stages = (int)std::min<size_t>(8, (227 * 1024 - base) / stage_sz);
+  size_t avail = 227 * 1024 - base;
+  g.raw_slots = 0;
+  if (tma) {
+    // the raw ring hides the global latency: give it up to 6 slots, keep at least one operand stage per group
+    avail -= 1024;  // alignment slack of the ring (1024-byte swizzle atoms)
+    const size_t min_stages = (size_t)kGroups * stage_sz;
+    if (avail >= min_stages + 2 * kRaw) {
+      g.raw_slots = (int)std::min<size_t>(6, (avail - min_stages) / kRaw);
+      if (const char* e = getenv("TENSORF_TC_RAW_SLOTS")) g.raw_slots = std::max(2, std::min(g.raw_slots, atoi(e)));
+      avail -= (size_t)g.raw_slots * kRaw;
+    } else {
+      avail += 1024;
+    }
+  }
+  int stages = (int)std::min<size_t>(g.raw_slots ? 6 : 8, avail / stage_sz);
   TF_CHECK_ARG(stages >= 2, "tc rowgemm: tile too large for shared memory");
   if (const char* e = getenv("TENSORF_TC_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));
   g.trace = getenv("TENSORF_TC_TRACE") != nullptr;
@@ -523,16 +621,16 @@ static int launch_rowgemm(cudaStream_t st, RowGemmArgs g) {
   stages = stages / g.groups * g.groups;
   g.stages = stages;
   g.tmem_cols = pow2_cols(2 * g.N_pad);
-  const size_t smem = base + stages * stage_sz;
+  const size_t smem = base + stages * stage_sz + (g.raw_slots ? 1024 + (size_t)g.raw_slots * kRaw : 0);
   const int64_t ntiles = (g.M + 127) / 128;
   const unsigned grid = (unsigned)std::min<int64_t>(ntiles, kSMs);
   const int epi = (g.bits_in ? EPI_BITS_IN : 0) | (g.bits_out ? EPI_BITS_OUT : 0) | (g.rgb_out ? EPI_OUT3 : 0);
   switch (epi) {
-    case 0: return launch_rowgemm_epi<NSPLIT, 0>(st, g, grid, smem);
-    case EPI_BITS_IN: return launch_rowgemm_epi<NSPLIT, EPI_BITS_IN>(st, g, grid, smem);
-    case EPI_BITS_OUT: return launch_rowgemm_epi<NSPLIT, EPI_BITS_OUT>(st, g, grid, smem);
-    case EPI_BITS_IN | EPI_BITS_OUT: return launch_rowgemm_epi<NSPLIT, EPI_BITS_IN | EPI_BITS_OUT>(st, g, grid, smem);
-    case EPI_OUT3: return launch_rowgemm_epi<NSPLIT, EPI_OUT3>(st, g, grid, smem);
+    case 0: return launch_rowgemm_epi<NSPLIT, 0>(st, g, tm, grid, smem);
+    case EPI_BITS_IN: return launch_rowgemm_epi<NSPLIT, EPI_BITS_IN>(st, g, tm, grid, smem);
+    case EPI_BITS_OUT: return launch_rowgemm_epi<NSPLIT, EPI_BITS_OUT>(st, g, tm, grid, smem);
+    case EPI_BITS_IN | EPI_BITS_OUT: return launch_rowgemm_epi<NSPLIT, EPI_BITS_IN | EPI_BITS_OUT>(st, g, tm, grid, smem);
+    case EPI_OUT3: return launch_rowgemm_epi<NSPLIT, EPI_OUT3>(st, g, tm, grid, smem);
     default: set_error("tc rowgemm: unsupported epilogue combination %d", epi); return TENSORF_ERR_UNSUPPORTED;
   }
 }

@@ -67,6 +67,15 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
                : "memory");
 }
 
+// TMA tiled load (UTMALDG): one 2-D box of a tensor map -> shared memory, completion on an mbarrier.
+// c0 = innermost (column) coordinate, c1 = row coordinate, in elements; out-of-bounds parts are zero-filled.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // shared -> global bulk store (UBLKCP.G.S) of a contiguous run, tracked by bulk groups
 __device__ __forceinline__ void bulk_store_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
