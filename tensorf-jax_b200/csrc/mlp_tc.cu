@@ -159,6 +159,9 @@ struct RowGemmArgs {
   const uint32_t* cams;       // camera index per ray
   int rows_per_ray;
   float* rgb_out;             // (M,3)
+  float* enc_x;               // EPI_ENC (Dense_0): the Fourier-encoded MLP input x (M, enc_ldx) is written by the epilogue
+  const float* enc_vd;        //   viewdirs (M / rows_per_ray, 3)
+  int enc_ldx, enc_squash, enc_Ff, enc_Fv;
   int groups;                 // active producer groups; stages % groups == 0 (see launch_rowgemm)
   int raw_slots;              // > 0: A chunks arrive by TMA (tensor map) into a raw fp32 ring of this many slots
   uint32_t tmem_cols;         // power of two >= 2*N_pad
@@ -179,7 +182,7 @@ constexpr int kMmaWarp = kEpiWarps, kLoadWarp = kEpiWarps + 1, kRawWarp = kEpiWa
 constexpr int kRowThreads = 32 * kProdWarp0 + kGroups * kGroupThreads;
 constexpr int kRawSlotsMax = 8;
 constexpr int kRowFixed = 6144;  // barriers [0,1K), bias [1K,2K), W3/b3 [2K,4K), out3 exchange [4K,6K)
-enum : int { EPI_BITS_IN = 1, EPI_BITS_OUT = 2, EPI_OUT3 = 4 };
+enum : int { EPI_BITS_IN = 1, EPI_BITS_OUT = 2, EPI_OUT3 = 4, EPI_ENC = 8 };
 
 template <int NSPLIT, int EPI>
 __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, const __grid_constant__ CUtensorMap tmapA) {
@@ -292,8 +295,6 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
           x[it][0] = v0.x; x[it][1] = v0.y; x[it][2] = v0.z; x[it][3] = v0.w;
           x[it][4] = v1.x; x[it][5] = v1.y; x[it][6] = v1.z; x[it][7] = v1.w;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&rempty[sl]);  // values are in registers: the slot may be refilled
       }
       mbar_wait_backoff(&empty[st], ph ^ 1, 100 + (int)seq);
       if (pw == 0 && lane == 0) TF_TRACE(1, seq);
@@ -307,6 +308,13 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
         split_store<NSPLIT>(x[it], sA, a_tile, tile_offset(row, k8 * 8, KC));
       }
       if (pw == 0 && lane == 0) TF_TRACE(2, seq);
+      if (T > 0) {
+        // Release the raw slot only now: the converted values have been consumed (true data dependence on the
+        // shared-memory loads).  Releasing right after ISSUING the loads let the TMA refill overwrite the slot
+        // before some loads had read it (measured: ~0.2 % of rows wrong, run to run).
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rempty[(uint32_t)(seq % T)]);
+      }
       fence_proxy_async();
       mbar_arrive(&full[st]);
       if (pw == 0 && lane == 0) TF_TRACE(3, seq);
@@ -410,6 +418,9 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
         if ((EPI & EPI_OUT3) && g.embed && mbase + TF_ROFF(rr) < g.M)
           em_off[rr] = (int)g.cams[(mbase + TF_ROFF(rr)) / g.rows_per_ray] * 128;
       }
+      int ray[4];  // EPI_ENC: viewdir row of each row's ray
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) ray[rr] = (EPI & EPI_ENC) ? (int)(min(mbase + TF_ROFF(rr), g.M - 1) / g.rows_per_ray) : 0;
       float o3[4][3];
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) o3[rr][0] = o3[rr][1] = o3[rr][2] = 0.f;
@@ -443,6 +454,30 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
             if ((EPI & EPI_BITS_IN) && !((mw >> q) & 1u)) y = 0.f;
             if ((EPI & EPI_BITS_OUT) && y > 0.f) ow[rr] |= 1u << q;
             v[blk][(e >> 1) * 4 + h * 2 + (e & 1)] = y;
+            if (EPI & EPI_ENC) {
+              // networks.py:13-35, :68-76: x = [f, v, enc(f), enc(v)]; this thread owns source dimension n of row mr
+              // (n < squash: the accumulator; the next 3 padding columns stand in for the view direction)
+              const int n = n0 + q;
+              if (mr < g.M && n < g.enc_squash + 3) {
+                const int D = g.enc_squash + 3;
+                float val = y;
+                int F = g.enc_Ff, off = D + n * 2 * g.enc_Ff;
+                if (n >= g.enc_squash) {
+                  val = __ldg(g.enc_vd + (int64_t)ray[rr] * 3 + (n - g.enc_squash));
+                  F = g.enc_Fv;
+                  off = D + g.enc_squash * 2 * g.enc_Ff + (n - g.enc_squash) * 2 * g.enc_Fv;
+                }
+                float* xr = g.enc_x + mr * g.enc_ldx;
+                xr[n] = val;
+                float scale = 1.0f;
+                for (int jf = 0; jf < F; ++jf) {
+                  const float in = val * scale;  // exact: power-of-two scaling
+                  xr[off + jf] = sinf(in);
+                  xr[off + F + jf] = sinf(__fadd_rn(in, 1.57079632679489661923f));
+                  scale *= 2.0f;
+                }
+              }
+            }
             if (EPI & EPI_OUT3) {
               const int n = n0 + q;
               float yf = y;
@@ -602,9 +637,11 @@ static int launch_rowgemm(cudaStream_t st, RowGemmArgs g) {
     // the raw ring hides the global latency: give it up to 6 slots, keep at least one operand stage per group
     avail -= 1024;  // alignment slack of the ring (1024-byte swizzle atoms)
     const size_t min_stages = (size_t)kGroups * stage_sz;
-    if (avail >= min_stages + 2 * kRaw) {
-      g.raw_slots = (int)std::min<size_t>(6, (avail - min_stages) / kRaw);
-      if (const char* e = getenv("TENSORF_TC_RAW_SLOTS")) g.raw_slots = std::max(2, std::min(g.raw_slots, atoi(e)));
+    if (avail >= min_stages + kGroups * kRaw) {
+      // A producer group may only wait on a raw slot whose previous occupant it consumed itself (a parity wait
+      // cannot tell "previous fill not landed yet" from "my fill landed"): slot count = multiple of the group count
+      g.raw_slots = (int)std::min<size_t>(2 * kGroups, (avail - min_stages) / kRaw) / kGroups * kGroups;
+      if (const char* e = getenv("TENSORF_TC_RAW_SLOTS")) g.raw_slots = std::max(kGroups, std::min(g.raw_slots, atoi(e)) / kGroups * kGroups);
       avail -= (size_t)g.raw_slots * kRaw;
     } else {
       avail += 1024;
@@ -624,9 +661,13 @@ static int launch_rowgemm(cudaStream_t st, RowGemmArgs g) {
   const size_t smem = base + stages * stage_sz + (g.raw_slots ? 1024 + (size_t)g.raw_slots * kRaw : 0);
   const int64_t ntiles = (g.M + 127) / 128;
   const unsigned grid = (unsigned)std::min<int64_t>(ntiles, kSMs);
-  const int epi = (g.bits_in ? EPI_BITS_IN : 0) | (g.bits_out ? EPI_BITS_OUT : 0) | (g.rgb_out ? EPI_OUT3 : 0);
+  if (getenv("TENSORF_TC_DEBUG"))
+    fprintf(stderr, "rowgemm<%d> M=%lld K=%d/%d N=%d resident=%d stages=%d groups=%d raw_slots=%d smem=%zu\n", NSPLIT, (long long)g.M,
+            g.K_valid, g.K_pad, g.N_pad, g.resident, g.stages, g.groups, g.raw_slots, smem);
+  const int epi = (g.bits_in ? EPI_BITS_IN : 0) | (g.bits_out ? EPI_BITS_OUT : 0) | (g.rgb_out ? EPI_OUT3 : 0) | (g.enc_x ? EPI_ENC : 0);
   switch (epi) {
     case 0: return launch_rowgemm_epi<NSPLIT, 0>(st, g, tm, grid, smem);
+    case EPI_ENC: return launch_rowgemm_epi<NSPLIT, EPI_ENC>(st, g, tm, grid, smem);
     case EPI_BITS_IN: return launch_rowgemm_epi<NSPLIT, EPI_BITS_IN>(st, g, tm, grid, smem);
     case EPI_BITS_OUT: return launch_rowgemm_epi<NSPLIT, EPI_BITS_OUT>(st, g, tm, grid, smem);
     case EPI_BITS_IN | EPI_BITS_OUT: return launch_rowgemm_epi<NSPLIT, EPI_BITS_IN | EPI_BITS_OUT>(st, g, tm, grid, smem);
@@ -1103,6 +1144,9 @@ static int launch_pack_jobs(cudaStream_t st, const PackJobs& jobs) {
 }
 
 struct RowEpilogue {  // optional fused pieces of a row GEMM
+  float* enc_x = nullptr;  // Dense_0: write the encoded input x = [f, v, enc(f), enc(v)] from the epilogue
+  const float* enc_vd = nullptr;
+  int enc_ldx = 0, enc_squash = 0, enc_Ff = 0, enc_Fv = 0;
   const uint32_t* bits_in = nullptr;
   uint32_t* bits_out = nullptr;
   const float *w3 = nullptr, *b3 = nullptr, *embed = nullptr;
@@ -1135,6 +1179,9 @@ static int rowgemm_tiled(cudaStream_t st, const float* A, int64_t lda, int64_t M
       TF_CHECK_ARG(!ep.rgb_out || nn == 128, "fused output layer needs N == 128");
       g.bits_in = ep.bits_in; g.bits_out = ep.bits_out;
       g.w3 = ep.w3; g.b3 = ep.b3; g.embed = ep.embed; g.cams = ep.cams; g.rows_per_ray = ep.rows_per_ray; g.rgb_out = ep.rgb_out;
+      TF_CHECK_ARG(!ep.enc_x || (N_total <= 256 && ep.enc_squash + 3 <= nn && ep.rows_per_ray >= 1 && !ep.rgb_out && !ep.bits_in && !ep.bits_out),
+                   "fused encode needs a single column tile with 3 spare columns");
+      g.enc_x = ep.enc_x; g.enc_vd = ep.enc_vd; g.enc_ldx = ep.enc_ldx; g.enc_squash = ep.enc_squash; g.enc_Ff = ep.enc_Ff; g.enc_Fv = ep.enc_Fv;
       TF_RETURN_IF_ERROR(launch_rowgemm<NSPLIT>(st, g));
     }
     scratch += packed_weight_bytes<NSPLIT>(K_pad, nn);
@@ -1213,8 +1260,18 @@ int mlp_tc_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const flo
   RowEpilogue none;
   for (int i = 0; i < 6; ++i) TF_RETURN_IF_ERROR(plan.gemm(st, i, &jobs, none, nullptr));
   TF_RETURN_IF_ERROR(launch_pack_jobs(st, jobs));
-  TF_RETURN_IF_ERROR(plan.gemm(st, 0, nullptr, none, nullptr));
-  TF_RETURN_IF_ERROR(mlp_encode_fwd(st, s, ws, viewdirs, M, rows_per_ray));
+  // Dense_0 with the Fourier encode fused into its epilogue: x = [f, v, enc(f), enc(v)] is written straight from the
+  // accumulator fragments (the three padding columns after f stand in for the view direction), so there is no encode
+  // kernel and f is not re-read.  Needs squash + 3 <= ceil16(squash) columns; otherwise the standalone kernel runs.
+  if (s.squash + 3 <= ws.ldf && getenv("TENSORF_TC_ENC_FUSION")) {  // off by default: measured slower than the standalone kernel so far
+    RowEpilogue e0;
+    e0.enc_x = ws.x; e0.enc_vd = viewdirs; e0.enc_ldx = ws.ldx; e0.enc_squash = s.squash; e0.enc_Ff = s.Ff; e0.enc_Fv = s.Fv;
+    e0.rows_per_ray = rows_per_ray;
+    TF_RETURN_IF_ERROR(plan.gemm(st, 0, nullptr, e0, nullptr));
+  } else {
+    TF_RETURN_IF_ERROR(plan.gemm(st, 0, nullptr, none, nullptr));
+    TF_RETURN_IF_ERROR(mlp_encode_fwd(st, s, ws, viewdirs, M, rows_per_ray));
+  }
   RowEpilogue e1;
   e1.bits_out = ws.bits1;
   TF_RETURN_IF_ERROR(plan.gemm(st, 1, nullptr, e1, nullptr));

@@ -60,3 +60,30 @@ def test_redgemm(cuda, rows, Mg, Nx):
     ref = X.double().cpu().T @ G.double().cpu()
     err = _rel(out.cpu().numpy(), ref.numpy())
     assert err < 2e-5, f"redgemm rows={rows} Mg={Mg} Nx={Nx}: rel err {err:.3e}"
+
+
+@pytest.mark.parametrize("K,N,nsplit", [(128, 128, 2), (160, 128, 3), (128, 128, 3), (144, 32, 3)])
+def test_rowgemm_bitwise_reproducible(cuda, K, N, nsplit):
+    """Race detector for the warp-specialised pipeline (TMA raw ring, operand stages, TMEM double buffer): the
+    same launch on the same data must give bit-identical results, and every run must match fp64.  148 CTAs x
+    8 tiles each keeps all rings wrapping many times."""
+    from tensorf_b200 import _lib, ops
+    M = 148 * 8 * 128
+    rng = np.random.default_rng(7)
+    A = torch.from_numpy(rng.normal(size=(M, K)).astype(np.float32)).to(cuda)
+    W = torch.from_numpy((rng.normal(size=(K, N)) / np.sqrt(K)).astype(np.float32)).to(cuda)
+    bias = torch.zeros(N, device=cuda)
+    scratch = torch.empty(8 << 20, dtype=torch.uint8, device=cuda)
+    ref = (A.double() @ W.double()).clamp_min(0)
+    lib = _lib.load()
+    first = None
+    for rep in range(4):
+        out = torch.full((M, N), float("nan"), dtype=torch.float32, device=cuda)
+        _lib.check(lib.tensorf_tc_rowgemm_test(ops._stream(), A.data_ptr(), M, K, W.data_ptr(), N, bias.data_ptr(), 1, None, None,
+                                               out.data_ptr(), scratch.data_ptr(), scratch.numel(), nsplit))
+        err = float((out.double() - ref).abs().max())
+        assert err < (2e-4 if nsplit == 2 else 3e-5), (rep, err)
+        if first is None:
+            first = out
+        else:
+            assert torch.equal(out, first), f"run {rep} differs from run 0 in {int((out != first).sum())} elements"
