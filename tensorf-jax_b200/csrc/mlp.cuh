@@ -65,8 +65,9 @@ int mlp_tc_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const flo
 size_t mlp_tc_wpack_bytes(const MlpShape& s);
 
 // pieces shared by both implementations (mlp_simt.cu)
-int mlp_encode_fwd(cudaStream_t st, const MlpShape& s, const MlpWs& ws, const float* viewdirs, int64_t M, int rows_per_ray);
-int mlp_encode_bwd(cudaStream_t st, const MlpShape& s, const MlpWs& ws, int64_t M);
+int mlp_encode_fwd(cudaStream_t st, const MlpShape& s, const MlpWs& ws, const float* viewdirs, int64_t M, int rows_per_ray,
+                   bool fast = false);
+int mlp_encode_bwd(cudaStream_t st, const MlpShape& s, const MlpWs& ws, int64_t M, bool fast = false);
 int mlp_out_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const MlpWs& ws, const uint32_t* cams, int64_t M,
                 int rows_per_ray, float* rgb);
 int mlp_out_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const MlpWs& ws, const uint32_t* cams, int64_t M,

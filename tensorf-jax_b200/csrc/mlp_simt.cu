@@ -156,6 +156,10 @@ static int launch_sgemm(cudaStream_t st, GemmArgs g, int splits) {
 // ---------------------------------------------------------------------------------------------
 // Fourier encoding (networks.py:13-35, :68-76)
 // ---------------------------------------------------------------------------------------------
+// FAST (tensor-core path): even frequency levels by sincosf (one shared range reduction; cos(a) stands in for the
+// reference's sin(a + pi/2), equal up to the rounding of a + pi/2), odd levels by the double-angle identities
+// (~3 ulp) - half the transcendental work.  !FAST (exact fp32 path): the reference's expressions verbatim.
+template <bool FAST>
 __global__ void __launch_bounds__(256) k_encode_fwd(const float* __restrict__ f, const float* __restrict__ viewdirs,
                                                     float* __restrict__ x, int64_t M, int rows_per_ray, MlpShape s, int ldf,
                                                     int ldx) {
@@ -181,6 +185,20 @@ __global__ void __launch_bounds__(256) k_encode_fwd(const float* __restrict__ f,
   row[d] = val;
   const float half_pi = 1.57079632679489661923f;
   float scale = 1.0f;
+  if (FAST) {
+    for (int j = 0; j < F; j += 2) {
+      float sn, cs;
+      sincosf(val * scale, &sn, &cs);
+      row[off + j] = sn;
+      row[off + F + j] = cs;
+      if (j + 1 < F) {
+        row[off + j + 1] = 2.0f * sn * cs;
+        row[off + F + j + 1] = fmaf(-2.0f * sn, sn, 1.0f);
+      }
+      scale *= 4.0f;
+    }
+    return;
+  }
   for (int j = 0; j < F; ++j) {
     float in = val * scale;  // exact: power-of-two scaling
     row[off + j] = sinf(in);
@@ -189,6 +207,7 @@ __global__ void __launch_bounds__(256) k_encode_fwd(const float* __restrict__ f,
   }
 }
 
+template <bool FAST>
 __global__ void __launch_bounds__(256) k_encode_bwd(const float* __restrict__ f, const float* __restrict__ dx,
                                                     float* __restrict__ df, int64_t M, MlpShape s, int ldf, int ldx) {
   int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -201,6 +220,18 @@ __global__ void __launch_bounds__(256) k_encode_bwd(const float* __restrict__ f,
   int off = s.squash + 3 + d * 2 * s.Ff;
   const float half_pi = 1.57079632679489661923f;
   float scale = 1.0f;
+  if (FAST) {  // d/din sin(in) = cos(in), d/din sin(in + pi/2) = -sin(in); odd levels by double angle
+    for (int j = 0; j < s.Ff; j += 2) {
+      float sn, cs;
+      sincosf(val * scale, &sn, &cs);
+      g += scale * (row[off + j] * cs - row[off + s.Ff + j] * sn);
+      if (j + 1 < s.Ff)
+        g += 2.0f * scale * (row[off + j + 1] * fmaf(-2.0f * sn, sn, 1.0f) - row[off + s.Ff + j + 1] * (2.0f * sn * cs));
+      scale *= 4.0f;
+    }
+    df[m * ldf + d] = g;
+    return;
+  }
   for (int j = 0; j < s.Ff; ++j) {
     float in = val * scale;
     g += scale * (row[off + j] * cosf(in) + row[off + s.Ff + j] * cosf(__fadd_rn(in, half_pi)));
@@ -401,14 +432,22 @@ __global__ void __launch_bounds__(256) k_colsum128(const float* __restrict__ G, 
 }
 
 // ---------------------------------------------------------------------------------------------
-int mlp_encode_fwd(cudaStream_t st, const MlpShape& s, const MlpWs& ws, const float* viewdirs, int64_t M, int rows_per_ray) {
-  k_encode_fwd<<<(unsigned)ceil_div64(M * (s.squash + 3), 256), 256, 0, st>>>(ws.f, viewdirs, ws.x, M, rows_per_ray, s, ws.ldf,
-                                                                            ws.ldx);
+int mlp_encode_fwd(cudaStream_t st, const MlpShape& s, const MlpWs& ws, const float* viewdirs, int64_t M, int rows_per_ray,
+                   bool fast) {
+  const unsigned grid = (unsigned)ceil_div64(M * (s.squash + 3), 256);
+  if (fast)
+    k_encode_fwd<true><<<grid, 256, 0, st>>>(ws.f, viewdirs, ws.x, M, rows_per_ray, s, ws.ldf, ws.ldx);
+  else
+    k_encode_fwd<false><<<grid, 256, 0, st>>>(ws.f, viewdirs, ws.x, M, rows_per_ray, s, ws.ldf, ws.ldx);
   TF_CHECK_LAUNCH();
   return 0;
 }
-int mlp_encode_bwd(cudaStream_t st, const MlpShape& s, const MlpWs& ws, int64_t M) {
-  k_encode_bwd<<<(unsigned)ceil_div64(M * s.squash, 256), 256, 0, st>>>(ws.f, ws.dx, ws.df, M, s, ws.ldf, ws.ldx);
+int mlp_encode_bwd(cudaStream_t st, const MlpShape& s, const MlpWs& ws, int64_t M, bool fast) {
+  const unsigned grid = (unsigned)ceil_div64(M * s.squash, 256);
+  if (fast)
+    k_encode_bwd<true><<<grid, 256, 0, st>>>(ws.f, ws.dx, ws.df, M, s, ws.ldf, ws.ldx);
+  else
+    k_encode_bwd<false><<<grid, 256, 0, st>>>(ws.f, ws.dx, ws.df, M, s, ws.ldf, ws.ldx);
   TF_CHECK_LAUNCH();
   return 0;
 }
@@ -436,16 +475,38 @@ int mlp_colsum128(cudaStream_t st, const float* G, float* out, int64_t M) {
   TF_CHECK_LAUNCH();
   return 0;
 }
+// All MLP gradient leaves are zeroed by ONE launch (8 separate memsets cost ~2 us each in launch gaps).
+struct ZeroJobs {
+  float* p[8];
+  int64_t n[8];
+};
+__global__ void __launch_bounds__(256) k_zero_multi(ZeroJobs z) {
+  float* p = z.p[blockIdx.y];
+  const int64_t n = z.n[blockIdx.y];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0.f;
+}
 int mlp_zero_grads(cudaStream_t st, const MlpShape& s, const MlpGrads& gr) {
   const int U = s.units;
-  TF_CHECK_CUDA(cudaMemsetAsync(gr.w0, 0, sizeof(float) * s.Ca * s.squash, st));
-  TF_CHECK_CUDA(cudaMemsetAsync(gr.w1, 0, sizeof(float) * s.enc * U, st));
-  TF_CHECK_CUDA(cudaMemsetAsync(gr.b1, 0, sizeof(float) * U, st));
-  TF_CHECK_CUDA(cudaMemsetAsync(gr.w2, 0, sizeof(float) * U * U, st));
-  TF_CHECK_CUDA(cudaMemsetAsync(gr.b2, 0, sizeof(float) * U, st));
-  TF_CHECK_CUDA(cudaMemsetAsync(gr.w3, 0, sizeof(float) * U * 3, st));
-  TF_CHECK_CUDA(cudaMemsetAsync(gr.b3, 0, sizeof(float) * 3, st));
-  if (s.ncam) TF_CHECK_CUDA(cudaMemsetAsync(gr.embed, 0, sizeof(float) * (int64_t)s.ncam * U, st));
+  ZeroJobs z{};
+  int k = 0;
+  auto add = [&](float* p, int64_t n) {
+    if (p && n > 0) {
+      z.p[k] = p;
+      z.n[k] = n;
+      ++k;
+    }
+  };
+  add(gr.w0, (int64_t)s.Ca * s.squash);
+  add(gr.w1, (int64_t)s.enc * U);
+  add(gr.b1, U);
+  add(gr.w2, (int64_t)U * U);
+  add(gr.b2, U);
+  add(gr.w3, (int64_t)U * 3);
+  add(gr.b3, 3);
+  if (s.ncam) add(gr.embed, (int64_t)s.ncam * U);
+  if (k == 0) return 0;
+  k_zero_multi<<<dim3(64, k), 256, 0, st>>>(z);
+  TF_CHECK_LAUNCH();
   return 0;
 }
 

@@ -469,12 +469,26 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
                 }
                 float* xr = g.enc_x + mr * g.enc_ldx;
                 xr[n] = val;
+                // Even frequency levels are evaluated directly (sincosf shares one range reduction; cos(a) stands in
+                // for the reference's sin(a + pi/2), which differs by the rounding of a + pi/2 only); odd levels come
+                // from the double-angle identities, ~3 ulp.  Half the transcendental work of 2F sinf calls.
                 float scale = 1.0f;
-                for (int jf = 0; jf < F; ++jf) {
-                  const float in = val * scale;  // exact: power-of-two scaling
-                  xr[off + jf] = sinf(in);
-                  xr[off + F + jf] = sinf(__fadd_rn(in, 1.57079632679489661923f));
-                  scale *= 2.0f;
+                for (int jf = 0; jf < F; jf += 2) {
+                  float sn, cs;
+                  sincosf(val * scale, &sn, &cs);  // val * 2^jf is exact
+                  const float sn2 = 2.0f * sn * cs, cs2 = fmaf(-2.0f * sn, sn, 1.0f);
+                  if (jf + 1 < F && ((reinterpret_cast<uintptr_t>(xr + off + jf) | reinterpret_cast<uintptr_t>(xr + off + F + jf)) & 7) == 0) {
+                    *reinterpret_cast<float2*>(xr + off + jf) = make_float2(sn, sn2);
+                    *reinterpret_cast<float2*>(xr + off + F + jf) = make_float2(cs, cs2);
+                  } else {
+                    xr[off + jf] = sn;
+                    xr[off + F + jf] = cs;
+                    if (jf + 1 < F) {
+                      xr[off + jf + 1] = sn2;
+                      xr[off + F + jf + 1] = cs2;
+                    }
+                  }
+                  scale *= 4.0f;
                 }
               }
             }
@@ -1270,7 +1284,7 @@ int mlp_tc_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const flo
     TF_RETURN_IF_ERROR(plan.gemm(st, 0, nullptr, e0, nullptr));
   } else {
     TF_RETURN_IF_ERROR(plan.gemm(st, 0, nullptr, none, nullptr));
-    TF_RETURN_IF_ERROR(mlp_encode_fwd(st, s, ws, viewdirs, M, rows_per_ray));
+    TF_RETURN_IF_ERROR(mlp_encode_fwd(st, s, ws, viewdirs, M, rows_per_ray, true));
   }
   RowEpilogue e1;
   e1.bits_out = ws.bits1;
@@ -1306,7 +1320,7 @@ int mlp_tc_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const flo
   r.out = gr.w1; r.ldo = U; r.colsum = gr.b1;
   TF_RETURN_IF_ERROR(launch_redgemm(st, r));
   TF_RETURN_IF_ERROR(plan.gemm(st, 4, nullptr, none, nullptr));
-  TF_RETURN_IF_ERROR(mlp_encode_bwd(st, s, ws, M));
+  TF_RETURN_IF_ERROR(mlp_encode_bwd(st, s, ws, M, true));
   // dW0[k][n] = sum_rows feat[row][k] * df[row][n]
   r = RedGemmArgs{};
   r.G = ws.df; r.ldg = ws.ldf; r.Mg = s.squash; r.X = feat; r.ldx = s.Ca; r.Nx = s.Ca; r.N_pad = round_up(s.Ca, 16); r.rows = M;
