@@ -378,8 +378,8 @@ int tensorf_render_rgb_fwd(tensorf_stream_t s, const tensorf_render_desc* d, con
 
   {
     StageTimer t_(st, "pack");
-    TF_RETURN_IF_ERROR(vm_pack(st, p->density_vector, p->density_matrix, w.packed_d, d->cd, d->G));
-    TF_RETURN_IF_ERROR(vm_pack(st, p->appearance_vector, p->appearance_matrix, w.packed_a, d->ca, d->G));
+    TF_RETURN_IF_ERROR(vm_pack2(st, p->density_vector, p->density_matrix, w.packed_d, d->cd, p->appearance_vector,
+                                p->appearance_matrix, w.packed_a, d->ca, d->G));
   }
 
   DensityArgs a{};
@@ -506,8 +506,8 @@ int tensorf_render_rgb_bwd(tensorf_stream_t s, const tensorf_render_desc* d, con
     TF_RETURN_IF_ERROR(launch_appearance_scatter(st, ap));
   }
   StageTimer t_(st, "unpack");
-  TF_RETURN_IF_ERROR(vm_unpack(st, w.gpacked_d, grads->density_vector, grads->density_matrix, d->cd, d->G));
-  TF_RETURN_IF_ERROR(vm_unpack(st, w.gpacked_a, grads->appearance_vector, grads->appearance_matrix, d->ca, d->G));
+  TF_RETURN_IF_ERROR(vm_unpack2(st, w.gpacked_d, grads->density_vector, grads->density_matrix, d->cd, w.gpacked_a,
+                                grads->appearance_vector, grads->appearance_matrix, d->ca, d->G));
   return 0;
 }
 

@@ -80,6 +80,9 @@ int launch_appearance_scatter(cudaStream_t st, const AppearanceArgs& A);
 
 int vm_pack(cudaStream_t st, const float* vector, const float* matrix, float* packed, int C, int G);
 int vm_unpack(cudaStream_t st, const float* packed, float* vector, float* matrix, int C, int G);
+int vm_pack2(cudaStream_t st, const float* v0, const float* m0, float* p0, int C0, const float* v1, const float* m1, float* p1, int C1,
+             int G);
+int vm_unpack2(cudaStream_t st, const float* p0, float* v0, float* m0, int C0, const float* p1, float* v1, float* m1, int C1, int G);
 int vm_interp_fwd(cudaStream_t st, const float* packed, const float* ijk, float* out, int C, int G, int64_t B, int feature_major);
 int vm_interp_bwd(cudaStream_t st, const float* packed, const float* ijk, const float* d_out, float* d_packed, int C, int G,
                   int64_t B, int feature_major);

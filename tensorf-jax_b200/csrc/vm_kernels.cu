@@ -1,5 +1,7 @@
 // TensorVM kernels: layout pack/unpack and the standalone `TensorVM.interpolate`
 // forward / reverse (tensor_vm.py:42-89, :140-167, :226-250).
+#include <algorithm>
+
 #include "vm.cuh"
 
 namespace tf {
@@ -7,30 +9,50 @@ namespace tf {
 // ---- pack: channel-first (C, T) -> texel-major (T, Cp) ---------------------------------------
 // One CTA moves 32 texels x all channels through shared memory: reads are coalesced along the
 // texel axis (the reference's contiguous axis), writes are one contiguous 32*Cp-float run.
+// Up to 4 arrays (lines and planes of the density and appearance factors) go out in ONE launch: the
+// per-array kernels were launch-bound at 128^3 (4 launches of 5-12 us for 12.7 MB).
+struct PackJob {
+  const float* src;
+  float* dst;
+  int C, Cp;
+  int64_t T;               // texels per pair
+  int64_t tiles_per_pair;  // ceil(T / 32)
+  int64_t block_begin;     // first CTA of this job
+};
+struct PackJobsVm {
+  PackJob j[4];
+  int n;
+};
+
 template <bool UNPACK>
-__global__ void __launch_bounds__(256) k_pack(const float* __restrict__ src, float* __restrict__ dst, int C, int Cp,
-                                              int64_t T /* texels per pair */, int64_t tiles_per_pair) {
+__global__ void __launch_bounds__(256) k_pack(const __grid_constant__ PackJobsVm jobs) {
   extern __shared__ float tile[];  // [Cp][33]
-  int64_t tile_id = blockIdx.x;
-  int P = (int)(tile_id / tiles_per_pair);
-  int64_t t0 = (tile_id % tiles_per_pair) * 32;
+  int ji = 0;
+#pragma unroll 1
+  while (ji + 1 < jobs.n && (int64_t)blockIdx.x >= jobs.j[ji + 1].block_begin) ++ji;
+  const PackJob& J = jobs.j[ji];
+  const int C = J.C, Cp = J.Cp;
+  const int64_t T = J.T;
+  const int64_t tile_id = (int64_t)blockIdx.x - J.block_begin;
+  const int P = (int)(tile_id / J.tiles_per_pair);
+  const int64_t t0 = (tile_id % J.tiles_per_pair) * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 warps
   if (!UNPACK) {
-    const float* s = src + (int64_t)P * C * T;
+    const float* s = J.src + (int64_t)P * C * T;
     for (int c = ty; c < Cp; c += 8) {
       int64_t t = t0 + tx;
       tile[c * 33 + tx] = (c < C && t < T) ? s[(int64_t)c * T + t] : 0.0f;
     }
     __syncthreads();
-    float* d = dst + ((int64_t)P * T + t0) * Cp;
+    float* d = J.dst + ((int64_t)P * T + t0) * Cp;
     int64_t n = min((int64_t)32, T - t0) * Cp;
     for (int i = threadIdx.x; i < n; i += 256) d[i] = tile[(i % Cp) * 33 + (i / Cp)];
   } else {
-    const float* s = src + ((int64_t)P * T + t0) * Cp;
+    const float* s = J.src + ((int64_t)P * T + t0) * Cp;
     int64_t n = min((int64_t)32, T - t0) * Cp;
     for (int i = threadIdx.x; i < n; i += 256) tile[(i % Cp) * 33 + (i / Cp)] = s[i];
     __syncthreads();
-    float* d = dst + (int64_t)P * C * T;
+    float* d = J.dst + (int64_t)P * C * T;
     for (int c = ty; c < C; c += 8) {
       int64_t t = t0 + tx;
       if (t < T) d[(int64_t)c * T + t] = tile[c * 33 + tx];
@@ -38,26 +60,62 @@ __global__ void __launch_bounds__(256) k_pack(const float* __restrict__ src, flo
   }
 }
 
+// factors[i] = {vector, matrix, packed, C}; G shared.  UNPACK: packed -> vector/matrix.
 template <bool UNPACK>
-static int launch_pack(cudaStream_t st, const float* src, float* dst, int C, int64_t T) {
-  int Cp = packed_cp(C);
-  int64_t tiles = ceil_div64(T, 32);
-  size_t smem = (size_t)Cp * 33 * sizeof(float);
-  TF_CHECK_ARG(smem <= 48 * 1024, "channel dim %d too large for pack kernel", C);
-  k_pack<UNPACK><<<(unsigned)(3 * tiles), 256, smem, st>>>(src, dst, C, Cp, T, tiles);
+static int launch_pack_multi(cudaStream_t st, int nf, const float* const* vec, const float* const* mat, const float* const* packed,
+                             const int* C, int G) {
+  PackJobsVm jobs{};
+  int64_t blocks = 0;
+  int maxCp = 0;
+  for (int f = 0; f < nf; ++f) {
+    const int Cp = packed_cp(C[f]);
+    maxCp = std::max(maxCp, Cp);
+    for (int part = 0; part < 2; ++part) {
+      PackJob& J = jobs.j[jobs.n++];
+      const float* chan_first = part == 0 ? vec[f] : mat[f];
+      const float* pk = packed[f] + (part == 0 ? 0 : packed_line_floats(C[f], G));
+      J.src = UNPACK ? pk : chan_first;
+      J.dst = const_cast<float*>(UNPACK ? chan_first : pk);
+      J.C = C[f];
+      J.Cp = Cp;
+      J.T = part == 0 ? G : (int64_t)G * G;
+      J.tiles_per_pair = ceil_div64(J.T, 32);
+      J.block_begin = blocks;
+      blocks += 3 * J.tiles_per_pair;
+    }
+  }
+  const size_t smem = (size_t)maxCp * 33 * sizeof(float);
+  TF_CHECK_ARG(smem <= 48 * 1024, "channel dim too large for pack kernel (Cp=%d)", maxCp);
+  TF_CHECK_ARG(blocks < ((int64_t)1 << 31), "pack: grid too large");
+  k_pack<UNPACK><<<(unsigned)blocks, 256, smem, st>>>(jobs);
   TF_CHECK_LAUNCH();
   return 0;
 }
 
 int vm_pack(cudaStream_t st, const float* vector, const float* matrix, float* packed, int C, int G) {
-  TF_RETURN_IF_ERROR(launch_pack<false>(st, vector, packed, C, G));
-  TF_RETURN_IF_ERROR(launch_pack<false>(st, matrix, packed + packed_line_floats(C, G), C, (int64_t)G * G));
-  return 0;
+  const float* pk = packed;
+  return launch_pack_multi<false>(st, 1, &vector, &matrix, &pk, &C, G);
 }
 int vm_unpack(cudaStream_t st, const float* packed, float* vector, float* matrix, int C, int G) {
-  TF_RETURN_IF_ERROR(launch_pack<true>(st, packed, vector, C, G));
-  TF_RETURN_IF_ERROR(launch_pack<true>(st, packed + packed_line_floats(C, G), matrix, C, (int64_t)G * G));
-  return 0;
+  const float* v = vector;
+  const float* m = matrix;
+  return launch_pack_multi<true>(st, 1, &v, &m, &packed, &C, G);
+}
+// density + appearance factors in one launch
+int vm_pack2(cudaStream_t st, const float* v0, const float* m0, float* p0, int C0, const float* v1, const float* m1, float* p1, int C1,
+             int G) {
+  const float* v[2] = {v0, v1};
+  const float* m[2] = {m0, m1};
+  const float* p[2] = {p0, p1};
+  const int C[2] = {C0, C1};
+  return launch_pack_multi<false>(st, 2, v, m, p, C, G);
+}
+int vm_unpack2(cudaStream_t st, const float* p0, float* v0, float* m0, int C0, const float* p1, float* v1, float* m1, int C1, int G) {
+  const float* v[2] = {v0, v1};
+  const float* m[2] = {m0, m1};
+  const float* p[2] = {p0, p1};
+  const int C[2] = {C0, C1};
+  return launch_pack_multi<true>(st, 2, v, m, p, C, G);
 }
 
 // ---- standalone interpolate -----------------------------------------------------------------
