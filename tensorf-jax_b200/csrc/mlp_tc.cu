@@ -249,10 +249,16 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
     // 8 consecutive lanes fill one 128-byte core matrix (8 rows x 16 B).
     const int grp = (warp - kProdWarp0) >> 2, pw = (warp - kProdWarp0) & 3;
     const bool vec_ok = (g.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
-    for (int64_t seq = grp; seq < total && grp < g.groups; seq += g.groups) {
-      const int64_t t = blockIdx.x + (seq / nchunks) * gridDim.x;
-      const int k0 = (int)(seq % nchunks) * KC;
-      const uint32_t st = (uint32_t)(seq % S), ph = (uint32_t)((seq / S) & 1);
+    // chunk sequence number seq -> (tile, k-chunk), operand stage and raw slot are tracked incrementally: 64-bit
+    // divisions by run-time values cost ~25 instructions each and there were six of them per chunk.
+    // S and T are multiples of the group count, so stage / slot indices advance by `groups` and wrap exactly.
+    const int ngrp = g.groups, ntot = (int)total;
+    int c_idx = grp % nchunks;                                   // k-chunk of the tile
+    int64_t t = blockIdx.x + (int64_t)(grp / nchunks) * gridDim.x;  // tile
+    uint32_t st = (uint32_t)grp, ph = 0, sl = (uint32_t)grp, rph = 0;
+    const uint32_t raw_s = smem_u32(raw0);
+    for (int seq = grp; seq < ntot && grp < ngrp; seq += ngrp) {
+      const int k0 = c_idx * KC;
       if (pw == 0 && lane == 0) TF_TRACE(0, seq);
       float x[ITEMS][8];
 #pragma unroll
@@ -281,22 +287,21 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
       if (T > 0) {
         // raw slot: [128 rows][128 B], 16-byte unit u of row r stored at unit u ^ (r & 7) (SWIZZLE_128B);
         // 8 consecutive lanes read the same logical unit of 8 consecutive rows -> 8 distinct units
-        const uint32_t sl = (uint32_t)(seq % T), rph = (uint32_t)((seq / T) & 1);
-        const unsigned char* raw = raw0 + (size_t)sl * kRawBytes;
-        mbar_wait_backoff(&rfull[sl], rph, 300 + (int)seq);
+        const uint32_t raw = raw_s + sl * kRawBytes;
+        mbar_wait_backoff(&rfull[sl], rph, 300 + seq);
 #pragma unroll
         for (int it = 0; it < ITEMS; ++it) {
           const int q = it * 4 + pw;
           const int rb = q / (KC / 32), kh = q % (KC / 32);
           const int row = rb * 8 + (lane & 7);
           const int u = (kh * 4 + (lane >> 3)) * 2;
-          const float4 v0 = *reinterpret_cast<const float4*>(raw + row * 128 + ((u ^ (row & 7)) << 4));
-          const float4 v1 = *reinterpret_cast<const float4*>(raw + row * 128 + (((u + 1) ^ (row & 7)) << 4));
+          const float4 v0 = lds128(raw + row * 128 + ((u ^ (row & 7)) << 4));
+          const float4 v1 = lds128(raw + row * 128 + (((u + 1) ^ (row & 7)) << 4));
           x[it][0] = v0.x; x[it][1] = v0.y; x[it][2] = v0.z; x[it][3] = v0.w;
           x[it][4] = v1.x; x[it][5] = v1.y; x[it][6] = v1.z; x[it][7] = v1.w;
         }
       }
-      mbar_wait_backoff(&empty[st], ph ^ 1, 100 + (int)seq);
+      mbar_wait_backoff(&empty[st], ph ^ 1, 100 + seq);
       if (pw == 0 && lane == 0) TF_TRACE(1, seq);
       unsigned char* sA = stage0 + (size_t)st * stage_bytes;
 #pragma unroll
@@ -313,11 +318,29 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
         // shared-memory loads).  Releasing right after ISSUING the loads let the TMA refill overwrite the slot
         // before some loads had read it (measured: ~0.2 % of rows wrong, run to run).
         __syncwarp();
-        if (lane == 0) mbar_arrive(&rempty[(uint32_t)(seq % T)]);
+        if (lane == 0) mbar_arrive(&rempty[sl]);
       }
       fence_proxy_async();
       mbar_arrive(&full[st]);
       if (pw == 0 && lane == 0) TF_TRACE(3, seq);
+      // advance to this group's next chunk
+      c_idx += ngrp;
+      while (c_idx >= nchunks) {
+        c_idx -= nchunks;
+        t += gridDim.x;
+      }
+      st += (uint32_t)ngrp;
+      if (st >= (uint32_t)S) {
+        st -= (uint32_t)S;
+        ph ^= 1;
+      }
+      if (T > 0) {
+        sl += (uint32_t)ngrp;
+        if (sl >= (uint32_t)T) {
+          sl -= (uint32_t)T;
+          rph ^= 1;
+        }
+      }
     }
   } else if (warp == kLoadWarp) {
     // ================= weight loader: one bulk copy per chunk =================
@@ -327,25 +350,32 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
       for (int c = 0; c < nchunks; ++c)
         bulk_copy_g2s(wres + (size_t)c * NSPLIT * b_tile, g.Bp + (size_t)c * NSPLIT * b_tile, NSPLIT * b_tile, wfull);
     } else if (lane == 0) {
-      for (int64_t seq = 0; seq < total; ++seq) {
-        const uint32_t st = (uint32_t)(seq % S), ph = (uint32_t)((seq / S) & 1);
-        const int c = (int)(seq % nchunks);
-        mbar_wait_backoff(&empty[st], ph ^ 1, 200 + (int)seq);
+      uint32_t st = 0, ph = 0;
+      int c = 0;
+      for (int seq = 0; seq < (int)total; ++seq) {
+        mbar_wait_backoff(&empty[st], ph ^ 1, 200 + seq);
         unsigned char* sB = stage0 + (size_t)st * stage_bytes + NSPLIT * a_tile;
         mbar_arrive_expect_tx(&full[st], NSPLIT * b_tile);
         bulk_copy_g2s(sB, g.Bp + (size_t)c * NSPLIT * b_tile, NSPLIT * b_tile, &full[st]);
+        if (++c == nchunks) c = 0;
+        if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == kRawWarp) {
     // ================= TMA loader of the raw A ring: one 2-D box (128 rows x KC columns) per chunk ==========
     if (lane == 0 && T > 0) {
-      for (int64_t seq = 0; seq < total; ++seq) {
-        const uint32_t sl = (uint32_t)(seq % T), ph = (uint32_t)((seq / T) & 1);
-        const int64_t t = blockIdx.x + (seq / nchunks) * gridDim.x;
-        const int k0 = (int)(seq % nchunks) * KC;
-        mbar_wait_backoff(&rempty[sl], ph ^ 1, 400 + (int)seq);
+      uint32_t sl = 0, ph = 0;
+      int c = 0;
+      int64_t t = blockIdx.x;
+      for (int seq = 0; seq < (int)total; ++seq) {
+        mbar_wait_backoff(&rempty[sl], ph ^ 1, 400 + seq);
         mbar_arrive_expect_tx(&rfull[sl], kRawBytes);  // the whole box counts, zero-filled parts included
-        tma_load_2d(raw0 + (size_t)sl * kRawBytes, &tmapA, k0, (int)(t * 128), &rfull[sl]);
+        tma_load_2d(raw0 + (size_t)sl * kRawBytes, &tmapA, c * KC, (int)(t * 128), &rfull[sl]);
+        if (++c == nchunks) {
+          c = 0;
+          t += gridDim.x;
+        }
+        if (++sl == (uint32_t)T) { sl = 0; ph ^= 1; }
       }
     }
   } else if (warp == kMmaWarp) {
@@ -407,6 +437,9 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
     const int ch_begin = half ? (nch + 1) / 2 : 0, ch_end = half ? nch : (nch + 1) / 2;
     const int c_begin = ch_begin * 16, c_cols = (ch_end - ch_begin) * 16;
     const bool vec_ok = (g.ldc % 2 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 7) == 0);
+    // every column of the tile is stored and rows are 8-byte aligned: unconditional 8-byte stores
+    const bool fast_store = vec_ok && g.N_store == g.N_pad;
+    const float relu_floor = g.relu ? 0.f : -INFINITY;
     const int words = (g.N_pad + 31) / 32;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const int64_t mbase = t * 128 + quad * 32 + lrow;  // row rr = mbase + roff(rr)
@@ -421,6 +454,10 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
       int ray[4];  // EPI_ENC: viewdir row of each row's ray
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) ray[rr] = (EPI & EPI_ENC) ? (int)(min(mbase + TF_ROFF(rr), g.M - 1) / g.rows_per_ray) : 0;
+      float* crow[4];  // this thread's first column of each of its rows (null: row outside the matrix / no C)
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+        crow[rr] = (g.C != nullptr && mbase + TF_ROFF(rr) < g.M) ? g.C + (mbase + TF_ROFF(rr)) * g.ldc + c_begin + lc : nullptr;
       float o3[4][3];
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) o3[rr][0] = o3[rr][1] = o3[rr][2] = 0.f;
@@ -449,8 +486,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
 #pragma unroll
           for (int e = 0; e < 4; ++e) {               // e = 2*(8-column group) + (column within the pair)
             const int q = (e >> 1) * 8 + lc + (e & 1);  // column within the 16-column chunk
-            float y = v[blk][(e >> 1) * 4 + h * 2 + (e & 1)] + bq[e];
-            if (g.relu) y = fmaxf(y, 0.f);
+            const float y0 = v[blk][(e >> 1) * 4 + h * 2 + (e & 1)] + bq[e];
+            float y = fmaxf(y0, relu_floor);  // relu_floor = 0 or -inf: no per-element branch
             if ((EPI & EPI_BITS_IN) && !((mw >> q) & 1u)) y = 0.f;
             if ((EPI & EPI_BITS_OUT) && y > 0.f) ow[rr] |= 1u << q;
             v[blk][(e >> 1) * 4 + h * 2 + (e & 1)] = y;
@@ -514,16 +551,18 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
           const int64_t mq = mbase + TF_ROFF(lq);
           if (mq < g.M) reinterpret_cast<uint16_t*>(g.bits_out + mq * words)[n0 >> 4] = (uint16_t)(mine >> ((lq & 1) * 16));
         }
-        if (g.C != nullptr) {
 #pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
-            const int64_t mr = mbase + TF_ROFF(rr);
-            if (mr >= g.M) continue;
-            const int blk = rr >> 1, h = rr & 1;
+        for (int rr = 0; rr < 4; ++rr) {
+          if (crow[rr] == nullptr) continue;
+          const int blk = rr >> 1, h = rr & 1;
+          if (fast_store) {
+            *reinterpret_cast<float2*>(crow[rr]) = make_float2(v[blk][h * 2], v[blk][h * 2 + 1]);
+            *reinterpret_cast<float2*>(crow[rr] + 8) = make_float2(v[blk][4 + h * 2], v[blk][4 + h * 2 + 1]);
+          } else {
 #pragma unroll
             for (int gq = 0; gq < 2; ++gq) {
               const int n = n0 + gq * 8 + lc;
-              float* dst = g.C + mr * g.ldc + n;
+              float* dst = crow[rr] + gq * 8;
               const float y0 = v[blk][gq * 4 + h * 2], y1 = v[blk][gq * 4 + h * 2 + 1];
               if (vec_ok && n + 1 < g.N_store) {
                 *reinterpret_cast<float2*>(dst) = make_float2(y0, y1);
@@ -533,6 +572,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
               }
             }
           }
+          crow[rr] += 16;
         }
       }
       if (tid == 0) TF_TRACE(5, (t - blockIdx.x) / gridDim.x);
@@ -959,9 +999,8 @@ __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, 
     const int grp = (warp - 6) / kConvGroupWarps;
     const int ct = tid - 192 - grp * 32 * kConvGroupWarps;
     const int a_items = 128 * (kRC / 8), b_items = g.N_pad * (kRC / 8);
+    uint32_t sl = (uint32_t)grp, sph = 0, st = (uint32_t)grp, ph = 0;  // advanced incrementally (no run-time divisions)
     for (int c = grp; c < nchunks; c += kConvGroups) {
-      const uint32_t sl = (uint32_t)(c % T), sph = (uint32_t)((c / T) & 1);
-      const uint32_t st = (uint32_t)(c % S), ph = (uint32_t)((c / S) & 1);
       const int64_t r0 = r_begin + (int64_t)c * kRC;
       const int nrows = (int)min((int64_t)kRC, r_end - r0);
       const float* sG = slot0 + (size_t)sl * slot_floats;
@@ -1011,6 +1050,10 @@ __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, 
         mbar_arrive(&sempty[sl]);   // staging slot may be overwritten
       }
       if (ct == 0) TF_TRACE(3, c);
+      sl += kConvGroups;
+      if (sl >= (uint32_t)T) { sl -= (uint32_t)T; sph ^= 1; }
+      st += kConvGroups;
+      if (st >= (uint32_t)S) { st -= (uint32_t)S; ph ^= 1; }
     }
   } else if (warp == 4) {
     {  // warp-uniform issue loop (see k_tc_rowgemm): descriptors stay in uniform registers

@@ -76,6 +76,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
                : "memory");
 }
 
+// 16-byte load from a shared-window byte address (keeps the access an LDS even when the pointer's address space is
+// not visible to the compiler)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
 // shared -> global bulk store (UBLKCP.G.S) of a contiguous run, tracked by bulk groups
 __device__ __forceinline__ void bulk_store_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
