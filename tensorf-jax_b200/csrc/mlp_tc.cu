@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);                // tcgen05.commit
-      mbar_init(&tempty[a], 32 * kEpiWarps);  // epilogue threads
+      mbar_init(&tempty[a], 32 * kEpiWarps / 2);  // the 4 epilogue warps that own this accumulator
     }
     fence_barrier_init();
   }
@@ -430,18 +430,20 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
     // 2*(lane%4) + {0,1} of every 8-column group.  Row-wise results (ReLU bit masks, the fused output
     // layer) are combined across the 4 lanes of a row with two xor-shuffles.
     // ReLU masks travel as one bit per element (bits_out / bits_in), not as fp32 activations.
-    uint32_t acc = 0, acc_ph = 0;
-    const int quad = warp & 3, half = warp >> 2;
+    // The 8 warps form two sets of 4 (one warp per TMEM lane quadrant); set s owns the CTA's tiles s, s+2, ...
+    // and TMEM accumulator s, and handles all columns of its tiles.  Two tiles are in the epilogue at once, so
+    // one set's per-tile overhead (accumulator wait, row set-up) overlaps the other set's column loop.
+    const int quad = warp & 3, eset = warp >> 2;
+    const uint32_t acc = (uint32_t)eset;
+    uint32_t acc_ph = 0;
     const int lrow = lane >> 2, lq = lane & 3, lc = lq * 2;
-    const int nch = g.N_pad / 16;                               // 16-column chunks of the tile
-    const int ch_begin = half ? (nch + 1) / 2 : 0, ch_end = half ? nch : (nch + 1) / 2;
-    const int c_begin = ch_begin * 16, c_cols = (ch_end - ch_begin) * 16;
+    const int c_begin = 0, c_cols = g.N_pad;
     const bool vec_ok = (g.ldc % 2 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 7) == 0);
     // every column of the tile is stored and rows are 8-byte aligned: unconditional 8-byte stores
     const bool fast_store = vec_ok && g.N_store == g.N_pad;
     const float relu_floor = g.relu ? 0.f : -INFINITY;
     const int words = (g.N_pad + 31) / 32;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    for (int64_t t = blockIdx.x + (int64_t)eset * gridDim.x; t < ntiles; t += 2 * (int64_t)gridDim.x) {
       const int64_t mbase = t * 128 + quad * 32 + lrow;  // row rr = mbase + roff(rr)
 #define TF_ROFF(rr) ((((rr) >> 1) * 16) + (((rr) & 1) * 8))
       int em_off[4];  // FiLM conditioner row of each row's camera (networks.py:103-111), -1 = none
@@ -577,8 +579,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
       }
       if (tid == 0) TF_TRACE(5, (t - blockIdx.x) / gridDim.x);
       if (EPI & EPI_OUT3) {
-        // sum the row's partial outputs over its 4 lanes; both column halves contribute: half 1 publishes
-        // through s_xch ([128 rows][3]), half 0 adds, applies the sigmoid, stores
+        // sum the row's partial outputs over its 4 lanes, apply the sigmoid, store
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
@@ -589,23 +590,16 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
         float mine3[3];  // lane lq keeps row rr == lq
 #pragma unroll
         for (int c = 0; c < 3; ++c) mine3[c] = lq == 0 ? o3[0][c] : lq == 1 ? o3[1][c] : lq == 2 ? o3[2][c] : o3[3][c];
-        const int rloc = quad * 32 + TF_ROFF(lq) + lrow;
-        float* xch = s_xch + rloc * 3;
-        if (half == 1) {
-          xch[0] = mine3[0]; xch[1] = mine3[1]; xch[2] = mine3[2];
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
-        const int64_t mm = t * 128 + rloc;
-        if (half == 0 && mm < g.M) {
+        const int64_t mm = mbase + TF_ROFF(lq);
+        if (mm < g.M) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) g.rgb_out[3 * mm + c] = 1.0f / (1.0f + expf(-(mine3[c] + xch[c] + s_w3[384 + c])));
+          for (int c = 0; c < 3; ++c) g.rgb_out[3 * mm + c] = 1.0f / (1.0f + expf(-(mine3[c] + s_w3[384 + c])));
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       if (tid == 0) TF_TRACE(7, (t - blockIdx.x) / gridDim.x);
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
-      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      acc_ph ^= 1;
     }
 #undef TF_ROFF
   }
