@@ -167,7 +167,7 @@ def bench_render(ops, dev, world, rank, dist, chunks=6, warm=2):
     out = {"workload": w.name, "rays_per_chunk": w.R, "chunks_timed": chunks}
     for label, mode in (("rgb", ops.MODE_RGB), ("dist_median", ops.MODE_DIST_MEDIAN), ("dist_mean", ops.MODE_DIST_MEAN)):
         desc = ops.make_desc(R=w.R, N=w.N, K=w.K, G=w.G, cd=w.cd, ca=w.ca, mode=mode, feat_freqs=w.feat_freqs,
-                             view_freqs=w.view_freqs)
+                             view_freqs=w.view_freqs, inference=True)  # render_360.py never differentiates
         call = ops.RenderCall(desc, dev)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for i, st in enumerate(starts):

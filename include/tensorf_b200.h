@@ -43,6 +43,10 @@ enum tensorf_status {
 /* render.py:18-23 (RenderMode) */
 enum tensorf_render_mode { TENSORF_MODE_RGB = 0, TENSORF_MODE_DIST_MEDIAN = 1, TENSORF_MODE_DIST_MEAN = 2 };
 
+/* TENSORF_FLAG_INFERENCE: forward only (render_360.py, render_rays_batched): residuals that only the reverse pass
+ * reads (ReLU masks, second hidden layer) are not written; tensorf_render_rgb_bwd / tensorf_mlp_bwd then fail. */
+enum tensorf_render_flags { TENSORF_FLAG_INFERENCE = 1 };
+
 /* MLP arithmetic: exact fp32 on CUDA cores, or tcgen05 tensor cores with split-bf16 operands. */
 enum tensorf_mlp_impl { TENSORF_MLP_AUTO = 0, TENSORF_MLP_SIMT_FP32 = 1, TENSORF_MLP_TCGEN05 = 2 };
 
@@ -64,7 +68,7 @@ typedef struct tensorf_render_desc {
   int32_t num_cameras; /* 0 = no camera embeddings */
   int32_t mlp_impl;    /* tensorf_mlp_impl */
   float loss_scale;    /* 1/(3*R_global): training.py:140 is a mean over the WHOLE batch */
-  int32_t reserved;
+  int32_t flags;       /* tensorf_render_flags */
 } tensorf_render_desc;
 
 /* Leaves of render.py:39-46 (LearnableParams), reference layouts. `embed` may be NULL when

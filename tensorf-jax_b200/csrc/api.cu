@@ -439,6 +439,7 @@ int tensorf_render_rgb_bwd(tensorf_stream_t s, const tensorf_render_desc* d, con
                            const tensorf_params* grads) {
   TF_RETURN_IF_ERROR(check_desc(d));
   TF_CHECK_ARG(d->mode == TENSORF_MODE_RGB, "render_rgb_bwd needs mode RGB");
+  TF_CHECK_ARG(!(d->flags & TENSORF_FLAG_INFERENCE), "render_rgb_bwd after a forward with TENSORF_FLAG_INFERENCE (residuals were not kept)");
   TF_RETURN_IF_ERROR(check_inputs(d, in));
   TF_RETURN_IF_ERROR(check_mlp_params(*d, p, "params"));
   TF_RETURN_IF_ERROR(check_mlp_params(*d, grads, "grads"));

@@ -11,6 +11,7 @@ struct MlpShape {
   int Ff, Fv;  // fourier frequencies
   int enc;     // encoded dim (networks.py:77-82)
   int ncam;    // 0 = no embeddings
+  int inference;  // forward only: skip residuals of the reverse pass (TENSORF_FLAG_INFERENCE)
 };
 
 inline MlpShape mlp_shape(const tensorf_render_desc& d) {
@@ -18,6 +19,7 @@ inline MlpShape mlp_shape(const tensorf_render_desc& d) {
   s.Ca = 3 * d.ca;
   s.squash = d.squash;
   s.units = d.units;
+  s.inference = (d.flags & TENSORF_FLAG_INFERENCE) != 0;
   s.Ff = d.feat_freqs;
   s.Fv = d.view_freqs;
   s.enc = d.squash + 3 + 2 * d.feat_freqs * d.squash + 2 * d.view_freqs * 3;

@@ -1224,7 +1224,7 @@ static int rowgemm_tiled(cudaStream_t st, const float* A, int64_t lda, int64_t M
     } else {
       RowGemmArgs g{};
       g.A = A; g.lda = lda; g.M = M; g.K_valid = K_valid; g.K_pad = K_pad; g.Bp = scratch; g.N_pad = nn;
-      g.C = C + n0; g.ldc = ldc; g.N_store = std::min(nn, N_store_total - n0);
+      g.C = C ? C + n0 : nullptr; g.ldc = ldc; g.N_store = std::min(nn, N_store_total - n0);
       g.bias = bias ? bias + n0 : nullptr; g.relu = relu;
       TF_CHECK_ARG(!(ep.bits_in || ep.bits_out || ep.rgb_out) || N_total <= 256, "fused epilogues need a single column tile");
       TF_CHECK_ARG(!ep.rgb_out || nn == 128, "fused output layer needs N == 128");
@@ -1289,7 +1289,9 @@ struct TcPlan {
       case 1:  // Dense_1 + relu (+ ReLU bitmask for the reverse pass)
         return rowgemm_tiled<kFwdSplit>(st, ws.x, ws.ldx, M, s.enc, p.w1, U, 1, U, ws.h1, U, U, p.b1, 1, ep, sc[1], collect);
       case 2:  // Dense_2 + relu (+ fused FiLM / Dense_3 / sigmoid)
-        return rowgemm_tiled<kFwdSplit>(st, ws.h1, U, M, U, p.w2, U, 1, U, ws.h2, U, U, p.b2, 1, ep, sc[2], collect);
+        // (forward-only calls do not keep h2: the fused output layer consumes it in registers)
+        return rowgemm_tiled<kFwdSplit>(st, ws.h1, U, M, U, p.w2, U, 1, U, (s.inference && ep.rgb_out) ? nullptr : ws.h2, U, U, p.b2, 1,
+                                        ep, sc[2], collect);
       case 3:  // dp1 = (dp2 @ W2^T) * relu'(h1)
         return rowgemm_tiled<kBwdSplit>(st, ws.dp2, U, M, U, p.w2, 1, U, U, ws.dp1, U, U, nullptr, 0, ep, sc[3], collect);
       case 4:  // dx = dp1 @ W1^T
@@ -1324,7 +1326,7 @@ int mlp_tc_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const flo
     TF_RETURN_IF_ERROR(mlp_encode_fwd(st, s, ws, viewdirs, M, rows_per_ray, true));
   }
   RowEpilogue e1;
-  e1.bits_out = ws.bits1;
+  e1.bits_out = s.inference ? nullptr : ws.bits1;
   TF_RETURN_IF_ERROR(plan.gemm(st, 1, nullptr, e1, nullptr));
   RowEpilogue e2;
   e2.w3 = p.w3; e2.b3 = p.b3; e2.embed = s.ncam ? p.embed : nullptr; e2.cams = cams; e2.rows_per_ray = rows_per_ray;
@@ -1337,6 +1339,7 @@ int mlp_tc_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const flo
                float* d_feat, const MlpGrads& gr) {
   const int U = s.units;
   (void)viewdirs;
+  TF_CHECK_ARG(!s.inference, "mlp reverse pass after a forward with TENSORF_FLAG_INFERENCE (residuals were not kept)");
   TF_RETURN_IF_ERROR(mlp_zero_grads(st, s, gr));
   if (M == 0) return 0;
   TcPlan plan(s, p, ws, feat, M);  // weights were packed by mlp_tc_fwd on the same workspace

@@ -36,7 +36,7 @@ class RenderDesc(C.Structure):
         ("R", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("G", C.c_int32),
         ("cd", C.c_int32), ("ca", C.c_int32), ("mode", C.c_int32), ("contracted", C.c_int32),
         ("squash", C.c_int32), ("units", C.c_int32), ("feat_freqs", C.c_int32), ("view_freqs", C.c_int32),
-        ("num_cameras", C.c_int32), ("mlp_impl", C.c_int32), ("loss_scale", C.c_float), ("reserved", C.c_int32),
+        ("num_cameras", C.c_int32), ("mlp_impl", C.c_int32), ("loss_scale", C.c_float), ("flags", C.c_int32),
     ]
 
 

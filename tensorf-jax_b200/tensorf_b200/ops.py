@@ -16,6 +16,7 @@ from ._lib import PARAM_FIELDS, AdamDesc, Params, RenderDesc, RenderInputs, chec
 
 MODE_RGB, MODE_DIST_MEDIAN, MODE_DIST_MEAN = 0, 1, 2
 MLP_AUTO, MLP_SIMT_FP32, MLP_TCGEN05 = 0, 1, 2
+FLAG_INFERENCE = 1  # forward only: residuals of the reverse pass are not kept
 
 
 def _stream() -> C.c_void_p:
@@ -36,10 +37,10 @@ def _ptr(t: Optional[torch.Tensor], dtype=torch.float32, name: str = "tensor") -
 
 def make_desc(R: int, N: int, K: int, G: int, cd: int, ca: int, mode: int = MODE_RGB, contracted: bool = False,
               feat_freqs: int = 6, view_freqs: int = 6, num_cameras: Optional[int] = None, loss_scale: float = 0.0,
-              squash: int = 27, units: int = 128, mlp_impl: int = MLP_AUTO) -> RenderDesc:
+              squash: int = 27, units: int = 128, mlp_impl: int = MLP_AUTO, inference: bool = False) -> RenderDesc:
     return RenderDesc(R=R, N=N, K=K, G=G, cd=cd, ca=ca, mode=mode, contracted=int(bool(contracted)), squash=squash,
                       units=units, feat_freqs=feat_freqs, view_freqs=view_freqs, num_cameras=int(num_cameras or 0),
-                      mlp_impl=mlp_impl, loss_scale=loss_scale, reserved=0)
+                      mlp_impl=mlp_impl, loss_scale=loss_scale, flags=FLAG_INFERENCE if inference else 0)
 
 
 def encoded_dim(desc: RenderDesc) -> int:

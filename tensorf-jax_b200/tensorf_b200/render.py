@@ -169,6 +169,13 @@ def render_rays(appearance_mlp: networks.FeatureMlp, learnable_params: Learnable
         inputs["deltas"] = torch.from_numpy(delta).to(device)
     if config.mode is RenderMode.RGB:
         names = tuple(n for n in ops.param_shapes(desc))
+        if not (torch.is_grad_enabled() and any(flat[n].requires_grad for n in names)):
+            # nothing will be differentiated (render_360.py, validation): forward-only call, no residuals kept
+            desc.flags = ops.FLAG_INFERENCE
+            call = _acquire(desc, device)
+            rgb, _ = call.forward({n: flat[n].detach().contiguous() for n in names}, inputs)
+            _release(call)
+            return rgb
         return _RenderRgb.apply(desc, inputs, names, *[flat[n] for n in names])
     call = _acquire(desc, device)
     out = call.depth({k: flat[k].contiguous() for k in ("density_vector", "density_matrix")}, inputs)

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import tensorf_oracle as O
-from helpers import T, assert_close_grad, assert_close_out, kink_rows, oracle_cfgs
+from helpers import T, assert_close_grad, assert_close_out, device_inputs, kink_rows, oracle_cfgs
 from tensorf_b200 import synthetic as S
 
 pytestmark = pytest.mark.gpu
@@ -171,3 +171,23 @@ def test_training_step(cuda):
     after = state.learnable_params.flat()
     assert all(not torch.equal(before[k], after[k]) for k in ("w1", "appearance_matrix"))
     assert abs(log["train/lr_tensor"] - 0.02 * 0.1 ** (24 / 30000)) < 1e-7
+
+
+def test_inference_flag_matches_training_forward(cuda):
+    """TENSORF_FLAG_INFERENCE (render_360.py / validation): same pixels bit for bit, no residuals, and the reverse
+    pass refuses to run on such a call."""
+    from tensorf_b200 import _lib, ops
+    w = S.Workload("inf", 300, 16, 6, 8, 40, 12, 2, 2)
+    inp = S.make_inputs(w, bias_std=0.05)
+    params, dins = device_inputs(w, inp, cuda)
+    kw = dict(R=w.R, N=w.N, K=w.K, G=w.G, cd=w.cd, ca=w.ca, feat_freqs=w.feat_freqs, view_freqs=w.view_freqs,
+              loss_scale=1.0 / (3 * w.R))
+    train = ops.RenderCall(ops.make_desc(**kw), cuda)
+    infer = ops.RenderCall(ops.make_desc(inference=True, **kw), cuda)
+    rgb_t, loss_t = train.forward(params, dins)
+    rgb_i, loss_i = infer.forward(params, dins)
+    assert torch.equal(rgb_t, rgb_i)
+    assert abs(float(loss_t) - float(loss_i)) <= 1e-6 * float(loss_t)   # atomic sum over rays: order varies
+    train.backward()
+    with pytest.raises(_lib.TensorfError, match="INFERENCE"):
+        infer.backward()
