@@ -1,16 +1,20 @@
 // FeatureMlp (networks.py:38-121) on the 5th-generation tensor cores (tcgen05 + TMEM).
 //
-// fp32 parity (1e-4) on bf16 tensor cores: every operand x is split into hi = bf16(x) and
-// lo = bf16(x - hi); a product is accumulated as hi*hi + hi*lo + lo*hi in fp32 (TMEM), i.e.
-// three tcgen05.mma per k-step ("bf16x3", ~2^-16 relative per product).
+// fp32 parity (1e-4) on bf16 tensor cores: every operand x is split into bf16 terms hi + mid (+ lo) and a
+// product is accumulated term by term in fp32 (TMEM): 3 tcgen05.mma per k-step for the two-term split of
+// the reverse GEMMs (~2^-16 per product), 6 for the three-term split of the forward GEMMs (fp32-exact
+// operands; the composite reverse amplifies forward error).
 //
-//   k_tc_rowgemm : C[M x N] = epilogue(A[M x K] * W[K x N])     forward layers and dX
-//       persistent, warp-specialised: 4 producer warps (fp32 -> hi/lo bf16 into the canonical
-//       no-swizzle K-major UMMA layout), 1 bulk-copy thread streaming pre-packed weights
-//       (cp.async.bulk), 1 MMA-issuing thread, 4 epilogue warps (tcgen05.ld -> bias/relu/mask
-//       -> global). smem stage ring + double-buffered TMEM accumulators.
-//   k_tc_redgemm : dW^T[128 x N] += G^T[128 x rows] * X[rows x N]   weight gradients (split over
-//       rows across CTAs, RED-add epilogue).
+//   k_tc_rowgemm  : C[M x N] = epilogue(A[M x K] * W[K x N])     forward layers, dX chain
+//       persistent (1 CTA/SM), warp-specialised: one thread issues 2-D TMA loads (tensor map, 128-byte
+//       swizzle) of fp32 A chunks into a raw ring; 3 producer groups x 4 warps convert shared -> shared
+//       into the canonical no-swizzle K-major UMMA layout; weights pre-split once per call and resident in
+//       shared memory (or streamed by cp.async.bulk); one MMA warp (elect.sync leader, uniform-register
+//       descriptors); 8 epilogue warps in two sets, one TMEM accumulator each (tcgen05.ld.16x256b ->
+//       bias / ReLU / 1-bit masks / fused output layer / fused Fourier encode -> 32-byte-sector global stores).
+//   k_tc_redgemm2 : dW^T[128 x N] += G^T[128 x rows] * X[rows x N]   weight (and bias) gradients: rows split
+//       across CTAs, raw fp32 row chunks by cp.async.bulk, 2 converter groups transpose + split, RED-add
+//       epilogue.  k_tc_redgemm is the register-staged fallback for unaligned operands.
 #include <stdlib.h>
 #include <string.h>
 
@@ -147,11 +151,9 @@ struct RowGemmArgs {
   uint32_t* bits_out;         // receives bit(m,n) = C(m,n) > 0 (the ReLU mask for the reverse pass), or null
   int relu;
   int stages;
-  int no_bulk;                // debug: force the direct-store epilogue
   int trace;                  // debug: record the CTA-0 timeline into g_trace
-  int out_stride;             // floats per epilogue staging row (columns per half tile + 4), 0 = no staging
   int resident;               // 1: all weight chunks live in smem for the whole kernel (loaded once)
-  int header_bytes;           // kRowFixed + staging
+  int header_bytes;           // kRowFixed
   // fused output layer (networks.py:103-120): FiLM + Dense(3) + sigmoid on the epilogue's rows (N_pad == 128)
   const float* w3;            // (128,3) or null
   const float* b3;            // (3)
@@ -181,7 +183,7 @@ constexpr int kEpiWarps = 8;
 constexpr int kMmaWarp = kEpiWarps, kLoadWarp = kEpiWarps + 1, kRawWarp = kEpiWarps + 2, kProdWarp0 = kEpiWarps + 3;
 constexpr int kRowThreads = 32 * kProdWarp0 + kGroups * kGroupThreads;
 constexpr int kRawSlotsMax = 8;
-constexpr int kRowFixed = 6144;  // barriers [0,1K), bias [1K,2K), W3/b3 [2K,4K), out3 exchange [4K,6K)
+constexpr int kRowFixed = 4096;  // barriers [0,1K), bias [1K,2K), W3/b3 [2K,4K)
 enum : int { EPI_BITS_IN = 1, EPI_BITS_OUT = 2, EPI_OUT3 = 4, EPI_ENC = 8 };
 
 template <int NSPLIT, int EPI>
@@ -198,8 +200,6 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* s_bias = reinterpret_cast<float*>(smem + 1024);   // [256] bias staged once per CTA
   float* s_w3 = reinterpret_cast<float*>(smem + 2048);     // [128*3 + 3] output layer weights + bias
-  float* s_xch = reinterpret_cast<float*>(smem + 4096);    // [128][3] partial outputs of the second column half
-  float* s_out = reinterpret_cast<float*>(smem + kRowFixed);  // [2][128][out_stride] epilogue staging rows
   const uint32_t a_tile = tile_bytes(128, KC), b_tile = tile_bytes(g.N_pad, KC);
   const int nchunks_w = (g.K_pad + KC - 1) / KC;
   // resident weights: [header][all weight chunks][A stages]; streamed: [header][stages of A+B]
@@ -661,8 +661,6 @@ static int launch_rowgemm(cudaStream_t st, RowGemmArgs g) {
   TF_CHECK_ARG(g.N_pad % 16 == 0 && g.N_pad >= 16 && g.N_pad <= 256, "tc rowgemm: N_pad=%d unsupported", g.N_pad);
   TF_CHECK_ARG(g.K_pad % 16 == 0 && g.K_pad >= 16, "tc rowgemm: K_pad=%d unsupported", g.K_pad);
   const size_t stage = (size_t)NSPLIT * (tile_bytes(128, KC) + tile_bytes(g.N_pad, KC));
-  g.no_bulk = 1;  // the epilogue stores registers straight to global memory (no staging rows)
-  g.out_stride = 0;
   g.header_bytes = kRowFixed;
   // weights resident in smem for the whole kernel when they fit next to >= 2 A-only stages
   const size_t wres = (size_t)((g.K_pad + KC - 1) / KC) * NSPLIT * tile_bytes(g.N_pad, KC);

@@ -601,28 +601,57 @@ __global__ void __launch_bounds__(256, APP ? 2 : 3) k_scatter_walk(WalkArgs A) {
   auto flush_l = [&](int i, const float4& acc) { red_add_v4(A.d_packed + lbase + (int64_t)i * Cp, acc); };
   auto flush_m = [&](int a, int b, const float4& acc) { red_add_v4(A.d_packed + mbase + ((int64_t)a * G + b) * Cp, acc); };
 
-  for (int j = j_begin; j < j_end; ++j) {
-    int s;
-    float4 g;
+  // One-sample software pipeline over the per-sample operands: the cotangent (appearance: the d_feat row, the only
+  // operand that comes from DRAM, 90 MB per step read once; density: dz), the saved grid coordinates, and for the
+  // appearance walk the selected sample index two steps ahead (the coordinate address depends on it).
+  auto load_g = [&](int j, float4& g_out) {
     if (APP) {
-      const int64_t m = (int64_t)r * A.K + j;
-      s = A.idx[m];
-      const float* src = A.d_feat + m * (3 * A.C) + P * A.C + 4 * v;
+      const float* src = A.d_feat + ((int64_t)r * A.K + j) * (3 * A.C) + P * A.C + 4 * v;
       if ((A.C & 3) == 0) {
-        g = *reinterpret_cast<const float4*>(src);
+        g_out = __ldcs(reinterpret_cast<const float4*>(src));
       } else {
         float gv[4] = {0.f, 0.f, 0.f, 0.f};
         for (int q = 0; q < 4; ++q)
           if (4 * v + q < A.C) gv[q] = src[q];
-        g = make_float4(gv[0], gv[1], gv[2], gv[3]);
+        g_out = make_float4(gv[0], gv[1], gv[2], gv[3]);
       }
     } else {
-      s = j;
-      float gz = A.dz[(int64_t)r * A.N + s];
-      g = make_float4(gz, gz, gz, gz);
+      const float gz = __ldg(A.dz + (int64_t)r * A.N + j);
+      g_out = make_float4(gz, gz, gz, gz);
     }
-    const float* xp = A.xs + ((int64_t)r * A.N + s) * 3;  // coordinates saved by the forward gather
-    const float x[3] = {xp[0], xp[1], xp[2]};
+  };
+  auto load_s = [&](int j) -> int { return APP ? __ldg(A.idx + (int64_t)r * A.K + j) : j; };
+  auto load_x = [&](int sidx, float& x0, float& x1, float& x2) {
+    const float* xp = A.xs + ((int64_t)r * A.N + sidx) * 3;  // coordinates saved by the forward gather
+    x0 = __ldg(xp);
+    x1 = __ldg(xp + 1);
+    x2 = __ldg(xp + 2);
+  };
+  // (density walk: 80 registers at 3 CTAs/SM leave no room for the pipeline registers - it spilled and lost 12 %;
+  //  its operands are L2 hits, so it loads them in place)
+  float4 g_nxt = zero4;
+  float xn0 = 0.f, xn1 = 0.f, xn2 = 0.f;
+  int s_nxt2 = 0;  // sample index of step j+2
+  if (APP && j_begin < j_end) {
+    load_g(j_begin, g_nxt);
+    load_x(load_s(j_begin), xn0, xn1, xn2);
+    if (j_begin + 1 < j_end) s_nxt2 = load_s(j_begin + 1);
+  }
+  for (int j = j_begin; j < j_end; ++j) {
+    float4 g;
+    float x[3];
+    if (APP) {
+      g = g_nxt;
+      x[0] = xn0; x[1] = xn1; x[2] = xn2;
+      if (j + 1 < j_end) {
+        load_g(j + 1, g_nxt);
+        load_x(s_nxt2, xn0, xn1, xn2);
+        if (j + 2 < j_end) s_nxt2 = load_s(j + 2);
+      }
+    } else {
+      load_g(j, g);
+      load_x(j, x[0], x[1], x[2]);
+    }
     // axis roles of pair P (tensor_vm.py:50-52), selected without indexing local arrays
     const float xl = P == 0 ? x[0] : (P == 1 ? x[2] : x[1]);
     const float xa = P == 0 ? x[1] : (P == 1 ? x[0] : x[2]);
