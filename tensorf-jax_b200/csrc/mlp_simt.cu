@@ -2,6 +2,8 @@
 // path (what the JAX CPU oracle computes) and the on-device reference for the tcgen05 path.
 #include <algorithm>
 
+#include <stdlib.h>
+
 #include "mlp.cuh"
 
 namespace tf {
@@ -164,10 +166,20 @@ __global__ void __launch_bounds__(256) k_encode_fwd(const float* __restrict__ f,
                                                     float* __restrict__ x, int64_t M, int rows_per_ray, MlpShape s, int ldf,
                                                     int ldx) {
   const int D = s.squash + 3;
-  int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (item >= M * D) return;
-  int64_t m = item / D;
-  int d = (int)(item % D);
+  // 32 lanes per row (D <= 32 source dimensions; a division-free mapping: the 64-bit div/mod by D was ~40 of the
+  // kernel's ~90 instructions per item), or the flat mapping for wider inputs
+  int64_t m;
+  int d;
+  if (D <= 32) {
+    m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    d = threadIdx.x & 31;
+    if (m >= M || d >= D) return;
+  } else {
+    const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= M * D) return;
+    m = item / D;
+    d = (int)(item % D);
+  }
   float* row = x + m * ldx;
   float val;
   int F, off;
@@ -210,10 +222,18 @@ __global__ void __launch_bounds__(256) k_encode_fwd(const float* __restrict__ f,
 template <bool FAST>
 __global__ void __launch_bounds__(256) k_encode_bwd(const float* __restrict__ f, const float* __restrict__ dx,
                                                     float* __restrict__ df, int64_t M, MlpShape s, int ldf, int ldx) {
-  int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (item >= M * s.squash) return;
-  int64_t m = item / s.squash;
-  int d = (int)(item % s.squash);
+  int64_t m;
+  int d;
+  if (s.squash <= 32) {  // 32 lanes per row, no division (see k_encode_fwd)
+    m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    d = threadIdx.x & 31;
+    if (m >= M || d >= s.squash) return;
+  } else {
+    const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= M * s.squash) return;
+    m = item / s.squash;
+    d = (int)(item % s.squash);
+  }
   const float* row = dx + m * ldx;
   float val = f[m * ldf + d];
   float g = row[d];
@@ -434,7 +454,7 @@ __global__ void __launch_bounds__(256) k_colsum128(const float* __restrict__ G, 
 // ---------------------------------------------------------------------------------------------
 int mlp_encode_fwd(cudaStream_t st, const MlpShape& s, const MlpWs& ws, const float* viewdirs, int64_t M, int rows_per_ray,
                    bool fast) {
-  const unsigned grid = (unsigned)ceil_div64(M * (s.squash + 3), 256);
+  const unsigned grid = (unsigned)(s.squash + 3 <= 32 ? ceil_div64(M, 8) : ceil_div64(M * (s.squash + 3), 256));
   if (fast)
     k_encode_fwd<true><<<grid, 256, 0, st>>>(ws.f, viewdirs, ws.x, M, rows_per_ray, s, ws.ldf, ws.ldx);
   else
@@ -443,7 +463,7 @@ int mlp_encode_fwd(cudaStream_t st, const MlpShape& s, const MlpWs& ws, const fl
   return 0;
 }
 int mlp_encode_bwd(cudaStream_t st, const MlpShape& s, const MlpWs& ws, int64_t M, bool fast) {
-  const unsigned grid = (unsigned)ceil_div64(M * s.squash, 256);
+  const unsigned grid = (unsigned)(s.squash <= 32 ? ceil_div64(M, 8) : ceil_div64(M * s.squash, 256));
   if (fast)
     k_encode_bwd<true><<<grid, 256, 0, st>>>(ws.f, ws.dx, ws.df, M, s, ws.ldf, ws.ldx);
   else
@@ -462,7 +482,9 @@ int mlp_out_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const Ml
 int mlp_out_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const MlpWs& ws, const uint32_t* cams, int64_t M,
                 int rows_per_ray, const float* rgb, const float* d_rgb, const MlpGrads& gr) {
   // chunk = whole rays (one embedding flush per ray), ~64 rows per warp, 8 warps per block
-  int64_t chunk = ceil_div64(std::max<int64_t>(64, rows_per_ray), rows_per_ray) * rows_per_ray;
+  int64_t target = 64;
+  if (const char* e = getenv("TENSORF_OUTBWD_CHUNK")) target = std::max(1, atoi(e));
+  int64_t chunk = ceil_div64(std::max<int64_t>(target, rows_per_ray), rows_per_ray) * rows_per_ray;
   int64_t warps = ceil_div64(M, chunk);
   k_out_bwd<<<(unsigned)ceil_div64(warps, 8), 256, 0, st>>>(ws.h2, p.w3, s.ncam ? p.embed : nullptr, cams, rgb, d_rgb,
                                                                     ws.dp2, gr.w3, gr.b3, gr.embed, M, rows_per_ray, chunk);
