@@ -184,7 +184,7 @@ constexpr int kMmaWarp = kEpiWarps, kLoadWarp = kEpiWarps + 1, kRawWarp = kEpiWa
 constexpr int kRowThreads = 32 * kProdWarp0 + kGroups * kGroupThreads;
 constexpr int kRawSlotsMax = 8;
 constexpr int kRowFixed = 4096;  // barriers [0,1K), bias [1K,2K), W3/b3 [2K,4K)
-enum : int { EPI_BITS_IN = 1, EPI_BITS_OUT = 2, EPI_OUT3 = 4, EPI_ENC = 8 };
+enum : int { EPI_BITS_IN = 1, EPI_BITS_OUT = 2, EPI_OUT3 = 4, EPI_ENC = 8, EPI_FILM = 16 };  // FILM: OUT3 with camera embeddings
 
 template <int NSPLIT, int EPI>
 __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, const __grid_constant__ CUtensorMap tmapA) {
@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) {
         em_off[rr] = -1;
-        if ((EPI & EPI_OUT3) && g.embed && mbase + TF_ROFF(rr) < g.M)
+        if ((EPI & EPI_FILM) && mbase + TF_ROFF(rr) < g.M)
           em_off[rr] = (int)g.cams[(mbase + TF_ROFF(rr)) / g.rows_per_ray] * 128;
       }
       int ray[4];  // EPI_ENC: viewdir row of each row's ray
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
             if (EPI & EPI_OUT3) {
               const int n = n0 + q;
               float yf = y;
-              if (em_off[rr] >= 0 && n >= 64) yf = __fadd_rn(__fmul_rn(__ldg(g.embed + em_off[rr] + n - 64), y), __ldg(g.embed + em_off[rr] + n));
+              if ((EPI & EPI_FILM) && em_off[rr] >= 0 && n >= 64) yf = __fadd_rn(__fmul_rn(__ldg(g.embed + em_off[rr] + n - 64), y), __ldg(g.embed + em_off[rr] + n));
               o3[rr][0] = fmaf(yf, s_w3[3 * n + 0], o3[rr][0]);
               o3[rr][1] = fmaf(yf, s_w3[3 * n + 1], o3[rr][1]);
               o3[rr][2] = fmaf(yf, s_w3[3 * n + 2], o3[rr][2]);
@@ -710,7 +710,8 @@ static int launch_rowgemm(cudaStream_t st, RowGemmArgs g) {
   if (getenv("TENSORF_TC_DEBUG"))
     fprintf(stderr, "rowgemm<%d> M=%lld K=%d/%d N=%d resident=%d stages=%d groups=%d raw_slots=%d smem=%zu\n", NSPLIT, (long long)g.M,
             g.K_valid, g.K_pad, g.N_pad, g.resident, g.stages, g.groups, g.raw_slots, smem);
-  const int epi = (g.bits_in ? EPI_BITS_IN : 0) | (g.bits_out ? EPI_BITS_OUT : 0) | (g.rgb_out ? EPI_OUT3 : 0) | (g.enc_x ? EPI_ENC : 0);
+  const int epi = (g.bits_in ? EPI_BITS_IN : 0) | (g.bits_out ? EPI_BITS_OUT : 0) | (g.rgb_out ? EPI_OUT3 : 0) | (g.enc_x ? EPI_ENC : 0) |
+                  (g.rgb_out && g.embed ? EPI_FILM : 0);
   switch (epi) {
     case 0: return launch_rowgemm_epi<NSPLIT, 0>(st, g, tm, grid, smem);
     case EPI_ENC: return launch_rowgemm_epi<NSPLIT, EPI_ENC>(st, g, tm, grid, smem);
@@ -718,6 +719,7 @@ static int launch_rowgemm(cudaStream_t st, RowGemmArgs g) {
     case EPI_BITS_OUT: return launch_rowgemm_epi<NSPLIT, EPI_BITS_OUT>(st, g, tm, grid, smem);
     case EPI_BITS_IN | EPI_BITS_OUT: return launch_rowgemm_epi<NSPLIT, EPI_BITS_IN | EPI_BITS_OUT>(st, g, tm, grid, smem);
     case EPI_OUT3: return launch_rowgemm_epi<NSPLIT, EPI_OUT3>(st, g, tm, grid, smem);
+    case EPI_OUT3 | EPI_FILM: return launch_rowgemm_epi<NSPLIT, EPI_OUT3 | EPI_FILM>(st, g, tm, grid, smem);
     default: set_error("tc rowgemm: unsupported epilogue combination %d", epi); return TENSORF_ERR_UNSUPPORTED;
   }
 }
