@@ -456,10 +456,16 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
       int ray[4];  // EPI_ENC: viewdir row of each row's ray
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) ray[rr] = (EPI & EPI_ENC) ? (int)(min(mbase + TF_ROFF(rr), g.M - 1) / g.rows_per_ray) : 0;
-      float* crow[4];  // this thread's first column of each of its rows (null: row outside the matrix / no C)
+      // this thread's first column of each of its rows; rows outside the matrix are clamped (their stores are
+      // predicated off by row_ok), so the pointers advance unconditionally
+      float* crow[4];
+      uint32_t row_ok = 0;
 #pragma unroll
-      for (int rr = 0; rr < 4; ++rr)
-        crow[rr] = (g.C != nullptr && mbase + TF_ROFF(rr) < g.M) ? g.C + (mbase + TF_ROFF(rr)) * g.ldc + c_begin + lc : nullptr;
+      for (int rr = 0; rr < 4; ++rr) {
+        const int64_t mr = mbase + TF_ROFF(rr);
+        if (g.C != nullptr && mr < g.M) row_ok |= 1u << rr;
+        crow[rr] = g.C + min(mr, g.M - 1) * g.ldc + c_begin + lc;
+      }
       float o3[4][3];
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) o3[rr][0] = o3[rr][1] = o3[rr][2] = 0.f;
@@ -555,9 +561,9 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_tc_rowgemm(RowGemmArgs g, co
         }
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
-          if (crow[rr] == nullptr) continue;
           const int blk = rr >> 1, h = rr & 1;
-          if (fast_store) {
+          if (!((row_ok >> rr) & 1u)) {
+          } else if (fast_store) {
             *reinterpret_cast<float2*>(crow[rr]) = make_float2(v[blk][h * 2], v[blk][h * 2 + 1]);
             *reinterpret_cast<float2*>(crow[rr] + 8) = make_float2(v[blk][4 + h * 2], v[blk][4 + h * 2 + 1]);
           } else {
