@@ -112,6 +112,9 @@ static int check_desc(const tensorf_render_desc* d) {
     TF_CHECK_ARG((int64_t)d->R * d->K < (int64_t)1 << 31, "R*K too large");
   }
   TF_CHECK_ARG((int64_t)d->R * d->N < (int64_t)1 << 31, "R*N too large");
+  // the gather / scatter kernels index the packed factors with 32-bit float offsets
+  TF_CHECK_ARG(packed_floats(d->cd, d->G) < ((int64_t)1 << 31) && packed_floats(d->ca, d->G) < ((int64_t)1 << 31),
+               "factor grids too large (G=%d cd=%d ca=%d): >= 2^31 packed floats", d->G, d->cd, d->ca);
   return 0;
 }
 
@@ -219,12 +222,14 @@ int tensorf_vm_unpack(tensorf_stream_t s, const float* packed, float* vector, fl
 int tensorf_vm_interp_fwd(tensorf_stream_t s, const float* packed, const float* ijk, float* out, int C, int G, int64_t B,
                           int feature_major) {
   TF_CHECK_ARG(B >= 0 && C >= 1 && G >= 2, "bad shape C=%d G=%d B=%lld", C, G, (long long)B);
+  TF_CHECK_ARG(packed_floats(C, G) < ((int64_t)1 << 31), "factor grid too large (C=%d G=%d): >= 2^31 packed floats", C, G);
   TF_CHECK_ARG(B == 0 || (packed && ijk && out), "NULL buffer");
   return vm_interp_fwd((cudaStream_t)s, packed, ijk, out, C, G, B, feature_major);
 }
 int tensorf_vm_interp_bwd(tensorf_stream_t s, const float* packed, const float* ijk, const float* d_out, float* d_packed,
                           int C, int G, int64_t B, int feature_major) {
   TF_CHECK_ARG(B >= 0 && C >= 1 && G >= 2, "bad shape C=%d G=%d B=%lld", C, G, (long long)B);
+  TF_CHECK_ARG(packed_floats(C, G) < ((int64_t)1 << 31), "factor grid too large (C=%d G=%d): >= 2^31 packed floats", C, G);
   TF_CHECK_ARG(B == 0 || (packed && ijk && d_out && d_packed), "NULL buffer");
   return vm_interp_bwd((cudaStream_t)s, packed, ijk, d_out, d_packed, C, G, B, feature_major);
 }

@@ -589,16 +589,16 @@ __global__ void __launch_bounds__(256, APP ? 2 : 3) k_scatter_walk(WalkArgs A) {
   const int j_begin = seg * A.seg_len, j_end = min(A.count, j_begin + A.seg_len);
 
   const int G = A.G, Cp = A.Cp;
-  const int64_t lbase = (int64_t)P * G * Cp + 4 * v;
-  const int64_t mbase = (int64_t)3 * G * Cp + (int64_t)P * G * G * Cp + 4 * v;
+  const int lbase = P * G * Cp + 4 * v;  // 32-bit float offsets (entry points reject >= 2^31 packed floats)
+  const int mbase = 3 * G * Cp + P * G * G * Cp + 4 * v;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   constexpr int EMPTY = INT_MIN;
   int lw = EMPTY;           // line window covers texels lw, lw+1
   float4 la0 = zero4, la1 = zero4;
   int pa = EMPTY, pb = 0;   // plane window covers rows pa, pa+1 x cols pb, pb+1
   float4 m00 = zero4, m01 = zero4, m10 = zero4, m11 = zero4;
-  auto flush_l = [&](int i, const float4& acc) { red_add_v4(A.d_packed + lbase + (int64_t)i * Cp, acc); };
-  auto flush_m = [&](int a, int b, const float4& acc) { red_add_v4(A.d_packed + mbase + ((int64_t)a * G + b) * Cp, acc); };
+  auto flush_l = [&](int i, const float4& acc) { red_add_v4(A.d_packed + (lbase + i * Cp), acc); };
+  auto flush_m = [&](int a, int b, const float4& acc) { red_add_v4(A.d_packed + (mbase + (a * G + b) * Cp), acc); };
 
   // One-sample software pipeline over the per-sample operands: the cotangent (appearance: the d_feat row, the only
   // operand that comes from DRAM, 90 MB per step read once; density: dz), the saved grid coordinates, and for the
@@ -658,11 +658,11 @@ __global__ void __launch_bounds__(256, APP ? 2 : 3) k_scatter_walk(WalkArgs A) {
     const Tap L = make_tap(xl, G), Ta = make_tap(xa, G), Tb = make_tap(xb, G);
 
     // re-gather (bit-identical to the forward)
-    const float4 l0 = ld4(A.packed + lbase + (int64_t)L.i0 * Cp), l1 = ld4(A.packed + lbase + (int64_t)L.i1 * Cp);
-    const float4 v00 = ld4(A.packed + mbase + ((int64_t)Ta.i0 * G + Tb.i0) * Cp);
-    const float4 v01 = ld4(A.packed + mbase + ((int64_t)Ta.i0 * G + Tb.i1) * Cp);
-    const float4 v10 = ld4(A.packed + mbase + ((int64_t)Ta.i1 * G + Tb.i0) * Cp);
-    const float4 v11 = ld4(A.packed + mbase + ((int64_t)Ta.i1 * G + Tb.i1) * Cp);
+    const float4 l0 = ld4(A.packed + (lbase + L.i0 * Cp)), l1 = ld4(A.packed + (lbase + L.i1 * Cp));
+    const float4 v00 = ld4(A.packed + (mbase + (Ta.i0 * G + Tb.i0) * Cp));
+    const float4 v01 = ld4(A.packed + (mbase + (Ta.i0 * G + Tb.i1) * Cp));
+    const float4 v10 = ld4(A.packed + (mbase + (Ta.i1 * G + Tb.i0) * Cp));
+    const float4 v11 = ld4(A.packed + (mbase + (Ta.i1 * G + Tb.i1) * Cp));
     float4 lin = f4_fma(l1, L.w1, f4_scale(l0, L.w0));
     float4 bil = f4_scale(v00, __fmul_rn(Ta.w0, Tb.w0));
     bil = f4_fma(v01, __fmul_rn(Ta.w0, Tb.w1), bil);

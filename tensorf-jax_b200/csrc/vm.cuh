@@ -148,7 +148,9 @@ __device__ __forceinline__ float4 f4_fma(float4 a, float s, float4 c) {
 
 // Pointers to the six texel fragments (float4 group v) one pair touches.
 struct PairAddr {
-  int64_t l0, l1, m00, m01, m10, m11;  // float offsets into the packed buffer
+  // float offsets into the packed buffer; 32-bit: entry points reject factors with >= 2^31 packed floats
+  // (64-bit offsets cost two to three instructions per address in kernels that are issue-bound)
+  int l0, l1, m00, m01, m10, m11;
   float wl0, wl1, w00, w01, w10, w11;
 };
 __device__ __forceinline__ PairAddr pair_addr(const VmTaps& t, int P, int G, int Cp, int v) {
@@ -156,14 +158,14 @@ __device__ __forceinline__ PairAddr pair_addr(const VmTaps& t, int P, int G, int
   const Tap& A = t.ax[pair_row_axis(P)];
   const Tap& B = t.ax[pair_col_axis(P)];
   PairAddr pa;
-  int64_t lbase = (int64_t)P * G * Cp + 4 * v;
-  pa.l0 = lbase + (int64_t)L.i0 * Cp;
-  pa.l1 = lbase + (int64_t)L.i1 * Cp;
-  int64_t mbase = (int64_t)3 * G * Cp + (int64_t)P * G * G * Cp + 4 * v;
-  pa.m00 = mbase + ((int64_t)A.i0 * G + B.i0) * Cp;
-  pa.m01 = mbase + ((int64_t)A.i0 * G + B.i1) * Cp;
-  pa.m10 = mbase + ((int64_t)A.i1 * G + B.i0) * Cp;
-  pa.m11 = mbase + ((int64_t)A.i1 * G + B.i1) * Cp;
+  const int lbase = P * G * Cp + 4 * v;
+  pa.l0 = lbase + L.i0 * Cp;
+  pa.l1 = lbase + L.i1 * Cp;
+  const int mbase = 3 * G * Cp + P * G * G * Cp + 4 * v;
+  pa.m00 = mbase + (A.i0 * G + B.i0) * Cp;
+  pa.m01 = mbase + (A.i0 * G + B.i1) * Cp;
+  pa.m10 = mbase + (A.i1 * G + B.i0) * Cp;
+  pa.m11 = mbase + (A.i1 * G + B.i1) * Cp;
   pa.wl0 = L.w0;
   pa.wl1 = L.w1;
   // map_coordinates multiplies the weights first, then the gathered value.
