@@ -411,7 +411,9 @@ def main():
                               "frac": value / world * w.train_bytes_per_ray() / 1e9 / peak,
                               "note": "whole step per GPU, gather-model bytes 3*24*(N*3cd+K*3ca) per ray (SURVEY §8d); factors are L2-resident at 128^3"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": dom_ms, "peak_source": peak_src},
+                         "traffic": traffic, "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": dom_ms, "peak_source": peak_src,
+                         "note": "gather-model bytes (6 taps x 4 B per sample-channel, SURVEY 8d); at 128^3 the factors and their gradients are "
+                                 "L2-resident, so frac > 1 is an L2/LSU rate - `traffic` is the kernel's ncu DRAM bytes per launch"},
             "stages_ms": {k: round(v["ms"], 4) for k, v in sorted(stages.items(), key=lambda kv: -kv[1]["ms"])},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
