@@ -201,11 +201,18 @@ __global__ void __launch_bounds__(256) k_encode_fwd(const float* __restrict__ f,
     for (int j = 0; j < F; j += 2) {
       float sn, cs;
       sincosf(val * scale, &sn, &cs);
-      row[off + j] = sn;
-      row[off + F + j] = cs;
-      if (j + 1 < F) {
-        row[off + j + 1] = 2.0f * sn * cs;
-        row[off + F + j + 1] = fmaf(-2.0f * sn, sn, 1.0f);
+      // levels j and j+1 are adjacent in the row: 8-byte stores halve the number of store requests (the kernel is
+      // bound by the rate of scattered 4-byte stores, not by the arithmetic)
+      if (j + 1 < F && ((reinterpret_cast<uintptr_t>(row + off + j) | reinterpret_cast<uintptr_t>(row + off + F + j)) & 7) == 0) {
+        *reinterpret_cast<float2*>(row + off + j) = make_float2(sn, 2.0f * sn * cs);
+        *reinterpret_cast<float2*>(row + off + F + j) = make_float2(cs, fmaf(-2.0f * sn, sn, 1.0f));
+      } else {
+        row[off + j] = sn;
+        row[off + F + j] = cs;
+        if (j + 1 < F) {
+          row[off + j + 1] = 2.0f * sn * cs;
+          row[off + F + j + 1] = fmaf(-2.0f * sn, sn, 1.0f);
+        }
       }
       scale *= 4.0f;
     }
@@ -244,9 +251,16 @@ __global__ void __launch_bounds__(256) k_encode_bwd(const float* __restrict__ f,
     for (int j = 0; j < s.Ff; j += 2) {
       float sn, cs;
       sincosf(val * scale, &sn, &cs);
-      g += scale * (row[off + j] * cs - row[off + s.Ff + j] * sn);
-      if (j + 1 < s.Ff)
-        g += 2.0f * scale * (row[off + j + 1] * fmaf(-2.0f * sn, sn, 1.0f) - row[off + s.Ff + j + 1] * (2.0f * sn * cs));
+      if (j + 1 < s.Ff && ((reinterpret_cast<uintptr_t>(row + off + j) | reinterpret_cast<uintptr_t>(row + off + s.Ff + j)) & 7) == 0) {
+        const float2 ds = __ldg(reinterpret_cast<const float2*>(row + off + j));
+        const float2 dc = __ldg(reinterpret_cast<const float2*>(row + off + s.Ff + j));
+        g += scale * (ds.x * cs - dc.x * sn);
+        g += 2.0f * scale * (ds.y * fmaf(-2.0f * sn, sn, 1.0f) - dc.y * (2.0f * sn * cs));
+      } else {
+        g += scale * (row[off + j] * cs - row[off + s.Ff + j] * sn);
+        if (j + 1 < s.Ff)
+          g += 2.0f * scale * (row[off + j + 1] * fmaf(-2.0f * sn, sn, 1.0f) - row[off + s.Ff + j + 1] * (2.0f * sn * cs));
+      }
       scale *= 4.0f;
     }
     df[m * ldf + d] = g;
@@ -258,6 +272,53 @@ __global__ void __launch_bounds__(256) k_encode_bwd(const float* __restrict__ f,
     scale *= 2.0f;
   }
   df[m * ldf + d] = g;
+}
+
+// Row-staged forward variant for wide rows (tensor-core path, squash + 3 <= 32): one warp per row; lane d evaluates
+// source dimension d into a shared-memory copy of the row, then the warp stores the row with coalesced 16-byte accesses.
+// The element-wise kernel above issues one 4- or 8-byte request per value at a 2F-float stride and is bound by the
+// request rate (dozer, 400-float rows: 285 us for 325 MB with 4-byte stores, 150 us with 8-byte stores, 75 us staged).
+// Measured: wins for ldx = 400 (dozer), loses 4 us for ldx = 160 (lego); the reverse kernel gains nothing from staging.
+__global__ void __launch_bounds__(256) k_encode_fwd_rows(const float* __restrict__ f, const float* __restrict__ viewdirs,
+                                                         float* __restrict__ x, int64_t M, int rows_per_ray, MlpShape s,
+                                                         int ldf, int ldx) {
+  extern __shared__ __align__(16) float srow[];  // [8][ldx]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t m = (int64_t)blockIdx.x * 8 + wib;
+  if (m >= M) return;
+  float* row = srow + wib * ldx;
+  const int D = s.squash + 3;
+  for (int q = s.enc + lane; q < ldx; q += 32) row[q] = 0.f;  // padding columns stay finite
+  if (lane < D) {
+    float val;
+    int F, off;
+    if (lane < s.squash) {
+      val = f[m * ldf + lane];
+      F = s.Ff;
+      off = D + lane * 2 * s.Ff;
+    } else {
+      val = viewdirs[(m / rows_per_ray) * 3 + (lane - s.squash)];
+      F = s.Fv;
+      off = D + s.squash * 2 * s.Ff + (lane - s.squash) * 2 * s.Fv;
+    }
+    row[lane] = val;
+    float scale = 1.0f;
+    for (int j = 0; j < F; j += 2) {  // even levels by sincosf, odd levels by the double-angle identities
+      float sn, cs;
+      sincosf(val * scale, &sn, &cs);
+      row[off + j] = sn;
+      row[off + F + j] = cs;
+      if (j + 1 < F) {
+        row[off + j + 1] = 2.0f * sn * cs;
+        row[off + F + j + 1] = fmaf(-2.0f * sn, sn, 1.0f);
+      }
+      scale *= 4.0f;
+    }
+  }
+  __syncwarp();
+  float4* dst = reinterpret_cast<float4*>(x + m * ldx);
+  const float4* src = reinterpret_cast<const float4*>(row);
+  for (int q = lane; q < (ldx >> 2); q += 32) dst[q] = src[q];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -455,7 +516,12 @@ __global__ void __launch_bounds__(256) k_colsum128(const float* __restrict__ G, 
 int mlp_encode_fwd(cudaStream_t st, const MlpShape& s, const MlpWs& ws, const float* viewdirs, int64_t M, int rows_per_ray,
                    bool fast) {
   const unsigned grid = (unsigned)(s.squash + 3 <= 32 ? ceil_div64(M, 8) : ceil_div64(M * (s.squash + 3), 256));
-  if (fast)
+  const bool rows = fast && s.squash + 3 <= 32 && ws.ldx > 256 && ws.ldx % 4 == 0 && (size_t)8 * ws.ldx * 4 <= 48 * 1024 &&
+                    (reinterpret_cast<uintptr_t>(ws.x) & 15) == 0 && !getenv("TENSORF_ENC_ELEMENTWISE");
+  if (rows)
+    k_encode_fwd_rows<<<(unsigned)ceil_div64(M, 8), 256, (size_t)8 * ws.ldx * 4, st>>>(ws.f, viewdirs, ws.x, M, rows_per_ray, s,
+                                                                                     ws.ldf, ws.ldx);
+  else if (fast)
     k_encode_fwd<true><<<grid, 256, 0, st>>>(ws.f, viewdirs, ws.x, M, rows_per_ray, s, ws.ldf, ws.ldx);
   else
     k_encode_fwd<false><<<grid, 256, 0, st>>>(ws.f, viewdirs, ws.x, M, rows_per_ray, s, ws.ldf, ws.ldx);
