@@ -940,6 +940,9 @@ constexpr int kConvGroupWarps = 8;
 constexpr int kConvWarps = kConvGroups * kConvGroupWarps;
 constexpr int kRed2Threads = 192 + 32 * kConvWarps;
 
+// RC = rows per chunk (the MMA K extent of one operand stage): 32, or 16 when the wider staging of 32 rows does not fit
+// (dozer: X has 400 columns).
+template <int RC>
 __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, int T /*staging slots*/) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -950,9 +953,9 @@ __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, 
   uint64_t* sempty = sfull + T;                         // [T] staging slot read by all converter warps
   uint64_t* tfull = sempty + T;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
-  const uint32_t a_tile = tile_bytes(128, kRC), b_tile = tile_bytes(g.N_pad, kRC);
+  const uint32_t a_tile = tile_bytes(128, RC), b_tile = tile_bytes(g.N_pad, RC);
   const uint32_t stage_bytes = 2 * a_tile + 2 * b_tile;
-  const uint32_t slot_floats = (uint32_t)kRC * (uint32_t)(g.ldg + g.ldx);
+  const uint32_t slot_floats = (uint32_t)RC * (uint32_t)(g.ldg + g.ldx);
   unsigned char* stage0 = smem + 1024;
   float* slot0 = reinterpret_cast<float*>(stage0 + (size_t)S * stage_bytes);
 
@@ -976,7 +979,7 @@ __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, 
 
   const int64_t r_begin = (int64_t)blockIdx.x * g.rows_per_cta;
   const int64_t r_end = min(g.rows, r_begin + g.rows_per_cta);
-  const int nchunks = (int)((r_end - r_begin + kRC - 1) / kRC);
+  const int nchunks = (int)((r_end - r_begin + RC - 1) / RC);
 
   if (warp == 5) {
     // ===== loader: two bulk copies per chunk (raw fp32 rows of G and X) =====
@@ -985,26 +988,26 @@ __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, 
         const uint32_t sl = (uint32_t)(c % T), ph = (uint32_t)((c / T) & 1);
         mbar_wait_backoff(&sempty[sl], ph ^ 1);
         TF_TRACE(4, c);
-        const int64_t r0 = r_begin + (int64_t)c * kRC;
-        const uint32_t nrows = (uint32_t)min((int64_t)kRC, r_end - r0);
+        const int64_t r0 = r_begin + (int64_t)c * RC;
+        const uint32_t nrows = (uint32_t)min((int64_t)RC, r_end - r0);
         float* dst = slot0 + (size_t)sl * slot_floats;
         const uint32_t bg = nrows * (uint32_t)g.ldg * 4, bx = nrows * (uint32_t)g.ldx * 4;
         mbar_arrive_expect_tx(&sfull[sl], bg + bx);
         bulk_copy_g2s(dst, g.G + r0 * g.ldg, bg, &sfull[sl]);
-        bulk_copy_g2s(dst + (size_t)kRC * g.ldg, g.X + r0 * g.ldx, bx, &sfull[sl]);
+        bulk_copy_g2s(dst + (size_t)RC * g.ldg, g.X + r0 * g.ldx, bx, &sfull[sl]);
       }
     }
   } else if (warp >= 6) {
     // ===== converters: item = (operand, column, group of 8 rows) -> one 16-byte k-chunk per split =====
     const int grp = (warp - 6) / kConvGroupWarps;
     const int ct = tid - 192 - grp * 32 * kConvGroupWarps;
-    const int a_items = 128 * (kRC / 8), b_items = g.N_pad * (kRC / 8);
+    const int a_items = 128 * (RC / 8), b_items = g.N_pad * (RC / 8);
     uint32_t sl = (uint32_t)grp, sph = 0, st = (uint32_t)grp, ph = 0;  // advanced incrementally (no run-time divisions)
     for (int c = grp; c < nchunks; c += kConvGroups) {
-      const int64_t r0 = r_begin + (int64_t)c * kRC;
-      const int nrows = (int)min((int64_t)kRC, r_end - r0);
+      const int64_t r0 = r_begin + (int64_t)c * RC;
+      const int nrows = (int)min((int64_t)RC, r_end - r0);
       const float* sG = slot0 + (size_t)sl * slot_floats;
-      const float* sX = sG + (size_t)kRC * g.ldg;
+      const float* sX = sG + (size_t)RC * g.ldg;
       unsigned char* sA = stage0 + (size_t)st * stage_bytes;
       unsigned char* sB = sA + 2 * a_tile;
       if (ct == 0) TF_TRACE(0, c);
@@ -1012,16 +1015,16 @@ __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, 
       if (ct == 0) TF_TRACE(1, c);
       mbar_wait(&empty[st], ph ^ 1);
       if (ct == 0) TF_TRACE(2, c);
-      const bool full_chunk = nrows == kRC;
+      const bool full_chunk = nrows == RC;
       for (int item = ct; item < a_items + b_items; item += 32 * kConvGroupWarps) {
         const bool isA = item < a_items;
         int col, j;
         if (isA) {  // 128 columns: shifts
           col = item & 127;
           j = item >> 7;
-        } else {    // N_pad columns, kRC/8 = 4 row groups: three compares instead of a division
+        } else {    // N_pad columns, RC/8 <= 4 row groups: compares instead of a division
           const int e = item - a_items;
-          j = (e >= g.N_pad) + (e >= 2 * g.N_pad) + (e >= 3 * g.N_pad);
+          j = (e >= g.N_pad) + (RC > 16 ? (e >= 2 * g.N_pad) + (e >= 3 * g.N_pad) : 0);
           col = e - j * g.N_pad;
         }
         const float* src = (isA ? sG : sX) + col;
@@ -1041,7 +1044,7 @@ __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, 
 #pragma unroll
           for (int q = 0; q < 8; ++q) x[q] = (ones && j * 8 + q < nrows) ? 1.0f : 0.f;
         }
-        split_store<2>(x, isA ? sA : sB, isA ? a_tile : b_tile, tile_offset(col, j * 8, kRC));
+        split_store<2>(x, isA ? sA : sB, isA ? a_tile : b_tile, tile_offset(col, j * 8, RC));
       }
       fence_proxy_async();
       __syncwarp();
@@ -1057,10 +1060,10 @@ __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, 
     }
   } else if (warp == 4) {
     {  // warp-uniform issue loop (see k_tc_rowgemm): descriptors stay in uniform registers
-      const uint32_t desc_hi = ((kRC * 16) >> 4) | (1u << 14);
+      const uint32_t desc_hi = ((RC * 16) >> 4) | (1u << 14);
       const uint32_t lo_const = (128u >> 4) << 16;
       const uint32_t a_lo0 = ((smem_u32(smem) + 1024u) >> 4) | lo_const;
-      const uint32_t a_split = a_tile >> 4, b_split = b_tile >> 4, st_units = stage_bytes >> 4, sbo_units = (kRC * 16) >> 4;
+      const uint32_t a_split = a_tile >> 4, b_split = b_tile >> 4, st_units = stage_bytes >> 4, sbo_units = (RC * 16) >> 4;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t st = 0, ph = 0;
       for (int c = 0; c < nchunks; ++c) {
@@ -1071,7 +1074,7 @@ __global__ void __launch_bounds__(kRed2Threads, 1) k_tc_redgemm2(RedGemmArgs g, 
         const uint32_t b_st = a_st + 2 * a_split;
         if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < kRC / 16; ++ks) {
+          for (int ks = 0; ks < RC / 16; ++ks) {
             for (int n0 = 0; n0 < g.N_pad; n0 += 256) {
               const int nn = min(256, g.N_pad - n0);
               const uint32_t idesc = make_idesc_bf16(128, nn);
@@ -1131,20 +1134,33 @@ static int launch_redgemm(cudaStream_t st, RedGemmArgs g) {
   ctas = ceil_div64(g.rows, g.rows_per_cta);
   const size_t stage = 2 * (size_t)tile_bytes(128, kRC) + 2 * (size_t)tile_bytes(g.N_pad, kRC);
   // asynchronous-load variant: rows of G and X must be 16-byte multiples, and 2 operand stages plus
-  // >= 2 staging slots must fit in shared memory
-  const size_t slot = (size_t)kRC * (size_t)(g.ldg + g.ldx) * 4;
+  // >= 2 staging slots must fit in shared memory (with 32 rows per chunk, else with 16)
   const bool aligned = g.ldg % 4 == 0 && g.ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(g.G) & 15) == 0 &&
                        (reinterpret_cast<uintptr_t>(g.X) & 15) == 0;
-  if (aligned && !getenv("TENSORF_TC_RED_REGS") && 1024 + 2 * stage + 2 * slot <= 227 * 1024) {
-    g.stages = kConvGroups;
-    g.groups = kConvGroups;
-    int T = (int)std::min<size_t>(6, (227 * 1024 - 1024 - 2 * stage) / slot);
-    T = T / kConvGroups * kConvGroups;
-    const size_t smem = 1024 + g.stages * stage + (size_t)T * slot;
-    TF_CHECK_CUDA(cudaFuncSetAttribute(k_tc_redgemm2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_tc_redgemm2<<<(unsigned)ctas, kRed2Threads, smem, st>>>(g, T);
-    TF_CHECK_LAUNCH();
-    return 0;
+  if (aligned && !getenv("TENSORF_TC_RED_REGS")) {
+    for (int rc = 32; rc >= 16; rc >>= 1) {
+      const size_t stg = 2 * (size_t)tile_bytes(128, rc) + 2 * (size_t)tile_bytes(g.N_pad, rc);
+      const size_t slot = (size_t)rc * (size_t)(g.ldg + g.ldx) * 4;
+      if (1024 + 2 * stg + 2 * slot > 227 * 1024) continue;
+      g.stages = kConvGroups;
+      g.groups = kConvGroups;
+      int T = (int)std::min<size_t>(6, (227 * 1024 - 1024 - 2 * stg) / slot);
+      T = T / kConvGroups * kConvGroups;
+      const size_t smem = 1024 + g.stages * stg + (size_t)T * slot;
+      // rows per CTA: whole chunks
+      int64_t nct = std::min<int64_t>(kSMs, std::max<int64_t>(1, g.rows / 256));
+      g.rows_per_cta = round_up64(ceil_div64(g.rows, nct), rc);
+      nct = ceil_div64(g.rows, g.rows_per_cta);
+      if (rc == 32) {
+        TF_CHECK_CUDA(cudaFuncSetAttribute(k_tc_redgemm2<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_tc_redgemm2<32><<<(unsigned)nct, kRed2Threads, smem, st>>>(g, T);
+      } else {
+        TF_CHECK_CUDA(cudaFuncSetAttribute(k_tc_redgemm2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_tc_redgemm2<16><<<(unsigned)nct, kRed2Threads, smem, st>>>(g, T);
+      }
+      TF_CHECK_LAUNCH();
+      return 0;
+    }
   }
   int stages = (int)std::min<size_t>(8, (227 * 1024 - 1024) / stage);
   TF_CHECK_ARG(stages >= 2, "tc redgemm: tile too large for shared memory");

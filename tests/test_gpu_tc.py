@@ -49,7 +49,8 @@ def test_rowgemm(cuda, M, K, N, nsplit, tol):
             assert (np.abs(ref.numpy()[diff]) < 1e-4).all() and diff.mean() < 1e-3
 
 
-@pytest.mark.parametrize("rows,Mg,Nx", [(256, 128, 128), (5000, 128, 150), (3001, 27, 144), (40000, 128, 128), (999, 128, 390)])
+@pytest.mark.parametrize("rows,Mg,Nx", [(256, 128, 128), (5000, 128, 150), (3001, 27, 144), (40000, 128, 128), (999, 128, 390),
+                                          (20000, 128, 400), (7001, 32, 400)])
 def test_redgemm(cuda, rows, Mg, Nx):
     from tensorf_b200 import _lib, ops
     rng = np.random.default_rng(rows + Mg + Nx)
