@@ -777,7 +777,7 @@ static int launch_walk(cudaStream_t st, WalkArgs A) {
   int lps = pick_lps(nvec);
   if (lps == 1 && nvec > 2) lps = 4;  // odd channel counts: round the block up, idle lanes exit
   lps = min(lps, 4);                  // 64-byte texel fragments per item keep more items in flight
-  A.seg_len = APP ? 64 : 16;  // measured on B200 (A'): density 16: 0.218 ms (32: 0.232, 64: 0.259); appearance 64
+  A.seg_len = APP ? 128 : 16;  // measured on B200: density 16 (lego 0.151 ms; 8: 0.158, 32: 0.164); appearance 128 (dozer K=99: 0.089 ms vs 0.107 at 64; lego K=38 unchanged)
   if (const char* e = getenv(APP ? "TENSORF_SEG_LEN_APP" : "TENSORF_SEG_LEN")) A.seg_len = std::max(8, atoi(e));
   A.segs = (A.count + A.seg_len - 1) / A.seg_len;
   const int vblocks = (nvec + lps - 1) / lps;
