@@ -1,5 +1,7 @@
 // TensorVM kernels: layout pack/unpack and the standalone `TensorVM.interpolate`
 // forward / reverse (tensor_vm.py:42-89, :140-167, :226-250).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "vm.cuh"
@@ -24,9 +26,12 @@ struct PackJobsVm {
   int n;
 };
 
-template <bool UNPACK>
+// TW = texels per tile.  The channel-first side is read / written in runs of TW*4 bytes per channel, each in a different
+// DRAM page (channel stride = T*4 bytes): TW = 128 moves four lines per page visit, which matters once the factors no
+// longer fit in L2 (300^3: 139 MB per direction).
+template <bool UNPACK, int TW>
 __global__ void __launch_bounds__(256) k_pack(const __grid_constant__ PackJobsVm jobs) {
-  extern __shared__ float tile[];  // [Cp][33]
+  extern __shared__ float tile[];  // [Cp][TW + 1]
   int ji = 0;
 #pragma unroll 1
   while (ji + 1 < jobs.n && (int64_t)blockIdx.x >= jobs.j[ji + 1].block_begin) ++ji;
@@ -35,35 +40,54 @@ __global__ void __launch_bounds__(256) k_pack(const __grid_constant__ PackJobsVm
   const int64_t T = J.T;
   const int64_t tile_id = (int64_t)blockIdx.x - J.block_begin;
   const int P = (int)(tile_id / J.tiles_per_pair);
-  const int64_t t0 = (tile_id % J.tiles_per_pair) * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 warps
+  const int64_t t0 = (tile_id % J.tiles_per_pair) * TW;
+  constexpr int RPB = 256 / TW;  // channel rows handled per pass
+  const int tx = threadIdx.x % TW, ty = threadIdx.x / TW;
+  const int n = (int)min((int64_t)TW, T - t0) * Cp;
+  // (texel, channel) of packed element i = threadIdx.x + 256*k, advanced without a division per element
+  const int dq = 256 / Cp, dr = 256 % Cp;
+  int tq = threadIdx.x / Cp, c = threadIdx.x % Cp;
   if (!UNPACK) {
     const float* s = J.src + (int64_t)P * C * T;
-    for (int c = ty; c < Cp; c += 8) {
+    for (int ch = ty; ch < Cp; ch += RPB) {
       int64_t t = t0 + tx;
-      tile[c * 33 + tx] = (c < C && t < T) ? s[(int64_t)c * T + t] : 0.0f;
+      tile[ch * (TW + 1) + tx] = (ch < C && t < T) ? s[(int64_t)ch * T + t] : 0.0f;
     }
     __syncthreads();
     float* d = J.dst + ((int64_t)P * T + t0) * Cp;
-    int64_t n = min((int64_t)32, T - t0) * Cp;
-    for (int i = threadIdx.x; i < n; i += 256) d[i] = tile[(i % Cp) * 33 + (i / Cp)];
+    for (int i = threadIdx.x; i < n; i += 256) {
+      d[i] = tile[c * (TW + 1) + tq];
+      tq += dq;
+      c += dr;
+      if (c >= Cp) {
+        c -= Cp;
+        ++tq;
+      }
+    }
   } else {
     const float* s = J.src + ((int64_t)P * T + t0) * Cp;
-    int64_t n = min((int64_t)32, T - t0) * Cp;
-    for (int i = threadIdx.x; i < n; i += 256) tile[(i % Cp) * 33 + (i / Cp)] = s[i];
+    for (int i = threadIdx.x; i < n; i += 256) {
+      tile[c * (TW + 1) + tq] = s[i];
+      tq += dq;
+      c += dr;
+      if (c >= Cp) {
+        c -= Cp;
+        ++tq;
+      }
+    }
     __syncthreads();
     float* d = J.dst + (int64_t)P * C * T;
-    for (int c = ty; c < C; c += 8) {
+    for (int ch = ty; ch < C; ch += RPB) {
       int64_t t = t0 + tx;
-      if (t < T) d[(int64_t)c * T + t] = tile[c * 33 + tx];
+      if (t < T) d[(int64_t)ch * T + t] = tile[ch * (TW + 1) + tx];
     }
   }
 }
 
 // factors[i] = {vector, matrix, packed, C}; G shared.  UNPACK: packed -> vector/matrix.
-template <bool UNPACK>
-static int launch_pack_multi(cudaStream_t st, int nf, const float* const* vec, const float* const* mat, const float* const* packed,
-                             const int* C, int G) {
+template <bool UNPACK, int TW>
+static int launch_pack_tw(cudaStream_t st, int nf, const float* const* vec, const float* const* mat, const float* const* packed,
+                          const int* C, int G) {
   PackJobsVm jobs{};
   int64_t blocks = 0;
   int maxCp = 0;
@@ -79,17 +103,29 @@ static int launch_pack_multi(cudaStream_t st, int nf, const float* const* vec, c
       J.C = C[f];
       J.Cp = Cp;
       J.T = part == 0 ? G : (int64_t)G * G;
-      J.tiles_per_pair = ceil_div64(J.T, 32);
+      J.tiles_per_pair = ceil_div64(J.T, TW);
       J.block_begin = blocks;
       blocks += 3 * J.tiles_per_pair;
     }
   }
-  const size_t smem = (size_t)maxCp * 33 * sizeof(float);
+  const size_t smem = (size_t)maxCp * (TW + 1) * sizeof(float);
   TF_CHECK_ARG(smem <= 48 * 1024, "channel dim too large for pack kernel (Cp=%d)", maxCp);
   TF_CHECK_ARG(blocks < ((int64_t)1 << 31), "pack: grid too large");
-  k_pack<UNPACK><<<(unsigned)blocks, 256, smem, st>>>(jobs);
+  k_pack<UNPACK, TW><<<(unsigned)blocks, 256, smem, st>>>(jobs);
   TF_CHECK_LAUNCH();
   return 0;
+}
+template <bool UNPACK>
+static int launch_pack_multi(cudaStream_t st, int nf, const float* const* vec, const float* const* mat, const float* const* packed,
+                             const int* C, int G) {
+  int maxCp = 0;
+  for (int f = 0; f < nf; ++f) maxCp = std::max(maxCp, packed_cp(C[f]));
+  // measured on B200 (pack + unpack): 128^3: TW 32: 31.8 us, 64: 26.6, 128: 26.7; 300^3: 110.9, 74.9, 71.6
+  int tw = (size_t)maxCp * 129 * sizeof(float) <= 48 * 1024 ? 128 : ((size_t)maxCp * 65 * sizeof(float) <= 48 * 1024 ? 64 : 32);
+  if (const char* e = getenv("TENSORF_PACK_TW")) tw = atoi(e);
+  if (tw == 128) return launch_pack_tw<UNPACK, 128>(st, nf, vec, mat, packed, C, G);
+  if (tw == 64) return launch_pack_tw<UNPACK, 64>(st, nf, vec, mat, packed, C, G);
+  return launch_pack_tw<UNPACK, 32>(st, nf, vec, mat, packed, C, G);
 }
 
 int vm_pack(cudaStream_t st, const float* vector, const float* matrix, float* packed, int C, int G) {
