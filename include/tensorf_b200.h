@@ -220,6 +220,42 @@ int tensorf_adam_step(tensorf_stream_t s, const tensorf_adam_desc* d, const int6
                       const float* const* grads, float* const* mu, float* const* nu, const float* neg_lrs,
                       float* grad_norm, void* scratch, int64_t scratch_bytes);
 
+/* ---- SURVEY 8e fused follow-up: gradient reduce-scatter + Adam + parameter all-gather in ONE kernel over
+ * peer memory (NVLink 5 / NVSwitch) ---------------------------------------------------------------------
+ * Replaces `ncclAllReduce(grads)` followed by `tensorf_adam_step` on every rank (training.py:153-156 -> :158-243
+ * when the ray batch is sharded).  All leaves live in one FLAT fp32 buffer per rank (leaf i =
+ * elements [leaf_offsets[i], leaf_offsets[i+1]); elements from leaf_offsets[n_leaves] to `total` are padding),
+ * allocated symmetrically so that every rank holds a peer mapping of every other rank's buffer.  Rank r owns the
+ * element range [shard_begin, shard_end) (multiples of 4): it sums the `world` gradient copies of its range in
+ * rank order (P2P loads, or one `multimem.ld_reduce` through the NVSwitch when grad_mc != NULL), applies the Adam
+ * step of tensorf_adam_step with ITS shard of the moments (mu, nu: shard_end - shard_begin floats, local), and
+ * stores the new parameters into every rank's parameter buffer (P2P stores, or one `multimem.st` when
+ * param_mc != NULL).  The sum of squares of the reduced gradient over the shard goes to slot [rank] of every
+ * rank's `norm_slots` (world floats); tensorf_peer_grad_norm turns the slots into optax.global_norm(grads).
+ * The CALLER orders the ranks: a cross-rank barrier on the stream before this call (all gradients written) and
+ * one after it (all parameter / slot stores landed) - torch symmetric-memory `barrier()`, or any equivalent.
+ * With world == 1 (pointers to the rank's own buffers, no barrier) the result is bit-identical to
+ * tensorf_adam_step. */
+#define TENSORF_PEER_MAX_WORLD 16
+#define TENSORF_PEER_MAX_LEAVES 32 /* leaves + alignment gaps (a gap is a leaf with neg_lr 0 whose gradient stays 0) */
+typedef struct tensorf_peer_adam_desc {
+  tensorf_adam_desc adam;     /* n_leaves = leaves of the flat buffer, <= TENSORF_PEER_MAX_LEAVES */
+  int32_t rank, world;
+  int64_t total;              /* floats in the flat buffers, multiple of 4 */
+  int64_t shard_begin, shard_end; /* this rank's range, multiples of 4, within [0,total] */
+} tensorf_peer_adam_desc;
+/* Equal contiguous shards in units of 4 floats: [begin,end) of `rank`. */
+void tensorf_peer_shard(int64_t total, int rank, int world, int64_t* begin, int64_t* end);
+int64_t tensorf_peer_adam_scratch_bytes(int64_t shard_floats);
+/* HOST arrays: leaf_offsets [n_leaves+1], neg_lrs [n_leaves], grad_peers / param_peers / norm_slot_peers [world]
+ * (device pointers valid in THIS process: own buffer at [rank], peer mappings elsewhere). */
+int tensorf_adam_step_peer(tensorf_stream_t s, const tensorf_peer_adam_desc* d, const int64_t* leaf_offsets,
+                           const float* neg_lrs, const float* const* grad_peers, float* const* param_peers,
+                           const float* grad_mc, float* param_mc, float* mu_shard, float* nu_shard,
+                           float* const* norm_slot_peers, void* scratch, int64_t scratch_bytes);
+/* grad_norm[0] = sqrt(sum of the `world` slots, in rank order, fp64 accumulation): identical on every rank. */
+int tensorf_peer_grad_norm(tensorf_stream_t s, const float* norm_slots, int world, float* grad_norm);
+
 /* ---- tensor_vm.py:183-223 TensorVMSingle.resize ------------------------------ */
 /* vector (3,C,G_in) -> (3,C,G_out), matrix (3,C,G_in,G_in) -> (3,C,G_out,G_out): jax.image.scale_and_translate,
  * "linear" kernel, scale (G_out-1)/(G_in-1), translation -(scale/2 - 0.5) (align corners), antialiased when

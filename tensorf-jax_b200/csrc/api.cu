@@ -527,6 +527,26 @@ int tensorf_adam_step(tensorf_stream_t s, const tensorf_adam_desc* d, const int6
   return adam_step((cudaStream_t)s, d, sizes, params, grads, mu, nu, neg_lrs, grad_norm, scratch, scratch_bytes);
 }
 
+void tensorf_peer_shard(int64_t total, int rank, int world, int64_t* begin, int64_t* end) {
+  if (!begin || !end) return;
+  if (world < 1 || rank < 0 || rank >= world || total < 0) {
+    *begin = *end = 0;
+    return;
+  }
+  peer_shard(total, rank, world, begin, end);
+}
+int64_t tensorf_peer_adam_scratch_bytes(int64_t shard_floats) { return peer_adam_scratch_bytes(shard_floats); }
+int tensorf_adam_step_peer(tensorf_stream_t s, const tensorf_peer_adam_desc* d, const int64_t* leaf_offsets,
+                           const float* neg_lrs, const float* const* grad_peers, float* const* param_peers,
+                           const float* grad_mc, float* param_mc, float* mu_shard, float* nu_shard,
+                           float* const* norm_slot_peers, void* scratch, int64_t scratch_bytes) {
+  return adam_step_peer((cudaStream_t)s, d, leaf_offsets, neg_lrs, grad_peers, param_peers, grad_mc, param_mc, mu_shard,
+                        nu_shard, norm_slot_peers, scratch, scratch_bytes);
+}
+int tensorf_peer_grad_norm(tensorf_stream_t s, const float* norm_slots, int world, float* grad_norm) {
+  return peer_grad_norm((cudaStream_t)s, norm_slots, world, grad_norm);
+}
+
 int64_t tensorf_vm_resize_scratch_bytes(int C, int G_in, int G_out) {
   if (C < 1 || G_in < 2 || G_out < 2) return -1;
   return vm_resize_scratch_bytes(C, G_in, G_out);

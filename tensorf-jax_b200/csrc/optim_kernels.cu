@@ -36,18 +36,6 @@ struct AdamArgs {
   float* grad_norm;        // device scalar or nullptr
 };
 
-// One element, in optax's operation order with every rounding kept (no FMA contraction):
-//   mu' = (1-b1)*g + b1*mu ; nu' = (1-b2)*g^2 + b2*nu              (optax update_moment)
-//   u   = (mu'/bc1) / (sqrt(nu'/bc2 + eps_root) + eps)               (bias_correction, scale_by_adam)
-//   p'  = p + lr_decay * (neg_lr * u)                                (scale, training.py:186, apply_updates)
-__device__ __forceinline__ void adam_one(float& p, float g, float& mu, float& nu, const AdamArgs& a, float neg_lr) {
-  mu = __fadd_rn(__fmul_rn(a.one_minus_b1, g), __fmul_rn(a.b1, mu));
-  nu = __fadd_rn(__fmul_rn(a.one_minus_b2, __fmul_rn(g, g)), __fmul_rn(a.b2, nu));
-  const float mh = __fdiv_rn(mu, a.bc1), nh = __fdiv_rn(nu, a.bc2);
-  const float u = __fdiv_rn(mh, __fadd_rn(__fsqrt_rn(__fadd_rn(nh, a.eps_root)), a.eps));
-  p = __fadd_rn(p, __fmul_rn(a.lr_decay, __fmul_rn(neg_lr, u)));
-}
-
 __global__ void __launch_bounds__(kAdamThreads) k_adam(const __grid_constant__ AdamArgs a) {
   __shared__ float s_red[kAdamThreads / 32];
   __shared__ bool s_last;

@@ -71,7 +71,16 @@ class AdamDesc(C.Structure):
     ]
 
 
+class PeerAdamDesc(C.Structure):
+    """struct tensorf_peer_adam_desc"""
+
+    _fields_ = [("adam", AdamDesc), ("rank", C.c_int32), ("world", C.c_int32), ("total", C.c_int64),
+                ("shard_begin", C.c_int64), ("shard_end", C.c_int64)]
+
+
 ADAM_MAX_LEAVES = 16
+PEER_MAX_WORLD = 16
+PEER_MAX_LEAVES = 32
 
 _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
 _pd, _pp, _pi = C.POINTER(RenderDesc), C.POINTER(Params), C.POINTER(RenderInputs)
@@ -105,6 +114,11 @@ SIGNATURES = {
     "tensorf_adam_scratch_bytes": (_i64, [C.POINTER(_i64), _i]),
     "tensorf_adam_step": (_i, [_vp, C.POINTER(AdamDesc), C.POINTER(_i64), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
                                C.POINTER(_vp), C.POINTER(C.c_float), _vp, _vp, _i64]),
+    "tensorf_peer_shard": (None, [_i64, _i, _i, C.POINTER(_i64), C.POINTER(_i64)]),
+    "tensorf_peer_adam_scratch_bytes": (_i64, [_i64]),
+    "tensorf_adam_step_peer": (_i, [_vp, C.POINTER(PeerAdamDesc), C.POINTER(_i64), C.POINTER(C.c_float), C.POINTER(_vp),
+                                    C.POINTER(_vp), _vp, _vp, _vp, _vp, C.POINTER(_vp), _vp, _i64]),
+    "tensorf_peer_grad_norm": (_i, [_vp, _vp, _i, _vp]),
     "tensorf_vm_resize_scratch_bytes": (_i64, [_i, _i, _i]),
     "tensorf_vm_resize": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i64]),
     "tensorf_threefry2x32": (None, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]),

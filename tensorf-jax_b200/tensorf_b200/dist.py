@@ -66,3 +66,175 @@ class FlatGrads:
 def global_loss_scale(local_rays: int, world: int) -> float:
     """1/(3*R_global) for equal shards."""
     return 1.0 / (3.0 * local_rays * world)
+
+
+class PeerAdam:
+    """Gradient reduce-scatter + Adam + parameter all-gather as ONE kernel over peer memory
+    (`tensorf_adam_step_peer`, SURVEY §8e "fused follow-up"): replaces `FlatGrads.allreduce()` +
+    `ops.AdamCall.step()` (training.py:153-156 -> :158-243 with the ray batch sharded over ranks).
+
+    Every leaf of LearnableParams and of its gradient lives in one symmetric allocation per rank
+    (`torch.distributed._symmetric_memory`: cuMem handles exchanged at rendezvous, so every rank holds a
+    mapping of every other rank's buffer, plus the NVSwitch multicast address when the fabric has one):
+    `[params: T | grads: T | norm slots: 16]` floats, T = leaves rounded up to a multiple of 4.
+    Rank r owns elements `[shard_begin, shard_end)`; its shard of the Adam moments is local (memory and
+    traffic / world).  `params` / `grads` are views for the render calls (`RenderCall.backward(None, grads)`
+    writes straight into the symmetric buffer).  world == 1 needs no process group and runs the same kernel.
+    """
+
+    def __init__(self, shapes: Dict[str, Tuple[int, ...]], neg_lrs: Dict[str, float], device, group=None,
+                 b1: float = 0.9, b2: float = 0.99, eps: float = 1e-8, eps_root: float = 0.0, multicast=None):
+        import ctypes as C
+        import os
+
+        import torch.distributed as dist
+
+        from . import _lib
+
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("PeerAdam needs a CUDA device (there is no CPU path)")
+        self.names = list(shapes.keys())
+        self.shapes = {k: tuple(int(x) for x in shapes[k]) for k in self.names}
+        sizes = [int(np.prod(self.shapes[k])) for k in self.names]
+        # every leaf starts on a 16-byte boundary (the render kernels take vector paths on aligned leaves); a gap
+        # is a pseudo-leaf with learning rate 0 whose gradient is never written (stays 0)
+        self.leaf_offsets: Dict[str, int] = {}
+        table_offs, table_lrs, off = [0], [], 0
+        for k, n in zip(self.names, sizes):
+            self.leaf_offsets[k] = off
+            if n > 0:
+                table_offs.append(off + n)
+                table_lrs.append(float(neg_lrs[k]))
+            off += n
+            pad = -off % 4
+            if pad and k != self.names[-1]:
+                off += pad
+                table_offs.append(off)
+                table_lrs.append(0.0)
+        if not table_lrs:
+            raise ValueError("PeerAdam: no parameters")
+        if len(table_lrs) > _lib.PEER_MAX_LEAVES:
+            raise ValueError(f"PeerAdam: {len(table_lrs)} leaves and alignment gaps (max {_lib.PEER_MAX_LEAVES})")
+        self.leaf_total = int(table_offs[-1])
+        self.total = (self.leaf_total + 3) // 4 * 4
+        self.b1, self.b2, self.eps, self.eps_root = b1, b2, eps, eps_root
+        use_dist = dist.is_available() and dist.is_initialized()
+        self.group = group if group is not None else (dist.group.WORLD if use_dist else None)
+        self.world = dist.get_world_size(self.group) if use_dist else 1
+        self.rank = dist.get_rank(self.group) if use_dist else 0
+        if self.world > _lib.PEER_MAX_WORLD:
+            raise ValueError(f"PeerAdam: world {self.world} > {_lib.PEER_MAX_WORLD}")
+        n_all = 2 * self.total + 16
+        self._hdl = None
+        mc_base = 0
+        if self.world > 1:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            self.buf = symm_mem.empty(n_all, dtype=torch.float32, device=self.device)
+            self._hdl = symm_mem.rendezvous(self.buf, self.group)
+            bases = [int(x) for x in self._hdl.buffer_ptrs]
+            own_off = self.buf.data_ptr() - bases[self.rank]  # 0 unless the tensor sits inside a pooled block
+            if own_off < 0:
+                raise RuntimeError("PeerAdam: symmetric allocation does not contain its own tensor")
+            peer_ptrs = [b + own_off for b in bases]
+            env = os.environ.get("TENSORF_PEER_MULTICAST")
+            want_mc = multicast if multicast is not None else (None if env is None else env != "0")
+            mc = int(self._hdl.multicast_ptr or 0)
+            if want_mc is True and mc == 0:
+                raise RuntimeError("PeerAdam: multicast requested but the symmetric allocation has no multicast address")
+            if mc != 0 and want_mc is not False:
+                mc_base = mc + own_off
+        else:
+            self.buf = torch.empty(n_all, dtype=torch.float32, device=self.device)
+            peer_ptrs = [self.buf.data_ptr()]
+        self.buf.zero_()
+        self.multicast = mc_base != 0
+        self.params_flat = self.buf[:self.total]
+        self.grads_flat = self.buf[self.total:2 * self.total]
+        self.slots = self.buf[2 * self.total:2 * self.total + 16]
+        self.params: Dict[str, torch.Tensor] = {}
+        self.grads: Dict[str, torch.Tensor] = {}
+        for k, n in zip(self.names, sizes):
+            o = self.leaf_offsets[k]
+            self.params[k] = self.params_flat[o:o + n].view(self.shapes[k])
+            self.grads[k] = self.grads_flat[o:o + n].view(self.shapes[k])
+        b, e = C.c_int64(), C.c_int64()
+        self.lib.tensorf_peer_shard(self.total, self.rank, self.world, C.byref(b), C.byref(e))
+        self.shard = (int(b.value), int(e.value))
+        n_shard = self.shard[1] - self.shard[0]
+        self.mu = torch.zeros(max(n_shard, 4), dtype=torch.float32, device=self.device)
+        self.nu = torch.zeros(max(n_shard, 4), dtype=torch.float32, device=self.device)
+        nbytes = int(self.lib.tensorf_peer_adam_scratch_bytes(n_shard))
+        self.scratch = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.device)
+        self.grad_norm = torch.zeros((), dtype=torch.float32, device=self.device)
+        W = self.world
+        self._n_table = len(table_lrs)
+        self._offs = (C.c_int64 * (self._n_table + 1))(*table_offs)
+        self._neg_lrs = (C.c_float * self._n_table)(*table_lrs)
+        self._g = (C.c_void_p * W)(*[p + 4 * self.total for p in peer_ptrs])
+        self._p = (C.c_void_p * W)(*peer_ptrs)
+        self._s = (C.c_void_p * W)(*[p + 8 * self.total for p in peer_ptrs])
+        self._g_mc = C.c_void_p(mc_base + 4 * self.total) if mc_base else None
+        self._p_mc = C.c_void_p(mc_base) if mc_base else None
+        self.barrier()  # every rank's buffer is zeroed before anyone may store into it
+
+    def barrier(self) -> None:
+        """Cross-rank barrier ordered on the current stream (device-side signal pads, no host wait)."""
+        if self._hdl is not None:
+            self._hdl.barrier(channel=0)
+
+    def load_params(self, flat: Dict[str, torch.Tensor]) -> None:
+        """Copy replicated leaves into the symmetric buffer (every rank calls this with the same values)."""
+        with torch.no_grad():
+            for k in self.names:
+                self.params[k].copy_(flat[k].detach())
+
+    def step(self, count: int, lr_decay: float = 1.0) -> torch.Tensor:
+        """One fused exchange + optimiser step over `self.grads` (each rank's LOCAL gradient, already scaled by
+        the global 1/(3R)); afterwards `self.params` holds the same new parameters on every rank.  Returns the
+        device scalar optax.global_norm(sum of the ranks' gradients)."""
+        import ctypes as C
+
+        from . import _lib
+        from .ops import _stream
+
+        t = np.float32(count + 1)
+        bc1 = np.float32(1) - np.power(np.float32(self.b1), t)
+        bc2 = np.float32(1) - np.power(np.float32(self.b2), t)
+        d = _lib.PeerAdamDesc(
+            adam=_lib.AdamDesc(n_leaves=self._n_table, reserved=0, b1=self.b1, b2=self.b2, eps=self.eps,
+                               eps_root=self.eps_root, bias_correction1=float(bc1), bias_correction2=float(bc2),
+                               lr_decay=float(lr_decay), reserved2=0.0),
+            rank=self.rank, world=self.world, total=self.total, shard_begin=self.shard[0], shard_end=self.shard[1])
+        self.barrier()  # all ranks' gradients are complete
+        _lib.check(self.lib.tensorf_adam_step_peer(_stream(), C.byref(d), self._offs, self._neg_lrs, self._g, self._p,
+                                                   self._g_mc, self._p_mc, self.mu.data_ptr(), self.nu.data_ptr(), self._s,
+                                                   self.scratch.data_ptr(), self.scratch.numel()))
+        self.barrier()  # all parameter and slot stores have landed everywhere
+        _lib.check(self.lib.tensorf_peer_grad_norm(_stream(), self.slots.data_ptr(), self.world, self.grad_norm.data_ptr()))
+        return self.grad_norm
+
+    def gather_moments(self, shard: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Full moment leaves from the per-rank shards (grid resampling needs them whole, training.py:245-276)."""
+        full = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        b, e = self.shard
+        full[b:e] = shard[:e - b]
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(full, group=self.group)  # shards are disjoint: the sum is the concatenation
+        out = {}
+        for k in self.names:
+            o, n = self.leaf_offsets[k], int(np.prod(self.shapes[k]))
+            out[k] = full[o:o + n].view(self.shapes[k])
+        return out
+
+    def scatter_moments(self, shard: torch.Tensor, leaves: Dict[str, torch.Tensor]) -> None:
+        """Inverse of gather_moments: keep this rank's range of replicated full leaves."""
+        full = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        for k in self.names:
+            o, n = self.leaf_offsets[k], int(np.prod(self.shapes[k]))
+            full[o:o + n] = leaves[k].reshape(-1)
+        b, e = self.shard
+        shard[:e - b] = full[b:e]

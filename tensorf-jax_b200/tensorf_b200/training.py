@@ -42,6 +42,7 @@ class TrainState:
     world_size: int = 1  # rays sharded over ranks; gradients sum-allreduced
     _adam: Optional[ops.AdamCall] = dataclasses.field(default=None, repr=False, compare=False)
     _adam_names: Optional[list] = dataclasses.field(default=None, repr=False, compare=False)
+    _peer: Optional[object] = dataclasses.field(default=None, repr=False, compare=False)  # dist.PeerAdam
 
     @staticmethod
     def initialize(config: train_config.TensorfConfig, grid_dim: int, prng_key, num_cameras: int,
@@ -99,10 +100,35 @@ class TrainState:
         render._release(call)
         return loss, grads
 
+    def enable_peer_optimizer(self, group=None, multicast=None) -> "TrainState":
+        """SURVEY §8e fused follow-up: move the parameters into a symmetric peer-mapped buffer and replace
+        `all_reduce(grads)` + Adam by `tensorf_adam_step_peer` (one kernel: reduce-scatter over NVLink, Adam on the
+        owner's shard, parameter all-gather).  The Adam moments become per-rank shards (`optimizer_state` keeps
+        {"mu": {"shard": ...}, "nu": {"shard": ...}}); call before the first step (moments must still be zero)
+        and again after `resize_grid`."""
+        from . import dist as tdist
+        if self.step != 0 and self._peer is None:
+            raise ValueError("enable_peer_optimizer: call before the first training step (moments are re-created)")
+        oc = self.config.optimizer
+        flat = self.learnable_params.flat()
+        neg = {k: -(oc.lr_init_tensor if k.startswith(("density_", "appearance_")) else oc.lr_init_mlp) for k in flat}
+        peer = tdist.PeerAdam({k: tuple(v.shape) for k, v in flat.items()}, neg, self.aabb.device, group=group,
+                              b1=0.9, b2=0.99, eps=1e-8, multicast=multicast)
+        if peer.world != self.world_size:
+            raise ValueError(f"enable_peer_optimizer: process group has {peer.world} ranks, world_size={self.world_size}")
+        peer.load_params(flat)
+        peer.barrier()
+        self.learnable_params = render.LearnableParams.from_flat(peer.params, self.config.scene_contraction)
+        self.optimizer_state = {"mu": {"shard": peer.mu}, "nu": {"shard": peer.nu}}
+        self._peer, self._adam = peer, None
+        return self
+
     def training_step(self, minibatch: RenderedRays) -> Tuple["TrainState", Dict[str, float]]:
         """training.py:101-205."""
         keys = prng.split(self.prng_key)
         render_key, new_key = keys[0], keys[1]
+        if self._peer is not None:
+            return self._training_step_peer(minibatch, render_key, new_key)
         loss, grads = self.loss_and_grads(minibatch, render_key)
         if self.world_size > 1:
             import torch.distributed as dist
@@ -129,6 +155,23 @@ class TrainState:
                "train/lr_mlp": coeff * oc.lr_init_mlp, "train/grad_norm": float(gnorm.item())}
         return self, log
 
+    def _training_step_peer(self, minibatch: RenderedRays, render_key, new_key):
+        """training_step with the exchange and the optimiser fused (`enable_peer_optimizer`)."""
+        peer = self._peer
+        loss, _ = self.loss_and_grads(minibatch, render_key, grads=peer.grads)  # reverse pass writes the symmetric buffer
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(loss)
+        coeff = self.lr_decay_coeff()
+        oc = self.config.optimizer
+        gnorm = peer.step(count=self.step, lr_decay=coeff)
+        self.prng_key = new_key
+        self.step += 1
+        mse = float(loss.item())
+        log = {"train/mse": mse, "train/psnr": psnr_from_mse(mse), "train/lr_tensor": coeff * oc.lr_init_tensor,
+               "train/lr_mlp": coeff * oc.lr_init_mlp, "train/grad_norm": float(gnorm.item())}
+        return self, log
+
     def lr_decay_coeff(self) -> float:
         """training.py:158-181: optax.exponential_decay(1.0, decay_iters, ratio, end_value=ratio) at the step
         count since the last upsampling (when `lr_upsample_reset`)."""
@@ -143,6 +186,8 @@ class TrainState:
 
     def resize_grid(self, new_grid_dim: int) -> "TrainState":
         """training.py:245-276: resample the factor grids and their Adam moments (mu, nu)."""
+        if self._peer is not None:
+            return self._resize_grid_peer(new_grid_dim)
         lp = self.learnable_params
         lp.density_tensor = lp.density_tensor.resize(new_grid_dim)
         lp.appearance_tensor = lp.appearance_tensor.resize(new_grid_dim)
@@ -152,4 +197,28 @@ class TrainState:
                 v, m = ops.vm_resize(st[f"{which}_vector"], st[f"{which}_matrix"], int(new_grid_dim))
                 st[f"{which}_vector"], st[f"{which}_matrix"] = v, m
         self._adam = None  # leaf buffers changed: rebuild the pointer tables
+        return self
+
+    def _resize_grid_peer(self, new_grid_dim: int) -> "TrainState":
+        """resize_grid with sharded moments: gather the moment shards (5 times per training run), resample
+        parameters and moments on every rank, re-create the symmetric buffers at the new size."""
+        old = self._peer
+        full = {"mu": old.gather_moments(old.mu), "nu": old.gather_moments(old.nu)}
+        lp = self.learnable_params
+        dens, app = lp.density_tensor.resize(new_grid_dim), lp.appearance_tensor.resize(new_grid_dim)
+        flat = dict(lp.flat())
+        flat["density_vector"], flat["density_matrix"] = dens.stacked_single_vm.vector, dens.stacked_single_vm.matrix
+        flat["appearance_vector"], flat["appearance_matrix"] = app.stacked_single_vm.vector, app.stacked_single_vm.matrix
+        flat = {k: v.clone() for k, v in flat.items()}  # the old symmetric buffer is about to be released
+        for st in full.values():
+            for which in ("density", "appearance"):
+                st[f"{which}_vector"], st[f"{which}_matrix"] = ops.vm_resize(st[f"{which}_vector"].contiguous(),
+                                                                             st[f"{which}_matrix"].contiguous(), int(new_grid_dim))
+        self.learnable_params = render.LearnableParams.from_flat(flat, self.config.scene_contraction)
+        self._peer = None
+        step, self.step = self.step, 0
+        self.enable_peer_optimizer(group=old.group, multicast=old.multicast if old.world > 1 else None)
+        self.step = step
+        self._peer.scatter_moments(self._peer.mu, full["mu"])
+        self._peer.scatter_moments(self._peer.nu, full["nu"])
         return self

@@ -1,0 +1,166 @@
+"""Two-or-more-rank check of `tensorf_adam_step_peer` over real NVLink peer mappings (run under torchrun by
+tests/test_gpu_peer.py::test_two_ranks_over_nvlink, or by hand:
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/peer_worker.py).
+Per transport (P2P loads/stores, NVSwitch multicast when available): parameters after each step equal NCCL
+all-reduce + tensorf_adam_step (bit-for-bit at world 2, where the fp32 sum has one order), every rank holds the same
+bits, the gradient norm matches; then both paths are timed at the lego 128^3 parameter count."""
+import json
+import os
+import pathlib
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+for p in (ROOT, ROOT / "tensorf-jax_b200"):
+    sys.path.insert(0, str(p))
+
+from tensorf_b200 import dist as tdist, ops  # noqa: E402
+
+
+def ulp(a, b):
+    ia = a.view(torch.int32).long()
+    ib = b.view(torch.int32).long()
+    ia = torch.where(ia < 0, -(2 ** 31) - ia, ia)
+    ib = torch.where(ib < 0, -(2 ** 31) - ib, ib)
+    return int((ia - ib).abs().max().item()) if a.numel() else 0
+
+
+def check_transport(shapes, neg, dev, rank, world, multicast, report):
+    names = list(shapes)
+    peer = tdist.PeerAdam(shapes, neg, dev, multicast=multicast)
+    tag = "multicast" if peer.multicast else "p2p"
+    gen = torch.Generator(device=dev).manual_seed(11)            # same parameters on every rank
+    p0 = {k: torch.randn(shapes[k], generator=gen, device=dev) for k in names}
+    peer.load_params(p0)
+    rp = [p0[k].clone() for k in names]
+    rm, rv = [torch.zeros_like(t) for t in rp], [torch.zeros_like(t) for t in rp]
+    ref = ops.AdamCall(rp, rm, rv, [neg[k] for k in names])
+    fg = tdist.FlatGrads(shapes, dev)
+    gen_r = torch.Generator(device=dev).manual_seed(100 + rank)  # rank-local gradients
+    worst = 0
+    for step in range(4):
+        for k in names:
+            g = torch.randn(shapes[k], generator=gen_r, device=dev) * (10.0 ** ((step + rank) % 5 - 3))
+            peer.grads[k].copy_(g)
+            fg.leaves[k].copy_(g)
+        gn = peer.step(count=step, lr_decay=0.9 ** step)
+        fg.allreduce()
+        gn_ref = ref.step([fg.leaves[k] for k in names], count=step, lr_decay=0.9 ** step)
+        torch.cuda.synchronize()
+        for i, k in enumerate(names):
+            u = ulp(peer.params[k].reshape(-1), rp[i].reshape(-1))
+            worst = max(worst, u)
+            if world == 2 and not peer.multicast:
+                assert u == 0, f"{tag} step {step} leaf {k}: {u} ulp from NCCL+adam at world 2"
+        # a different summation order (ring vs rank order vs switch) moves g by an ulp; Adam's first steps normalise
+        # g, so compare the parameters at 1e-5 of the step size instead of bit-for-bit
+        for i, k in enumerate(names):
+            tol = 1e-5 * abs(neg[k]) + 1e-7
+            err = float((peer.params[k] - rp[i]).abs().max().item()) if rp[i].numel() else 0.0
+            assert err <= 50 * tol, f"{tag} step {step} leaf {k}: |dp| {err}"
+        gref = float(gn_ref.item())
+        assert abs(float(gn.item()) - gref) <= 1e-5 * max(1.0, gref), (tag, step, float(gn.item()), gref)
+        # every rank holds the same bits
+        mine = peer.params_flat.clone()
+        other = mine.clone()
+        dist.broadcast(other, src=0)
+        assert torch.equal(mine, other), f"{tag} step {step}: rank {rank} parameters differ from rank 0"
+    report[tag] = {"max_ulp_vs_nccl_adam": worst, "multicast": bool(peer.multicast), "shard": list(peer.shard)}
+    del peer
+    return tag
+
+
+def time_paths(dev, rank, world, multicast, report, iters=30):
+    """lego 128^3 parameter count (12.8 M floats): NCCL all-reduce + k_adam vs the fused kernel (with its barriers)."""
+    shapes = ops.param_shapes(ops.make_desc(R=4096, N=256, K=38, G=128, cd=16, ca=48, feat_freqs=2, view_freqs=2))
+    neg = {k: -(0.02 if k.startswith(("density_", "appearance_")) else 1e-3) for k in shapes}
+    names = list(shapes)
+    peer = tdist.PeerAdam(shapes, neg, dev, multicast=multicast)
+    tag = "multicast" if peer.multicast else "p2p"
+    fg = tdist.FlatGrads(shapes, dev)
+    fg.flat.normal_()
+    peer.grads_flat.normal_()
+    rp = [torch.randn(shapes[k], device=dev) for k in names]
+    ref = ops.AdamCall(rp, [torch.zeros_like(t) for t in rp], [torch.zeros_like(t) for t in rp], [neg[k] for k in names])
+
+    def run(fn):
+        for _ in range(5):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    count = [0]
+
+    def nccl_path():
+        fg.allreduce()
+        ref.step([fg.leaves[k] for k in names], count=count[0])
+        count[0] += 1
+
+    def fused_path():
+        peer.step(count=count[0])
+        count[0] += 1
+
+    ms_nccl = run(nccl_path)
+    ms_fused = run(fused_path)
+    report["timing_" + tag] = {"parameters": fg.total, "nccl_allreduce_plus_adam_ms": ms_nccl, "fused_peer_ms": ms_fused,
+                               "speedup": ms_nccl / ms_fused, "iters": iters}
+    del peer
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    report = {"world": world, "torch": torch.__version__}
+    shapes = {"density_vector": (3, 4, 9), "density_matrix": (3, 4, 9, 9), "w0": (144, 27), "w1": (150, 128), "b1": (128,),
+              "w3": (128, 3), "b3": (3,), "big": (1_000_003,)}
+    neg = {k: -(0.02 if i % 2 else 1e-3) for i, k in enumerate(shapes)}
+    try:
+        tag = check_transport(shapes, neg, dev, rank, world, False, report)
+        assert tag == "p2p"
+        time_paths(dev, rank, world, False, report)
+        mc_ok = True
+        try:
+            tag = check_transport(shapes, neg, dev, rank, world, None, report)
+        except Exception as e:  # multicast is optional hardware: report, do not hide
+            mc_ok = False
+            report["multicast_error"] = repr(e)[:500]
+            raise
+        if mc_ok and tag == "multicast":
+            time_paths(dev, rank, world, None, report)
+        else:
+            report["multicast"] = "no multicast address on this fabric"
+        report["ok"] = True
+    except Exception as e:
+        report["ok"] = False
+        report["error"] = repr(e)[:2000]
+        raise
+    finally:
+        if rank == 0:
+            out = os.environ.get("PEER_WORKER_OUT")
+            line = json.dumps(report)
+            print(line, flush=True)
+            if out:
+                pathlib.Path(out).write_text(line + "\n")
+        time.sleep(0.1)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

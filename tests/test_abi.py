@@ -71,3 +71,41 @@ def test_library_threefry_known_answers():
            ((0x13198A2E, 0x03707344), (0x243F6A88, 0x85A308D3), (0xC4923A9C, 0x483DF7A0))]
     for key, ctr, out in kat:
         assert ops.threefry2x32(key[0], key[1], ctr[0], ctr[1]) == out
+
+
+def test_peer_shard_ranges_and_host_validation():
+    """tensorf_peer_shard (host function) tiles [0,total) with 4-aligned ranges; tensorf_adam_step_peer validates
+    its descriptor before touching the device."""
+    from tensorf_b200 import _lib
+    lib = _lib.load()
+    for total in (0, 4, 8, 100, 3210420):
+        for world in (1, 2, 3, 8, 16):
+            prev, sizes = 0, []
+            for r in range(world):
+                b, e = ctypes.c_int64(), ctypes.c_int64()
+                lib.tensorf_peer_shard(total, r, world, ctypes.byref(b), ctypes.byref(e))
+                assert b.value == prev and b.value % 4 == 0 and e.value % 4 == 0 and e.value >= b.value
+                prev = e.value
+                sizes.append(e.value - b.value)
+            assert prev == total and max(sizes) - min(sizes) <= 4
+    assert ctypes.sizeof(_lib.PeerAdamDesc) == 72
+    assert lib.tensorf_peer_adam_scratch_bytes(0) >= 16 and lib.tensorf_peer_adam_scratch_bytes(-1) == -1
+    fake = (ctypes.c_void_p * 2)(0x1000, 0x2000)
+    offs = (ctypes.c_int64 * 2)(0, 8)
+    neg = (ctypes.c_float * 1)(-1.0)
+
+    def call(**kw):
+        f = dict(rank=0, world=2, total=8, shard_begin=0, shard_end=4, n_leaves=1)
+        f.update(kw)
+        d = _lib.PeerAdamDesc(adam=_lib.AdamDesc(n_leaves=f["n_leaves"], reserved=0, b1=0.9, b2=0.99, eps=1e-8, eps_root=0.0,
+                                                 bias_correction1=0.1, bias_correction2=0.01, lr_decay=1.0, reserved2=0.0),
+                              rank=f["rank"], world=f["world"], total=f["total"], shard_begin=f["shard_begin"],
+                              shard_end=f["shard_end"])
+        return lib.tensorf_adam_step_peer(None, ctypes.byref(d), offs, neg, fake, fake, None, None, 0x3000, 0x4000, fake,
+                                          None, 0)
+    assert call() == -1 and b"scratch" in lib.tensorf_last_error()            # everything else valid: stops at scratch
+    assert call(world=0) == -1 and b"world" in lib.tensorf_last_error()
+    assert call(rank=2) == -1 and b"rank" in lib.tensorf_last_error()
+    assert call(total=10) == -1 and b"multiple of 4" in lib.tensorf_last_error()
+    assert call(shard_end=6) == -1 and b"shard" in lib.tensorf_last_error()
+    assert call(n_leaves=33) == -1 and b"n_leaves" in lib.tensorf_last_error()
