@@ -253,6 +253,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--no-render", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: one all-reduce after the whole reverse pass")
     args = ap.parse_args()
     w = workload_from_name(args.workload)
     if args.impl == "reference":
@@ -307,17 +308,25 @@ def main():
 
     # all gradient leaves live in ONE flat buffer -> one NCCL allreduce per step
     from tensorf_b200 import dist as tdist
-    fg = tdist.FlatGrads(ops.param_shapes(desc), dev)
-    grads, flat = fg.leaves, fg.flat
+    # (with the loss in one extra slot); the reverse pass runs in two halves so that the exchange of everything but
+    # the density factors overlaps with the density scatter (tensorf_render_rgb_bwd_phase)
+    fg = tdist.FlatGrads(ops.param_shapes(desc), dev, loss_slot=True)
+    grads = fg.leaves
+    overlap = world > 1 and not args.no_overlap
 
     flush = None if args.no_l2_flush else torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
     def step():
-        rgb, loss = call.forward(params, dins)
-        call.backward(None, grads)
-        if world > 1:
-            dist.all_reduce(flat)
-            dist.all_reduce(loss)
+        rgb, loss = call.forward(params, dins, loss_out=fg.loss)
+        if overlap:
+            call.backward(None, grads, phase=1)
+            fg.start_allreduce("early")
+            call.backward(None, grads, phase=2)
+            fg.start_allreduce("late")
+            fg.finish()
+        else:
+            call.backward(None, grads)
+            fg.allreduce()
         return loss
 
     def barrier():
@@ -403,7 +412,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": w.name, "R_per_gpu": w.R, "R_global": R_global, "N": w.N, "K": w.K, "G": w.G,
                        "cd": w.cd, "ca": w.ca, "feat_freqs": w.feat_freqs, "view_freqs": w.view_freqs,
-                       "contracted": w.contracted, "parallelism": f"rays sharded x{world}, NCCL grad allreduce" if world > 1 else "single GPU",
+                       "contracted": w.contracted, "parallelism": (f"rays sharded x{world}, NCCL grad allreduce" + (" in two buckets overlapped with the density scatter" if overlap else "")) if world > 1 else "single GPU",
                        "l2": "flushed (256 MiB write) between timed steps" if flush is not None else "not flushed",
                        "timed": "render_rays fwd + MSE + reverse wrt all LearnableParams leaves; Adam excluded",
                        "loss": loss_host},

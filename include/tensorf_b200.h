@@ -187,6 +187,13 @@ int tensorf_render_rgb_fwd(tensorf_stream_t s, const tensorf_render_desc* d, con
 int tensorf_render_rgb_bwd(tensorf_stream_t s, const tensorf_render_desc* d, const tensorf_params* p,
                            const tensorf_render_inputs* in, void* workspace, const float* d_rgb,
                            const tensorf_params* grads);
+/* The same reverse pass in two halves, for sharded training: phase 1 = ray reverse, MLP reverse,
+ * appearance scatter (afterwards every leaf of `grads` except the density factors is final, so their exchange can
+ * start and overlap with) phase 2 = density scatter (density_vector / density_matrix of `grads`).  phase 0 = the whole
+ * pass, identical to tensorf_render_rgb_bwd.  Phase 2 must follow phase 1 of the same step on the same workspace. */
+int tensorf_render_rgb_bwd_phase(tensorf_stream_t s, const tensorf_render_desc* d, const tensorf_params* p,
+                                 const tensorf_render_inputs* in, void* workspace, const float* d_rgb,
+                                 const tensorf_params* grads, int phase);
 /* modes DIST_MEDIAN / DIST_MEAN (render.py:248-276): depth (R,). Only the density factors of
  * `p` are read. */
 int tensorf_render_depth(tensorf_stream_t s, const tensorf_render_desc* d, const tensorf_params* p,

@@ -439,10 +439,15 @@ int tensorf_render_rgb_fwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   return launch_composite_fwd(st, c);
 }
 
-int tensorf_render_rgb_bwd(tensorf_stream_t s, const tensorf_render_desc* d, const tensorf_params* p,
-                           const tensorf_render_inputs* in, void* workspace, const float* d_rgb,
-                           const tensorf_params* grads) {
+// phases: 0 = whole reverse pass (ray, density scatter, MLP, appearance scatter, one unpack);
+// 1 = appearance half (ray_bwd, MLP reverse, appearance scatter, unpack appearance): every gradient leaf except the
+//     density factors is final when it returns, so a sharded caller can start their exchange and overlap it with
+// 2 = density half (density scatter, unpack density); needs phase 1 of the same step (dz lives in the workspace).
+static int render_rgb_bwd_impl(tensorf_stream_t s, const tensorf_render_desc* d, const tensorf_params* p,
+                               const tensorf_render_inputs* in, void* workspace, const float* d_rgb,
+                               const tensorf_params* grads, int phase) {
   TF_RETURN_IF_ERROR(check_desc(d));
+  TF_CHECK_ARG(phase >= 0 && phase <= 2, "render_rgb_bwd: phase %d outside [0,2]", phase);
   TF_CHECK_ARG(d->mode == TENSORF_MODE_RGB, "render_rgb_bwd needs mode RGB");
   TF_CHECK_ARG(!(d->flags & TENSORF_FLAG_INFERENCE), "render_rgb_bwd after a forward with TENSORF_FLAG_INFERENCE (residuals were not kept)");
   TF_RETURN_IF_ERROR(check_inputs(d, in));
@@ -456,65 +461,89 @@ int tensorf_render_rgb_bwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   RenderWs w = carve(*d, (float*)workspace);
   const MlpShape ms = mlp_shape(*d);
   const int64_t M = (int64_t)d->R * d->K;
+  const bool do_app = phase != 2, do_den = phase != 1;
 
-  RayBwdArgs rb{};
-  fill_scene(rb, *d, *in);
-  rb.z = w.z;
-  rb.idx = w.idx;
-  rb.pt_sel = w.pt_sel;
-  rb.rgb_sel = w.rgb_sel;
-  rb.stats = w.stats;
-  rb.go = d_rgb ? d_rgb : w.go;
-  rb.d_rgb_sel = w.d_rgb_sel;
-  rb.dz = w.dz;
-  {
+  if (do_app) {
+    RayBwdArgs rb{};
+    fill_scene(rb, *d, *in);
+    rb.z = w.z;
+    rb.idx = w.idx;
+    rb.pt_sel = w.pt_sel;
+    rb.rgb_sel = w.rgb_sel;
+    rb.stats = w.stats;
+    rb.go = d_rgb ? d_rgb : w.go;
+    rb.d_rgb_sel = w.d_rgb_sel;
+    rb.dz = w.dz;
     StageTimer t_(st, "ray_bwd");
     TF_RETURN_IF_ERROR(launch_ray_bwd(st, rb));
   }
   {
     StageTimer t_(st, "zero_grads");
-    TF_CHECK_CUDA(cudaMemsetAsync(w.gpacked_d, 0, sizeof(float) * packed_floats(d->cd, d->G), st));
-    TF_CHECK_CUDA(cudaMemsetAsync(w.gpacked_a, 0, sizeof(float) * packed_floats(d->ca, d->G), st));
+    if (do_den) TF_CHECK_CUDA(cudaMemsetAsync(w.gpacked_d, 0, sizeof(float) * packed_floats(d->cd, d->G), st));
+    if (do_app) TF_CHECK_CUDA(cudaMemsetAsync(w.gpacked_a, 0, sizeof(float) * packed_floats(d->ca, d->G), st));
   }
 
-  DensityBwdArgs db{};
-  fill_scene(db, *d, *in);
-  db.packed_d = w.packed_d;
-  db.dz = w.dz;
-  db.xs = w.xs;
-  db.d_packed = w.gpacked_d;
-  db.Cp = packed_cp(d->cd);
-  {
+  if (do_den && phase == 0) {
+    DensityBwdArgs db{};
+    fill_scene(db, *d, *in);
+    db.packed_d = w.packed_d;
+    db.dz = w.dz;
+    db.xs = w.xs;
+    db.d_packed = w.gpacked_d;
+    db.Cp = packed_cp(d->cd);
     StageTimer t_(st, "density_scatter");
     TF_RETURN_IF_ERROR(launch_density_scatter(st, db));
   }
 
-  MlpWs mws = mlp_ws_carve(ms, M, w.mlp_base);
-  {
-    StageTimer t_(st, "mlp_bwd");
-    TF_RETURN_IF_ERROR((mlp_use_tc(d->mlp_impl) ? mlp_tc_bwd : mlp_simt_bwd)(st, ms, mlp_params(*p), w.feat, in->directions,
-                                                                              in->camera_indices, M, d->K, mws, w.rgb_sel,
-                                                                              w.d_rgb_sel, w.d_feat, mlp_grads(*grads)));
-  }
-
-  AppearanceArgs ap{};
-  fill_scene(ap, *d, *in);
-  ap.packed_a = w.packed_a;
-  ap.idx = w.idx;
-  ap.xs = w.xs;
-  ap.C = d->ca;
-  ap.Cp = packed_cp(d->ca);
-  ap.M = M;
-  ap.d_feat = w.d_feat;
-  ap.d_packed = w.gpacked_a;
-  {
+  if (do_app) {
+    MlpWs mws = mlp_ws_carve(ms, M, w.mlp_base);
+    {
+      StageTimer t_(st, "mlp_bwd");
+      TF_RETURN_IF_ERROR((mlp_use_tc(d->mlp_impl) ? mlp_tc_bwd : mlp_simt_bwd)(st, ms, mlp_params(*p), w.feat, in->directions,
+                                                                                in->camera_indices, M, d->K, mws, w.rgb_sel,
+                                                                                w.d_rgb_sel, w.d_feat, mlp_grads(*grads)));
+    }
+    AppearanceArgs ap{};
+    fill_scene(ap, *d, *in);
+    ap.packed_a = w.packed_a;
+    ap.idx = w.idx;
+    ap.xs = w.xs;
+    ap.C = d->ca;
+    ap.Cp = packed_cp(d->ca);
+    ap.M = M;
+    ap.d_feat = w.d_feat;
+    ap.d_packed = w.gpacked_a;
     StageTimer t_(st, "appearance_scatter");
     TF_RETURN_IF_ERROR(launch_appearance_scatter(st, ap));
   }
+  if (phase == 2) {
+    DensityBwdArgs db{};
+    fill_scene(db, *d, *in);
+    db.packed_d = w.packed_d;
+    db.dz = w.dz;
+    db.xs = w.xs;
+    db.d_packed = w.gpacked_d;
+    db.Cp = packed_cp(d->cd);
+    StageTimer t_(st, "density_scatter");
+    TF_RETURN_IF_ERROR(launch_density_scatter(st, db));
+  }
   StageTimer t_(st, "unpack");
-  TF_RETURN_IF_ERROR(vm_unpack2(st, w.gpacked_d, grads->density_vector, grads->density_matrix, d->cd, w.gpacked_a,
-                                grads->appearance_vector, grads->appearance_matrix, d->ca, d->G));
-  return 0;
+  if (phase == 0)
+    return vm_unpack2(st, w.gpacked_d, grads->density_vector, grads->density_matrix, d->cd, w.gpacked_a,
+                      grads->appearance_vector, grads->appearance_matrix, d->ca, d->G);
+  if (phase == 1) return vm_unpack(st, w.gpacked_a, grads->appearance_vector, grads->appearance_matrix, d->ca, d->G);
+  return vm_unpack(st, w.gpacked_d, grads->density_vector, grads->density_matrix, d->cd, d->G);
+}
+
+int tensorf_render_rgb_bwd(tensorf_stream_t s, const tensorf_render_desc* d, const tensorf_params* p,
+                           const tensorf_render_inputs* in, void* workspace, const float* d_rgb,
+                           const tensorf_params* grads) {
+  return render_rgb_bwd_impl(s, d, p, in, workspace, d_rgb, grads, 0);
+}
+int tensorf_render_rgb_bwd_phase(tensorf_stream_t s, const tensorf_render_desc* d, const tensorf_params* p,
+                                 const tensorf_render_inputs* in, void* workspace, const float* d_rgb,
+                                 const tensorf_params* grads, int phase) {
+  return render_rgb_bwd_impl(s, d, p, in, workspace, d_rgb, grads, phase);
 }
 
 int64_t tensorf_adam_scratch_bytes(const int64_t* sizes, int n_leaves) {

@@ -109,6 +109,7 @@ SIGNATURES = {
     "tensorf_render_workspace_bytes": (_i, [_pd, C.POINTER(_i64)]),
     "tensorf_render_rgb_fwd": (_i, [_vp, _pd, _pp, _pi, _vp, _vp, _vp]),
     "tensorf_render_rgb_bwd": (_i, [_vp, _pd, _pp, _pi, _vp, _vp, _pp]),
+    "tensorf_render_rgb_bwd_phase": (_i, [_vp, _pd, _pp, _pi, _vp, _vp, _pp, _i]),
     "tensorf_render_depth": (_i, [_vp, _pd, _pp, _pi, _vp, _vp]),
     "tensorf_render_workspace_view": (_i, [_pd, _vp, C.c_char_p, C.POINTER(_vp), C.POINTER(_i64)]),
     "tensorf_adam_scratch_bytes": (_i64, [C.POINTER(_i64), _i]),

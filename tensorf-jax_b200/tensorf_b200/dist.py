@@ -41,18 +41,33 @@ def tile_rows(height: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 class FlatGrads:
-    """All gradient leaves as views into one contiguous fp32 buffer (one allreduce per step)."""
+    """All gradient leaves as views into one contiguous fp32 buffer, plus (optionally) one slot for the loss, so
+    the exchange step is one or two collectives instead of one per leaf.
 
-    def __init__(self, shapes: Dict[str, Tuple[int, ...]], device):
+    Two buckets follow the order in which the reverse pass finishes its leaves (`RenderCall.backward(phase=1/2)`):
+    `early` = everything but the density factors (+ the loss slot), final after phase 1, exchanged while phase 2
+    (the density scatter) runs; `late` = the density factors.  Needs the density leaves first in `shapes`
+    (`ops.param_shapes` order); otherwise there is a single bucket."""
+
+    def __init__(self, shapes: Dict[str, Tuple[int, ...]], device, loss_slot: bool = False):
         self.shapes = dict(shapes)
         self.total = int(sum(int(np.prod(s)) for s in shapes.values()))
-        self.flat = torch.zeros(self.total, dtype=torch.float32, device=device)
+        self.buffer = torch.zeros(self.total + (1 if loss_slot else 0), dtype=torch.float32, device=device)
+        self.flat = self.buffer[:self.total]
+        self.loss = self.buffer[self.total:self.total + 1] if loss_slot else None
         self.leaves: Dict[str, torch.Tensor] = {}
-        off = 0
+        off, split, prefix = 0, 0, True
         for k, s in shapes.items():
             n = int(np.prod(s))
             self.leaves[k] = self.flat[off:off + n].view(s)
             off += n
+            if prefix and k.startswith("density_"):
+                split = off
+            else:
+                prefix = False
+        self.late = self.buffer[:split]
+        self.early = self.buffer[split:]
+        self._pending = []
 
     def allreduce(self, group=None) -> None:
         """Sum over ranks (training.py:140 is a mean over the whole batch: every rank already
@@ -60,7 +75,21 @@ class FlatGrads:
         import torch.distributed as dist
 
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(self.buffer, op=dist.ReduceOp.SUM, group=group)
+
+    def start_allreduce(self, which: str, group=None) -> None:
+        """Asynchronous sum of one bucket ("early" / "late"): the collective is ordered after the work already
+        enqueued on the current stream and runs beside whatever is enqueued next; `finish()` joins."""
+        import torch.distributed as dist
+
+        t = {"early": self.early, "late": self.late}[which]
+        if t.numel() and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            self._pending.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True))
+
+    def finish(self) -> None:
+        for w in self._pending:
+            w.wait()
+        self._pending = []
 
 
 def global_loss_scale(local_rays: int, world: int) -> float:

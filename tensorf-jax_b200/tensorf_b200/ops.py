@@ -238,20 +238,28 @@ class RenderCall:
             ri.colors = _ptr(colors, name="colors")
         return ri
 
-    def forward(self, params: Dict[str, torch.Tensor], inputs: Dict[str, Optional[torch.Tensor]]):
-        """Returns (rgb (R,3), loss or None). `inputs['colors']` enables the fused MSE."""
+    def forward(self, params: Dict[str, torch.Tensor], inputs: Dict[str, Optional[torch.Tensor]],
+                loss_out: Optional[torch.Tensor] = None):
+        """Returns (rgb (R,3), loss or None). `inputs['colors']` enables the fused MSE; `loss_out` (one fp32
+        element, e.g. the loss slot of `dist.FlatGrads`) receives it in place of a fresh scalar."""
         d = self.desc
         ps = _params_struct(d, params)
         ri = self._inputs(inputs)
         rgb = torch.empty((d.R, 3), dtype=torch.float32, device=self.device)
-        loss = torch.empty((), dtype=torch.float32, device=self.device) if inputs.get("colors") is not None else None
+        loss = None
+        if inputs.get("colors") is not None:
+            if loss_out is not None and loss_out.numel() != 1:
+                raise ValueError("loss_out must hold exactly one element")
+            loss = loss_out if loss_out is not None else torch.empty((), dtype=torch.float32, device=self.device)
         check(_lib.load().tensorf_render_rgb_fwd(_stream(), C.byref(d), C.byref(ps), C.byref(ri), _ptr(self.workspace),
                                                  _ptr(rgb), _ptr(loss)))
         self._keep = (params, inputs)
         return rgb, loss
 
-    def backward(self, d_rgb: Optional[torch.Tensor] = None, grads: Optional[Dict[str, torch.Tensor]] = None):
-        """Gradients w.r.t. every leaf of LearnableParams. d_rgb=None uses the fused loss cotangent."""
+    def backward(self, d_rgb: Optional[torch.Tensor] = None, grads: Optional[Dict[str, torch.Tensor]] = None, phase: int = 0):
+        """Gradients w.r.t. every leaf of LearnableParams. d_rgb=None uses the fused loss cotangent.
+        phase 1 / 2 = the appearance / density half of the pass (`tensorf_render_rgb_bwd_phase`): after phase 1
+        every leaf but the density factors is final (sharded training starts their exchange there)."""
         d = self.desc
         params, inputs = self._keep
         ps = _params_struct(d, params)
@@ -261,8 +269,8 @@ class RenderCall:
         gs = _params_struct(d, grads, "grads")
         if d_rgb is not None and tuple(d_rgb.shape) != (d.R, 3):
             raise ValueError(f"d_rgb must be {(d.R, 3)}")
-        check(_lib.load().tensorf_render_rgb_bwd(_stream(), C.byref(d), C.byref(ps), C.byref(ri), _ptr(self.workspace),
-                                                 _ptr(d_rgb, name="d_rgb"), C.byref(gs)))
+        check(_lib.load().tensorf_render_rgb_bwd_phase(_stream(), C.byref(d), C.byref(ps), C.byref(ri), _ptr(self.workspace),
+                                                       _ptr(d_rgb, name="d_rgb"), C.byref(gs), int(phase)))
         return grads
 
     def depth(self, params: Dict[str, torch.Tensor], inputs: Dict[str, Optional[torch.Tensor]]) -> torch.Tensor:

@@ -43,6 +43,7 @@ class TrainState:
     _adam: Optional[ops.AdamCall] = dataclasses.field(default=None, repr=False, compare=False)
     _adam_names: Optional[list] = dataclasses.field(default=None, repr=False, compare=False)
     _peer: Optional[object] = dataclasses.field(default=None, repr=False, compare=False)  # dist.PeerAdam
+    _fg: Optional[object] = dataclasses.field(default=None, repr=False, compare=False)    # dist.FlatGrads (world_size > 1)
 
     @staticmethod
     def initialize(config: train_config.TensorfConfig, grid_dim: int, prng_key, num_cameras: int,
@@ -73,9 +74,13 @@ class TrainState:
         n = int(math.sqrt(3 * g**2) * self.config.train_ray_sample_multiplier)
         return n, int(0.15 * n)
 
-    def loss_and_grads(self, minibatch: RenderedRays, render_prng_key, grads: Optional[Dict[str, torch.Tensor]] = None):
+    def loss_and_grads(self, minibatch: RenderedRays, render_prng_key, grads: Optional[Dict[str, torch.Tensor]] = None,
+                       flat_grads=None):
         """training.py:108-156: (mse, grads w.r.t. every LearnableParams leaf). The mean is over the
-        GLOBAL batch (`world_size` x local rays); the caller allreduces the gradients."""
+        GLOBAL batch (`world_size` x local rays); the caller allreduces the gradients - or passes
+        `flat_grads` (dist.FlatGrads with a loss slot): then the reverse pass runs in its two halves, the exchange
+        of everything but the density factors overlaps with the density scatter, and loss and gradients come back
+        already summed over the ranks."""
         (R,) = minibatch.get_batch_axes()
         N, K = self.sample_counts()
         flat = self.learnable_params.flat()
@@ -95,6 +100,16 @@ class TrainState:
             base, delta = render.contracted_schedule(self.config.render_near, self.config.render_far, N)
             inputs["base_ts"], inputs["deltas"] = torch.from_numpy(base).to(dev), torch.from_numpy(delta).to(dev)
         call = render._acquire(desc, dev)
+        if flat_grads is not None:
+            fg = flat_grads
+            _, loss = call.forward({k: v.contiguous() for k, v in flat.items()}, inputs, loss_out=fg.loss)
+            call.backward(None, fg.leaves, phase=1)
+            fg.start_allreduce("early")
+            call.backward(None, fg.leaves, phase=2)
+            fg.start_allreduce("late")
+            fg.finish()
+            render._release(call)
+            return loss, fg.leaves
         _, loss = call.forward({k: v.contiguous() for k, v in flat.items()}, inputs)
         grads = call.backward(None, grads)
         render._release(call)
@@ -129,12 +144,14 @@ class TrainState:
         render_key, new_key = keys[0], keys[1]
         if self._peer is not None:
             return self._training_step_peer(minibatch, render_key, new_key)
-        loss, grads = self.loss_and_grads(minibatch, render_key)
         if self.world_size > 1:
-            import torch.distributed as dist
-            for g in grads.values():
-                dist.all_reduce(g)
-            dist.all_reduce(loss)
+            from . import dist as tdist
+            shapes = {k: tuple(v.shape) for k, v in self.learnable_params.flat().items()}
+            if self._fg is None or self._fg.shapes != shapes:
+                self._fg = tdist.FlatGrads(shapes, self.aabb.device, loss_slot=True)
+            loss, grads = self.loss_and_grads(minibatch, render_key, flat_grads=self._fg)
+        else:
+            loss, grads = self.loss_and_grads(minibatch, render_key)
         coeff = self.lr_decay_coeff()
         oc = self.config.optimizer
         # optax.scale_by_adam(b1=0.9, b2=0.99, eps=1e-8) + masked group learning rates (:213-243), one launch

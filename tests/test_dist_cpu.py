@@ -51,6 +51,22 @@ def _worker(rank, world, port, out):
         expect = {k: float(sum(range(10)) + world * i) for i, k in enumerate(shapes)}
         ok = all(torch.all(fg.leaves[k] == expect[k]).item() for k in shapes)
         scale = tdist.global_loss_scale(b - a, world)
+        # two buckets + loss slot (the overlapped exchange of bench.py / TrainState.training_step)
+        fb = tdist.FlatGrads(shapes, "cpu", loss_slot=True)
+        assert fb.buffer.numel() == fb.total + 1 and fb.late.numel() == 30 and fb.early.numel() == 28 + 3 + 1
+        assert fb.late.data_ptr() == fb.leaves["density_vector"].data_ptr() and fb.early.data_ptr() == fb.leaves["w1"].data_ptr()
+        for i, (k, t) in enumerate(fb.leaves.items()):
+            t.copy_(torch.full(t.shape, float(rank + 1 + i)))
+        fb.loss.fill_(0.25 * (rank + 1))
+        fb.start_allreduce("early")
+        late_before = fb.late.clone()
+        fb.start_allreduce("late")
+        fb.finish()
+        tri = world * (world + 1) / 2
+        ok = ok and all(torch.all(fb.leaves[k] == tri + world * i).item() for i, k in enumerate(shapes))
+        ok = ok and float(fb.loss.item()) == 0.25 * tri and torch.all(late_before == rank + 1).item() and not fb._pending
+        single = tdist.FlatGrads({"w1": (2,), "density_vector": (3,)}, "cpu")   # density not first: one bucket
+        ok = ok and single.late.numel() == 0 and single.early.numel() == 5
         out[rank] = (ok, scale)
     finally:
         dist.destroy_process_group()

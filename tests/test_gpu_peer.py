@@ -226,3 +226,38 @@ def test_two_ranks_over_nvlink(tmp_path):
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=420)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert out.exists()
+
+
+def test_backward_phases_match_whole_pass(cuda):
+    """tensorf_render_rgb_bwd_phase: phase 1 (appearance half) then phase 2 (density half) give the gradients of the
+    whole pass (atomics reorder sums: 1e-5 of the leaf's largest entry); phase 1 leaves the density leaves alone and
+    phase 2 touches nothing else - what the overlapped exchange relies on."""
+    from helpers import device_inputs
+    from tensorf_b200 import ops, synthetic as S
+    w = S.Workload("phases", 256, 32, 16, 48, 55, 8, 2, 2)
+    inp = S.make_inputs(w, bias_std=0.05)
+    desc = ops.make_desc(R=w.R, N=w.N, K=w.K, G=w.G, cd=w.cd, ca=w.ca, feat_freqs=2, view_freqs=2, loss_scale=1.0 / (3 * w.R))
+    call = ops.RenderCall(desc, cuda)
+    params, dins = device_inputs(w, inp, cuda)
+    slot = torch.zeros(1, device=cuda)
+    _, loss = call.forward(params, dins, loss_out=slot)
+    assert loss.data_ptr() == slot.data_ptr() and float(slot.item()) > 0.0
+    whole = {k: v.clone() for k, v in call.backward(None).items()}
+    g = {k: torch.full_like(v, float("nan")) for k, v in whole.items()}
+    call.forward(params, dins, loss_out=slot)      # fresh residuals (the reverse pass may reuse activation buffers)
+    call.backward(None, g, phase=1)
+    torch.cuda.synchronize()
+    dens = ("density_vector", "density_matrix")
+    assert all(torch.isnan(g[k]).all() for k in dens)
+    assert all(not torch.isnan(g[k]).any() for k in g if k not in dens)
+    after1 = {k: v.clone() for k, v in g.items()}
+    call.backward(None, g, phase=2)
+    torch.cuda.synchronize()
+    for k in g:
+        if k not in dens:
+            assert torch.equal(g[k], after1[k]), k
+        ref = whole[k]
+        tol = 1e-5 * float(ref.abs().max()) + 1e-12
+        assert float((g[k] - ref).abs().max()) <= tol, (k, float((g[k] - ref).abs().max()), tol)
+    with pytest.raises(Exception):
+        call.backward(None, g, phase=3)
