@@ -253,7 +253,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--no-render", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="N>1: one all-reduce after the whole reverse pass")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1, NCCL exchange: one all-reduce after the whole reverse pass")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer-p2p", "peer-multicast", "nccl"],
+                    help="N>1 gradient exchange: own kernel over peer memory (auto = multicast when the fabric has it) or NCCL")
     args = ap.parse_args()
     w = workload_from_name(args.workload)
     if args.impl == "reference":
@@ -313,10 +315,34 @@ def main():
     fg = tdist.FlatGrads(ops.param_shapes(desc), dev, loss_slot=True)
     grads = fg.leaves
     overlap = world > 1 and not args.no_overlap
+    # exchange over peer memory (tensorf_peer_allreduce on the launch stream: P2P loads/stores or NVSwitch multicast
+    # through torch symmetric memory) unless --exchange nccl; every rank must agree, else all fall back to NCCL
+    peer, exchange = None, "nccl"
+    if world > 1 and args.exchange != "nccl":
+        err = None
+        try:
+            shapes = ops.param_shapes(desc)
+            peer = tdist.PeerAdam(shapes, {k: 0.0 for k in shapes}, dev,
+                                  multicast={"peer-p2p": False, "peer-multicast": True}.get(args.exchange))
+        except Exception as e:  # no symmetric memory on this box: say so, use NCCL
+            err = repr(e)
+            print(f"[bench] rank {rank}: peer-memory exchange unavailable ({err[:300]}); using NCCL", file=sys.stderr)
+        ok = torch.tensor([0 if peer is None else 1], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
+            exchange = "peer-multicast" if peer.multicast else "peer-p2p"
+            grads = peer.grads
+        else:
+            peer = None
 
     flush = None if args.no_l2_flush else torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
     def step():
+        if peer is not None:
+            rgb, loss = call.forward(params, dins, loss_out=peer.loss)
+            call.backward(None, grads)
+            peer.allreduce()
+            return loss
         rgb, loss = call.forward(params, dins, loss_out=fg.loss)
         if overlap:
             call.backward(None, grads, phase=1)
@@ -412,7 +438,8 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": w.name, "R_per_gpu": w.R, "R_global": R_global, "N": w.N, "K": w.K, "G": w.G,
                        "cd": w.cd, "ca": w.ca, "feat_freqs": w.feat_freqs, "view_freqs": w.view_freqs,
-                       "contracted": w.contracted, "parallelism": (f"rays sharded x{world}, NCCL grad allreduce" + (" in two buckets overlapped with the density scatter" if overlap else "")) if world > 1 else "single GPU",
+                       "contracted": w.contracted, "parallelism": (f"rays sharded x{world}, " + (f"gradient all-reduce by tensorf_peer_allreduce ({exchange}) on the launch stream" if peer is not None else
+                                                                      "NCCL grad allreduce" + (" in two buckets overlapped with the density scatter" if overlap else ""))) if world > 1 else "single GPU",
                        "l2": "flushed (256 MiB write) between timed steps" if flush is not None else "not flushed",
                        "timed": "render_rays fwd + MSE + reverse wrt all LearnableParams leaves; Adam excluded",
                        "loss": loss_host},

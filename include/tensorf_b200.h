@@ -260,6 +260,12 @@ int tensorf_adam_step_peer(tensorf_stream_t s, const tensorf_peer_adam_desc* d, 
                            const float* neg_lrs, const float* const* grad_peers, float* const* param_peers,
                            const float* grad_mc, float* param_mc, float* mu_shard, float* nu_shard,
                            float* const* norm_slot_peers, void* scratch, int64_t scratch_bytes);
+/* The exchange alone (sum all-reduce, in place) over the same symmetric buffers, for callers that keep their own
+ * optimiser: rank r sums elements tensorf_peer_shard(total, r, world) of the `world` buffers in rank order (or through
+ * the multicast address `mc` when non-NULL) and stores the sums into every rank's buffer.  HOST array peers[world];
+ * total a multiple of 4.  Same barrier contract as tensorf_adam_step_peer.  Runs on the caller's stream, so it
+ * is ordered with the reverse pass without a second stream. */
+int tensorf_peer_allreduce(tensorf_stream_t s, int rank, int world, int64_t total, float* const* peers, float* mc);
 /* grad_norm[0] = sqrt(sum of the `world` slots, in rank order, fp64 accumulation): identical on every rank. */
 int tensorf_peer_grad_norm(tensorf_stream_t s, const float* norm_slots, int world, float* grad_norm);
 

@@ -572,6 +572,9 @@ int tensorf_adam_step_peer(tensorf_stream_t s, const tensorf_peer_adam_desc* d, 
   return adam_step_peer((cudaStream_t)s, d, leaf_offsets, neg_lrs, grad_peers, param_peers, grad_mc, param_mc, mu_shard,
                         nu_shard, norm_slot_peers, scratch, scratch_bytes);
 }
+int tensorf_peer_allreduce(tensorf_stream_t s, int rank, int world, int64_t total, float* const* peers, float* mc) {
+  return peer_allreduce((cudaStream_t)s, rank, world, total, peers, mc);
+}
 int tensorf_peer_grad_norm(tensorf_stream_t s, const float* norm_slots, int world, float* grad_norm) {
   return peer_grad_norm((cudaStream_t)s, norm_slots, world, grad_norm);
 }

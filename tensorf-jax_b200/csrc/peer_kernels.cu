@@ -164,6 +164,60 @@ __global__ void __launch_bounds__(kPeerThreads) k_adam_peer(const __grid_constan
   if ((int)threadIdx.x < world) a.slots[threadIdx.x][a.rank] = (float)s_acc[0];
 }
 
+// All-reduce only (no optimiser step): rank r sums its range of every rank's buffer and stores the sum back into
+// every rank's buffer, in place (ranges are disjoint, so no rank reads what another is writing).  Used where the
+// caller keeps its own optimiser (bench.py's timed step, jax-side optax) but wants the exchange on the launch
+// stream over peer memory instead of a library collective on a second stream.
+struct PeerReduceArgs {
+  float* x[TENSORF_PEER_MAX_WORLD];
+  float* x_mc;
+  int64_t begin, end;
+  int n_tiles;
+  int world;
+};
+constexpr int kPeerRedV4 = 4;  // float4 per thread and tile
+constexpr int kPeerRedTile = kPeerThreads * kPeerRedV4 * 4;
+
+template <int W, bool MC>
+__global__ void __launch_bounds__(kPeerThreads) k_peer_allreduce(const __grid_constant__ PeerReduceArgs a) {
+  const int world = W > 0 ? W : a.world;
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const int64_t base = a.begin + (int64_t)tile * kPeerRedTile;
+    float4 acc[kPeerRedV4];
+#pragma unroll
+    for (int i = 0; i < kPeerRedV4; ++i) {
+      const int64_t e = base + ((int64_t)i * kPeerThreads + threadIdx.x) * 4;
+      if (e >= a.end) continue;
+      if (MC) {
+        acc[i] = multimem_ld_reduce_add(a.x_mc + e);
+      } else if (W > 0) {
+        float4 t[W > 0 ? W : 1];
+#pragma unroll
+        for (int r = 0; r < W; ++r) t[r] = __ldcg(reinterpret_cast<const float4*>(a.x[r] + e));
+        acc[i] = t[0];
+#pragma unroll
+        for (int r = 1; r < W; ++r) acc[i] = add4(acc[i], t[r]);
+      } else {
+        acc[i] = __ldcg(reinterpret_cast<const float4*>(a.x[0] + e));
+        for (int r = 1; r < world; ++r) acc[i] = add4(acc[i], __ldcg(reinterpret_cast<const float4*>(a.x[r] + e)));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kPeerRedV4; ++i) {
+      const int64_t e = base + ((int64_t)i * kPeerThreads + threadIdx.x) * 4;
+      if (e >= a.end) continue;
+      if (MC) {
+        multimem_st(a.x_mc + e, acc[i]);
+      } else if (W > 0) {
+#pragma unroll
+        for (int r = 0; r < W; ++r) *reinterpret_cast<float4*>(a.x[r] + e) = acc[i];
+      } else {
+        for (int r = 0; r < world; ++r) *reinterpret_cast<float4*>(a.x[r] + e) = acc[i];
+      }
+    }
+  }
+}
+
 __global__ void k_peer_grad_norm(const float* __restrict__ slots, int world, float* __restrict__ out) {
   double acc = 0.0;
   for (int r = 0; r < world; ++r) acc += (double)__ldcg(slots + r);
@@ -268,6 +322,48 @@ int adam_step_peer(cudaStream_t st, const tensorf_peer_adam_desc* d, const int64
     else k_adam_peer<W_, false><<<grid, kPeerThreads, 0, st>>>(a);                 \
   } while (0)
   switch (d->world) {
+    case 1: TF_PEER_LAUNCH(1); break;
+    case 2: TF_PEER_LAUNCH(2); break;
+    case 4: TF_PEER_LAUNCH(4); break;
+    case 8: TF_PEER_LAUNCH(8); break;
+    default: TF_PEER_LAUNCH(0); break;
+  }
+#undef TF_PEER_LAUNCH
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+
+int peer_allreduce(cudaStream_t st, int rank, int world, int64_t total, float* const* peers, float* mc) {
+  TF_CHECK_ARG(peers, "peer_allreduce: null argument");
+  TF_CHECK_ARG(world >= 1 && world <= TENSORF_PEER_MAX_WORLD, "peer_allreduce: world=%d outside [1,%d]", world,
+               TENSORF_PEER_MAX_WORLD);
+  TF_CHECK_ARG(rank >= 0 && rank < world, "peer_allreduce: rank %d outside world of %d", rank, world);
+  TF_CHECK_ARG(total >= 0 && total % 4 == 0, "peer_allreduce: total=%lld must be a non-negative multiple of 4", (long long)total);
+  PeerReduceArgs a{};
+  for (int r = 0; r < world; ++r) {
+    TF_CHECK_ARG(peers[r] && (reinterpret_cast<uintptr_t>(peers[r]) & 15) == 0,
+                 "peer_allreduce: rank %d buffer must be non-NULL and 16-byte aligned", r);
+    a.x[r] = peers[r];
+  }
+  TF_CHECK_ARG((reinterpret_cast<uintptr_t>(mc) & 15) == 0, "peer_allreduce: multicast address must be 16-byte aligned");
+  a.x_mc = mc;
+  a.world = world;
+  peer_shard(total, rank, world, &a.begin, &a.end);
+  const int64_t shard = a.end - a.begin;
+  if (shard == 0) return 0;
+  const int64_t tiles = ceil_div64(shard, kPeerRedTile);
+  TF_CHECK_ARG(tiles < ((int64_t)1 << 31), "peer_allreduce: shard too large");
+  a.n_tiles = (int)tiles;
+  const int64_t cap = (int64_t)kSMs * 8;
+  const int grid = (int)(tiles < cap ? tiles : cap);
+  StageTimer t(st, "peer_allreduce");
+  const bool use_mc = mc != nullptr;
+#define TF_PEER_LAUNCH(W_)                                                        \
+  do {                                                                            \
+    if (use_mc) k_peer_allreduce<W_, true><<<grid, kPeerThreads, 0, st>>>(a);     \
+    else k_peer_allreduce<W_, false><<<grid, kPeerThreads, 0, st>>>(a);           \
+  } while (0)
+  switch (world) {
     case 1: TF_PEER_LAUNCH(1); break;
     case 2: TF_PEER_LAUNCH(2); break;
     case 4: TF_PEER_LAUNCH(4); break;

@@ -105,7 +105,9 @@ class PeerAdam:
     Every leaf of LearnableParams and of its gradient lives in one symmetric allocation per rank
     (`torch.distributed._symmetric_memory`: cuMem handles exchanged at rendezvous, so every rank holds a
     mapping of every other rank's buffer, plus the NVSwitch multicast address when the fabric has one):
-    `[params: T | grads: T | norm slots: 16]` floats, T = leaves rounded up to a multiple of 4.
+    `[params: T | grads: T | aux: 16 (aux[0] = loss) | norm slots: 16]` floats, T = leaves (each 16-byte aligned)
+    rounded up to a multiple of 4.  `allreduce()` is the exchange alone (`tensorf_peer_allreduce` over grads + aux, on
+    the launch stream) for callers that keep their own optimiser.
     Rank r owns elements `[shard_begin, shard_end)`; its shard of the Adam moments is local (memory and
     traffic / world).  `params` / `grads` are views for the render calls (`RenderCall.backward(None, grads)`
     writes straight into the symmetric buffer).  world == 1 needs no process group and runs the same kernel.
@@ -155,7 +157,7 @@ class PeerAdam:
         self.rank = dist.get_rank(self.group) if use_dist else 0
         if self.world > _lib.PEER_MAX_WORLD:
             raise ValueError(f"PeerAdam: world {self.world} > {_lib.PEER_MAX_WORLD}")
-        n_all = 2 * self.total + 16
+        n_all = 2 * self.total + 32
         self._hdl = None
         mc_base = 0
         if self.world > 1:
@@ -182,7 +184,9 @@ class PeerAdam:
         self.multicast = mc_base != 0
         self.params_flat = self.buf[:self.total]
         self.grads_flat = self.buf[self.total:2 * self.total]
-        self.slots = self.buf[2 * self.total:2 * self.total + 16]
+        self.aux = self.buf[2 * self.total:2 * self.total + 16]
+        self.loss = self.aux[0:1]
+        self.slots = self.buf[2 * self.total + 16:2 * self.total + 32]
         self.params: Dict[str, torch.Tensor] = {}
         self.grads: Dict[str, torch.Tensor] = {}
         for k, n in zip(self.names, sizes):
@@ -204,7 +208,8 @@ class PeerAdam:
         self._neg_lrs = (C.c_float * self._n_table)(*table_lrs)
         self._g = (C.c_void_p * W)(*[p + 4 * self.total for p in peer_ptrs])
         self._p = (C.c_void_p * W)(*peer_ptrs)
-        self._s = (C.c_void_p * W)(*[p + 8 * self.total for p in peer_ptrs])
+        self._s = (C.c_void_p * W)(*[p + 8 * self.total + 64 for p in peer_ptrs])
+        self._x_mc = C.c_void_p(mc_base + 4 * self.total) if mc_base else None
         self._g_mc = C.c_void_p(mc_base + 4 * self.total) if mc_base else None
         self._p_mc = C.c_void_p(mc_base) if mc_base else None
         self.barrier()  # every rank's buffer is zeroed before anyone may store into it
@@ -213,6 +218,19 @@ class PeerAdam:
         """Cross-rank barrier ordered on the current stream (device-side signal pads, no host wait)."""
         if self._hdl is not None:
             self._hdl.barrier(channel=0)
+
+    def allreduce(self) -> None:
+        """Sum `grads` and `aux` (the loss slot) over the ranks in place, on the current stream: barrier (all
+        gradients written), one kernel (each rank reduces 1/world of the buffer from every peer and stores the sums
+        to every peer), barrier (all stores landed)."""
+        from . import _lib
+        from .ops import _stream
+
+        if self.world == 1:
+            return
+        self.barrier()
+        _lib.check(self.lib.tensorf_peer_allreduce(_stream(), self.rank, self.world, self.total + 16, self._g, self._x_mc))
+        self.barrier()
 
     def load_params(self, flat: Dict[str, torch.Tensor]) -> None:
         """Copy replicated leaves into the symmetric buffer (every rank calls this with the same values)."""

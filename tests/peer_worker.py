@@ -64,6 +64,19 @@ def check_transport(shapes, neg, dev, rank, world, multicast, report):
             assert err <= 50 * tol, f"{tag} step {step} leaf {k}: |dp| {err}"
         gref = float(gn_ref.item())
         assert abs(float(gn.item()) - gref) <= 1e-5 * max(1.0, gref), (tag, step, float(gn.item()), gref)
+        # the exchange alone: grads + loss slot summed in place
+        for k in names:
+            g = torch.randn(shapes[k], generator=gen_r, device=dev)
+            peer.grads[k].copy_(g)
+            fg.leaves[k].copy_(g)
+        peer.loss.fill_(0.5 + rank)
+        peer.allreduce()
+        fg.allreduce()
+        torch.cuda.synchronize()
+        assert float(peer.loss.item()) == sum(0.5 + r for r in range(world)), (tag, float(peer.loss.item()))
+        for k in names:
+            u = ulp(peer.grads[k].reshape(-1), fg.leaves[k].reshape(-1))
+            assert u <= (0 if world == 2 and not peer.multicast else 64), f"{tag} allreduce leaf {k}: {u} ulp from NCCL"
         # every rank holds the same bits
         mine = peer.params_flat.clone()
         other = mine.clone()
@@ -115,8 +128,11 @@ def time_paths(dev, rank, world, multicast, report, iters=30):
 
     ms_nccl = run(nccl_path)
     ms_fused = run(fused_path)
+    ms_nccl_ar = run(fg.allreduce)
+    ms_peer_ar = run(peer.allreduce)
     report["timing_" + tag] = {"parameters": fg.total, "nccl_allreduce_plus_adam_ms": ms_nccl, "fused_peer_ms": ms_fused,
-                               "speedup": ms_nccl / ms_fused, "iters": iters}
+                               "speedup": ms_nccl / ms_fused, "nccl_allreduce_ms": ms_nccl_ar, "peer_allreduce_ms": ms_peer_ar,
+                               "iters": iters}
     del peer
 
 

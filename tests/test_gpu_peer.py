@@ -86,7 +86,7 @@ def _simulated_step(lib, world, total, offs, neg, bufs, mus, nus, scratch, count
     c_neg = (C.c_float * n)(*neg)
     gp = (C.c_void_p * world)(*[b.data_ptr() + 4 * total for b in bufs])
     pp = (C.c_void_p * world)(*[b.data_ptr() for b in bufs])
-    sp = (C.c_void_p * world)(*[b.data_ptr() + 8 * total for b in bufs])
+    sp = (C.c_void_p * world)(*[b.data_ptr() + 8 * total + 64 for b in bufs])
     for r in range(world):
         sb, se = C.c_int64(), C.c_int64()
         lib.tensorf_peer_shard(total, r, world, C.byref(sb), C.byref(se))
@@ -113,7 +113,7 @@ def test_simulated_ranks_on_one_device(cuda, world, shapes):
     total = (leaf_total + 3) // 4 * 4
     neg = [_neg_lrs(shapes)[k] for k in names]
     p0 = rng.normal(size=leaf_total).astype(np.float32)
-    bufs = [torch.zeros(2 * total + 16, device=cuda) for _ in range(world)]
+    bufs = [torch.zeros(2 * total + 32, device=cuda) for _ in range(world)]
     for b in bufs:
         b[:leaf_total] = T(p0, device=cuda)
     shard_sizes = []
@@ -142,18 +142,41 @@ def test_simulated_ranks_on_one_device(cuda, world, shapes):
         torch.cuda.synchronize()
         for r in range(world):
             assert torch.equal(bufs[r][:leaf_total], ref_p), (step, r)
-            assert torch.equal(bufs[r][2 * total:2 * total + world], bufs[0][2 * total:2 * total + world])
-        slots = bufs[0][2 * total:2 * total + world].double().cpu().numpy()
+            assert torch.equal(bufs[r][2 * total + 16:2 * total + 16 + world], bufs[0][2 * total + 16:2 * total + 16 + world])
+        slots = bufs[0][2 * total + 16:2 * total + 16 + world].double().cpu().numpy()
         for r, (b, e) in enumerate(shard_sizes):
             want = float(np.sum(gsum[b:min(e, leaf_total)].astype(np.float64) ** 2))
             assert abs(slots[r] - want) <= 2e-6 * max(1e-30, want), (step, r)
         gn = torch.zeros((), device=cuda)
-        _lib.check(lib.tensorf_peer_grad_norm(None, bufs[1].data_ptr() + 8 * total, world, gn.data_ptr()))
+        _lib.check(lib.tensorf_peer_grad_norm(None, bufs[1].data_ptr() + 8 * total + 64, world, gn.data_ptr()))
         want = float(np.sqrt(np.sum(gsum.astype(np.float64) ** 2)))
         assert abs(float(gn.item()) - want) <= 2e-6 * max(1.0, want)
         mu_cat = torch.cat([m[:e - b] for m, (b, e) in zip(mus, shard_sizes)])[:leaf_total]
         nu_cat = torch.cat([v[:e - b] for v, (b, e) in zip(nus, shard_sizes)])[:leaf_total]
         assert torch.equal(mu_cat, ref_m) and torch.equal(nu_cat, ref_v)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_simulated_allreduce_on_one_device(cuda, world):
+    """tensorf_peer_allreduce with `world` buffers on one GPU: after every rank's launch all buffers hold the
+    rank-ordered fp32 sum."""
+    from tensorf_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(8)
+    for total in (4, 8 * 4096 + 20, 1_000_004):
+        xs = [rng.normal(size=total).astype(np.float32) * 10.0 ** rng.integers(-3, 3) for _ in range(world)]
+        bufs = [T(x, device=cuda) for x in xs]
+        want = xs[0].copy()
+        for r in range(1, world):
+            want = (want + xs[r]).astype(np.float32)
+        ptrs = (C.c_void_p * world)(*[b.data_ptr() for b in bufs])
+        for r in range(world):
+            _lib.check(lib.tensorf_peer_allreduce(None, r, world, total, ptrs, None))
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert np.array_equal(bufs[r].cpu().numpy(), want), (total, r)
+    assert lib.tensorf_peer_allreduce(None, 0, world, 6, ptrs, None) == -1
+    assert lib.tensorf_peer_allreduce(None, world, world, 8, ptrs, None) == -1
 
 
 def test_peer_rejects_bad_arguments(cuda):
