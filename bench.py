@@ -255,7 +255,7 @@ def main():
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N>1, NCCL exchange: one all-reduce after the whole reverse pass")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer-p2p", "peer-multicast", "nccl"],
-                    help="N>1 gradient exchange: own kernel over peer memory (auto = multicast when the fabric has it) or NCCL")
+                    help="N>1 gradient exchange: own kernel over peer memory (auto = peer-p2p, NCCL if symmetric memory is unavailable) or NCCL")
     args = ap.parse_args()
     w = workload_from_name(args.workload)
     if args.impl == "reference":
@@ -323,7 +323,7 @@ def main():
         try:
             shapes = ops.param_shapes(desc)
             peer = tdist.PeerAdam(shapes, {k: 0.0 for k in shapes}, dev,
-                                  multicast={"peer-p2p": False, "peer-multicast": True}.get(args.exchange))
+                                  multicast=(args.exchange == "peer-multicast"))  # auto = P2P: measured faster (profiles/)
         except Exception as e:  # no symmetric memory on this box: say so, use NCCL
             err = repr(e)
             print(f"[bench] rank {rank}: peer-memory exchange unavailable ({err[:300]}); using NCCL", file=sys.stderr)

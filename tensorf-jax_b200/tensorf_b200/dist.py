@@ -170,12 +170,14 @@ class PeerAdam:
             if own_off < 0:
                 raise RuntimeError("PeerAdam: symmetric allocation does not contain its own tensor")
             peer_ptrs = [b + own_off for b in bases]
+            # transport: P2P loads / stores by default (measured faster than the switch reduction at this payload,
+            # profiles/r01_v17_peer_exchange_2gpu.json); multicast=True or TENSORF_PEER_MULTICAST=1 selects NVLS
             env = os.environ.get("TENSORF_PEER_MULTICAST")
-            want_mc = multicast if multicast is not None else (None if env is None else env != "0")
+            want_mc = multicast if multicast is not None else (env is not None and env != "0")
             mc = int(self._hdl.multicast_ptr or 0)
-            if want_mc is True and mc == 0:
+            if want_mc and mc == 0:
                 raise RuntimeError("PeerAdam: multicast requested but the symmetric allocation has no multicast address")
-            if mc != 0 and want_mc is not False:
+            if want_mc:
                 mc_base = mc + own_off
         else:
             self.buf = torch.empty(n_all, dtype=torch.float32, device=self.device)

@@ -57,11 +57,14 @@ def check_transport(shapes, neg, dev, rank, world, multicast, report):
             if world == 2 and not peer.multicast:
                 assert u == 0, f"{tag} step {step} leaf {k}: {u} ulp from NCCL+adam at world 2"
         # a different summation order (ring vs rank order vs switch) moves g by an ulp; Adam's first steps normalise
-        # g, so compare the parameters at 1e-5 of the step size instead of bit-for-bit
+        # g, so compare the parameters at 1e-5 of the step size instead of bit-for-bit - and where a sum cancels to
+        # ~0 its sign may flip the whole update: allow that for at most 1e-5 of the elements
         for i, k in enumerate(names):
-            tol = 1e-5 * abs(neg[k]) + 1e-7
-            err = float((peer.params[k] - rp[i]).abs().max().item()) if rp[i].numel() else 0.0
-            assert err <= 50 * tol, f"{tag} step {step} leaf {k}: |dp| {err}"
+            if not rp[i].numel():
+                continue
+            tol = 50 * (1e-5 * abs(neg[k]) + 1e-7)
+            bad = ((peer.params[k] - rp[i]).abs() > tol).float().mean().item()
+            assert bad <= 1e-5, f"{tag} step {step} leaf {k}: {bad:.2e} of the elements differ by more than {tol:.1e}"
         gref = float(gn_ref.item())
         assert abs(float(gn.item()) - gref) <= 1e-5 * max(1.0, gref), (tag, step, float(gn.item()), gref)
         # the exchange alone: grads + loss slot summed in place
@@ -75,8 +78,11 @@ def check_transport(shapes, neg, dev, rank, world, multicast, report):
         torch.cuda.synchronize()
         assert float(peer.loss.item()) == sum(0.5 + r for r in range(world)), (tag, float(peer.loss.item()))
         for k in names:
-            u = ulp(peer.grads[k].reshape(-1), fg.leaves[k].reshape(-1))
-            assert u <= (0 if world == 2 and not peer.multicast else 64), f"{tag} allreduce leaf {k}: {u} ulp from NCCL"
+            if world == 2 and not peer.multicast:
+                assert torch.equal(peer.grads[k], fg.leaves[k]), f"{tag} allreduce leaf {k} differs from NCCL at world 2"
+            elif fg.leaves[k].numel():   # other summation orders: a few roundings of the largest partial sum
+                err = float((peer.grads[k] - fg.leaves[k]).abs().max().item())
+                assert err <= 2e-6 * world * max(1.0, float(fg.leaves[k].abs().max().item())), (tag, k, err)
         # every rank holds the same bits
         mine = peer.params_flat.clone()
         other = mine.clone()
@@ -150,17 +156,9 @@ def main():
         tag = check_transport(shapes, neg, dev, rank, world, False, report)
         assert tag == "p2p"
         time_paths(dev, rank, world, False, report)
-        mc_ok = True
-        try:
-            tag = check_transport(shapes, neg, dev, rank, world, None, report)
-        except Exception as e:  # multicast is optional hardware: report, do not hide
-            mc_ok = False
-            report["multicast_error"] = repr(e)[:500]
-            raise
-        if mc_ok and tag == "multicast":
-            time_paths(dev, rank, world, None, report)
-        else:
-            report["multicast"] = "no multicast address on this fabric"
+        tag = check_transport(shapes, neg, dev, rank, world, True, report)   # raises without a multicast address
+        assert tag == "multicast"
+        time_paths(dev, rank, world, True, report)
         report["ok"] = True
     except Exception as e:
         report["ok"] = False

@@ -164,7 +164,7 @@ def test_simulated_allreduce_on_one_device(cuda, world):
     lib = _lib.load()
     rng = np.random.default_rng(8)
     for total in (4, 8 * 4096 + 20, 1_000_004):
-        xs = [rng.normal(size=total).astype(np.float32) * 10.0 ** rng.integers(-3, 3) for _ in range(world)]
+        xs = [(rng.normal(size=total) * 10.0 ** rng.integers(-3, 3)).astype(np.float32) for _ in range(world)]
         bufs = [T(x, device=cuda) for x in xs]
         want = xs[0].copy()
         for r in range(1, world):
