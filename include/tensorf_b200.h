@@ -266,6 +266,15 @@ int tensorf_adam_step_peer(tensorf_stream_t s, const tensorf_peer_adam_desc* d, 
  * total a multiple of 4.  Same barrier contract as tensorf_adam_step_peer.  Runs on the caller's stream, so it
  * is ordered with the reverse pass without a second stream. */
 int tensorf_peer_allreduce(tensorf_stream_t s, int rank, int world, int64_t total, float* const* peers, float* mc);
+/* The same exchange with the two cross-rank barriers INSIDE the kernel (no barrier launches around it):
+ * signal_peers[world] (HOST array) = every rank's signal pad, 32 uint32 in symmetric memory, zeroed once before the
+ * first call ([0,16) "buffer complete", [16,32) "stores landed", slot = signalling rank); local_flags = 2 uint32 of this
+ * rank's own device memory, zeroed once; epoch = 1, 2, 3, ... the call number, identical on every rank.  Block 0
+ * signals / awaits "complete" with st.release.sys / ld.acquire.sys and opens a gate for the grid; the last block to
+ * finish its stores signals / awaits "landed", so stream completion of the kernel means every buffer holds every sum.
+ * Every rank must make the call (even with an empty shard).  Not CUDA-graph capturable (epoch is a launch argument). */
+int tensorf_peer_allreduce_sync(tensorf_stream_t s, int rank, int world, int64_t total, float* const* peers, float* mc,
+                                uint32_t* const* signal_peers, uint32_t* local_flags, uint32_t epoch);
 /* grad_norm[0] = sqrt(sum of the `world` slots, in rank order, fp64 accumulation): identical on every rank. */
 int tensorf_peer_grad_norm(tensorf_stream_t s, const float* norm_slots, int world, float* grad_norm);
 

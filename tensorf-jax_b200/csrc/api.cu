@@ -573,7 +573,15 @@ int tensorf_adam_step_peer(tensorf_stream_t s, const tensorf_peer_adam_desc* d, 
                         nu_shard, norm_slot_peers, scratch, scratch_bytes);
 }
 int tensorf_peer_allreduce(tensorf_stream_t s, int rank, int world, int64_t total, float* const* peers, float* mc) {
-  return peer_allreduce((cudaStream_t)s, rank, world, total, peers, mc);
+  return peer_allreduce((cudaStream_t)s, rank, world, total, peers, mc, nullptr, nullptr, 0);
+}
+int tensorf_peer_allreduce_sync(tensorf_stream_t s, int rank, int world, int64_t total, float* const* peers, float* mc,
+                                uint32_t* const* signal_peers, uint32_t* local_flags, uint32_t epoch) {
+  if (!signal_peers || !local_flags) {
+    set_error("peer_allreduce_sync: signal_peers and local_flags are required");
+    return TENSORF_ERR_INVALID_ARGUMENT;
+  }
+  return peer_allreduce((cudaStream_t)s, rank, world, total, peers, mc, signal_peers, local_flags, epoch);
 }
 int tensorf_peer_grad_norm(tensorf_stream_t s, const float* norm_slots, int world, float* grad_norm) {
   return peer_grad_norm((cudaStream_t)s, norm_slots, world, grad_norm);

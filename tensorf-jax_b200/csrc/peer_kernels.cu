@@ -174,13 +174,78 @@ struct PeerReduceArgs {
   int64_t begin, end;
   int n_tiles;
   int world;
+  // in-kernel cross-rank ordering (sig[0] == nullptr: the caller brackets the launch with its own barriers)
+  uint32_t* sig[TENSORF_PEER_MAX_WORLD];  // rank p's signal pad: [0,16) "gradients ready", [16,32) "stores landed"
+  uint32_t* local;                        // this rank only: [0] gate, [1] arrival counter
+  uint32_t epoch;                         // call number, starts at 1, the same on every rank
+  int rank;
 };
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool epoch_reached(uint32_t seen, uint32_t epoch) { return (int32_t)(seen - epoch) >= 0; }
+
+// Entry: block 0 tells every rank "my buffer is complete" (everything enqueued before this kernel has finished) and
+// waits for the same from every rank, then opens the gate for the other blocks of this grid.  All blocks are
+// co-resident (grid <= 8 per SM), block 0 is dispatched first: the spinning blocks cannot starve it.
+__device__ __forceinline__ void peer_entry_barrier(const PeerReduceArgs& a, int world) {
+  if (blockIdx.x == 0) {
+    if ((int)threadIdx.x < world) {
+      st_release_sys(a.sig[threadIdx.x] + a.rank, a.epoch);
+      while (!epoch_reached(ld_acquire_sys(a.sig[a.rank] + threadIdx.x), a.epoch)) {
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_gpu(a.local, a.epoch);
+  } else {
+    if (threadIdx.x == 0) {
+      while (!epoch_reached(ld_acquire_gpu(a.local), a.epoch)) {
+      }
+    }
+    __syncthreads();
+  }
+}
+// Exit: the last block of this grid to finish its stores tells every rank "my stores have landed" and waits for the
+// same from every rank, so the kernel (and with it the stream) only completes once every buffer holds every sum.
+__device__ __forceinline__ void peer_exit_barrier(const PeerReduceArgs& a, int world) {
+  __shared__ bool s_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_last = atomicAdd(a.local + 1, 1u) == gridDim.x - 1;
+    if (s_last) a.local[1] = 0;  // every block has arrived: reset for the next call
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if ((int)threadIdx.x < world) {
+    st_release_sys(a.sig[threadIdx.x] + 16 + a.rank, a.epoch);
+    while (!epoch_reached(ld_acquire_sys(a.sig[a.rank] + 16 + threadIdx.x), a.epoch)) {
+    }
+  }
+}
 constexpr int kPeerRedV4 = 4;  // float4 per thread and tile
 constexpr int kPeerRedTile = kPeerThreads * kPeerRedV4 * 4;
 
 template <int W, bool MC>
 __global__ void __launch_bounds__(kPeerThreads) k_peer_allreduce(const __grid_constant__ PeerReduceArgs a) {
   const int world = W > 0 ? W : a.world;
+  const bool sync = a.sig[0] != nullptr;
+  if (sync) peer_entry_barrier(a, world);
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int64_t base = a.begin + (int64_t)tile * kPeerRedTile;
     float4 acc[kPeerRedV4];
@@ -216,6 +281,7 @@ __global__ void __launch_bounds__(kPeerThreads) k_peer_allreduce(const __grid_co
       }
     }
   }
+  if (sync) peer_exit_barrier(a, world);
 }
 
 __global__ void k_peer_grad_norm(const float* __restrict__ slots, int world, float* __restrict__ out) {
@@ -333,8 +399,11 @@ int adam_step_peer(cudaStream_t st, const tensorf_peer_adam_desc* d, const int64
   return 0;
 }
 
-int peer_allreduce(cudaStream_t st, int rank, int world, int64_t total, float* const* peers, float* mc) {
+int peer_allreduce(cudaStream_t st, int rank, int world, int64_t total, float* const* peers, float* mc,
+                   uint32_t* const* signal_peers, uint32_t* local_flags, uint32_t epoch) {
   TF_CHECK_ARG(peers, "peer_allreduce: null argument");
+  TF_CHECK_ARG((signal_peers == nullptr) == (local_flags == nullptr),
+               "peer_allreduce: signal_peers and local_flags must both be set (in-kernel ordering) or both be NULL");
   TF_CHECK_ARG(world >= 1 && world <= TENSORF_PEER_MAX_WORLD, "peer_allreduce: world=%d outside [1,%d]", world,
                TENSORF_PEER_MAX_WORLD);
   TF_CHECK_ARG(rank >= 0 && rank < world, "peer_allreduce: rank %d outside world of %d", rank, world);
@@ -348,14 +417,23 @@ int peer_allreduce(cudaStream_t st, int rank, int world, int64_t total, float* c
   TF_CHECK_ARG((reinterpret_cast<uintptr_t>(mc) & 15) == 0, "peer_allreduce: multicast address must be 16-byte aligned");
   a.x_mc = mc;
   a.world = world;
+  a.rank = rank;
+  if (signal_peers) {
+    for (int r = 0; r < world; ++r) {
+      TF_CHECK_ARG(signal_peers[r], "peer_allreduce: rank %d has a null signal pad", r);
+      a.sig[r] = signal_peers[r];
+    }
+    a.local = local_flags;
+    a.epoch = epoch;
+  }
   peer_shard(total, rank, world, &a.begin, &a.end);
   const int64_t shard = a.end - a.begin;
-  if (shard == 0) return 0;
+  if (shard == 0 && !signal_peers) return 0;  // with in-kernel ordering every rank must still take part
   const int64_t tiles = ceil_div64(shard, kPeerRedTile);
   TF_CHECK_ARG(tiles < ((int64_t)1 << 31), "peer_allreduce: shard too large");
   a.n_tiles = (int)tiles;
-  const int64_t cap = (int64_t)kSMs * 8;
-  const int grid = (int)(tiles < cap ? tiles : cap);
+  const int64_t cap = (int64_t)kSMs * 8;  // all blocks co-resident: the in-kernel gate relies on it
+  const int grid = (int)(tiles < 1 ? 1 : (tiles < cap ? tiles : cap));
   StageTimer t(st, "peer_allreduce");
   const bool use_mc = mc != nullptr;
 #define TF_PEER_LAUNCH(W_)                                                        \

@@ -105,7 +105,7 @@ class PeerAdam:
     Every leaf of LearnableParams and of its gradient lives in one symmetric allocation per rank
     (`torch.distributed._symmetric_memory`: cuMem handles exchanged at rendezvous, so every rank holds a
     mapping of every other rank's buffer, plus the NVSwitch multicast address when the fabric has one):
-    `[params: T | grads: T | aux: 16 (aux[0] = loss) | norm slots: 16]` floats, T = leaves (each 16-byte aligned)
+    `[params: T | grads: T | aux: 16 (aux[0] = loss) | norm slots: 16 | signal pad: 32 x u32]` floats, T = leaves (each 16-byte aligned)
     rounded up to a multiple of 4.  `allreduce()` is the exchange alone (`tensorf_peer_allreduce` over grads + aux, on
     the launch stream) for callers that keep their own optimiser.
     Rank r owns elements `[shard_begin, shard_end)`; its shard of the Adam moments is local (memory and
@@ -157,7 +157,7 @@ class PeerAdam:
         self.rank = dist.get_rank(self.group) if use_dist else 0
         if self.world > _lib.PEER_MAX_WORLD:
             raise ValueError(f"PeerAdam: world {self.world} > {_lib.PEER_MAX_WORLD}")
-        n_all = 2 * self.total + 32
+        n_all = 2 * self.total + 64
         self._hdl = None
         mc_base = 0
         if self.world > 1:
@@ -212,6 +212,11 @@ class PeerAdam:
         self._p = (C.c_void_p * W)(*peer_ptrs)
         self._s = (C.c_void_p * W)(*[p + 8 * self.total + 64 for p in peer_ptrs])
         self._x_mc = C.c_void_p(mc_base + 4 * self.total) if mc_base else None
+        # in-kernel ordering of tensorf_peer_allreduce_sync: signal pads (zeroed with the buffer), local gate, call count
+        self._sig = (C.c_void_p * W)(*[p + 8 * self.total + 128 for p in peer_ptrs])
+        self._local_flags = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self._epoch = 0
+        self.sync = os.environ.get("TENSORF_PEER_SYNC", "kernel")  # "kernel" | "barrier"
         self._g_mc = C.c_void_p(mc_base + 4 * self.total) if mc_base else None
         self._p_mc = C.c_void_p(mc_base) if mc_base else None
         self.barrier()  # every rank's buffer is zeroed before anyone may store into it
@@ -229,6 +234,12 @@ class PeerAdam:
         from .ops import _stream
 
         if self.world == 1:
+            return
+        if self.sync == "kernel":  # both barriers inside the kernel (signal pads in the symmetric buffer)
+            self._epoch += 1
+            _lib.check(self.lib.tensorf_peer_allreduce_sync(_stream(), self.rank, self.world, self.total + 16, self._g,
+                                                            self._x_mc, self._sig, self._local_flags.data_ptr(),
+                                                            self._epoch & 0xFFFFFFFF))
             return
         self.barrier()
         _lib.check(self.lib.tensorf_peer_allreduce(_stream(), self.rank, self.world, self.total + 16, self._g, self._x_mc))

@@ -29,6 +29,15 @@ def ulp(a, b):
     return int((ia - ib).abs().max().item()) if a.numel() else 0
 
 
+def check_allreduce(peer, fg, names, world, tag):
+    for k in names:
+        if world == 2 and not peer.multicast:
+            assert torch.equal(peer.grads[k], fg.leaves[k]), f"{tag} allreduce leaf {k} differs from NCCL at world 2"
+        elif fg.leaves[k].numel():   # other summation orders: a few roundings of the largest partial sum
+            err = float((peer.grads[k] - fg.leaves[k]).abs().max().item())
+            assert err <= 2e-6 * world * max(1.0, float(fg.leaves[k].abs().max().item())), (tag, k, err)
+
+
 def check_transport(shapes, neg, dev, rank, world, multicast, report):
     names = list(shapes)
     peer = tdist.PeerAdam(shapes, neg, dev, multicast=multicast)
@@ -68,21 +77,21 @@ def check_transport(shapes, neg, dev, rank, world, multicast, report):
         gref = float(gn_ref.item())
         assert abs(float(gn.item()) - gref) <= 1e-5 * max(1.0, gref), (tag, step, float(gn.item()), gref)
         # the exchange alone: grads + loss slot summed in place
+        fg_local = {}
         for k in names:
             g = torch.randn(shapes[k], generator=gen_r, device=dev)
-            peer.grads[k].copy_(g)
+            fg_local[k] = g
             fg.leaves[k].copy_(g)
-        peer.loss.fill_(0.5 + rank)
-        peer.allreduce()
         fg.allreduce()
-        torch.cuda.synchronize()
-        assert float(peer.loss.item()) == sum(0.5 + r for r in range(world)), (tag, float(peer.loss.item()))
-        for k in names:
-            if world == 2 and not peer.multicast:
-                assert torch.equal(peer.grads[k], fg.leaves[k]), f"{tag} allreduce leaf {k} differs from NCCL at world 2"
-            elif fg.leaves[k].numel():   # other summation orders: a few roundings of the largest partial sum
-                err = float((peer.grads[k] - fg.leaves[k]).abs().max().item())
-                assert err <= 2e-6 * world * max(1.0, float(fg.leaves[k].abs().max().item())), (tag, k, err)
+        for mode in ("barrier", "kernel", "kernel"):     # ordering by barrier launches / inside the kernel (twice: epochs)
+            for k in names:
+                peer.grads[k].copy_(fg_local[k])
+            peer.loss.fill_(0.5 + rank)
+            peer.sync = mode
+            peer.allreduce()
+            torch.cuda.synchronize()
+            assert float(peer.loss.item()) == sum(0.5 + r for r in range(world)), (tag, mode, float(peer.loss.item()))
+            check_allreduce(peer, fg, names, world, tag + "/" + mode)
         # every rank holds the same bits
         mine = peer.params_flat.clone()
         other = mine.clone()
@@ -135,10 +144,13 @@ def time_paths(dev, rank, world, multicast, report, iters=30):
     ms_nccl = run(nccl_path)
     ms_fused = run(fused_path)
     ms_nccl_ar = run(fg.allreduce)
+    peer.sync = "barrier"
     ms_peer_ar = run(peer.allreduce)
+    peer.sync = "kernel"
+    ms_peer_ar_k = run(peer.allreduce)
     report["timing_" + tag] = {"parameters": fg.total, "nccl_allreduce_plus_adam_ms": ms_nccl, "fused_peer_ms": ms_fused,
                                "speedup": ms_nccl / ms_fused, "nccl_allreduce_ms": ms_nccl_ar, "peer_allreduce_ms": ms_peer_ar,
-                               "iters": iters}
+                               "peer_allreduce_inkernel_sync_ms": ms_peer_ar_k, "iters": iters}
     del peer
 
 

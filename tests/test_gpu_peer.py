@@ -284,3 +284,35 @@ def test_backward_phases_match_whole_pass(cuda):
         assert float((g[k] - ref).abs().max()) <= tol, (k, float((g[k] - ref).abs().max()), tol)
     with pytest.raises(Exception):
         call.backward(None, g, phase=3)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_inkernel_sync_ranks_on_streams(cuda, world):
+    """tensorf_peer_allreduce_sync: the two cross-rank barriers inside the kernel (signal pads, epochs, grid gate).
+    `world` simulated ranks launch on separate streams of one GPU and have to meet inside their kernels; three calls
+    in a row exercise the epoch logic and the arrival-counter reset."""
+    from tensorf_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(9)
+    total = 8 * 4096 + 20                                    # a few blocks per rank: all co-resident
+    sig = [torch.zeros(32, dtype=torch.int32, device=cuda) for _ in range(world)]
+    local = [torch.zeros(4, dtype=torch.int32, device=cuda) for _ in range(world)]
+    streams = [torch.cuda.Stream(device=cuda) for _ in range(world)]
+    sig_ptrs = (C.c_void_p * world)(*[s.data_ptr() for s in sig])
+    for epoch in (1, 2, 3):
+        xs = [rng.normal(size=total).astype(np.float32) for _ in range(world)]
+        bufs = [T(x, device=cuda) for x in xs]
+        want = xs[0].copy()
+        for r in range(1, world):
+            want = (want + xs[r]).astype(np.float32)
+        ptrs = (C.c_void_p * world)(*[b.data_ptr() for b in bufs])
+        torch.cuda.synchronize()
+        for r in range(world):
+            _lib.check(lib.tensorf_peer_allreduce_sync(C.c_void_p(streams[r].cuda_stream), r, world, total, ptrs, None, sig_ptrs,
+                                                       local[r].data_ptr(), epoch))
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert np.array_equal(bufs[r].cpu().numpy(), want), (epoch, r)
+            assert sig[r][:world].tolist() == [epoch] * world and sig[r][16:16 + world].tolist() == [epoch] * world
+            assert local[r][:2].tolist() == [epoch, 0]
+    assert lib.tensorf_peer_allreduce_sync(None, 0, world, total, ptrs, None, None, None, 4) == -1
