@@ -438,7 +438,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": w.name, "R_per_gpu": w.R, "R_global": R_global, "N": w.N, "K": w.K, "G": w.G,
                        "cd": w.cd, "ca": w.ca, "feat_freqs": w.feat_freqs, "view_freqs": w.view_freqs,
-                       "contracted": w.contracted, "parallelism": (f"rays sharded x{world}, " + (f"gradient all-reduce by tensorf_peer_allreduce ({exchange}) on the launch stream" if peer is not None else
+                       "contracted": w.contracted, "parallelism": (f"rays sharded x{world}, " + (f"gradient all-reduce by tensorf_peer_allreduce ({exchange}, {peer.sync} sync) on the launch stream" if peer is not None else
                                                                       "NCCL grad allreduce" + (" in two buckets overlapped with the density scatter" if overlap else ""))) if world > 1 else "single GPU",
                        "l2": "flushed (256 MiB write) between timed steps" if flush is not None else "not flushed",
                        "timed": "render_rays fwd + MSE + reverse wrt all LearnableParams leaves; Adam excluded",

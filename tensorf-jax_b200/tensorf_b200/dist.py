@@ -216,7 +216,11 @@ class PeerAdam:
         self._sig = (C.c_void_p * W)(*[p + 8 * self.total + 128 for p in peer_ptrs])
         self._local_flags = torch.zeros(4, dtype=torch.int32, device=self.device)
         self._epoch = 0
-        self.sync = os.environ.get("TENSORF_PEER_SYNC", "kernel")  # "kernel" | "barrier"
+        # "barrier" (two torch symmetric-memory barrier launches around the kernel; measured on 2 and 4 GPUs) or
+        # "kernel" (both barriers inside tensorf_peer_allreduce_sync: 37 vs 40 us at 2 GPUs, measured on 2 GPUs only)
+        self.sync = os.environ.get("TENSORF_PEER_SYNC", "barrier")
+        if self.sync not in ("barrier", "kernel"):
+            raise ValueError(f"TENSORF_PEER_SYNC={self.sync!r}: expected 'barrier' or 'kernel'")
         self._g_mc = C.c_void_p(mc_base + 4 * self.total) if mc_base else None
         self._p_mc = C.c_void_p(mc_base) if mc_base else None
         self.barrier()  # every rank's buffer is zeroed before anyone may store into it
