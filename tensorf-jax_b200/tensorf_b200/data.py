@@ -102,3 +102,37 @@ class DeviceRayLoader:
             for b in range(self.minibatch_count()):
                 yield self.gather(perm[b * self.minibatch_size:(b + 1) * self.minibatch_size])
             epoch += 1
+
+
+class HostStage:
+    """Host-resident minibatches (the reference's loader hands NumPy batches to `training_step`,
+    training.py:318-343): every per-step input lives in ONE pinned host buffer mirrored by ONE device buffer, so a
+    step's inputs cross PCIe as a single copy instead of one per array (each small copy costs a fixed ~2-3 us of
+    stream time).  `host[name]` / `device[name]` are views; all arrays must be 4-byte typed (fp32, int32, uint32)."""
+
+    def __init__(self, arrays, device="cuda"):
+        import numpy as np
+        metas, off = [], 0
+        for k, a in arrays.items():
+            t = torch.from_numpy(np.ascontiguousarray(a)) if not isinstance(a, torch.Tensor) else a.contiguous().cpu()
+            if t.dtype == torch.uint32:
+                t = t.view(torch.int32)
+            if t.element_size() != 4:
+                raise TypeError(f"HostStage: '{k}' has dtype {t.dtype}; only 4-byte element types are staged")
+            metas.append((k, t, off))
+            off += (t.numel() + 3) // 4 * 4        # every view starts on a 16-byte boundary
+        self._host = torch.empty(max(off, 4), dtype=torch.float32)
+        if torch.device(device).type == "cuda":
+            self._host = self._host.pin_memory()
+        self._dev = torch.empty(max(off, 4), dtype=torch.float32, device=device)
+        self.host, self.device = {}, {}
+        for k, t, o in metas:
+            n = t.numel()
+            self.host[k] = self._host[o:o + n].view(t.dtype).view(t.shape)
+            self.device[k] = self._dev[o:o + n].view(t.dtype).view(t.shape)
+            self.host[k].copy_(t)
+        self.nbytes = off * 4
+
+    def upload(self) -> None:
+        """One asynchronous host-to-device copy of every staged array, on the current stream."""
+        self._dev.copy_(self._host, non_blocking=True)

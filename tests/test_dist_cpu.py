@@ -81,3 +81,22 @@ def test_flat_grads_allreduce_gloo_world2():
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0][0] and out[1][0]
     assert out[0][1] == pytest.approx(1.0 / 30.0)   # 1/(3*R_global) with R_global = 10
+
+
+def test_host_stage_layout_cpu():
+    """data.HostStage: one buffer, 16-byte aligned views, dtypes and values preserved (layout logic only; the pinned
+    H2D path runs in tests/test_gpu_data.py)."""
+    from tensorf_b200.data import HostStage
+    arrays = {"origins": np.arange(15, dtype=np.float32).reshape(5, 3), "camera_indices": np.array([7, 2**32 - 1, 3], np.uint32),
+              "gumbel": np.linspace(0, 1, 7, dtype=np.float32)}
+    st = HostStage(arrays, "cpu")
+    assert st.nbytes == (16 + 4 + 8) * 4
+    st.host["gumbel"][0] = 5.0
+    st.upload()
+    assert np.array_equal(st.device["origins"].numpy(), arrays["origins"])
+    assert st.device["camera_indices"].dtype == torch.int32
+    assert np.array_equal(st.device["camera_indices"].numpy().view(np.uint32), arrays["camera_indices"])
+    assert float(st.device["gumbel"][0]) == 5.0 and st.device["gumbel"].shape == (7,)
+    assert all(v.data_ptr() % 16 == 0 for v in st.device.values())
+    with pytest.raises(TypeError):
+        HostStage({"x": np.zeros(3, np.float64)}, "cpu")

@@ -77,3 +77,23 @@ def test_gather_edge_cases(cuda):
     assert torch.equal(mb.colors[1], table.colors[19]) and torch.equal(mb.colors[4], table.colors[0])
     with pytest.raises(ValueError):
         data.DeviceRayLoader(table, minibatch_size=21)
+
+
+def test_host_stage_single_copy(cuda):
+    """data.HostStage: all staged arrays reach the device with one copy; re-upload after a host-side edit."""
+    from tensorf_b200.data import HostStage
+    rng = np.random.default_rng(12)
+    arrays = {"origins": rng.normal(size=(33, 3)).astype(np.float32), "camera_indices": rng.integers(0, 2**32, 33, dtype=np.uint32),
+              "jitter": rng.uniform(size=(33, 5)).astype(np.float32)}
+    st = HostStage(arrays, cuda)
+    assert st._host.is_pinned() and st.nbytes == (100 + 36 + 168) * 4
+    st.upload()
+    torch.cuda.synchronize()
+    for k, a in arrays.items():
+        got = st.device[k].cpu().numpy()
+        assert np.array_equal(got.view(a.dtype) if a.dtype == np.uint32 else got, a), k
+        assert st.device[k].data_ptr() % 16 == 0
+    st.host["jitter"].zero_()
+    st.upload()
+    torch.cuda.synchronize()
+    assert float(st.device["jitter"].abs().sum()) == 0.0 and np.array_equal(st.device["origins"].cpu().numpy(), arrays["origins"])
