@@ -474,13 +474,18 @@ static int render_rgb_bwd_impl(tensorf_stream_t s, const tensorf_render_desc* d,
     rb.go = d_rgb ? d_rgb : w.go;
     rb.d_rgb_sel = w.d_rgb_sel;
     rb.dz = w.dz;
+    // the packed gradient accumulators are zeroed by k_ray_bwd's threads (no memset launches)
+    rb.zero0 = reinterpret_cast<float4*>(w.gpacked_a);
+    rb.zero0_n4 = packed_floats(d->ca, d->G) / 4;
+    if (do_den) {
+      rb.zero1 = reinterpret_cast<float4*>(w.gpacked_d);
+      rb.zero1_n4 = packed_floats(d->cd, d->G) / 4;
+    }
     StageTimer t_(st, "ray_bwd");
     TF_RETURN_IF_ERROR(launch_ray_bwd(st, rb));
-  }
-  {
+  } else {  // phase 2: the density accumulator was left alone by phase 1
     StageTimer t_(st, "zero_grads");
-    if (do_den) TF_CHECK_CUDA(cudaMemsetAsync(w.gpacked_d, 0, sizeof(float) * packed_floats(d->cd, d->G), st));
-    if (do_app) TF_CHECK_CUDA(cudaMemsetAsync(w.gpacked_a, 0, sizeof(float) * packed_floats(d->ca, d->G), st));
+    TF_CHECK_CUDA(cudaMemsetAsync(w.gpacked_d, 0, sizeof(float) * packed_floats(d->cd, d->G), st));
   }
 
   if (do_den && phase == 0) {

@@ -460,6 +460,12 @@ __global__ void __launch_bounds__(128) k_ray_bwd(RayBwdArgs A) {
   const int Npad = round_up(A.N, 32);
   float* gE_s = reinterpret_cast<float*>(smem_raw) + (size_t)warp * 2 * Npad;  // gpt_s * E_s
   float* q_s = gE_s + Npad;                                                    // gpt_s, then gpt_s * pt_s
+  {  // zero the scatter kernels' accumulators (fire-and-forget stores, issued before the ray work)
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = gtid; i < A.zero0_n4; i += nthr) A.zero0[i] = z4;
+    for (int64_t i = gtid; i < A.zero1_n4; i += nthr) A.zero1[i] = z4;
+  }
   const int r = blockIdx.x * 4 + warp;
   if (r >= A.R) return;
 
@@ -539,7 +545,11 @@ __global__ void __launch_bounds__(128) k_ray_bwd(RayBwdArgs A) {
 }
 
 int launch_ray_bwd(cudaStream_t st, const RayBwdArgs& A) {
-  if (A.R == 0) return 0;
+  if (A.R == 0) {  // no rays: the accumulators still have to read as zero
+    if (A.zero0_n4) TF_CHECK_CUDA(cudaMemsetAsync(A.zero0, 0, sizeof(float4) * A.zero0_n4, st));
+    if (A.zero1_n4) TF_CHECK_CUDA(cudaMemsetAsync(A.zero1, 0, sizeof(float4) * A.zero1_n4, st));
+    return 0;
+  }
   size_t smem = 4 * (size_t)2 * round_up(A.N, 32) * sizeof(float);
   if (smem > 48 * 1024) TF_CHECK_CUDA(cudaFuncSetAttribute(k_ray_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_ray_bwd<<<(A.R + 3) / 4, 128, smem, st>>>(A);

@@ -59,6 +59,12 @@ struct RayBwdArgs : SceneArgs {
   const float* go;       // (R,3)
   float* d_rgb_sel;      // (M,3)
   float* dz;             // (R,N)
+  // packed gradient accumulators zeroed by this kernel's threads before their ray work (the stores overlap the
+  // latency-bound reverse scan instead of costing two memsets): float4 counts, either may be 0
+  float4* zero0;
+  int64_t zero0_n4;
+  float4* zero1;
+  int64_t zero1_n4;
 };
 
 struct DensityBwdArgs : SceneArgs {
