@@ -481,6 +481,25 @@ static int render_rgb_bwd_impl(tensorf_stream_t s, const tensorf_render_desc* d,
       rb.zero1 = reinterpret_cast<float4*>(w.gpacked_d);
       rb.zero1_n4 = packed_floats(d->cd, d->G) / 4;
     }
+    {  // ... and so are the MLP gradient leaves (mlp_*_bwd accumulates into them)
+      const MlpGrads g = mlp_grads(*grads);
+      const int U = ms.units;
+      auto add = [&](float* ptr, int64_t n) {
+        if (ptr && n > 0) {
+          rb.zleaf[rb.n_zleaf] = ptr;
+          rb.zleaf_n[rb.n_zleaf] = (int)n;
+          ++rb.n_zleaf;
+        }
+      };
+      add(g.w0, (int64_t)ms.Ca * ms.squash);
+      add(g.w1, (int64_t)ms.enc * U);
+      add(g.b1, U);
+      add(g.w2, (int64_t)U * U);
+      add(g.b2, U);
+      add(g.w3, (int64_t)U * 3);
+      add(g.b3, 3);
+      if (ms.ncam) add(g.embed, (int64_t)ms.ncam * U);
+    }
     StageTimer t_(st, "ray_bwd");
     TF_RETURN_IF_ERROR(launch_ray_bwd(st, rb));
   } else {  // phase 2: the density accumulator was left alone by phase 1
@@ -504,9 +523,11 @@ static int render_rgb_bwd_impl(tensorf_stream_t s, const tensorf_render_desc* d,
     MlpWs mws = mlp_ws_carve(ms, M, w.mlp_base);
     {
       StageTimer t_(st, "mlp_bwd");
+      MlpGrads mg = mlp_grads(*grads);
+      mg.prezeroed = true;  // by k_ray_bwd above
       TF_RETURN_IF_ERROR((mlp_use_tc(d->mlp_impl) ? mlp_tc_bwd : mlp_simt_bwd)(st, ms, mlp_params(*p), w.feat, in->directions,
                                                                                 in->camera_indices, M, d->K, mws, w.rgb_sel,
-                                                                                w.d_rgb_sel, w.d_feat, mlp_grads(*grads)));
+                                                                                w.d_rgb_sel, w.d_feat, mg));
     }
     AppearanceArgs ap{};
     fill_scene(ap, *d, *in);

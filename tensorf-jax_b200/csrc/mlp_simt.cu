@@ -619,7 +619,7 @@ int mlp_simt_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const f
                  const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, const float* rgb, const float* d_rgb,
                  float* d_feat, const MlpGrads& gr) {
   const int U = s.units;
-  TF_RETURN_IF_ERROR(mlp_zero_grads(st, s, gr));
+  if (!gr.prezeroed) TF_RETURN_IF_ERROR(mlp_zero_grads(st, s, gr));
   if (M == 0) return 0;
   (void)viewdirs;
   TF_RETURN_IF_ERROR(mlp_out_bwd(st, s, p, ws, cams, M, rows_per_ray, rgb, d_rgb, gr));

@@ -1362,7 +1362,7 @@ int mlp_tc_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const flo
   const int U = s.units;
   (void)viewdirs;
   TF_CHECK_ARG(!s.inference, "mlp reverse pass after a forward with TENSORF_FLAG_INFERENCE (residuals were not kept)");
-  TF_RETURN_IF_ERROR(mlp_zero_grads(st, s, gr));
+  if (!gr.prezeroed) TF_RETURN_IF_ERROR(mlp_zero_grads(st, s, gr));
   if (M == 0) return 0;
   TcPlan plan(s, p, ws, feat, M);  // weights were packed by mlp_tc_fwd on the same workspace
   RowEpilogue none;

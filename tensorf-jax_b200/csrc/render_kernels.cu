@@ -465,6 +465,8 @@ __global__ void __launch_bounds__(128) k_ray_bwd(RayBwdArgs A) {
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t i = gtid; i < A.zero0_n4; i += nthr) A.zero0[i] = z4;
     for (int64_t i = gtid; i < A.zero1_n4; i += nthr) A.zero1[i] = z4;
+    for (int j = 0; j < A.n_zleaf; ++j)
+      for (int64_t i = gtid; i < A.zleaf_n[j]; i += nthr) A.zleaf[j][i] = 0.f;
   }
   const int r = blockIdx.x * 4 + warp;
   if (r >= A.R) return;
@@ -548,6 +550,7 @@ int launch_ray_bwd(cudaStream_t st, const RayBwdArgs& A) {
   if (A.R == 0) {  // no rays: the accumulators still have to read as zero
     if (A.zero0_n4) TF_CHECK_CUDA(cudaMemsetAsync(A.zero0, 0, sizeof(float4) * A.zero0_n4, st));
     if (A.zero1_n4) TF_CHECK_CUDA(cudaMemsetAsync(A.zero1, 0, sizeof(float4) * A.zero1_n4, st));
+    for (int j = 0; j < A.n_zleaf; ++j) TF_CHECK_CUDA(cudaMemsetAsync(A.zleaf[j], 0, sizeof(float) * A.zleaf_n[j], st));
     return 0;
   }
   size_t smem = 4 * (size_t)2 * round_up(A.N, 32) * sizeof(float);

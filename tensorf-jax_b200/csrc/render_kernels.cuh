@@ -65,6 +65,9 @@ struct RayBwdArgs : SceneArgs {
   int64_t zero0_n4;
   float4* zero1;
   int64_t zero1_n4;
+  float* zleaf[8];  // small unaligned leaves (the MLP gradients), zeroed the same way
+  int zleaf_n[8];
+  int n_zleaf;
 };
 
 struct DensityBwdArgs : SceneArgs {
