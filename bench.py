@@ -454,7 +454,9 @@ def main():
                          "note": "gather-model bytes (6 taps x 4 B per sample-channel, SURVEY 8d); at 128^3 the factors and their gradients are "
                                  "L2-resident, so frac > 1 is an L2/LSU rate - `traffic` is the kernel's ncu DRAM bytes per launch"},
             "stages_ms": {k: round(v["ms"], 4) for k, v in sorted(stages.items(), key=lambda kv: -kv[1]["ms"])},
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "note": "public API (RenderCall + data.HostStage): one pinned H2D copy of the minibatch and a blocking loss read per "
+                            "step; no L2 flush in this loop (the inputs arrive from the host every step), hence ~= the flushed device-timed value"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
