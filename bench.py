@@ -254,7 +254,7 @@ def main():
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N>1, NCCL exchange: one all-reduce after the whole reverse pass")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "peer-p2p", "peer-multicast", "nccl"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer-p2p", "peer-multicast", "peer-overlap", "nccl"],
                     help="N>1 gradient exchange: own kernel over peer memory (auto = peer-p2p, NCCL if symmetric memory is unavailable) or NCCL")
     args = ap.parse_args()
     w = workload_from_name(args.workload)
@@ -341,7 +341,25 @@ def main():
 
     flush = None if args.no_l2_flush else torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
+    # --exchange peer-overlap (NOT measured yet, opt-in): the early bucket's exchange on a side stream beside the
+    # density scatter, as the NCCL path does
+    peer_overlap = peer is not None and args.exchange == "peer-overlap"
+    if peer_overlap:
+        side, ev_early, ev_done = torch.cuda.Stream(device=dev), torch.cuda.Event(), torch.cuda.Event()
+
     def step():
+        if peer_overlap:
+            rgb, loss = call.forward(params, dins, loss_out=peer.loss)
+            call.backward(None, grads, phase=1)
+            ev_early.record()
+            with torch.cuda.stream(side):
+                side.wait_event(ev_early)
+                peer.allreduce("early", channel=1)
+                ev_done.record()
+            call.backward(None, grads, phase=2)
+            peer.allreduce("late", channel=0)
+            torch.cuda.current_stream().wait_event(ev_done)
+            return loss
         if peer is not None:
             rgb, loss = call.forward(params, dins, loss_out=peer.loss)
             call.backward(None, grads)
@@ -441,7 +459,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": w.name, "R_per_gpu": w.R, "R_global": R_global, "N": w.N, "K": w.K, "G": w.G,
                        "cd": w.cd, "ca": w.ca, "feat_freqs": w.feat_freqs, "view_freqs": w.view_freqs,
-                       "contracted": w.contracted, "parallelism": (f"rays sharded x{world}, " + (f"gradient all-reduce by tensorf_peer_allreduce ({exchange}, {peer.sync} sync) on the launch stream" if peer is not None else
+                       "contracted": w.contracted, "parallelism": (f"rays sharded x{world}, " + (f"gradient all-reduce by tensorf_peer_allreduce ({exchange}, {peer.sync} sync) " + ("in two buckets, the early one on a side stream" if peer_overlap else "on the launch stream") if peer is not None else
                                                                       "NCCL grad allreduce" + (" in two buckets overlapped with the density scatter" if overlap else ""))) if world > 1 else "single GPU",
                        "l2": "flushed (256 MiB write) between timed steps" if flush is not None else "not flushed",
                        "timed": "render_rays fwd + MSE + reverse wrt all LearnableParams leaves; Adam excluded",

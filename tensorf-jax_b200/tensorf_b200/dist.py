@@ -195,6 +195,12 @@ class PeerAdam:
             o = self.leaf_offsets[k]
             self.params[k] = self.params_flat[o:o + n].view(self.shapes[k])
             self.grads[k] = self.grads_flat[o:o + n].view(self.shapes[k])
+        # end of the leading density_* leaves (a multiple of 4: every leaf is 16-byte aligned): the "late" bucket
+        self._density_end = 0
+        for k, n in zip(self.names, sizes):
+            if not k.startswith("density_"):
+                break
+            self._density_end = (self.leaf_offsets[k] + n + 3) // 4 * 4
         b, e = C.c_int64(), C.c_int64()
         self.lib.tensorf_peer_shard(self.total, self.rank, self.world, C.byref(b), C.byref(e))
         self.shard = (int(b.value), int(e.value))
@@ -230,24 +236,35 @@ class PeerAdam:
         if self._hdl is not None:
             self._hdl.barrier(channel=0)
 
-    def allreduce(self) -> None:
+    def allreduce(self, which: str = "all", channel: int = 0) -> None:
         """Sum `grads` and `aux` (the loss slot) over the ranks in place, on the current stream: barrier (all
-        gradients written), one kernel (each rank reduces 1/world of the buffer from every peer and stores the sums
-        to every peer), barrier (all stores landed)."""
+        gradients written), one kernel (each rank reduces 1/world of the range from every peer and stores the sums
+        to every peer), barrier (all stores landed).  `which` = "late" (the leading density leaves) / "early"
+        (everything else + aux) reduces one bucket of the two-half reverse pass (`RenderCall.backward(phase=1/2)`);
+        buckets running on different streams must use different barrier channels."""
+        import ctypes as C
+
         from . import _lib
         from .ops import _stream
 
         if self.world == 1:
             return
-        if self.sync == "kernel":  # both barriers inside the kernel (signal pads in the symmetric buffer)
+        if which == "all" and self.sync == "kernel":  # both barriers inside the kernel (signal pads in the symmetric buffer)
             self._epoch += 1
             _lib.check(self.lib.tensorf_peer_allreduce_sync(_stream(), self.rank, self.world, self.total + 16, self._g,
                                                             self._x_mc, self._sig, self._local_flags.data_ptr(),
                                                             self._epoch & 0xFFFFFFFF))
             return
-        self.barrier()
-        _lib.check(self.lib.tensorf_peer_allreduce(_stream(), self.rank, self.world, self.total + 16, self._g, self._x_mc))
-        self.barrier()
+        lo, hi = {"all": (0, self.total + 16), "late": (0, self._density_end), "early": (self._density_end, self.total + 16)}[which]
+        if hi == lo:
+            return
+        ptrs = self._g if lo == 0 else (C.c_void_p * self.world)(*[int(p) + 4 * lo for p in self._g])
+        mc = self._x_mc if (lo == 0 or self._x_mc is None) else C.c_void_p(self._x_mc.value + 4 * lo)
+        if self._hdl is not None:
+            self._hdl.barrier(channel=channel)
+        _lib.check(self.lib.tensorf_peer_allreduce(_stream(), self.rank, self.world, hi - lo, ptrs, mc))
+        if self._hdl is not None:
+            self._hdl.barrier(channel=channel)
 
     def load_params(self, flat: Dict[str, torch.Tensor]) -> None:
         """Copy replicated leaves into the symmetric buffer (every rank calls this with the same values)."""
