@@ -286,6 +286,8 @@ def test_backward_phases_match_whole_pass(cuda):
         call.backward(None, g, phase=3)
 
 
+@pytest.mark.skipif(os.environ.get("CUDA_LAUNCH_BLOCKING") == "1",
+                    reason="the simulated ranks must run concurrently (they meet inside their kernels)")
 @pytest.mark.parametrize("world", [2, 4])
 def test_inkernel_sync_ranks_on_streams(cuda, world):
     """tensorf_peer_allreduce_sync: the two cross-rank barriers inside the kernel (signal pads, epochs, grid gate).
