@@ -201,7 +201,8 @@ __device__ __forceinline__ bool epoch_reached(uint32_t seen, uint32_t epoch) { r
 
 // Entry: block 0 tells every rank "my buffer is complete" (everything enqueued before this kernel has finished) and
 // waits for the same from every rank, then opens the gate for the other blocks of this grid.  All blocks are
-// co-resident (grid <= 8 per SM), block 0 is dispatched first: the spinning blocks cannot starve it.
+// co-resident (grid <= 4 per SM, see peer_allreduce) and block 0 is dispatched first: the spinning blocks cannot
+// starve it, and block 0 only depends on the block 0 of every other rank's kernel.
 __device__ __forceinline__ void peer_entry_barrier(const PeerReduceArgs& a, int world) {
   if (blockIdx.x == 0) {
     if ((int)threadIdx.x < world) {
@@ -432,7 +433,9 @@ int peer_allreduce(cudaStream_t st, int rank, int world, int64_t total, float* c
   const int64_t tiles = ceil_div64(shard, kPeerRedTile);
   TF_CHECK_ARG(tiles < ((int64_t)1 << 31), "peer_allreduce: shard too large");
   a.n_tiles = (int)tiles;
-  const int64_t cap = (int64_t)kSMs * 8;  // all blocks co-resident: the in-kernel gate relies on it
+  // 4 CTAs of 256 threads x <= 48 registers per SM: every block of the grid is resident at once, so the blocks
+  // spinning on the in-kernel gate never keep block 0 (dispatched first in any case) off an SM
+  const int64_t cap = (int64_t)kSMs * 4;
   const int grid = (int)(tiles < 1 ? 1 : (tiles < cap ? tiles : cap));
   StageTimer t(st, "peer_allreduce");
   const bool use_mc = mc != nullptr;
