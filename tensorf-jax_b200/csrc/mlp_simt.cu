@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(256) k_out_fwd(const float* __restrict__ h2, c
   }
 }
 
-// Reverse of the output layer. Each warp walks a contiguous chunk of rows (two rows in flight),
+// Reverse of the output layer. Each warp walks a contiguous chunk of rows (four rows in flight),
 // keeps the dW3 / db3 / dEmbed partial sums in registers; dW3/db3 are reduced across the block in
 // shared memory so only one set of atomics per block reaches L2 (the 387 addresses are a hot
 // spot otherwise). Embedding rows are flushed whenever the camera index changes: consecutive
@@ -452,22 +452,28 @@ __global__ void __launch_bounds__(256) k_out_bwd(const float* __restrict__ h2, c
     o.w = hv[3] > 0.f ? dh[3] : 0.f;
     *reinterpret_cast<float4*>(dp2 + m * 128 + 4 * lane) = o;
   };
+  // kOutBwdRows independent rows in flight per warp (all their loads are issued before the first row is processed;
+  // rows are still processed in order, so the partial sums - and the results - do not depend on the depth).  The
+  // kernel is one wave of ~14 warps per SM: with 2 rows (1 KB per warp) it had ~14 KB per SM in flight against the
+  // ~35 KB that saturate HBM at its latency.
+  constexpr int kOutBwdRows = 4;
   int64_t m = mbeg;
-  for (; m + 1 < mend; m += 2) {  // two independent rows in flight
-    float4 ha = *reinterpret_cast<const float4*>(h2 + m * 128 + 4 * lane);
-    float4 hb = *reinterpret_cast<const float4*>(h2 + (m + 1) * 128 + 4 * lane);
-    float ya[3], da[3], yb[3], dbv[3];
+  for (; m + kOutBwdRows <= mend; m += kOutBwdRows) {
+    float4 h[kOutBwdRows];
+    float y[kOutBwdRows][3], dy_in[kOutBwdRows][3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      ya[c] = rgb[3 * m + c];
-      da[c] = d_rgb[3 * m + c];
-      yb[c] = rgb[3 * (m + 1) + c];
-      dbv[c] = d_rgb[3 * (m + 1) + c];
+    for (int r = 0; r < kOutBwdRows; ++r) {
+      h[r] = *reinterpret_cast<const float4*>(h2 + (m + r) * 128 + 4 * lane);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        y[r][c] = rgb[3 * (m + r) + c];
+        dy_in[r][c] = d_rgb[3 * (m + r) + c];
+      }
     }
-    process(m, ha, ya, da);
-    process(m + 1, hb, yb, dbv);
+#pragma unroll
+    for (int r = 0; r < kOutBwdRows; ++r) process(m + r, h[r], y[r], dy_in[r]);
   }
-  if (m < mend) {
+  for (; m < mend; ++m) {
     float4 ha = *reinterpret_cast<const float4*>(h2 + m * 128 + 4 * lane);
     float ya[3], da[3];
 #pragma unroll
