@@ -159,6 +159,11 @@ int tensorf_tc_trace_read(long long* host, int n);
 int tensorf_tc_umma_bench(tensorf_stream_t s, int N, int layout_type, int lbo, int sbo, int count, long long* out_dev);
 /* out (Nx, Mg) += X^T (Nx,rows) @ G (rows,Mg): the weight-gradient contraction over rows. Mg <= 128, Nx <= 512. */
 int tensorf_tc_redgemm_test(tensorf_stream_t s, const float* G, int Mg, const float* X, int Nx, int64_t rows, float* out);
+/* Test entry point of the fused MLP kernels' operand conventions (csrc/umma_tiles.cuh): D[128 x N] = A[128 x K] * B[N x K]^T
+ * with two-term 16-bit split operands.  a_mode 0 = shared memory K-major, 1 = shared memory MN-major, 2 = tensor memory;
+ * b_mode 0 = K-major, 1 = MN-major; a_fmt / b_fmt 0 = fp16, 1 = bf16.  N % 16 == 0 <= 128, K % 16 == 0 <= 160. */
+int tensorf_tc_umma_probe(tensorf_stream_t s, const float* A, const float* B, float* D, int N, int K, int a_mode, int b_mode,
+                          int a_fmt, int b_fmt);
 
 /* ---- networks.py:46-121 FeatureMlp.__call__ ----------------------------------------------- */
 /* features (M, 3*ca); viewdirs (M/rows_per_ray, 3); camera_indices (M/rows_per_ray); rgb (M,3).

@@ -160,6 +160,7 @@ int tc_rowgemm_test(cudaStream_t st, const float* A, int64_t M, int K, const flo
 int tc_redgemm_test(cudaStream_t st, const float* G, int Mg, const float* X, int Nx, int64_t rows, float* out);
 int tc_trace_read(long long* host, int n);
 int tc_umma_bench(cudaStream_t st, int N, int layout_type, int lbo, int sbo, int count, long long* out_dev);
+int umma_probe(cudaStream_t st, const float* A, const float* B, float* D, int N, int K, int a_mode, int b_mode, int a_fmt, int b_fmt);
 
 }  // namespace tf
 
@@ -264,6 +265,12 @@ int tensorf_tc_trace_read(long long* host, int n) { return tc_trace_read(host, n
 int tensorf_tc_umma_bench(tensorf_stream_t s, int N, int layout_type, int lbo, int sbo, int count, long long* out_dev) {
   TF_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && count > 0 && out_dev, "bad argument");
   return tc_umma_bench((cudaStream_t)s, N, layout_type, lbo, sbo, count, out_dev);
+}
+
+int tensorf_tc_umma_probe(tensorf_stream_t s, const float* A, const float* B, float* D, int N, int K, int a_mode, int b_mode,
+                          int a_fmt, int b_fmt) {
+  TF_CHECK_ARG(A && B && D, "NULL buffer");
+  return umma_probe((cudaStream_t)s, A, B, D, N, K, a_mode, b_mode, a_fmt, b_fmt);
 }
 
 int64_t tensorf_mlp_workspace_bytes(const tensorf_render_desc* d, int64_t M) {
