@@ -4,7 +4,7 @@ import csv
 import sys
 
 KEYS = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram rd"), ("dram__bytes_write.sum", "dram wr"),
-        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"), ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+        ("lts__t_bytes.sum", "L2 bytes"), ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"), ("lts__t_sector_hit_rate.pct", "L2 hit %"),
         ("l1tex__t_sector_hit_rate.pct", "L1 hit %"), ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps %"), ("launch__registers_per_thread", "regs"),
         ("sm__inst_executed.avg.per_cycle_elapsed", "IPC")]
