@@ -54,11 +54,13 @@ def workload_from_name(name: str) -> S.Workload:
 
 
 def measured_peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s sustained, where they come from)."""
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
-    return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+        return (float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", 1400.0)),
+                "measured (MEASURED_PEAKS.json: hbm_gbs burst copy; bf16_tflops_sustained for kernels timed inside the step)")
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md: 6.65 TB/s, ~1.4 PFLOP/s sustained bf16)"
 
 
 class ClockSampler:
@@ -148,46 +150,50 @@ def run_reference_arm(args, w):
 # ---------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------
-def bench_render(ops, dev, world, rank, dist, chunks=6, warm=2):
-    """Forward rendering at the render_360 shapes (render_360.py:43-51 with the BASELINE sizes: 800x800
-    frames, N=512, K=128, 300^3 lego model, chunks of 16384 rays). Frames are split into row bands
-    across ranks (no collective); every rank renders `chunks` raster-ordered chunks of its band.
-    Reports whole-job Mpix/s for RGB and for the two distance modes."""
-    from tensorf_b200 import dist as tdist
+def bench_render(ops, dev, world, rank, dist, frames=2, warm=1):
+    """render_360 as a job (render_360.py:118-161 through render.py:49-102, BASELINE configs[4] shapes): full 800x800
+    frames of the 300^3 lego model at N=512 / K=128, chunks of 16384 rays with the ragged last chunk, per mode
+    (RGB, median distance, mean distance).  Per frame and rank: `tensorf_pixel_rays` on the device -> chunk loop ->
+    ONE device-to-host copy of the rank's rows into pinned memory, all inside the timed region.  The frame is dealt to
+    the ranks in interleaved 16-row stripes (`dist.stripe_rows`), no collective.  Whole-job Mpix/s = frame pixels x
+    frames / max-over-ranks device time (CUDA events around the frames, including the copies)."""
+    from tensorf_b200 import networks, render as trender
     w = S.render360_workload()
-    params = {k: torch.from_numpy(v).to(dev) for k, v in S.make_params(w.G, w.cd, w.ca, w.feat_freqs, w.view_freqs, None, 0).items()}
-    r0, r1 = tdist.tile_rows(800, rank, world)
-    o, d, c = S.frame_rays(800, 800, rows=(r0, r1))
+    H = W_ = 800
+    flat = {k: torch.from_numpy(v).to(dev) for k, v in S.make_params(w.G, w.cd, w.ca, w.feat_freqs, w.view_freqs, None, 0).items()}
+    lp = trender.LearnableParams.from_flat(flat, scene_contraction=False)
+    mlp = networks.FeatureMlp(feature_n_freqs=w.feat_freqs, viewdir_n_freqs=w.view_freqs)
+    aabb = torch.from_numpy(w.aabb()).to(dev)
     jitter, gumbel = S.make_noise(w.N, w.R, False, 2)
-    shared = {"aabb": torch.from_numpy(w.aabb()).to(dev), "jitter": torch.from_numpy(jitter).to(dev),
-              "gumbel": torch.from_numpy(gumbel).to(dev)}
-    nrays = o.shape[0]
-    starts = [(i * w.R) % max(1, nrays - w.R + 1) for i in range(chunks + warm)]
-    O_, D_, C_ = (torch.from_numpy(x).to(dev) for x in (o, d, c.view(np.int32)))
-    out = {"workload": w.name, "rays_per_chunk": w.R, "chunks_timed": chunks}
-    for label, mode in (("rgb", ops.MODE_RGB), ("dist_median", ops.MODE_DIST_MEDIAN), ("dist_mean", ops.MODE_DIST_MEAN)):
-        desc = ops.make_desc(R=w.R, N=w.N, K=w.K, G=w.G, cd=w.cd, ca=w.ca, mode=mode, feat_freqs=w.feat_freqs,
-                             view_freqs=w.view_freqs, inference=True)  # render_360.py never differentiates
-        call = ops.RenderCall(desc, dev)
+    noise = {"jitter": torch.from_numpy(jitter).to(dev), "gumbel": torch.from_numpy(gumbel).to(dev)}
+    cams = [S.frame_camera(W_, H, angle=0.3 + 2 * 3.14159265 * i / 120) for i in range(frames + warm)]  # consecutive poses of the orbit
+    out = {"workload": w.name, "frame": [H, W_], "rays_per_chunk": w.R, "frames_timed": frames,
+           "tiling": f"16-row stripes round-robin over {world} rank(s), no collective",
+           "e2e": "pixel rays generated on the device, one D2H copy of the rank's rows per frame into pinned memory (inside the timed region)"}
+    for label, mode in (("rgb", trender.RenderMode.RGB), ("dist_median", trender.RenderMode.DIST_MEDIAN), ("dist_mean", trender.RenderMode.DIST_MEAN)):
+        cfg = trender.RenderConfig(near=0.1, far=10.0, mode=mode, density_samples_per_ray=w.N, appearance_samples_per_ray=w.K)
+        fr = trender.FrameRenderer(mlp, lp, aabb, cfg, H, W_, batch_size=w.R, rank=rank, world=world)
+        ns = {k: v for k, v in noise.items() if k == "jitter" or mode is trender.RenderMode.RGB}
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for i, st in enumerate(starts):
+        for i, cam in enumerate(cams):
             if i == warm:
+                if dist is not None:
+                    dist.barrier()
                 torch.cuda.synchronize()
                 ev0.record()
-            ins = dict(shared, origins=O_[st:st + w.R].contiguous(), directions=D_[st:st + w.R].contiguous(),
-                       camera_indices=C_[st:st + w.R].contiguous())
-            if mode == ops.MODE_RGB:
-                call.forward(params, ins)
-            else:
-                call.depth(params, ins)
+            fr.render(cam, i, ns, sync=False)
         ev1.record()
         torch.cuda.synchronize()
         t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item()) / chunks
-        out[label] = {"mpix_per_s": world * w.R / (ms * 1e-3) / 1e6, "ms_per_chunk": ms}
-        del call
+        ms = float(t.item()) / frames
+        bytes_d2h = fr.frame_host.numel() * 4
+        out[label] = {"mpix_per_s": H * W_ / (ms * 1e-3) / 1e6, "ms_per_frame": ms, "rays_this_rank": fr.n,
+                      "chunks_per_frame_this_rank": (fr.n + w.R - 1) // w.R, "ragged_last_chunk": fr.n % w.R, "d2h_bytes_per_frame_this_rank": bytes_d2h,
+                      "finite": bool(torch.isfinite(fr.frame_host).all())}
+        del fr
+        torch.cuda.empty_cache()
     return out
 
 
@@ -306,7 +312,6 @@ def main():
     dins = dict(stage.device)
     dins["aabb"] = dv(inp["aabb"])
     if w.contracted:
-        sys.path.insert(0, str(ROOT / "oracle"))
         # host constants of render.py:127-155 (numpy, float64 -> fp32), computed once
         from tensorf_b200.render import contracted_schedule
         base, delta = contracted_schedule(w.near, w.far, w.N)
@@ -436,7 +441,7 @@ def main():
         render = bench_render(ops, dev, world, rank, dist if world > 1 else None)
 
     if rank == 0:
-        peak, peak_src = measured_peaks()
+        peak, tc_peak, peak_src = measured_peaks()
         # Algorithmic bytes of the gather model: 6 taps x 4 B per sample-channel,
         # the reverse pass re-gathers and scatter-adds the same count (2x).
         alg = {
@@ -445,14 +450,48 @@ def main():
             "density_scatter": 48 * w.N * 3 * w.cd * w.R,
             "appearance_scatter": 48 * w.K * 3 * w.ca * w.R,
         }
+        # Algorithmic flops of the MLP (networks.py:57-117): 2 x (3ca*27 + enc*128 + 128*128 + 128*3) per row forward,
+        # twice that in the reverse pass (activation and weight gradients).
+        enc = w.encoded_dim()
+        mlp_row = 2 * (3 * w.ca * 27 + enc * 128 + 128 * 128 + 128 * 3)
+        flops = {"mlp_fwd": mlp_row * w.R * w.K, "mlp_bwd": 2 * mlp_row * w.R * w.K}
         stages = {k: {"ms": v[0] / max(v[1], 1), "share": v[0] / total_ms} for k, v in prof.items()}
-        dom = max(alg, key=lambda k: stages.get(k, {"ms": 0})["ms"])
-        dom_ms = stages[dom]["ms"]
-        achieved = alg[dom] / (dom_ms * 1e-3) / 1e9
-        traffic = None
-        tp = ROOT / "profiles" / "traffic.json"  # per-launch dram bytes from the committed ncu --set full capture
+        traffic_all = {}
+        tp = ROOT / "profiles" / "traffic.json"  # per-step ncu numbers of the committed --set full capture (tools/traffic_from_ncu.py)
         if tp.exists():
-            traffic = json.loads(tp.read_text()).get(args.workload, {}).get(dom)
+            traffic_all = json.loads(tp.read_text()).get(args.workload, {})
+        # per-stage rooflines: gather / scatter stages against HBM (gather-model bytes; DRAM and L2 rates from the ncu
+        # capture's bytes over the LIVE stage time), MLP stages against the tensor pipe
+        stage_roofs = {}
+        for k, st_ in stages.items():
+            tr = traffic_all.get(k) if isinstance(traffic_all.get(k), dict) else None
+            e = {"ms": round(st_["ms"], 4)}
+            if k in alg:
+                e.update(bound="hbm", algorithmic_gbs=alg[k] / (st_["ms"] * 1e-3) / 1e9)
+            if k in flops:
+                e.update(bound="tensor", algorithmic_tflops=flops[k] / (st_["ms"] * 1e-3) / 1e12,
+                         frac_of_bf16_sustained=flops[k] / (st_["ms"] * 1e-3) / 1e12 / tc_peak)
+            if tr:
+                e.update(dram_gbs=tr["dram_bytes"] / (st_["ms"] * 1e-3) / 1e9, lts_gbs=tr["l2_bytes"] / (st_["ms"] * 1e-3) / 1e9,
+                         dram_frac_of_hbm_peak=tr["dram_bytes"] / (st_["ms"] * 1e-3) / 1e9 / peak)
+            stage_roofs[k] = e
+        dom = max(stages, key=lambda k: stages[k]["ms"])  # the dominant stage over ALL stages
+        dom_ms = stages[dom]["ms"]
+        dtr = traffic_all.get(dom) if isinstance(traffic_all.get(dom), dict) else None
+        traffic = dtr["dram_bytes"] if dtr else None
+        if dom in flops:
+            achieved = flops[dom] / (dom_ms * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak,
+                        "traffic": traffic, "algorithmic_flops_per_launch": flops[dom], "avg_launch_ms": dom_ms, "peak_source": peak_src,
+                        "split_factor": 3,
+                        "note": "algorithmic fp32 flops of the FeatureMlp stage (all its kernels) over the measured dense bf16 peak; fp32 parity on "
+                                "16-bit tensor cores costs 3 tcgen05.mma per product (two-term operand split), so the issued-MMA fraction is 3x frac"}
+        else:
+            achieved = alg.get(dom, 0) / (dom_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": traffic, "algorithmic_bytes_per_launch": alg.get(dom), "avg_launch_ms": dom_ms, "peak_source": peak_src,
+                        "note": "gather-model bytes (6 taps x 4 B per sample-channel, SURVEY 8d); at 128^3 the factors and their gradients are "
+                                "L2-resident, so frac > 1 is an L2/LSU rate - `traffic` is the stage's ncu DRAM bytes per step"}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -467,10 +506,8 @@ def main():
             "roofline_step": {"bound": "hbm", "achieved": value / world * w.train_bytes_per_ray() / 1e9, "peak": peak, "unit": "GB/s",
                               "frac": value / world * w.train_bytes_per_ray() / 1e9 / peak,
                               "note": "whole step per GPU, gather-model bytes 3*24*(N*3cd+K*3ca) per ray (SURVEY §8d); factors are L2-resident at 128^3"},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": dom_ms, "peak_source": peak_src,
-                         "note": "gather-model bytes (6 taps x 4 B per sample-channel, SURVEY 8d); at 128^3 the factors and their gradients are "
-                                 "L2-resident, so frac > 1 is an L2/LSU rate - `traffic` is the kernel's ncu DRAM bytes per launch"},
+            "roofline": roofline,
+            "stage_rooflines": stage_roofs,
             "stages_ms": {k: round(v["ms"], 4) for k, v in sorted(stages.items(), key=lambda kv: -kv[1]["ms"])},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "note": "public API (RenderCall + data.HostStage): one pinned H2D copy of the minibatch and a blocking loss read per "

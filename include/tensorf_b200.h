@@ -47,8 +47,11 @@ enum tensorf_render_mode { TENSORF_MODE_RGB = 0, TENSORF_MODE_DIST_MEDIAN = 1, T
  * reads (ReLU masks, second hidden layer) are not written; tensorf_render_rgb_bwd / tensorf_mlp_bwd then fail. */
 enum tensorf_render_flags { TENSORF_FLAG_INFERENCE = 1 };
 
-/* MLP arithmetic: exact fp32 on CUDA cores, or tcgen05 tensor cores with split-bf16 operands. */
-enum tensorf_mlp_impl { TENSORF_MLP_AUTO = 0, TENSORF_MLP_SIMT_FP32 = 1, TENSORF_MLP_TCGEN05 = 2 };
+/* MLP arithmetic: exact fp32 on CUDA cores; tcgen05 tensor cores with split-bf16 operands, one kernel per layer;
+ * or the per-row-tile fused tcgen05 kernels (split-fp16 operands, activations stay in tensor memory between the
+ * layers; networks with feature_squash_dim 27, units 128, 2 + 2 frequencies and no camera embeddings only -
+ * TENSORF_ERR_UNSUPPORTED otherwise).  AUTO picks the fused kernels when the network qualifies. */
+enum tensorf_mlp_impl { TENSORF_MLP_AUTO = 0, TENSORF_MLP_SIMT_FP32 = 1, TENSORF_MLP_TCGEN05 = 2, TENSORF_MLP_FUSED = 3 };
 
 /* Static configuration of one render call: render.py:26-36 (RenderConfig), the static fields
  * of networks.py:38-43 (FeatureMlp) and the array shapes render.py:105-113 receives. */
@@ -169,6 +172,10 @@ int tensorf_tc_umma_probe(tensorf_stream_t s, const float* A, const float* B, fl
 /* features (M, 3*ca); viewdirs (M/rows_per_ray, 3); camera_indices (M/rows_per_ray); rgb (M,3).
  * workspace: tensorf_mlp_workspace_bytes. */
 int64_t tensorf_mlp_workspace_bytes(const tensorf_render_desc* d, int64_t M);
+/* Test entry point: float offsets into the MLP workspace of the saved activations, in the order f, df, x, dx, h1, h2,
+ * dp2, dp1, relu-mask words of layer 1, of layer 2.  With TENSORF_MLP_FUSED x / h1 / h2 / dp2 / dp1 hold two-term
+ * 16-bit slab tiles per 128 rows (csrc/umma_tiles.cuh) and f / df hold [tile][4-column group][row][4] floats. */
+int tensorf_mlp_workspace_layout(const tensorf_render_desc* d, int64_t M, int64_t* offsets);
 int tensorf_mlp_fwd(tensorf_stream_t s, const tensorf_render_desc* d, const tensorf_params* p, const float* features,
                     const float* viewdirs, const uint32_t* camera_indices, int64_t M, int rows_per_ray, void* workspace,
                     float* rgb);

@@ -148,6 +148,32 @@ static MlpParams mlp_params(const tensorf_params& p) {
 }
 static MlpGrads mlp_grads(const tensorf_params& p) { return MlpGrads{p.w0, p.w1, p.b1, p.w2, p.b2, p.w3, p.b3, p.embed}; }
 
+// MLP implementation of a call: SIMT fp32, per-layer tcgen05 kernels, or the per-row-tile fused tcgen05 kernels
+// (AUTO = fused when the network qualifies, else per-layer).
+static int mlp_pick(const tensorf_render_desc& d, const MlpShape& ms, int* impl) {
+  int m = d.mlp_impl;
+  if (m == TENSORF_MLP_AUTO)
+    m = (mlp_fused_supported(ms) && (ms.inference || mlp_fused_bwd_ready()) && !getenv("TENSORF_NO_FUSED_MLP")) ? TENSORF_MLP_FUSED
+                                                                                                              : TENSORF_MLP_TCGEN05;
+  if (m == TENSORF_MLP_FUSED && !mlp_fused_supported(ms)) {
+    set_error("mlp_impl FUSED needs squash 27, units 128, 2 + 2 frequencies, no camera embeddings, 3*ca %% 16 == 0 <= 160");
+    return TENSORF_ERR_UNSUPPORTED;
+  }
+  *impl = m;
+  return 0;
+}
+static int mlp_fwd_any(int impl, cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs,
+                       const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, float* rgb) {
+  if (impl == TENSORF_MLP_FUSED) return mlp_fused_fwd(st, s, p, feat, viewdirs, cams, M, rows_per_ray, ws, rgb);
+  return (impl == TENSORF_MLP_SIMT_FP32 ? mlp_simt_fwd : mlp_tc_fwd)(st, s, p, feat, viewdirs, cams, M, rows_per_ray, ws, rgb);
+}
+static int mlp_bwd_any(int impl, cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs,
+                       const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, const float* rgb, const float* d_rgb,
+                       float* d_feat, const MlpGrads& g) {
+  if (impl == TENSORF_MLP_FUSED) return mlp_fused_bwd(st, s, p, feat, viewdirs, cams, M, rows_per_ray, ws, rgb, d_rgb, d_feat, g);
+  return (impl == TENSORF_MLP_SIMT_FP32 ? mlp_simt_bwd : mlp_tc_bwd)(st, s, p, feat, viewdirs, cams, M, rows_per_ray, ws, rgb, d_rgb, d_feat, g);
+}
+
 static int check_mlp_params(const tensorf_render_desc& d, const tensorf_params* p, const char* what) {
   TF_CHECK_ARG(p != nullptr, "%s is NULL", what);
   TF_CHECK_ARG(p->w0 && p->w1 && p->b1 && p->w2 && p->b2 && p->w3 && p->b3, "%s: MLP leaves must be non-NULL", what);
@@ -278,6 +304,17 @@ int64_t tensorf_mlp_workspace_bytes(const tensorf_render_desc* d, int64_t M) {
   return (int64_t)sizeof(float) * mlp_ws_floats(mlp_shape(*d), M);
 }
 
+int tensorf_mlp_workspace_layout(const tensorf_render_desc* d, int64_t M, int64_t* offsets) {
+  TF_CHECK_ARG(d && M >= 0 && offsets, "bad arguments");
+  const MlpShape ms = mlp_shape(*d);
+  float* base = reinterpret_cast<float*>(uintptr_t(1) << 40);
+  const MlpWs w = mlp_ws_carve(ms, M, base);
+  const float* p[10] = {w.f, w.df, w.x, w.dx, w.h1, w.h2, w.dp2, w.dp1, reinterpret_cast<float*>(w.bits1),
+                        reinterpret_cast<float*>(w.bits1) + round_up64(M, 128) * 4};
+  for (int i = 0; i < 10; ++i) offsets[i] = p[i] - base;
+  return 0;
+}
+
 int tensorf_mlp_fwd(tensorf_stream_t s, const tensorf_render_desc* d, const tensorf_params* p, const float* features,
                     const float* viewdirs, const uint32_t* camera_indices, int64_t M, int rows_per_ray, void* workspace,
                     float* rgb) {
@@ -294,7 +331,9 @@ int tensorf_mlp_fwd(tensorf_stream_t s, const tensorf_render_desc* d, const tens
   if (d->num_cameras > 0) TF_CHECK_ARG(M == 0 || camera_indices, "camera embeddings need camera_indices");
   MlpShape ms = mlp_shape(*d);
   MlpWs ws = mlp_ws_carve(ms, M, (float*)workspace);
-  return (mlp_use_tc(d->mlp_impl) ? mlp_tc_fwd : mlp_simt_fwd)((cudaStream_t)s, ms, mlp_params(*p), features, viewdirs,
+  int impl;
+  TF_RETURN_IF_ERROR(mlp_pick(*d, ms, &impl));
+  return mlp_fwd_any(impl, (cudaStream_t)s, ms, mlp_params(*p), features, viewdirs,
                                                                 camera_indices, M, rows_per_ray, ws, rgb);
 }
 
@@ -313,7 +352,9 @@ int tensorf_mlp_bwd(tensorf_stream_t s, const tensorf_render_desc* d, const tens
   TF_CHECK_ARG(M == 0 || (features && viewdirs && workspace && rgb && d_rgb && d_features), "NULL buffer");
   MlpShape ms = mlp_shape(*d);
   MlpWs ws = mlp_ws_carve(ms, M, (float*)workspace);
-  return (mlp_use_tc(d->mlp_impl) ? mlp_tc_bwd : mlp_simt_bwd)((cudaStream_t)s, ms, mlp_params(*p), features, viewdirs,
+  int impl;
+  TF_RETURN_IF_ERROR(mlp_pick(*d, ms, &impl));
+  return mlp_bwd_any(impl, (cudaStream_t)s, ms, mlp_params(*p), features, viewdirs,
                                                                 camera_indices, M, rows_per_ray, ws, rgb, d_rgb, d_features,
                                                                 mlp_grads(*grads));
 }
@@ -386,6 +427,8 @@ int tensorf_render_rgb_fwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   cudaStream_t st = (cudaStream_t)s;
   RenderWs w = carve(*d, (float*)workspace);
   const MlpShape ms = mlp_shape(*d);
+  int mlp_impl;
+  TF_RETURN_IF_ERROR(mlp_pick(*d, ms, &mlp_impl));
   const int64_t M = (int64_t)d->R * d->K;
 
   {
@@ -427,7 +470,7 @@ int tensorf_render_rgb_fwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   MlpWs mws = mlp_ws_carve(ms, M, w.mlp_base);
   {
     StageTimer t_(st, "mlp_fwd");
-    TF_RETURN_IF_ERROR((mlp_use_tc(d->mlp_impl) ? mlp_tc_fwd : mlp_simt_fwd)(st, ms, mlp_params(*p), w.feat, in->directions,
+    TF_RETURN_IF_ERROR(mlp_fwd_any(mlp_impl, st, ms, mlp_params(*p), w.feat, in->directions,
                                                                               in->camera_indices, M, d->K, mws, w.rgb_sel));
   }
   StageTimer t_(st, "composite");
@@ -467,6 +510,8 @@ static int render_rgb_bwd_impl(tensorf_stream_t s, const tensorf_render_desc* d,
   cudaStream_t st = (cudaStream_t)s;
   RenderWs w = carve(*d, (float*)workspace);
   const MlpShape ms = mlp_shape(*d);
+  int mlp_impl;
+  TF_RETURN_IF_ERROR(mlp_pick(*d, ms, &mlp_impl));
   const int64_t M = (int64_t)d->R * d->K;
   const bool do_app = phase != 2, do_den = phase != 1;
 
@@ -532,7 +577,7 @@ static int render_rgb_bwd_impl(tensorf_stream_t s, const tensorf_render_desc* d,
       StageTimer t_(st, "mlp_bwd");
       MlpGrads mg = mlp_grads(*grads);
       mg.prezeroed = true;  // by k_ray_bwd above
-      TF_RETURN_IF_ERROR((mlp_use_tc(d->mlp_impl) ? mlp_tc_bwd : mlp_simt_bwd)(st, ms, mlp_params(*p), w.feat, in->directions,
+      TF_RETURN_IF_ERROR(mlp_bwd_any(mlp_impl, st, ms, mlp_params(*p), w.feat, in->directions,
                                                                                 in->camera_indices, M, d->K, mws, w.rgb_sel,
                                                                                 w.d_rgb_sel, w.d_feat, mg));
     }

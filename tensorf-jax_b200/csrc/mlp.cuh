@@ -40,7 +40,8 @@ struct MlpWs {
   float* dp1;  // (M, units)
   float* dx;   // (M, enc)
   float* df;   // (M, squash)
-  uint32_t* bits1;  // (M, units/32) ReLU mask of layer 1, one bit per unit (tensor-core path)
+  uint32_t* bits1;  // (M, units/32) ReLU mask of layer 1, one bit per unit (tensor-core path); layer 2's follow (fused path)
+  float* aux;       // fused path: [64] scalars (gradient scale), then the d(output) slab tiles (M, 16)
 };
 int64_t mlp_ws_floats(const MlpShape& s, int64_t M);
 MlpWs mlp_ws_carve(const MlpShape& s, int64_t M, float* base);
@@ -66,6 +67,16 @@ int mlp_tc_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const flo
                const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, const float* rgb, const float* d_rgb,
                float* d_feat, const MlpGrads& g);
 size_t mlp_tc_wpack_bytes(const MlpShape& s);
+bool tc_make_a_tensor_map(void* tensor_map, const float* A, int64_t M, int K_valid, int64_t lda, int kc);  // CUtensorMap*, mlp_tc.cu
+// per-row-tile fused kernels (mlp_fused.cu): lego-type networks only (mlp_fused_supported), same contract
+bool mlp_fused_supported(const MlpShape& s);
+size_t mlp_fused_wpack_bytes(const MlpShape& s);
+int mlp_fused_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs,
+                  const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, float* rgb);
+bool mlp_fused_bwd_ready();
+int mlp_fused_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs,
+                  const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, const float* rgb, const float* d_rgb,
+                  float* d_feat, const MlpGrads& g);
 
 // pieces shared by both implementations (mlp_simt.cu)
 int mlp_encode_fwd(cudaStream_t st, const MlpShape& s, const MlpWs& ws, const float* viewdirs, int64_t M, int rows_per_ray,

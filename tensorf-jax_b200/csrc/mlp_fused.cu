@@ -8,6 +8,8 @@
 
 #include <algorithm>
 
+#include <cuda.h>
+
 #include "mlp.cuh"
 #include "umma_tiles.cuh"
 
@@ -131,6 +133,947 @@ int umma_probe(cudaStream_t st, const float* A, const float* B, float* D, int N,
   const size_t smem = 1024 + 2 * (size_t)slab_tile_bytes(128, 160);
   TF_CHECK_CUDA(cudaFuncSetAttribute(k_umma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_umma_probe<<<1, 128, smem, st>>>(A, B, D, N, K, a_mode, b_mode, a_fmt, b_fmt);
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+
+
+// ===============================================================================================================
+// Fused FeatureMlp for the lego-type network (networks.py:38-121 with feature_squash_dim 27, units 128,
+// feature_n_freqs = viewdir_n_freqs = 2, no camera embeddings; 3*ca a multiple of 16, <= 160).
+//
+// Encoded input in kernel order ("x'", 160 columns): column 80*s + 5*i + v holds, for source dimension d = 15*s + i
+// (d < 27: squashed feature f_d, d >= 27: view direction component d - 27), v = 0: the value, 1: sin, 2: sin 2x,
+// 3: cos, 4: cos 2x.  Columns 75..79 and 155..159 are padding; column 75 is the constant 1 (its Dense_1 weight row
+// is zero; in the weight-gradient product it yields the bias gradient as one more column sum).  fz_perm maps a
+// kernel column to the reference's column of networks.py:68-76 ([f, v, enc(f), enc(v)]).
+// ===============================================================================================================
+namespace fz {
+constexpr int kU = 128, kSq = 27, kHalfDims = 15, kPer = 5, kXH = 80, kX = 160, kOnesCol = 75;
+constexpr int kConvWarp0 = 8, kMmaWarp = 12, kLoadWarp = 13, kThreads = 448;
+constexpr int kRawSlots = 3, kRawBytes = 128 * 32 * 4, kHeader = 8192;
+constexpr uint32_t kAcc0 = 0, kAcc1 = 128, kAop = 256, kAopLo = 80;  // tensor-memory columns
+constexpr uint32_t kB1Bytes = 2u * kX * kU * 2u, kB2Bytes = 2u * kU * kU * 2u;
+__host__ __device__ inline int perm(int kp) {
+  const int s = kp / kXH, e = kp % kXH;
+  if (e >= kHalfDims * kPer) return -1;
+  const int d = kHalfDims * s + e / kPer, v = e % kPer;
+  return v == 0 ? d : 30 + 4 * d + (v - 1);
+}
+// Dense_0 output columns in kernel order (32 columns): worker set 0 owns columns 0..15 (f_0..f_14, one zero column),
+// set 1 columns 16..31 (f_15..f_26, four zero columns), so each set's reverse-pass df is a whole 16-column k-chunk.
+__host__ __device__ inline int sq_nat(int np) { return np < 15 ? np : (np >= 16 && np < 28) ? np - 1 : -1; }
+__host__ __device__ inline uint32_t b0_bytes(int K0) { return (uint32_t)K0 * 128u; }  // 32 rows x K0 columns x 2 terms x 2 B
+}  // namespace fz
+
+bool mlp_fused_supported(const MlpShape& s) {
+  return s.squash == fz::kSq && s.units == fz::kU && s.Ff == 2 && s.Fv == 2 && s.ncam == 0 && s.Ca % 16 == 0 && s.Ca >= 16 && s.Ca <= 160;
+}
+size_t mlp_fused_wpack_bytes(const MlpShape& s) { return (size_t)fz::b0_bytes(s.Ca) + fz::kB1Bytes + fz::kB2Bytes; }
+
+// Weights -> fp16 two-term slab tiles [B0 | B1 | B2]: tile rows = output unit n, columns = input k (K-major B of the
+// forward; the same bytes are the MN-major B of the reverse products, umma_tiles.cuh).
+struct FusedPackArgs {
+  const float *w0, *w1, *w2;
+  int Ca;
+  unsigned char* out;
+};
+__global__ void __launch_bounds__(256) k_fused_pack(FusedPackArgs a) {
+  const int K0 = a.Ca;
+  const int n0 = 32 * (K0 / 8), n1 = fz::kU * (fz::kX / 8), n2 = fz::kU * (fz::kU / 8);
+  int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= n0 + n1 + n2) return;
+  float x[8];
+  unsigned char* tile;
+  int rows, n, c8;
+  if (item < n0) {
+    rows = 32; n = item % 32; c8 = item / 32; tile = a.out;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) x[q] = fz::sq_nat(n) >= 0 ? a.w0[(c8 * 8 + q) * fz::kSq + fz::sq_nat(n)] : 0.f;
+  } else if (item < n0 + n1) {
+    item -= n0;
+    rows = fz::kU; n = item % fz::kU; c8 = item / fz::kU; tile = a.out + fz::b0_bytes(K0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int nat = fz::perm(c8 * 8 + q);
+      x[q] = nat >= 0 ? a.w1[nat * fz::kU + n] : 0.f;
+    }
+  } else {
+    item -= n0 + n1;
+    rows = fz::kU; n = item % fz::kU; c8 = item / fz::kU; tile = a.out + fz::b0_bytes(K0) + fz::kB1Bytes;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) x[q] = a.w2[(c8 * 8 + q) * fz::kU + n];
+  }
+  uint4 hi, lo;
+  split8_fmt<FMT_F16>(x, hi, lo);
+  *reinterpret_cast<uint4*>(tile + slab_offset(rows, 0, n, c8 * 8)) = hi;
+  *reinterpret_cast<uint4*>(tile + slab_offset(rows, 1, n, c8 * 8)) = lo;
+}
+
+struct FusedFwdArgs {
+  const unsigned char* wpack;
+  const float *b1, *b2, *w3, *b3;
+  const float* viewdirs;
+  int rows_per_ray;
+  int64_t M;
+  int K0;  // 3*ca
+  float* rgb;
+  // residuals of the reverse pass (TRAIN): slab tiles per 128-row tile, ReLU masks, Dense_0 output
+  unsigned char *xs, *h1s, *h2s, *feats;
+  float* fs;
+  uint32_t *bits1, *bits2;
+};
+
+// 16 fp32 values of one row -> fp16 (hi, lo) words; hi[0..3] / lo[0..3] = columns 0-7, [4..7] = columns 8-15
+__device__ __forceinline__ void split16(const float* y, uint32_t* hi, uint32_t* lo) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) split_pair<FMT_F16>(y[2 * q], y[2 * q + 1], hi[q], lo[q]);
+}
+// One 16-column k-chunk of the next layer's A operand: tensor memory (hi at column 8c, lo at 80 + 8c of the operand
+// region) and, for the reverse pass, the slab tile in global memory; then "chunk ready" for the MMA warp.
+template <bool TRAIN>
+__device__ __forceinline__ void emit_chunk(const uint32_t* hi, const uint32_t* lo, uint32_t aop_lane, int c, unsigned char* slab_row,
+                                           uint64_t* bar, int lane) {
+  tmem_st8(aop_lane + 8u * c, hi);
+  tmem_st8(aop_lane + fz::kAopLo + 8u * c, lo);
+  if (TRAIN) {
+    uint4* p = reinterpret_cast<uint4*>(slab_row + (size_t)(4 * c) * 2048);
+    p[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    p[128] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    p[256] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    p[384] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
+// Dense_0 accumulator -> Fourier-encoded input x' (this set's 80 columns = 5 k-chunks)
+template <int SET, bool TRAIN>
+__device__ __forceinline__ void fused_epi0(const FusedFwdArgs& g, uint32_t acc_lane, uint32_t aop_lane, int64_t m, int64_t tile, int row,
+                                           uint64_t* kready, int lane) {
+  float f[32];
+  tmem_ld32(acc_lane, f);
+  tmem_ld_wait();
+  if (TRAIN) {
+    float4* fp = reinterpret_cast<float4*>(g.fs + (size_t)tile * 4096 + (size_t)(4 * SET) * 512) + row;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) fp[j * 128] = make_float4(f[16 * SET + 4 * j], f[16 * SET + 4 * j + 1], f[16 * SET + 4 * j + 2], f[16 * SET + 4 * j + 3]);
+  }
+  float val[fz::kHalfDims], sn[fz::kHalfDims], cs[fz::kHalfDims];
+  float vd[3] = {0.f, 0.f, 0.f};
+  if (SET == 1 && m < g.M) {
+    const float* v = g.viewdirs + (m / g.rows_per_ray) * 3;
+    vd[0] = __ldg(v); vd[1] = __ldg(v + 1); vd[2] = __ldg(v + 2);
+  }
+#pragma unroll
+  for (int i = 0; i < fz::kHalfDims; ++i) {
+    const int d = fz::kHalfDims * SET + i;
+    val[i] = d < fz::kSq ? f[d < fz::kSq ? 16 * SET + i : 0] : vd[d >= fz::kSq ? d - fz::kSq : 0];
+    sincosf(val[i], &sn[i], &cs[i]);
+  }
+  unsigned char* slab_row = TRAIN ? g.xs + (size_t)tile * (fz::kX * 512) + (size_t)row * 16 : nullptr;
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    float y[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int e = 16 * c + q, i = e / fz::kPer < fz::kHalfDims ? e / fz::kPer : 0, v = e % fz::kPer;
+      float r;
+      if (e >= fz::kHalfDims * fz::kPer) r = (SET == 0 && e == fz::kOnesCol) ? 1.0f : 0.0f;
+      else if (v == 0) r = val[i];
+      else if (v == 1) r = sn[i];
+      else if (v == 2) r = 2.0f * sn[i] * cs[i];
+      else if (v == 3) r = cs[i];
+      else r = fmaf(-2.0f * sn[i], sn[i], 1.0f);
+      y[q] = r;
+    }
+    uint32_t hi[8], lo[8];
+    split16(y, hi, lo);
+    emit_chunk<TRAIN>(hi, lo, aop_lane, 5 * SET + c, slab_row, &kready[5 * SET + c], lane);
+  }
+}
+
+// hidden-layer accumulator -> bias, ReLU, mask bits -> next layer's A operand (this set's 64 columns = 4 k-chunks).
+// LAST: no next layer; the output layer (networks.py:114-120) is accumulated into o3 instead.
+template <int SET, bool TRAIN, bool LAST>
+__device__ __forceinline__ void fused_epi_hidden(uint32_t acc_lane, uint32_t aop_lane, const float* s_bias, const float* s_w3, unsigned char* slab_row,
+                                                 uint32_t* bits_row, uint64_t* kready, int lane, float* o3) {
+  uint32_t bw[2] = {0u, 0u};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int n0 = 64 * SET + 16 * c;
+    float y[16];
+    tmem_ld16(acc_lane + n0, y);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      y[q] = fmaxf(y[q] + s_bias[n0 + q], 0.f);
+      if (TRAIN && y[q] > 0.f) bw[c >> 1] |= 1u << (16 * (c & 1) + q);
+      if (LAST) {
+        o3[0] = fmaf(y[q], s_w3[3 * (n0 + q) + 0], o3[0]);
+        o3[1] = fmaf(y[q], s_w3[3 * (n0 + q) + 1], o3[1]);
+        o3[2] = fmaf(y[q], s_w3[3 * (n0 + q) + 2], o3[2]);
+      }
+    }
+    if (!LAST || TRAIN) {
+      uint32_t hi[8], lo[8];
+      split16(y, hi, lo);
+      if (!LAST) {
+        emit_chunk<TRAIN>(hi, lo, aop_lane, 4 * SET + c, slab_row, &kready[4 * SET + c], lane);
+      } else {
+        uint4* p = reinterpret_cast<uint4*>(slab_row + (size_t)(4 * (4 * SET + c)) * 2048);
+        p[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        p[128] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        p[256] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        p[384] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+      }
+    }
+  }
+  if (TRAIN) *reinterpret_cast<uint2*>(bits_row + 2 * SET) = make_uint2(bw[0], bw[1]);
+}
+
+template <int SET, bool TRAIN>
+__device__ __forceinline__ void fused_fwd_worker(const FusedFwdArgs& g, uint32_t tmem, int quad, int lane, uint64_t* kready, uint64_t* accfull,
+                                                 const float* s_b1, const float* s_b2, const float* s_w3, float* s_part) {
+  const int64_t ntiles = (g.M + 127) / 128;
+  const int row = quad * 32 + lane;
+  const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+  uint32_t it = 0;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    const uint32_t accA = lane_base + ((it & 1) ? fz::kAcc1 : fz::kAcc0), accB = lane_base + ((it & 1) ? fz::kAcc0 : fz::kAcc1);
+    const uint32_t aop = lane_base + fz::kAop;
+    const int64_t m = t * 128 + row;
+    const uint32_t ph = it & 1;
+    // Dense_0 -> x'
+    mbar_wait(&accfull[0], ph, 10);
+    tc_fence_after();
+    fused_epi0<SET, TRAIN>(g, accA, aop, m, t, row, kready, lane);
+    // Dense_1 -> h1
+    mbar_wait(&accfull[1], ph, 11);
+    tc_fence_after();
+    fused_epi_hidden<SET, TRAIN, false>(accB, aop, s_b1, s_w3, TRAIN ? g.h1s + (size_t)t * (fz::kU * 512) + (size_t)row * 16 : nullptr,
+                                        TRAIN ? g.bits1 + m * 4 : nullptr, kready, lane, nullptr);
+    // Dense_2 -> h2 -> Dense_3 + sigmoid
+    float o3[3] = {0.f, 0.f, 0.f};
+    mbar_wait(&accfull[2], ph, 12);
+    tc_fence_after();
+    fused_epi_hidden<SET, TRAIN, true>(accA, aop, s_b2, s_w3, TRAIN ? g.h2s + (size_t)t * (fz::kU * 512) + (size_t)row * 16 : nullptr,
+                                       TRAIN ? g.bits2 + m * 4 : nullptr, kready, lane, o3);
+    tc_fence_before();
+    if (SET == 1) {
+      s_part[3 * row + 0] = o3[0]; s_part[3 * row + 1] = o3[1]; s_part[3 * row + 2] = o3[2];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (SET == 0 && m < g.M) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) g.rgb[3 * m + c] = 1.0f / (1.0f + expf(-(o3[c] + s_part[3 * row + c] + s_w3[384 + c])));
+    }
+  }
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(fz::kThreads, 1) k_mlp_fused_fwd(FusedFwdArgs g, const __grid_constant__ CUtensorMap tmapA) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint64_t* wfull = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* rfull = wfull + 1;               // [kRawSlots]
+  uint64_t* rempty = rfull + fz::kRawSlots;  // [kRawSlots]
+  uint64_t* kready = rempty + fz::kRawSlots; // [10]
+  uint64_t* accfull = kready + 10;           // [3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 3);
+  float* s_b1 = reinterpret_cast<float*>(smem + 1024);
+  float* s_b2 = s_b1 + 128;
+  float* s_w3 = s_b2 + 128;   // [384 + 3]
+  float* s_part = s_w3 + 388; // [384]
+  const uint32_t wbytes = fz::b0_bytes(g.K0) + fz::kB1Bytes + fz::kB2Bytes;
+  unsigned char* sW = smem + fz::kHeader;
+  unsigned char* raw0 = smem + ((fz::kHeader + wbytes + 1023u) & ~1023u);
+  const int nk0 = g.K0 / 16, nbox = (g.K0 + 31) / 32;
+  const int64_t ntiles = (g.M + 127) / 128;
+  const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+  if (tid == 0) {
+    mbar_init(wfull, 1);
+    for (int r = 0; r < fz::kRawSlots; ++r) {
+      mbar_init(&rfull[r], 1);
+      mbar_init(&rempty[r], 4);
+    }
+    for (int c = 0; c < 10; ++c) mbar_init(&kready[c], 4);
+    for (int l = 0; l < 3; ++l) mbar_init(&accfull[l], 1);
+    fence_barrier_init();
+  }
+  for (int n = tid; n < 128; n += fz::kThreads) {
+    s_b1[n] = g.b1[n];
+    s_b2[n] = g.b2[n];
+  }
+  for (int n = tid; n < 387; n += fz::kThreads) s_w3[n] = n < 384 ? g.w3[n] : g.b3[n - 384];
+  if (warp == fz::kMmaWarp) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 8) {
+    // ================= row workers: thread = row; set 0 / 1 (warps 0-3 / 4-7) own halves of the columns =================
+    if (warp < 4) fused_fwd_worker<0, TRAIN>(g, tmem, warp & 3, lane, kready, accfull, s_b1, s_b2, s_w3, s_part);
+    else fused_fwd_worker<1, TRAIN>(g, tmem, warp & 3, lane, kready, accfull, s_b1, s_b2, s_w3, s_part);
+  } else if (warp < fz::kMmaWarp) {
+    // ================= converters: raw fp32 feature rows (TMA ring) -> Dense_0's A operand in tensor memory =============
+    const int quad = warp - fz::kConvWarp0, row = quad * 32 + lane;
+    const uint32_t aop = tmem + ((uint32_t)(quad * 32) << 16) + fz::kAop;
+    const uint32_t raw_s = smem_u32(raw0);
+    uint32_t sl = 0, rph = 0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      if (it > 0) {  // operand region free: the previous tile's Dense_2 has read it
+        mbar_wait(&accfull[2], (uint32_t)(it - 1) & 1, 20);
+        tc_fence_after();
+      }
+      for (int b = 0; b < nbox; ++b) {
+        mbar_wait(&rfull[sl], rph, 21);
+        const uint32_t rrow = raw_s + sl * fz::kRawBytes + row * 128;
+        float x[32];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4 v = lds128(rrow + ((u ^ (row & 7)) << 4));
+          x[4 * u] = v.x; x[4 * u + 1] = v.y; x[4 * u + 2] = v.z; x[4 * u + 3] = v.w;
+        }
+        uint32_t hi[16], lo[16];
+        split16(x, hi, lo);
+        split16(x + 16, hi + 8, lo + 8);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rempty[sl]);  // after the values were consumed (see k_tc_rowgemm)
+        if (TRAIN) {  // the weight-gradient kernel reads the features as slab tiles
+          const int64_t t = blockIdx.x + it * gridDim.x;
+          uint4* p = reinterpret_cast<uint4*>(g.feats + (size_t)t * ((size_t)g.K0 * 512) + (size_t)(8 * b) * 2048 + (size_t)row * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)  // column group 4b + j: hi slab, lo slab
+            if ((4 * b + j) * 8 < g.K0) {
+              p[(2 * j) * 128] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              p[(2 * j + 1) * 128] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = 2 * b + h;
+          if (c < nk0) {
+            tmem_st8(aop + 8u * c, hi + 8 * h);
+            tmem_st8(aop + fz::kAopLo + 8u * c, lo + 8 * h);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&kready[2 * b]);
+          if (2 * b + 1 < nk0) mbar_arrive(&kready[2 * b + 1]);
+        }
+        if (++sl == fz::kRawSlots) { sl = 0; rph ^= 1; }
+      }
+    }
+  } else if (warp == fz::kLoadWarp) {
+    // ================= loader: weights once, then one TMA box (128 rows x 32 columns) per feature chunk =================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wfull, wbytes);
+      for (uint32_t off = 0; off < wbytes; off += 16384u)
+        bulk_copy_g2s(sW + off, g.wpack + off, min(16384u, wbytes - off), wfull);
+      uint32_t sl = 0, ph = 0;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const int64_t t = blockIdx.x + it * gridDim.x;
+        for (int b = 0; b < nbox; ++b) {
+          mbar_wait(&rempty[sl], ph ^ 1, 30);
+          mbar_arrive_expect_tx(&rfull[sl], fz::kRawBytes);
+          tma_load_2d(raw0 + (size_t)sl * fz::kRawBytes, &tmapA, b * 32, (int)(t * 128), &rfull[sl]);
+          if (++sl == fz::kRawSlots) { sl = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ================= MMA issuer (warp-uniform loop, one elected lane issues) =================
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc0 = make_idesc(128, 32, FMT_F16, FMT_F16, 0, 0), idesc1 = make_idesc(128, 128, FMT_F16, FMT_F16, 0, 0);
+    const uint32_t sw = smem_u32(sW);
+    const uint32_t b0_lo = desc_lo(sw, 2u * slab_bytes(32)), b1_lo = desc_lo(sw + fz::b0_bytes(g.K0), 2u * slab_bytes(128)),
+                   b2_lo = desc_lo(sw + fz::b0_bytes(g.K0) + fz::kB1Bytes, 2u * slab_bytes(128));
+    const uint32_t b_hi = desc_hi(128u);
+    const uint32_t t32 = slab_bytes(32) >> 4, s32 = (4u * slab_bytes(32)) >> 4, t128 = slab_bytes(128) >> 4, s128 = (4u * slab_bytes(128)) >> 4;
+    const uint32_t aop = tm + fz::kAop;
+    uint32_t kph = 0;
+    mbar_wait(wfull, 0, 40);
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const uint32_t accA = tm + ((it & 1) ? fz::kAcc1 : fz::kAcc0), accB = tm + ((it & 1) ? fz::kAcc0 : fz::kAcc1);
+      for (int c = 0; c < nk0; ++c) {  // Dense_0
+        mbar_wait(&kready[c], (kph >> c) & 1u, 41);
+        kph ^= 1u << c;
+        tc_fence_after();
+        if (elect_one()) umma_ts_split2(accA, aop + 8u * c, fz::kAopLo, b0_lo + c * s32, t32, b_hi, idesc0, c == 0);
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&accfull[0]);
+      __syncwarp();
+      for (int i = 0; i < 10; ++i) {  // Dense_1: chunks in the order the two worker sets produce them
+        const int c = (i & 1) * 5 + (i >> 1);
+        mbar_wait(&kready[c], (kph >> c) & 1u, 42);
+        kph ^= 1u << c;
+        tc_fence_after();
+        if (elect_one()) umma_ts_split2(accB, aop + 8u * c, fz::kAopLo, b1_lo + c * s128, t128, b_hi, idesc1, i == 0);
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&accfull[1]);
+      __syncwarp();
+      for (int i = 0; i < 8; ++i) {  // Dense_2
+        const int c = (i & 1) * 4 + (i >> 1);
+        mbar_wait(&kready[c], (kph >> c) & 1u, 43);
+        kph ^= 1u << c;
+        tc_fence_after();
+        if (elect_one()) umma_ts_split2(accA, aop + 8u * c, fz::kAopLo, b2_lo + c * s128, t128, b_hi, idesc1, i == 0);
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&accfull[2]);
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == fz::kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+int mlp_fused_pack(cudaStream_t st, const MlpShape& s, const MlpParams& p, const MlpWs& ws) {
+  TF_CHECK_ARG(mlp_fused_supported(s), "fused MLP: unsupported network shape");
+  TF_CHECK_ARG(ws.wpack_bytes >= mlp_fused_wpack_bytes(s), "fused MLP: weight scratch too small");
+  FusedPackArgs a{p.w0, p.w1, p.w2, s.Ca, ws.wpack};
+  const int items = 32 * (s.Ca / 8) + fz::kU * (fz::kX / 8) + fz::kU * (fz::kU / 8);
+  k_fused_pack<<<(items + 255) / 256, 256, 0, st>>>(a);
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+
+int mlp_fused_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs, const uint32_t* cams,
+                  int64_t M, int rows_per_ray, const MlpWs& ws, float* rgb) {
+  (void)cams;
+  if (M == 0) return 0;
+  TF_RETURN_IF_ERROR(mlp_fused_pack(st, s, p, ws));
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  TF_CHECK_ARG(tc_make_a_tensor_map(&tm, feat, M, s.Ca, s.Ca, 32), "fused MLP: features must be 16-byte aligned (tensor map)");
+  FusedFwdArgs g{};
+  g.wpack = ws.wpack; g.b1 = p.b1; g.b2 = p.b2; g.w3 = p.w3; g.b3 = p.b3;
+  g.viewdirs = viewdirs; g.rows_per_ray = rows_per_ray; g.M = M; g.K0 = s.Ca; g.rgb = rgb;
+  const bool train = !s.inference;
+  if (train) {
+    g.xs = reinterpret_cast<unsigned char*>(ws.x);
+    g.h1s = reinterpret_cast<unsigned char*>(ws.h1);
+    g.h2s = reinterpret_cast<unsigned char*>(ws.h2);
+    g.fs = ws.f;
+    g.bits1 = ws.bits1;
+    g.bits2 = ws.bits1 + round_up64(M, 128) * 4;
+    g.feats = reinterpret_cast<unsigned char*>(ws.dx);
+  }
+  const size_t smem = ((fz::kHeader + mlp_fused_wpack_bytes(s) + 1023) & ~(size_t)1023) + (size_t)fz::kRawSlots * fz::kRawBytes;
+  TF_CHECK_ARG(smem <= 227 * 1024, "fused MLP: shared memory budget exceeded");
+  const unsigned grid = (unsigned)std::min<int64_t>((M + 127) / 128, kSMs);
+  if (train) {
+    TF_CHECK_CUDA(cudaFuncSetAttribute(k_mlp_fused_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_mlp_fused_fwd<true><<<grid, fz::kThreads, smem, st>>>(g, tm);
+  } else {
+    TF_CHECK_CUDA(cudaFuncSetAttribute(k_mlp_fused_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_mlp_fused_fwd<false><<<grid, fz::kThreads, smem, st>>>(g, tm);
+  }
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+
+
+// ===============================================================================================================
+// Reverse pass, kernel 1 of 2: the activation-gradient chain of one 128-row tile,
+//   d(out) -> dp2 = (d(out) W3^T) * relu'(h2) -> dp1 = (dp2 W2^T) * relu'(h1) -> dx' = dp1 W1'^T -> df (Fourier reverse)
+//   -> d_features = df W0^T,
+// with every intermediate in tensor memory (A operands) and the forward's packed weights as MN-major B operands.
+// All gradients are carried multiplied by a power of two S (|d_rgb|_max * S in [1, 2)) so that two fp16 terms keep
+// ~22 significant bits; outputs are rescaled.  dp2 / dp1 / df / d(out) are also written as slab tiles for kernel 2.
+// ===============================================================================================================
+namespace fz {
+constexpr uint32_t kBAccA = 0, kBAccB = 160, kBAop = 320;  // reverse: accumulators up to 160 columns wide
+constexpr int kBwdThreads = 320;                          // warps 0-7 workers, 8 MMA, 9 weight loader
+}
+__device__ __forceinline__ void grad_scale(const float* amax_slot, float& S, float& invS) {
+  const uint32_t E = (__float_as_uint(*amax_slot) >> 23) & 0xFFu;
+  const bool ok = E >= 1u && E <= 253u;
+  S = ok ? __uint_as_float((254u - E) << 23) : 1.0f;
+  invS = ok ? __uint_as_float(E << 23) : 1.0f;
+}
+__global__ void __launch_bounds__(256) k_fused_amax(const float* x, int64_t n, float* slot) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(slot), __float_as_uint(m));
+}
+
+struct FusedBwdArgs {
+  const unsigned char* wpack;
+  const float* w3;
+  const float *rgb, *d_rgb;
+  const float* fs;
+  const uint32_t *bits1, *bits2;
+  const float* amax;
+  int64_t M;
+  int K0;
+  unsigned char *dp2s, *dp1s, *dfs, *douts;
+  float* d_feat;
+  float* db3;
+};
+
+__device__ __forceinline__ void store_chunk_slab(unsigned char* slab_row, int c, const uint32_t* hi, const uint32_t* lo) {
+  uint4* p = reinterpret_cast<uint4*>(slab_row + (size_t)(4 * c) * 2048);
+  p[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  p[128] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  p[256] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+  p[384] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+}
+
+template <int SET>
+__device__ __forceinline__ void fused_bwd_worker(const FusedBwdArgs& g, uint32_t tmem, int quad, int lane, uint64_t* kready, uint64_t* accfull,
+                                                 const float* s_w3) {
+  const int64_t ntiles = (g.M + 127) / 128;
+  const int row = quad * 32 + lane;
+  const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+  const uint32_t accA = lane_base + fz::kBAccA, accB = lane_base + fz::kBAccB, aop = lane_base + fz::kBAop;
+  float S, invS;
+  grad_scale(g.amax, S, invS);
+  const int nk0 = g.K0 / 16;
+  uint32_t it = 0;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    const int64_t m = t * 128 + row;
+    const uint32_t ph = it & 1;
+    // ---- output layer reverse (networks.py:114-120) and relu'(h2) ----
+    float dout[3] = {0.f, 0.f, 0.f};
+    if (m < g.M) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float y = g.rgb[3 * m + c];
+        dout[c] = S * g.d_rgb[3 * m + c] * y * (1.0f - y);
+      }
+    }
+    {
+      const uint2 bw = *reinterpret_cast<const uint2*>(g.bits2 + m * 4 + 2 * SET);
+      unsigned char* slab_row = g.dp2s + (size_t)t * (fz::kU * 512) + (size_t)row * 16;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int n0 = 64 * SET + 16 * c;
+        const uint32_t w = (c >> 1) ? bw.y : bw.x;
+        float y[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const float v = fmaf(dout[2], s_w3[3 * (n0 + q) + 2], fmaf(dout[1], s_w3[3 * (n0 + q) + 1], dout[0] * s_w3[3 * (n0 + q)]));
+          y[q] = ((w >> (16 * (c & 1) + q)) & 1u) ? v : 0.f;
+        }
+        uint32_t hi[8], lo[8];
+        split16(y, hi, lo);
+        emit_chunk<true>(hi, lo, aop, 4 * SET + c, slab_row, &kready[4 * SET + c], lane);
+      }
+    }
+    if (SET == 0) {
+      float y[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) y[q] = q < 3 ? dout[q < 3 ? q : 0] : 0.f;
+      uint32_t hi[8], lo[8];
+      split16(y, hi, lo);
+      store_chunk_slab(g.douts + (size_t)t * (16 * 512) + (size_t)row * 16, 0, hi, lo);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float sum = warp_sum(dout[c]);
+        if (lane == 0) atomicAdd(g.db3 + c, sum * invS);
+      }
+    }
+    // ---- dp1 = (dp2 W2^T) * relu'(h1) ----
+    mbar_wait(&accfull[0], ph, 50);
+    tc_fence_after();
+    {
+      const uint2 bw = *reinterpret_cast<const uint2*>(g.bits1 + m * 4 + 2 * SET);
+      unsigned char* slab_row = g.dp1s + (size_t)t * (fz::kU * 512) + (size_t)row * 16;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int n0 = 64 * SET + 16 * c;
+        const uint32_t w = (c >> 1) ? bw.y : bw.x;
+        float y[16];
+        tmem_ld16(accA + n0, y);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 16; ++q) y[q] = ((w >> (16 * (c & 1) + q)) & 1u) ? y[q] : 0.f;
+        uint32_t hi[8], lo[8];
+        split16(y, hi, lo);
+        emit_chunk<true>(hi, lo, aop, 4 * SET + c, slab_row, &kready[4 * SET + c], lane);
+      }
+    }
+    // ---- Fourier reverse (networks.py:13-35, :68-76): df_d = dx_d + cos(f) dx_sin1 + 2 cos(2f) dx_sin2 - sin(f) dx_cos1 - 2 sin(2f) dx_cos2 ----
+    mbar_wait(&accfull[1], ph, 51);
+    tc_fence_after();
+    {
+      float fv[16];
+      const float4* fp = reinterpret_cast<const float4*>(g.fs + (size_t)t * 4096 + (size_t)(4 * SET) * 512) + row;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 v = fp[j * 128];
+        fv[4 * j] = v.x; fv[4 * j + 1] = v.y; fv[4 * j + 2] = v.z; fv[4 * j + 3] = v.w;
+      }
+      float dx[80];
+#pragma unroll
+      for (int c = 0; c < 5; ++c) tmem_ld16(accB + 80 * SET + 16 * c, dx + 16 * c);
+      tmem_ld_wait();
+      float y[16];
+      constexpr int ND = SET == 0 ? 15 : 12;  // feature dimensions of this set (the view direction needs no gradient)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (i < ND) {
+          float sn, cs;
+          sincosf(fv[i], &sn, &cs);
+          const float sn2 = 2.0f * sn * cs, cs2 = fmaf(-2.0f * sn, sn, 1.0f);
+          const int e = 5 * (i < ND ? i : 0);
+          y[i] = dx[e] + cs * dx[e + 1] + 2.0f * cs2 * dx[e + 2] - sn * dx[e + 3] - 2.0f * sn2 * dx[e + 4];
+        } else {
+          y[i] = 0.f;
+        }
+      }
+      uint32_t hi[8], lo[8];
+      split16(y, hi, lo);
+      emit_chunk<true>(hi, lo, aop, SET, g.dfs + (size_t)t * (32 * 512) + (size_t)row * 16, &kready[SET], lane);
+    }
+    // ---- d_features = df W0^T: accumulator fragments (16 rows x 256 bit) -> whole 32-byte sectors ----
+    mbar_wait(&accfull[2], ph, 52);
+    tc_fence_after();
+    {
+      const int lrow = lane >> 2, lc = (lane & 3) * 2;
+      const int c_beg = SET == 0 ? 0 : (nk0 + 1) / 2, c_end = SET == 0 ? (nk0 + 1) / 2 : nk0;
+      for (int c = c_beg; c < c_end; ++c) {
+        float v[2][8];
+        tmem_ld_16x256b_x2(tmem + ((uint32_t)(quad * 32) << 16) + fz::kBAccA + 16u * c, v[0]);
+        tmem_ld_16x256b_x2(tmem + ((uint32_t)(quad * 32 + 16) << 16) + fz::kBAccA + 16u * c, v[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int64_t mr = t * 128 + quad * 32 + blk * 16 + h * 8 + lrow;
+            if (mr < g.M) {
+              float* dst = g.d_feat + mr * g.K0 + 16 * c + lc;
+              *reinterpret_cast<float2*>(dst) = make_float2(v[blk][h * 2] * invS, v[blk][h * 2 + 1] * invS);
+              *reinterpret_cast<float2*>(dst + 8) = make_float2(v[blk][4 + h * 2] * invS, v[blk][4 + h * 2 + 1] * invS);
+            }
+          }
+      }
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // both sets have read accumulator A before the next tile's chunks release it
+  }
+}
+
+__global__ void __launch_bounds__(fz::kBwdThreads, 1) k_mlp_fused_bwd(FusedBwdArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint64_t* wfull = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* kready = wfull + 1;     // [8]
+  uint64_t* accfull = kready + 8;   // [3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 3);
+  float* s_w3 = reinterpret_cast<float*>(smem + 1024);  // [384]
+  const uint32_t wbytes = fz::b0_bytes(g.K0) + fz::kB1Bytes + fz::kB2Bytes;
+  unsigned char* sW = smem + fz::kHeader;
+  const int64_t ntiles = (g.M + 127) / 128;
+  const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  if (tid == 0) {
+    mbar_init(wfull, 1);
+    for (int c = 0; c < 8; ++c) mbar_init(&kready[c], 4);
+    for (int l = 0; l < 3; ++l) mbar_init(&accfull[l], 1);
+    fence_barrier_init();
+  }
+  for (int n = tid; n < 384; n += fz::kBwdThreads) s_w3[n] = g.w3[n];
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    fused_bwd_worker<0>(g, tmem, warp & 3, lane, kready, accfull, s_w3);
+  } else if (warp < 8) {
+    fused_bwd_worker<1>(g, tmem, warp & 3, lane, kready, accfull, s_w3);
+  } else if (warp == 9) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wfull, wbytes);
+      for (uint32_t off = 0; off < wbytes; off += 16384u) bulk_copy_g2s(sW + off, g.wpack + off, min(16384u, wbytes - off), wfull);
+    }
+  } else {
+    // ================= MMA issuer: the weight tiles of the forward, read as MN-major B (tile rows = contraction index) ======
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t sw = smem_u32(sW);
+    const uint32_t b0_lo = desc_lo(sw, 128u), b1_lo = desc_lo(sw + fz::b0_bytes(g.K0), 128u),
+                   b2_lo = desc_lo(sw + fz::b0_bytes(g.K0) + fz::kB1Bytes, 128u);
+    const uint32_t bh32 = desc_hi(2u * slab_bytes(32)), bh128 = desc_hi(2u * slab_bytes(128));
+    const uint32_t t32 = slab_bytes(32) >> 4, t128 = slab_bytes(128) >> 4;
+    const uint32_t id2 = make_idesc(128, fz::kU, FMT_F16, FMT_F16, 0, 1), id1 = make_idesc(128, fz::kX, FMT_F16, FMT_F16, 0, 1),
+                   id0 = make_idesc(128, g.K0, FMT_F16, FMT_F16, 0, 1);
+    const uint32_t accA = tm + fz::kBAccA, accB = tm + fz::kBAccB, aop = tm + fz::kBAop;
+    uint32_t kph = 0;
+    mbar_wait(wfull, 0, 60);
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      for (int i = 0; i < 8; ++i) {  // dh1 = dp2 W2^T
+        const int c = (i & 1) * 4 + (i >> 1);
+        mbar_wait(&kready[c], (kph >> c) & 1u, 61);
+        kph ^= 1u << c;
+        tc_fence_after();
+        if (elect_one()) umma_ts_split2(accA, aop + 8u * c, fz::kAopLo, b2_lo + 16u * c, t128, bh128, id2, i == 0);
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&accfull[0]);
+      __syncwarp();
+      for (int i = 0; i < 8; ++i) {  // dx' = dp1 W1'^T
+        const int c = (i & 1) * 4 + (i >> 1);
+        mbar_wait(&kready[c], (kph >> c) & 1u, 62);
+        kph ^= 1u << c;
+        tc_fence_after();
+        if (elect_one()) umma_ts_split2(accB, aop + 8u * c, fz::kAopLo, b1_lo + 16u * c, t128, bh128, id1, i == 0);
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&accfull[1]);
+      __syncwarp();
+      for (int c = 0; c < 2; ++c) {  // d_features = df W0^T
+        mbar_wait(&kready[c], (kph >> c) & 1u, 63);
+        kph ^= 1u << c;
+        tc_fence_after();
+        if (elect_one()) umma_ts_split2(accA, aop + 8u * c, fz::kAopLo, b0_lo + 16u * c, t32, bh32, id0, c == 0);
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&accfull[2]);
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ===============================================================================================================
+// Reverse pass, kernel 2 of 2: every weight / bias gradient of the MLP as products over the rows, K = 128 rows per tile,
+// both operands MN-major views of slab tiles streamed from global memory in 16 KB pieces (cp.async.bulk):
+//   dW3^T[n][c]  += h2^T  d(out)          dW2^T[n][k] += dp2^T [h1 | 1]
+//   dW1'^T[n][k'] += dp1^T x'  (x' has a ones column: db1)          dW0'^T[n'][k] += df^T features
+// The four accumulators (16 + 144 + 160 + 3*ca columns of tensor memory) stay resident over all tiles of the CTA and
+// are added to the gradient leaves once at the end.
+// ===============================================================================================================
+namespace fz {
+constexpr int kWgThreads = 192;  // warps 0-3 epilogue, 4 MMA, 5 loader
+constexpr int kWgSlots = 5;
+constexpr uint32_t kPiece = 16384, kATile = 65536;
+constexpr uint32_t kWgOnes = 1024, kWgA = kWgOnes + 8192, kWgB = kWgA + 2 * kATile, kWgSmem = kWgB + kWgSlots * kPiece;
+constexpr uint32_t kD3 = 0, kD2 = 16, kD1 = 160, kD0 = 320;
+}
+struct FusedWgradArgs {
+  const unsigned char *h2s, *douts, *dp2s, *h1s, *dp1s, *xs, *dfs, *feats;
+  const float* amax;
+  int64_t M;
+  int K0;
+  float *dw0, *dw1, *db1, *dw2, *db2, *dw3;
+};
+
+__global__ void __launch_bounds__(fz::kWgThreads, 1) k_mlp_fused_wgrad(FusedWgradArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint64_t* afull = reinterpret_cast<uint64_t*>(smem);  // [2]
+  uint64_t* aempty = afull + 2;                          // [2]
+  uint64_t* bfull = aempty + 2;                          // [kWgSlots]
+  uint64_t* bempty = bfull + fz::kWgSlots;               // [kWgSlots]
+  uint64_t* done = bempty + fz::kWgSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  unsigned char* sOnes = smem + fz::kWgOnes;
+  unsigned char* sA = smem + fz::kWgA;
+  unsigned char* sB = smem + fz::kWgB;
+  const int64_t ntiles = (g.M + 127) / 128;
+  const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const int K0 = g.K0;
+  // pieces of the B operand per product: (bytes, columns)
+  const int npf = (K0 + 31) / 32;  // feature pieces; the last one may be half (16 columns)
+
+  if (tid == 0) {
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&afull[a], 1);
+      mbar_init(&aempty[a], 1);
+    }
+    for (int b = 0; b < fz::kWgSlots; ++b) {
+      mbar_init(&bfull[b], 1);
+      mbar_init(&bempty[b], 1);
+    }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  // constant B piece [128 rows x 16 columns]: column 0 = 1 (hi term), everything else 0
+  for (int i = tid; i < 8192 / 16; i += fz::kWgThreads)
+    reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(i < 128 ? 0x00003C00u : 0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 5) {
+    // ================= loader =================
+    if (lane == 0) {
+      uint32_t ab = 0, aph = 0, sl = 0, bph = 0;
+      auto load_a = [&](const unsigned char* src, uint32_t bytes) {
+        mbar_wait(&aempty[ab], aph ^ 1, 70);
+        mbar_arrive_expect_tx(&afull[ab], bytes);
+        for (uint32_t off = 0; off < bytes; off += fz::kPiece) bulk_copy_g2s(sA + ab * fz::kATile + off, src + off, fz::kPiece, &afull[ab]);
+        if (++ab == 2) { ab = 0; aph ^= 1; }
+      };
+      auto load_b = [&](const unsigned char* src, uint32_t bytes) {
+        mbar_wait(&bempty[sl], bph ^ 1, 71);
+        mbar_arrive_expect_tx(&bfull[sl], bytes);
+        bulk_copy_g2s(sB + sl * fz::kPiece, src, bytes, &bfull[sl]);
+        if (++sl == fz::kWgSlots) { sl = 0; bph ^= 1; }
+      };
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const size_t t = (size_t)(blockIdx.x + it * gridDim.x);
+        load_a(g.h2s + t * fz::kATile, fz::kATile);
+        load_b(g.douts + t * 8192, 8192);
+        load_a(g.dp2s + t * fz::kATile, fz::kATile);
+        for (int j = 0; j < 4; ++j) load_b(g.h1s + t * fz::kATile + j * fz::kPiece, fz::kPiece);
+        load_a(g.dp1s + t * fz::kATile, fz::kATile);
+        for (int j = 0; j < 5; ++j) load_b(g.xs + t * (fz::kX * 512) + j * fz::kPiece, fz::kPiece);
+        load_a(g.dfs + t * fz::kPiece, fz::kPiece);
+        for (int j = 0; j < npf; ++j) load_b(g.feats + t * ((size_t)K0 * 512) + j * fz::kPiece, (uint32_t)min(32, K0 - 32 * j) * 512u);
+      }
+    }
+  } else if (warp == 4) {
+    // ================= MMA issuer =================
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t a_hi = desc_hi(2u * slab_bytes(128)), term = slab_bytes(128) >> 4;
+    const uint32_t id32 = make_idesc(128, 32, FMT_F16, FMT_F16, 1, 1), id16 = make_idesc(128, 16, FMT_F16, FMT_F16, 1, 1);
+    const uint32_t sa = smem_u32(sA), sb = smem_u32(sB), so = smem_u32(sOnes);
+    uint32_t ab = 0, aph = 0, sl = 0, bph = 0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const bool first = it == 0;
+      auto wait_a = [&]() {
+        mbar_wait(&afull[ab], aph, 80);
+        tc_fence_after();
+      };
+      auto piece = [&](uint32_t b_addr, uint32_t dcol, uint32_t idesc, uint64_t* release) {
+        const uint32_t a_lo = desc_lo(sa + ab * fz::kATile, 128u), b_lo = desc_lo(b_addr, 128u);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) umma_ss_split2(tm + dcol, a_lo + 16u * ks, term, a_hi, b_lo + 16u * ks, term, a_hi, idesc, first && ks == 0);
+          if (release) umma_commit(release);
+        }
+        __syncwarp();
+      };
+      auto ring_piece = [&](uint32_t dcol, uint32_t idesc) {
+        mbar_wait(&bfull[sl], bph, 81);
+        tc_fence_after();
+        piece(sb + sl * fz::kPiece, dcol, idesc, &bempty[sl]);
+        if (++sl == fz::kWgSlots) { sl = 0; bph ^= 1; }
+      };
+      auto release_a = [&]() {
+        if (elect_one()) umma_commit(&aempty[ab]);
+        __syncwarp();
+        if (++ab == 2) { ab = 0; aph ^= 1; }
+      };
+      wait_a();  // h2^T d(out)
+      ring_piece(fz::kD3, id16);
+      release_a();
+      wait_a();  // dp2^T [h1 | 1]
+      for (int j = 0; j < 4; ++j) ring_piece(fz::kD2 + 32u * j, id32);
+      piece(so, fz::kD2 + 128u, id16, nullptr);
+      release_a();
+      wait_a();  // dp1^T x'
+      for (int j = 0; j < 5; ++j) ring_piece(fz::kD1 + 32u * j, id32);
+      release_a();
+      wait_a();  // df^T features (rows >= 32 of this accumulator are meaningless and never read)
+      for (int j = 0; j < npf; ++j) ring_piece(fz::kD0 + 32u * j, (K0 - 32 * j) >= 32 ? id32 : id16);
+      release_a();
+    }
+    if (elect_one()) umma_commit(done);
+    __syncwarp();
+  } else {
+    // ================= epilogue: accumulators -> gradient leaves (RED), once per CTA =================
+    mbar_wait(done, 0, 90);
+    tc_fence_after();
+    float S, invS;
+    grad_scale(g.amax, S, invS);
+    const int n = warp * 32 + lane;  // accumulator row = output unit of the layer (Dense_0: kernel column order)
+    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+    const int ncols = fz::kD0 + (warp == 0 ? K0 : 0);
+    const int nat0 = fz::sq_nat(n < 32 ? n : 31);
+    for (int c0 = 0; c0 < ncols; c0 += 16) {
+      float v[16];
+      tmem_ld16(tl + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int col = c0 + q;
+        const float x = v[q] * invS;
+        if (col < (int)fz::kD2) {
+          if (col < 3) atomicAdd(g.dw3 + n * 3 + col, x);
+        } else if (col < (int)fz::kD1) {
+          const int k = col - fz::kD2;
+          if (k < fz::kU) atomicAdd(g.dw2 + k * fz::kU + n, x);
+          else if (k == fz::kU) atomicAdd(g.db2 + n, x);
+        } else if (col < (int)fz::kD0) {
+          const int kp = col - fz::kD1, nat = fz::perm(kp);
+          if (nat >= 0) atomicAdd(g.dw1 + nat * fz::kU + n, x);
+          else if (kp == fz::kOnesCol) atomicAdd(g.db1 + n, x);
+        } else {
+          if (nat0 >= 0) atomicAdd(g.dw0 + (col - fz::kD0) * fz::kSq + nat0, x);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+bool mlp_fused_bwd_ready() { return true; }
+int mlp_fused_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs, const uint32_t* cams,
+                  int64_t M, int rows_per_ray, const MlpWs& ws, const float* rgb, const float* d_rgb, float* d_feat, const MlpGrads& gr) {
+  (void)feat; (void)viewdirs; (void)cams; (void)rows_per_ray;
+  TF_CHECK_ARG(!s.inference, "mlp reverse pass after a forward with TENSORF_FLAG_INFERENCE (residuals were not kept)");
+  TF_CHECK_ARG(mlp_fused_supported(s), "fused MLP: unsupported network shape");
+  if (!gr.prezeroed) TF_RETURN_IF_ERROR(mlp_zero_grads(st, s, gr));
+  if (M == 0) return 0;
+  const int64_t Mp = round_up64(M, 128);
+  float* amax = ws.aux;
+  TF_CHECK_CUDA(cudaMemsetAsync(amax, 0, sizeof(float), st));
+  k_fused_amax<<<kSMs, 256, 0, st>>>(d_rgb, 3 * M, amax);
+  TF_CHECK_LAUNCH();
+  FusedBwdArgs b{};
+  b.wpack = ws.wpack; b.w3 = p.w3; b.rgb = rgb; b.d_rgb = d_rgb; b.fs = ws.f; b.bits1 = ws.bits1; b.bits2 = ws.bits1 + Mp * 4;
+  b.amax = amax; b.M = M; b.K0 = s.Ca;
+  b.dp2s = reinterpret_cast<unsigned char*>(ws.dp2); b.dp1s = reinterpret_cast<unsigned char*>(ws.dp1);
+  b.dfs = reinterpret_cast<unsigned char*>(ws.df); b.douts = reinterpret_cast<unsigned char*>(ws.aux + 64);
+  b.d_feat = d_feat; b.db3 = gr.b3;
+  const size_t smem_b = fz::kHeader + mlp_fused_wpack_bytes(s);
+  const unsigned grid = (unsigned)std::min<int64_t>((M + 127) / 128, kSMs);
+  TF_CHECK_CUDA(cudaFuncSetAttribute(k_mlp_fused_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+  k_mlp_fused_bwd<<<grid, fz::kBwdThreads, smem_b, st>>>(b);
+  TF_CHECK_LAUNCH();
+  FusedWgradArgs w{};
+  w.h2s = reinterpret_cast<unsigned char*>(ws.h2); w.douts = b.douts; w.dp2s = b.dp2s; w.h1s = reinterpret_cast<unsigned char*>(ws.h1);
+  w.dp1s = b.dp1s; w.xs = reinterpret_cast<unsigned char*>(ws.x); w.dfs = b.dfs; w.feats = reinterpret_cast<unsigned char*>(ws.dx);
+  w.amax = amax; w.M = M; w.K0 = s.Ca;
+  w.dw0 = gr.w0; w.dw1 = gr.w1; w.db1 = gr.b1; w.dw2 = gr.w2; w.db2 = gr.b2; w.dw3 = gr.w3;
+  TF_CHECK_CUDA(cudaFuncSetAttribute(k_mlp_fused_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::kWgSmem));
+  k_mlp_fused_wgrad<<<grid, fz::kWgThreads, fz::kWgSmem, st>>>(w);
   TF_CHECK_LAUNCH();
   return 0;
 }

@@ -10,7 +10,7 @@ namespace tf {
 
 int64_t mlp_ws_floats(const MlpShape& s, int64_t M) {
   int64_t Mp = round_up64(M, 128);
-  return Mp * ((int64_t)2 * round_up(s.squash, 16) + 2 * round_up(s.enc, 16) + 4 * s.units + 8) +
+  return Mp * ((int64_t)2 * round_up(s.squash, 16) + 2 * round_up(s.enc, 16) + 4 * s.units + 8 + 16) + 64 +
          (int64_t)round_up64((int64_t)mlp_tc_wpack_bytes(s), 256) / 4;
 }
 MlpWs mlp_ws_carve(const MlpShape& s, int64_t M, float* base) {
@@ -31,6 +31,7 @@ MlpWs mlp_ws_carve(const MlpShape& s, int64_t M, float* base) {
   w.dp2 = p; p += Mp * s.units;
   w.dp1 = p; p += Mp * s.units;
   w.bits1 = reinterpret_cast<uint32_t*>(p); p += Mp * 8;
+  w.aux = p; p += Mp * 16 + 64;
   return w;
 }
 

@@ -641,6 +641,7 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 // Tensor map over the fp32 activation matrix A (M rows, K_valid columns, row stride lda): box = 128 rows x
 // KC columns (one A chunk), 128-byte swizzle, zero fill outside the matrix (row and column tails).
+bool tc_make_a_tensor_map(void* tm_, const float* A, int64_t M, int K_valid, int64_t lda, int kc);
 static bool make_a_tensor_map(CUtensorMap* tm, const float* A, int64_t M, int K_valid, int64_t lda, int kc) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc || (reinterpret_cast<uintptr_t>(A) & 15) != 0 || (lda * 4) % 16 != 0 || K_valid < 1 || M < 1 || kc * 4 != 128) return false;
@@ -650,6 +651,10 @@ static bool make_a_tensor_map(CUtensorMap* tm, const float* A, int64_t M, int K_
   const cuuint32_t estr[2] = {1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool tc_make_a_tensor_map(void* tm_, const float* A, int64_t M, int K_valid, int64_t lda, int kc) {
+  return make_a_tensor_map(reinterpret_cast<CUtensorMap*>(tm_), A, M, K_valid, lda, kc);
 }
 
 template <int NSPLIT, int EPI>

@@ -105,6 +105,7 @@ SIGNATURES = {
     "tensorf_tc_redgemm_test": (_i, [_vp, _vp, _i, _vp, _i, _i64, _vp]),
     "tensorf_tc_umma_probe": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i]),
     "tensorf_mlp_workspace_bytes": (_i64, [_pd, _i64]),
+    "tensorf_mlp_workspace_layout": (_i, [_pd, _i64, C.POINTER(_i64)]),
     "tensorf_mlp_fwd": (_i, [_vp, _pd, _pp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
     "tensorf_mlp_bwd": (_i, [_vp, _pd, _pp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _pp]),
     "tensorf_render_workspace_bytes": (_i, [_pd, C.POINTER(_i64)]),

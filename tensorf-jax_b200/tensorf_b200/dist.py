@@ -12,7 +12,7 @@ torch.distributed is plumbing (NCCL on GPUs, gloo in the CPU tests); nothing her
 """
 from __future__ import annotations
 
-from typing import Dict, Sequence, Tuple
+from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -38,6 +38,18 @@ def shard_rays(arrays: Dict[str, np.ndarray], rank: int, world: int, per_ray: Se
 def tile_rows(height: int, rank: int, world: int) -> Tuple[int, int]:
     """Row band of a frame rendered by `rank` (render_360-style frames, no collective)."""
     return shard_range(height, rank, world)
+
+
+def stripe_rows(height: int, rank: int, world: int, stripe: int = 16) -> List[Tuple[int, int]]:
+    """Rows of a frame rendered by `rank` as interleaved stripes: stripe s = rows [s*stripe, (s+1)*stripe) belongs to
+    rank s % world.  Rays through the middle of the frame cross more of the scene than those near its border, so
+    contiguous bands (`tile_rows`) leave the central ranks with the longest job; 16-row stripes dealt round-robin give
+    every rank the same mix.  No collective: every rank writes its own rows of the frame."""
+    out = []
+    for s in range((height + stripe - 1) // stripe):
+        if s % world == rank:
+            out.append((s * stripe, min(height, (s + 1) * stripe)))
+    return out
 
 
 class FlatGrads:

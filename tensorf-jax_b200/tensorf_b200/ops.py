@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import PARAM_FIELDS, AdamDesc, Params, RenderDesc, RenderInputs, check
 
 MODE_RGB, MODE_DIST_MEDIAN, MODE_DIST_MEAN = 0, 1, 2
-MLP_AUTO, MLP_SIMT_FP32, MLP_TCGEN05 = 0, 1, 2
+MLP_AUTO, MLP_SIMT_FP32, MLP_TCGEN05, MLP_FUSED = 0, 1, 2, 3
 FLAG_INFERENCE = 1  # forward only: residuals of the reverse pass are not kept
 
 
@@ -239,13 +239,16 @@ class RenderCall:
         return ri
 
     def forward(self, params: Dict[str, torch.Tensor], inputs: Dict[str, Optional[torch.Tensor]],
-                loss_out: Optional[torch.Tensor] = None):
+                loss_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
         """Returns (rgb (R,3), loss or None). `inputs['colors']` enables the fused MSE; `loss_out` (one fp32
-        element, e.g. the loss slot of `dist.FlatGrads`) receives it in place of a fresh scalar."""
+        element, e.g. the loss slot of `dist.FlatGrads`) receives it in place of a fresh scalar; `out` (R,3)
+        receives the colours in place of a fresh tensor (a slice of a frame buffer)."""
         d = self.desc
         ps = _params_struct(d, params)
         ri = self._inputs(inputs)
-        rgb = torch.empty((d.R, 3), dtype=torch.float32, device=self.device)
+        if out is not None and (tuple(out.shape) != (d.R, 3) or not out.is_contiguous()):
+            raise ValueError(f"out must be a contiguous {(d.R, 3)} tensor")
+        rgb = out if out is not None else torch.empty((d.R, 3), dtype=torch.float32, device=self.device)
         loss = None
         if inputs.get("colors") is not None:
             if loss_out is not None and loss_out.numel() != 1:
@@ -273,7 +276,8 @@ class RenderCall:
                                                        _ptr(d_rgb, name="d_rgb"), C.byref(gs), int(phase)))
         return grads
 
-    def depth(self, params: Dict[str, torch.Tensor], inputs: Dict[str, Optional[torch.Tensor]]) -> torch.Tensor:
+    def depth(self, params: Dict[str, torch.Tensor], inputs: Dict[str, Optional[torch.Tensor]],
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
         d = self.desc
         ps = Params()
         for name in ("density_vector", "density_matrix"):
@@ -282,7 +286,9 @@ class RenderCall:
                 raise ValueError(f"params['{name}'] has shape {tuple(t.shape)}")
             setattr(ps, name, _ptr(t, name=name))
         ri = self._inputs(inputs)
-        out = torch.empty((d.R,), dtype=torch.float32, device=self.device)
+        if out is not None and (tuple(out.shape) != (d.R,) or not out.is_contiguous()):
+            raise ValueError(f"out must be a contiguous {(d.R,)} tensor")
+        out = out if out is not None else torch.empty((d.R,), dtype=torch.float32, device=self.device)
         check(_lib.load().tensorf_render_depth(_stream(), C.byref(d), C.byref(ps), C.byref(ri), _ptr(self.workspace), _ptr(out)))
         return out
 
@@ -388,14 +394,20 @@ def prng_gumbel(k0: int, k1: int, shape, device) -> torch.Tensor:
     return out
 
 
-def pixel_rays(M, origin, width: int, rows: Tuple[int, int], camera_index: int, device):
+def pixel_rays(M, origin, width: int, rows: Tuple[int, int], camera_index: int, device, out=None):
     """cameras.py:124-143 for image rows [rows[0], rows[1]): M = R_world_camera @ K^-1 (3x3), origin (3,), host
-    values. Returns (origins (n,3), directions (n,3), camera_indices (n,) int32 with uint32 bits)."""
+    values. Returns (origins (n,3), directions (n,3), camera_indices (n,) int32 with uint32 bits); `out` = such a
+    triple of contiguous tensors to fill (slices of a frame's ray table) instead of fresh ones."""
     r0, r1 = rows
     n = (r1 - r0) * width
-    o = torch.empty((n, 3), dtype=torch.float32, device=device)
-    d = torch.empty((n, 3), dtype=torch.float32, device=device)
-    c = torch.empty((n,), dtype=torch.int32, device=device)
+    if out is not None:
+        o, d, c = out
+        if tuple(o.shape) != (n, 3) or tuple(d.shape) != (n, 3) or tuple(c.shape) != (n,):
+            raise ValueError("pixel_rays: `out` tensors do not match the row range")
+    else:
+        o = torch.empty((n, 3), dtype=torch.float32, device=device)
+        d = torch.empty((n, 3), dtype=torch.float32, device=device)
+        c = torch.empty((n,), dtype=torch.int32, device=device)
     Mh = (C.c_float * 9)(*[float(x) for x in M])
     oh = (C.c_float * 3)(*[float(x) for x in origin])
     check(_lib.load().tensorf_pixel_rays(_stream(), Mh, oh, width, r0, r1, camera_index, o.data_ptr(), d.data_ptr(), c.data_ptr()))

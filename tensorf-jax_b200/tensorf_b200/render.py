@@ -12,7 +12,7 @@ from __future__ import annotations
 import dataclasses
 import enum
 import math
-from typing import Dict, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -65,25 +65,7 @@ class LearnableParams:  # render.py:39-46
             scene_contraction=scene_contraction)
 
 
-def contracted_schedule(near: float, far: float, n: int) -> Tuple[np.ndarray, np.ndarray]:
-    """Host constants of the contracted branch (render.py:127-155): the `ts` schedule and step
-    sizes, computed as the reference does (close_ts fp32 linspace, far_ts float64 numpy)."""
-    nc = n // 2
-    nf = n - nc
-    f32 = np.float32
-    if nc > 1:  # jnp.linspace [upstream]: start*(1-s_i) + stop*s_i, s_i = i/(num-1); endpoint appended exactly
-        sv = np.arange(nc - 1, dtype=np.float32) * f32(1.0 / (nc - 1))
-        close = (f32(near) * (f32(1.0) - sv) + f32(near + 1.0) * sv).astype(np.float32)
-        close = np.concatenate([close, np.array([near + 1.0], dtype=np.float32)])
-    else:
-        close = np.full((nc,), near, dtype=np.float32)
-    far_start = near + 1.0 + 1.0 / nc
-    k = 10.0
-    far_deltas = (1.0 / (1.0 - np.linspace(0.0, 1.0 - 1 / ((far - far_start) / k + 1), nf)) - 1.0) * np.linspace(1.0, k, nf)
-    base = np.concatenate([close, (far_start + far_deltas).astype(np.float32)]).astype(np.float32)
-    delta = np.roll(base, -1) - base
-    delta[-1] = delta[-2]
-    return base, delta.astype(np.float32)
+from .schedule import contracted_schedule  # noqa: E402,F401  (numpy only; shared with the JAX binding)
 
 
 # ---- workspace pool: one RenderCall per (shape, device), never shared by two live graphs ------
@@ -208,6 +190,79 @@ def render_rays_batched(appearance_mlp: networks.FeatureMlp, learnable_params: L
                                    shared if shared is not None else prng_key, config))
     res = torch.cat(out, dim=0).cpu().numpy()
     return res.reshape(batch_axes + res.shape[1:])
+
+
+class FrameRenderer:
+    """One rank's share of render_360.py:118-161 (a camera path of full frames through render.py:49-102), kept on the
+    device from pixel to pixel: `tensorf_pixel_rays` fills this rank's rows of the frame's ray table, the table is
+    rendered in chunks of `batch_size` rays (the last chunk is ragged, as in the reference's chunk loop), every chunk
+    writes straight into the rank's slice of a device frame buffer, and ONE device-to-host copy per frame lands it
+    in pinned memory.  Rows are dealt to ranks as interleaved stripes (`dist.stripe_rows`); there is no collective:
+    rank r's rows of the final image are `rows` and the host just places them (`scatter_into`).
+    Every chunk uses the same jitter / Gumbel vectors (same key), as render_rays_batched does."""
+
+    def __init__(self, appearance_mlp: networks.FeatureMlp, learnable_params: LearnableParams, aabb: torch.Tensor, config: RenderConfig,
+                 image_height: int, image_width: int, *, batch_size: int = 16384, rank: int = 0, world: int = 1, stripe: int = 16):
+        from . import dist as tdist
+        self.config, self.aabb, self.device = config, aabb.to(torch.float32).contiguous(), aabb.device
+        self.H, self.W, self.batch = image_height, image_width, batch_size
+        self.rows: List[Tuple[int, int]] = tdist.stripe_rows(image_height, rank, world, stripe)
+        self.n = sum(b - a for a, b in self.rows) * image_width
+        flat = learnable_params.flat()
+        if bool(learnable_params.scene_contraction):
+            raise NotImplementedError("FrameRenderer: per-ray jitter of contracted scenes goes through render_rays_batched")
+        self.rgb = config.mode is RenderMode.RGB
+        names = tuple(ops.param_shapes(self._desc(appearance_mlp, flat, 1))) if self.rgb else ("density_vector", "density_matrix")
+        self.params = {k: flat[k].detach().contiguous() for k in names}
+        self.calls: Dict[int, ops.RenderCall] = {}
+        for R in {min(batch_size, self.n), self.n % batch_size} - {0}:
+            self.calls[R] = ops.RenderCall(self._desc(appearance_mlp, flat, R), self.device)
+        dev = self.device
+        self.o = torch.empty((self.n, 3), dtype=torch.float32, device=dev)
+        self.d = torch.empty((self.n, 3), dtype=torch.float32, device=dev)
+        self.c = torch.empty((self.n,), dtype=torch.int32, device=dev)
+        shape = (self.n, 3) if self.rgb else (self.n,)
+        self.frame_dev = torch.empty(shape, dtype=torch.float32, device=dev)
+        self.frame_host = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+
+    def _desc(self, mlp, flat, R):
+        c = self.config
+        return ops.make_desc(R=R, N=c.density_samples_per_ray, K=c.appearance_samples_per_ray if c.mode is RenderMode.RGB else 1,
+                             G=flat["density_vector"].shape[2], cd=flat["density_vector"].shape[1], ca=flat["appearance_vector"].shape[1],
+                             mode=_MODE_CODE[c.mode], feat_freqs=mlp.feature_n_freqs, view_freqs=mlp.viewdir_n_freqs,
+                             num_cameras=mlp.num_cameras, squash=mlp.feature_squash_dim, units=mlp.units, inference=True)
+
+    def render(self, camera: cameras.Camera, camera_index: int, noise: Dict[str, torch.Tensor], sync: bool = True) -> torch.Tensor:
+        """Renders this rank's rows of one frame; returns the pinned host tensor (n, 3) or (n,) in `rows` order.
+        `noise`: device tensors 'jitter' (N,) and, for RGB, 'gumbel' (N,)."""
+        M, origin = camera.ray_matrices()
+        a = 0
+        for r0, r1 in self.rows:  # this rank's stripes of the pixel grid -> one contiguous ray table
+            b = a + (r1 - r0) * self.W
+            ops.pixel_rays(M.reshape(-1), origin, self.W, (r0, r1), int(camera_index), self.device, out=(self.o[a:b], self.d[a:b], self.c[a:b]))
+            a = b
+        for a in range(0, self.n, self.batch):
+            b = min(self.n, a + self.batch)
+            call = self.calls[b - a]
+            ins = dict(noise, aabb=self.aabb, origins=self.o[a:b], directions=self.d[a:b], camera_indices=self.c[a:b])
+            if self.rgb:
+                call.forward(self.params, ins, out=self.frame_dev[a:b])
+            else:
+                call.depth(self.params, ins, out=self.frame_dev[a:b])
+        self.frame_host.copy_(self.frame_dev, non_blocking=True)
+        if sync:
+            torch.cuda.current_stream().synchronize()
+        return self.frame_host
+
+    def scatter_into(self, image: np.ndarray, part: Optional[torch.Tensor] = None) -> np.ndarray:
+        """Places this rank's rows into a full (H, W[, 3]) image (host)."""
+        src = (part if part is not None else self.frame_host).numpy()
+        a = 0
+        for r0, r1 in self.rows:
+            b = a + (r1 - r0) * self.W
+            image[r0:r1] = src[a:b].reshape((r1 - r0, self.W) + src.shape[1:])
+            a = b
+        return image
 
 
 @dataclasses.dataclass

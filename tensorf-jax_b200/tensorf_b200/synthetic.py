@@ -152,6 +152,17 @@ def frame_rays(width: int, height: int, angle: float = 0.3, elevation: float = 0
     return (np.broadcast_to(o.astype(np.float32), (n, 3)).copy(), d.astype(np.float32), np.zeros(n, np.uint32))
 
 
+def frame_camera(width: int, height: int, angle: float = 0.3, elevation: float = 0.5, fov_x: float = 0.6911, radius: float = 4.0311):
+    """The `cameras.Camera` whose pixel rays are `frame_rays` (one pose of a render_360-style orbit)."""
+    from .cameras import Camera
+    o = radius * np.array([math.cos(angle) * math.cos(elevation), math.sin(angle) * math.cos(elevation), math.sin(elevation)])
+    rot = _look_at_rotation(o[None])[0]  # R_world_camera
+    T = np.eye(4)
+    T[:3, :3] = rot.T
+    T[:3, 3] = -rot.T @ o
+    return Camera.from_fov(T.astype(np.float32), width, height, fov_x_radians=fov_x)
+
+
 def dozer_rays(R: int, ncam: int = 256, seed: int = 1):
     """Unbounded-scene rays: origins uniform in [-1,1]^3 (poses are normalised into that cube,
     data.py:167-181), forward axis toward the scene centre plus a fisheye-like direction inside

@@ -26,6 +26,20 @@ def test_shard_ranges_cover_and_balance():
     assert tdist.tile_rows(800, 3, 8) == (300, 400)
 
 
+def test_stripe_rows_cover_every_row_once():
+    for H in (1, 16, 21, 800):
+        for world in (1, 2, 3, 8):
+            seen = np.zeros(H, int)
+            for r in range(world):
+                for a, b in tdist.stripe_rows(H, r, world):
+                    assert 0 <= a < b <= H and b - a <= 16
+                    seen[a:b] += 1
+            assert (seen == 1).all()
+    # 800 rows over 8 ranks: 50 stripes, 6 or 7 per rank -> at most one stripe of imbalance
+    sizes = [sum(b - a for a, b in tdist.stripe_rows(800, r, 8)) for r in range(8)]
+    assert max(sizes) - min(sizes) <= 16 and sum(sizes) == 800
+
+
 def test_shard_rays_slices_only_per_ray_arrays():
     w = S.dozer_workload(R=10, G=8)
     inp = S.make_inputs(w)

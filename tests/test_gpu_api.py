@@ -134,6 +134,40 @@ def test_render_rays_batched_ragged(cuda):
     assert depth.shape == (10, 10)
 
 
+@pytest.mark.parametrize("mode", ["rgb", "median", "mean"])
+def test_frame_renderer_matches_batched_and_stripes(cuda, mode):
+    """render.FrameRenderer (device pixel rays -> chunks incl. the ragged one -> one D2H per frame) against
+    render_rays_batched over the same camera, and two interleaved-stripe ranks against one (render_360.py:118-161)."""
+    from tensorf_b200 import cameras, networks, prng, render
+    w = S.Workload("frame", 64, 12, 4, 8, 40, 6, 2, 2)
+    inp = S.make_inputs(w)
+    lp, _ = _learnable(w, inp, cuda)
+    mlp = networks.FeatureMlp(feature_n_freqs=2, viewdir_n_freqs=2)
+    H, W = 21, 18                                    # 378 rays: 5 chunks of 64 + a ragged one of 58
+    cam = S.frame_camera(W, H)
+    o, d, c = S.frame_rays(W, H)
+    rays_dev = cam.pixel_rays_wrt_world(0, cuda)
+    np.testing.assert_allclose(rays_dev.directions.reshape(-1, 3).cpu().numpy(), d, atol=2e-6)
+    np.testing.assert_allclose(rays_dev.origins.reshape(-1, 3).cpu().numpy(), o, atol=2e-6)
+    aabb = T(inp["aabb"], device=cuda)
+    rmode = {"rgb": render.RenderMode.RGB, "median": render.RenderMode.DIST_MEDIAN, "mean": render.RenderMode.DIST_MEAN}[mode]
+    cfg = render.RenderConfig(0.05, 200.0, rmode, w.N, w.K)
+    noise_np = prng.render_noise(prng.Key.from_seed(3), 64, w.N, False, need_gumbel=mode == "rgb")
+    ref = render.render_rays_batched(mlp, lp, aabb, rays_dev, noise_np, cfg, batch_size=64)
+    noise = {"jitter": T(np.asarray(noise_np.jitter), device=cuda)}
+    if mode == "rgb":
+        noise["gumbel"] = T(np.asarray(noise_np.gumbel), device=cuda)
+    one = render.FrameRenderer(mlp, lp, aabb, cfg, H, W, batch_size=64)
+    assert one.n == H * W and sorted(one.calls) == [58, 64]
+    img = one.scatter_into(np.zeros(ref.shape, np.float32), one.render(cam, 0, noise))
+    np.testing.assert_array_equal(img, ref)
+    parts = np.full(ref.shape, np.nan, np.float32)
+    for rank in range(2):
+        fr = render.FrameRenderer(mlp, lp, aabb, cfg, H, W, batch_size=64, rank=rank, world=2, stripe=4)
+        fr.scatter_into(parts, fr.render(cam, 0, noise))
+    np.testing.assert_array_equal(parts, ref)
+
+
 def dataclass_replace(cfg, mode):
     import dataclasses
     return dataclasses.replace(cfg, mode=mode)
