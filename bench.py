@@ -249,6 +249,229 @@ def bench_optimizer(ops, dev, params, grads, peak_gbs, reps=10):
     return out
 
 
+class TrainBench:
+    """One sharded training step (render_rays forward + MSE + reverse w.r.t. every leaf + the gradient exchange) of a
+    workload, set up once: parameters replicated, this rank's ray shard resident in HBM (and mirrored in one pinned host
+    buffer for the end-to-end loop), all gradient leaves in one flat buffer."""
+
+    def __init__(self, args, w, world, rank, dev, dist, exchange_arg):
+        from tensorf_b200 import dist as tdist, ops
+        from tensorf_b200.data import HostStage
+        self.ops, self.dist, self.w, self.world, self.rank, self.dev = ops, dist, w, world, rank, dev
+        self.R_global = w.R * world
+        inp = S.make_inputs(w, seed_rays=1 + rank)
+        desc = ops.make_desc(R=w.R, N=w.N, K=w.K, G=w.G, cd=w.cd, ca=w.ca, contracted=w.contracted, feat_freqs=w.feat_freqs,
+                             view_freqs=w.view_freqs, num_cameras=w.num_cameras, loss_scale=1.0 / (3 * self.R_global))
+        self.desc = desc
+        self.call = ops.RenderCall(desc, dev)
+
+        def dv(x):
+            t = torch.from_numpy(np.ascontiguousarray(x))
+            if t.dtype == torch.uint32:
+                t = t.view(torch.int32)
+            return t.to(dev)
+
+        self.params = {k: dv(v) for k, v in inp["params"].items()}
+        self.host_keys = ["origins", "directions", "camera_indices", "colors", "jitter", "gumbel"]
+        # e2e path: the minibatch lives in ONE pinned host buffer mirrored by one device buffer (data.HostStage), so a
+        # step's inputs are a single H2D copy; the device views are what both timed loops read
+        self.stage = HostStage({k: inp[k] for k in self.host_keys}, dev)
+        self.stage.upload()
+        self.dins = dict(self.stage.device)
+        self.dins["aabb"] = dv(inp["aabb"])
+        if w.contracted:
+            # host constants of render.py:127-155 (numpy, float64 -> fp32), computed once
+            from tensorf_b200.schedule import contracted_schedule
+            base, delta = contracted_schedule(w.near, w.far, w.N)
+            self.dins["base_ts"], self.dins["deltas"] = dv(base), dv(delta)
+        # all gradient leaves live in ONE flat buffer (with the loss in one extra slot) -> one exchange per step; the
+        # reverse pass can run in two halves so that the exchange of everything but the density factors overlaps with
+        # the density scatter (tensorf_render_rgb_bwd_phase)
+        self.fg = tdist.FlatGrads(ops.param_shapes(desc), dev, loss_slot=True)
+        self.grads = self.fg.leaves
+        self.overlap = world > 1 and not args.no_overlap
+        # exchange over peer memory (tensorf_peer_allreduce: P2P loads/stores or NVSwitch multicast through torch
+        # symmetric memory) unless --exchange nccl; every rank must agree, else all fall back to NCCL
+        self.peer, self.exchange = None, "nccl"
+        if world > 1 and exchange_arg != "nccl":
+            try:
+                shapes = ops.param_shapes(desc)
+                self.peer = tdist.PeerAdam(shapes, {k: 0.0 for k in shapes}, dev, multicast=(exchange_arg == "peer-multicast"))
+            except Exception as e:  # no symmetric memory on this box: say so, use NCCL
+                print(f"[bench] rank {rank}: peer-memory exchange unavailable ({repr(e)[:300]}); using NCCL", file=sys.stderr)
+            ok = torch.tensor([0 if self.peer is None else 1], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 1:
+                self.exchange = "peer-multicast" if self.peer.multicast else "peer-p2p"
+                self.grads = self.peer.grads
+            else:
+                self.peer = None
+        # the early bucket's exchange on a side stream beside the density scatter (as the NCCL path does)
+        self.peer_overlap = self.peer is not None and exchange_arg in ("peer-overlap", "auto") and not args.no_overlap
+        if self.peer_overlap:
+            self.side, self.ev_early, self.ev_done = torch.cuda.Stream(device=dev), torch.cuda.Event(), torch.cuda.Event()
+        self.flush = None if args.no_l2_flush else torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def describe_exchange(self):
+        if self.world == 1:
+            return "single GPU"
+        if self.peer is not None:
+            how = "in two buckets, the early one on a side stream beside the density scatter" if self.peer_overlap else "on the launch stream"
+            return f"rays sharded x{self.world}, gradient all-reduce by tensorf_peer_allreduce ({self.exchange}, {self.peer.sync} sync) {how}"
+        return f"rays sharded x{self.world}, NCCL grad allreduce" + (" in two buckets overlapped with the density scatter" if self.overlap else "")
+
+    def step(self):
+        call, params, dins, grads, peer, fg = self.call, self.params, self.dins, self.grads, self.peer, self.fg
+        if self.peer_overlap:
+            rgb, loss = call.forward(params, dins, loss_out=peer.loss)
+            call.backward(None, grads, phase=1)
+            self.ev_early.record()
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(self.ev_early)
+                peer.allreduce("early", channel=1)
+                self.ev_done.record()
+            call.backward(None, grads, phase=2)
+            peer.allreduce("late", channel=0)
+            torch.cuda.current_stream().wait_event(self.ev_done)
+            return loss
+        if peer is not None:
+            rgb, loss = call.forward(params, dins, loss_out=peer.loss)
+            call.backward(None, grads)
+            peer.allreduce()
+            return loss
+        rgb, loss = call.forward(params, dins, loss_out=fg.loss)
+        if self.overlap:
+            call.backward(None, grads, phase=1)
+            fg.start_allreduce("early")
+            call.backward(None, grads, phase=2)
+            fg.start_allreduce("late")
+            fg.finish()
+        else:
+            call.backward(None, grads)
+            fg.allreduce()
+        return loss
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, steps, warmup):
+        """`warmup` untimed steps, then exactly `steps` steps: CUDA events per step, L2 flushed between steps, barrier +
+        synchronize on both sides, max over ranks.  Returns (ms_per_step, launches, {stage: (total ms, calls)}, total ms)."""
+        ops = self.ops
+        for _ in range(warmup):
+            self.step()
+        self.barrier()
+        ops.profile_enable(True)
+        launches0 = ops.launch_count()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        self.barrier()
+        for i in range(steps):
+            if self.flush is not None:
+                self.flush.zero_()
+            ev[i][0].record()
+            self.step()
+            ev[i][1].record()
+        self.barrier()
+        launches = ops.launch_count() - launches0
+        prof = ops.profile_read()
+        ops.profile_enable(False)
+        total_ms = self.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+        return total_ms / steps, launches, prof, total_ms
+
+    def timed_e2e(self, steps):
+        """The same step through the public API with HOST inputs: one pinned H2D copy of the minibatch and a blocking read
+        of the loss every step, inside the timed region."""
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss_host = 0.0
+        for i in range(steps):
+            self.stage.upload()
+            loss = self.step()
+            loss_host = float(loss.item())  # blocking D2H read, like training.py:342
+        e1.record()
+        self.barrier()
+        h2d = sum(self.stage.host[k].numel() * self.stage.host[k].element_size() for k in self.host_keys)
+        return self.max_over_ranks(e0.elapsed_time(e1)) / steps, h2d, loss_host
+
+
+def multi_rank_parity(ops, dev, world, rank, dist):
+    """N > 1, outside every timed region: the sharded path against one rank doing the whole batch.  A small lego-type
+    global batch (64 rays per rank) is differentiated two ways - every rank its shard + `tensorf_peer_allreduce`
+    (k_peer_allreduce), and rank 0 alone over the concatenated rays - and one optimiser step is taken two ways -
+    `tensorf_adam_step_peer` (k_adam_peer: reduce-scatter + Adam on the owner's shard + all-gather) and
+    `tensorf_adam_step` on the single-rank gradient.  Reports the largest relative differences over the leaves."""
+    from tensorf_b200 import dist as tdist
+    Rl = 64
+    w = S.Workload("parity", Rl * world, 24, 8, 16, 60, 9, 2, 2)
+    inp = S.make_inputs(w, seed_rays=7)  # same global batch on every rank
+
+    def dv(x):
+        t = torch.from_numpy(np.ascontiguousarray(x))
+        return (t.view(torch.int32) if t.dtype == torch.uint32 else t).to(dev)
+
+    shapes = None
+    out = {}
+    try:
+        desc_l = ops.make_desc(R=Rl, N=w.N, K=w.K, G=w.G, cd=w.cd, ca=w.ca, feat_freqs=2, view_freqs=2, loss_scale=1.0 / (3 * w.R))
+        shapes = ops.param_shapes(desc_l)
+        lrs = {k: -(0.02 if k.startswith(("density_", "appearance_")) else 1e-3) for k in shapes}
+        peer = tdist.PeerAdam(shapes, lrs, dev)
+    except Exception as e:
+        return {"unavailable": repr(e)[:200]}
+    params = {k: dv(v) for k, v in inp["params"].items()}
+    peer.load_params(params)
+    a, b = rank * Rl, (rank + 1) * Rl
+    per_ray = ("origins", "directions", "camera_indices", "colors")
+    dins = {k: dv(inp[k][a:b] if k in per_ray else inp[k]) for k in per_ray + ("jitter", "gumbel", "aabb")}
+    call = ops.RenderCall(desc_l, dev)
+    call.forward(peer.params, dins, loss_out=peer.loss)
+    call.backward(None, peer.grads)
+    local = {k: v.clone() for k, v in peer.grads.items()}
+    peer.allreduce()
+    torch.cuda.synchronize()
+    summed = {k: v.clone() for k, v in peer.grads.items()}
+    # fused exchange + Adam from the LOCAL gradients again
+    for k in local:
+        peer.grads[k].copy_(local[k])
+    peer.step(count=0)
+    torch.cuda.synchronize()
+    new_params = {k: v.clone() for k, v in peer.params.items()}
+    if rank == 0:
+        desc_g = ops.make_desc(R=w.R, N=w.N, K=w.K, G=w.G, cd=w.cd, ca=w.ca, feat_freqs=2, view_freqs=2, loss_scale=1.0 / (3 * w.R))
+        full = ops.RenderCall(desc_g, dev)
+        fins = {k: dv(inp[k]) for k in per_ray + ("jitter", "gumbel", "aabb")}
+        full.forward(params, fins, loss_out=torch.zeros(1, device=dev))
+        g1 = full.backward(None)
+        rel_inf = rel_l2 = 0.0
+        for k in g1:
+            ref, x = g1[k].double(), summed[k].double()
+            rel_inf = max(rel_inf, float((x - ref).abs().max() / ref.abs().max().clamp_min(1e-300)))
+            rel_l2 = max(rel_l2, float((x - ref).norm() / ref.norm().clamp_min(1e-300)))
+        names = list(shapes)
+        p1 = [params[k].clone() for k in names]
+        adam = ops.AdamCall(p1, [torch.zeros_like(x) for x in p1], [torch.zeros_like(x) for x in p1], [lrs[k] for k in names])
+        adam.step([g1[k] for k in names], count=0)
+        torch.cuda.synchronize()
+        step_inf = 0.0
+        for k, x in zip(names, p1):
+            upd_ref, upd = (x - params[k]).double(), (new_params[k] - params[k]).double()
+            step_inf = max(step_inf, float((upd - upd_ref).abs().max() / upd_ref.abs().max().clamp_min(1e-300)))
+        out = {"max_rel_inf": rel_inf, "max_rel_l2": rel_l2, "adam_update_max_rel_inf": step_inf, "rays_global": w.R, "ranks": world,
+               "covers": "k_peer_allreduce (summed gradient) and k_adam_peer (parameter update) vs one rank over the concatenated rays",
+               "note": "sums are re-associated across ranks: differences are fp32 rounding of the ray partition"}
+    del peer
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -259,9 +482,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--no-render", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="N>1, NCCL exchange: one all-reduce after the whole reverse pass")
+    ap.add_argument("--no-config3", action="store_true", help="skip the BASELINE configs[2] sub-record (300^3, 16384 global rays, strong scaling)")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: one exchange after the whole reverse pass")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer-p2p", "peer-multicast", "peer-overlap", "nccl"],
-                    help="N>1 gradient exchange: own kernel over peer memory (auto = peer-p2p, NCCL if symmetric memory is unavailable) or NCCL")
+                    help="N>1 gradient exchange: own kernel over peer memory (auto = peer-overlap: two buckets, the early one beside the "
+                         "density scatter; NCCL if symmetric memory is unavailable), peer-p2p / peer-multicast = one exchange on the launch stream, or NCCL")
     args = ap.parse_args()
     w = workload_from_name(args.workload)
     if args.impl == "reference":
@@ -288,157 +513,45 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
     steps = args.steps
+    dist_or_none = dist if world > 1 else None
 
-    # ---- inputs: same parameters on every rank, a different ray shard per rank ------------------
-    R_global = w.R * world
-    inp = S.make_inputs(w, seed_rays=1 + rank)
-    desc = ops.make_desc(R=w.R, N=w.N, K=w.K, G=w.G, cd=w.cd, ca=w.ca, contracted=w.contracted, feat_freqs=w.feat_freqs,
-                         view_freqs=w.view_freqs, num_cameras=w.num_cameras, loss_scale=1.0 / (3 * R_global))
-    call = ops.RenderCall(desc, dev)
-
-    def dv(x):
-        t = torch.from_numpy(np.ascontiguousarray(x))
-        if t.dtype == torch.uint32:
-            t = t.view(torch.int32)
-        return t.to(dev)
-
-    params = {k: dv(v) for k, v in inp["params"].items()}
-    host_keys = ["origins", "directions", "camera_indices", "colors", "jitter", "gumbel"]
-    # e2e path: the minibatch lives in ONE pinned host buffer mirrored by one device buffer (data.HostStage), so a
-    # step's inputs are a single H2D copy; the device views are what both timed loops read
-    from tensorf_b200.data import HostStage
-    stage = HostStage({k: inp[k] for k in host_keys}, dev)
-    stage.upload()
-    dins = dict(stage.device)
-    dins["aabb"] = dv(inp["aabb"])
-    if w.contracted:
-        # host constants of render.py:127-155 (numpy, float64 -> fp32), computed once
-        from tensorf_b200.render import contracted_schedule
-        base, delta = contracted_schedule(w.near, w.far, w.N)
-        dins["base_ts"], dins["deltas"] = dv(base), dv(delta)
-
-    # all gradient leaves live in ONE flat buffer -> one NCCL allreduce per step
-    from tensorf_b200 import dist as tdist
-    # (with the loss in one extra slot); the reverse pass runs in two halves so that the exchange of everything but
-    # the density factors overlaps with the density scatter (tensorf_render_rgb_bwd_phase)
-    fg = tdist.FlatGrads(ops.param_shapes(desc), dev, loss_slot=True)
-    grads = fg.leaves
-    overlap = world > 1 and not args.no_overlap
-    # exchange over peer memory (tensorf_peer_allreduce on the launch stream: P2P loads/stores or NVSwitch multicast
-    # through torch symmetric memory) unless --exchange nccl; every rank must agree, else all fall back to NCCL
-    peer, exchange = None, "nccl"
-    if world > 1 and args.exchange != "nccl":
-        err = None
-        try:
-            shapes = ops.param_shapes(desc)
-            peer = tdist.PeerAdam(shapes, {k: 0.0 for k in shapes}, dev,
-                                  multicast=(args.exchange == "peer-multicast"))  # auto = P2P: measured faster (profiles/)
-        except Exception as e:  # no symmetric memory on this box: say so, use NCCL
-            err = repr(e)
-            print(f"[bench] rank {rank}: peer-memory exchange unavailable ({err[:300]}); using NCCL", file=sys.stderr)
-        ok = torch.tensor([0 if peer is None else 1], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 1:
-            exchange = "peer-multicast" if peer.multicast else "peer-p2p"
-            grads = peer.grads
-        else:
-            peer = None
-
-    flush = None if args.no_l2_flush else torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
-
-    # --exchange peer-overlap (NOT measured yet, opt-in): the early bucket's exchange on a side stream beside the
-    # density scatter, as the NCCL path does
-    peer_overlap = peer is not None and args.exchange == "peer-overlap"
-    if peer_overlap:
-        side, ev_early, ev_done = torch.cuda.Stream(device=dev), torch.cuda.Event(), torch.cuda.Event()
-
-    def step():
-        if peer_overlap:
-            rgb, loss = call.forward(params, dins, loss_out=peer.loss)
-            call.backward(None, grads, phase=1)
-            ev_early.record()
-            with torch.cuda.stream(side):
-                side.wait_event(ev_early)
-                peer.allreduce("early", channel=1)
-                ev_done.record()
-            call.backward(None, grads, phase=2)
-            peer.allreduce("late", channel=0)
-            torch.cuda.current_stream().wait_event(ev_done)
-            return loss
-        if peer is not None:
-            rgb, loss = call.forward(params, dins, loss_out=peer.loss)
-            call.backward(None, grads)
-            peer.allreduce()
-            return loss
-        rgb, loss = call.forward(params, dins, loss_out=fg.loss)
-        if overlap:
-            call.backward(None, grads, phase=1)
-            fg.start_allreduce("early")
-            call.backward(None, grads, phase=2)
-            fg.start_allreduce("late")
-            fg.finish()
-        else:
-            call.backward(None, grads)
-            fg.allreduce()
-        return loss
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    tb = TrainBench(args, w, world, rank, dev, dist, args.exchange)
+    R_global = tb.R_global
     # clocks are sampled from the warm-up through the timed and end-to-end loops (the timed region
     # alone is only tens of milliseconds, shorter than nvidia-smi's sampling period)
     sampler = ClockSampler(local) if rank == 0 else None
-    for _ in range(warmup):
-        step()
-    barrier()
-
-    # ---- timed region: exactly `steps` steps, CUDA events per step, L2 flushed between steps ----
-    ops.profile_enable(True)
-    launches0 = ops.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    barrier()
-    for i in range(steps):
-        if flush is not None:
-            flush.zero_()
-        ev[i][0].record()
-        step()
-        ev[i][1].record()
-    barrier()
-    launches = ops.launch_count() - launches0
-    prof = ops.profile_read()
-    ops.profile_enable(False)
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / steps
+    ms_per_step, launches, prof, total_ms = tb.timed(steps, warmup)
     value = R_global / (ms_per_step * 1e-3)
-
-    # ---- e2e: public API with HOST buffers; H2D of the minibatch + D2H of the loss every step -----
-    h2d = sum(stage.host[k].numel() * stage.host[k].element_size() for k in host_keys)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        stage.upload()
-        loss = step()
-        loss_host = float(loss.item())  # blocking D2H read, like training.py:342
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item()) / steps
+    e2e_ms, h2d, loss_host = tb.timed_e2e(steps)
     e2e_value = R_global / (e2e_ms * 1e-3)
     clocks = sampler.stop() if sampler else None
+    exchange_desc = tb.describe_exchange()
+    params, grads = tb.params, tb.grads
 
-    # ---- render_360-style forward rendering (BASELINE configs[4] shapes), this rank's image tiles ----
+    # ---- BASELINE configs[2]: upsampled 300^3 grid, 16384-ray global batch strong-scaled over the ranks ----------------
+    config3 = None
+    if not args.no_config3 and args.workload == "lego_256":
+        Rg = 16384
+        w3 = S.lego_workload(R=Rg // world, G=300, name=f"lego_G300_Rglobal{Rg}_N519_K77 (BASELINE configs[2])")
+        tb3 = TrainBench(args, w3, world, rank, dev, dist, args.exchange)
+        ms3, _, prof3, tot3 = tb3.timed(max(4, steps // 2), 3)
+        st3 = {k: round(v[0] / max(v[1], 1), 4) for k, v in sorted(prof3.items(), key=lambda kv: -kv[1][0])}
+        n_par = sum(int(np.prod(s_)) for s_ in ops.param_shapes(tb3.desc).values())
+        config3 = {"workload": w3.name, "scaling": "strong", "R_global": Rg, "R_per_gpu": w3.R, "N": w3.N, "K": w3.K, "G": 300,
+                   "value": Rg / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3, "exchange_bytes": 4 * n_par, "exchange": tb3.describe_exchange(),
+                   "stages_ms": st3,
+                   "roofline_step_frac": Rg / world / (ms3 * 1e-3) * w3.train_bytes_per_ray() / 1e9 / measured_peaks()[0]}
+        del tb3
+        torch.cuda.empty_cache()
+
+    parity = multi_rank_parity(ops, dev, world, rank, dist) if world > 1 else None
+
+    # ---- render_360 as a job (BASELINE configs[4] shapes), this rank's stripes of every frame ----
     render = None
     if not args.no_render:
-        render = bench_render(ops, dev, world, rank, dist if world > 1 else None)
+        del tb.call
+        torch.cuda.empty_cache()
+        render = bench_render(ops, dev, world, rank, dist_or_none)
 
     if rank == 0:
         peak, tc_peak, peak_src = measured_peaks()
@@ -498,9 +611,8 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": w.name, "R_per_gpu": w.R, "R_global": R_global, "N": w.N, "K": w.K, "G": w.G,
                        "cd": w.cd, "ca": w.ca, "feat_freqs": w.feat_freqs, "view_freqs": w.view_freqs,
-                       "contracted": w.contracted, "parallelism": (f"rays sharded x{world}, " + (f"gradient all-reduce by tensorf_peer_allreduce ({exchange}, {peer.sync} sync) " + ("in two buckets, the early one on a side stream" if peer_overlap else "on the launch stream") if peer is not None else
-                                                                      "NCCL grad allreduce" + (" in two buckets overlapped with the density scatter" if overlap else ""))) if world > 1 else "single GPU",
-                       "l2": "flushed (256 MiB write) between timed steps" if flush is not None else "not flushed",
+                       "contracted": w.contracted, "parallelism": exchange_desc,
+                       "l2": "flushed (256 MiB write) between timed steps" if tb.flush is not None else "not flushed",
                        "timed": "render_rays fwd + MSE + reverse wrt all LearnableParams leaves; Adam excluded",
                        "loss": loss_host},
             "roofline_step": {"bound": "hbm", "achieved": value / world * w.train_bytes_per_ray() / 1e9, "peak": peak, "unit": "GB/s",
@@ -515,6 +627,10 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if config3 is not None:
+            out["config3"] = config3
+        if parity is not None:
+            out["parity_check"] = parity
         if render is not None:
             out["render"] = render
         if not args.no_render:

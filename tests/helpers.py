@@ -85,3 +85,24 @@ def kink_rows(aux, tau=KINK_TAU):
     treatment the selection stage gets for near-ties)."""
     bad = (aux["z1"].abs() < tau).any(dim=-1) | (aux["z2"].abs() < tau).any(dim=-1)
     return torch.where(bad)[0].numpy()
+
+
+def audit_median_mismatches(depth, ref, aux64, N):
+    """DIST_MEDIAN picks the first sample whose 1 - p_exit exceeds 0.5 (render.py:250-266): a discontinuous output.
+    Every ray on which the kernel and the fp32 oracle disagree must be a rounding case of that threshold: in the
+    fp64 oracle (`aux64`), all samples between the two answers have |1 - E - 0.5| within fp32 rounding of the
+    cumulative sum (4 N eps).  Returns the number of (audited) mismatching rays."""
+    same = np.isclose(depth, ref, rtol=1e-4, atol=1e-6) | (np.isinf(depth) & np.isinf(ref))
+    ts = aux64["ts"].numpy()
+    pna = 1.0 - aux64["p_exits"].numpy()
+    tol = 4 * N * np.finfo(np.float32).eps
+    for r in np.where(~same)[0]:
+        def index_of(v):  # sample whose distance the value is (N = "never crossed": inf)
+            return N if np.isinf(v) else int(np.argmin(np.abs(ts[r] - v)))
+        a, b = sorted((index_of(depth[r]), index_of(ref[r])))
+        assert a != b, f"ray {r}: depth {depth[r]} vs {ref[r]} but the same sample"
+        if not np.isinf(depth[r]):
+            assert abs(ts[r][index_of(depth[r])] - depth[r]) <= 1e-4 * max(1.0, abs(depth[r])), f"ray {r}: {depth[r]} is not a sample distance"
+        between = pna[r, a:b]
+        assert (np.abs(between - 0.5) <= tol).all(), f"ray {r}: samples {a}..{b} are not at the 0.5 threshold: {between}"
+    return int((~same).sum())

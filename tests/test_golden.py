@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import tensorf_oracle as O
-from helpers import T, assert_close_grad, assert_close_out, device_inputs, kink_rows, oracle_cfgs, oracle_inputs
+from helpers import audit_median_mismatches, T, assert_close_grad, assert_close_out, device_inputs, kink_rows, oracle_cfgs, oracle_inputs
 from tensorf_b200 import synthetic as S
 
 sys.path.insert(0, str(pathlib.Path(__file__).parent / "golden"))
@@ -67,5 +67,12 @@ def test_cuda_reproduces_golden(cuda, name):
     for mode, key in ((O.DIST_MEDIAN, "depth_median"), (O.DIST_MEAN, "depth_mean")):
         d = ops.make_desc(R=w.R, N=w.N, K=w.K, G=w.G, cd=w.cd, ca=w.ca, mode=mode, contracted=w.contracted)
         depth = ops.RenderCall(d, cuda).depth(params, {k: v for k, v in dins.items() if k != "colors"}).cpu().numpy()
-        ok = np.isclose(depth, g[key], rtol=1e-4, atol=1e-6) | (np.isinf(depth) & np.isinf(g[key]))
-        assert ok.mean() >= 0.97, key
+        if mode == O.DIST_MEDIAN:  # a threshold output: every mismatching ray is audited against the fp64 oracle
+            cfg_m, mc_m = oracle_cfgs(w, mode)
+            o64m = oracle_inputs(inp, torch.float64)
+            _, aux64 = O.render_rays(cfg_m, mc_m, o64m["params"], w.contracted, o64m["aabb"], o64m["origins"], o64m["directions"],
+                                     o64m["camera_indices"], o64m["jitter"], None, return_aux=True)
+            assert audit_median_mismatches(depth, g[key], aux64, w.N) <= max(1, w.R // 30), key
+        else:
+            ok = np.isclose(depth, g[key], rtol=1e-4, atol=1e-6)
+            assert ok.all(), key

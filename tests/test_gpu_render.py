@@ -9,7 +9,8 @@ import pytest
 import torch
 
 import tensorf_oracle as O
-from helpers import T, assert_close_grad, assert_close_out, device_inputs, kink_rows, oracle_cfgs, oracle_inputs
+from helpers import (T, assert_close_grad, assert_close_out, audit_median_mismatches, device_inputs, kink_rows, oracle_cfgs,
+                     oracle_inputs)
 from tensorf_b200 import synthetic as S
 
 pytestmark = pytest.mark.gpu
@@ -20,6 +21,24 @@ MID = S.Workload("mid", 512, 48, 16, 48, 83, 12, 2, 2)
 ODD = S.Workload("odd", 33, 11, 5, 6, 50, 50, 1, 3)  # cd, ca not multiples of 4; K == N
 DOZER_S = S.Workload("dozer_s", 48, 16, 32, 48, 90, 13, 6, 6, contracted=True, num_cameras=7)
 DOZER_T = S.Workload("dozer_t", 40, 9, 4, 3, 41, 6, 2, 2, contracted=True, num_cameras=None)
+FUSED_S = S.Workload("fused_s", 96, 12, 4, 16, 45, 7, 2, 2)  # 3*ca = 48: smallest shape family of the fused MLP kernels
+FUSED_C = S.Workload("fused_c", 40, 9, 4, 32, 41, 6, 2, 2, contracted=True, num_cameras=None)
+
+
+# BASELINE.json shapes at grid_dim_final = 300 (training.py:115-118, render_360.py:43-51) on a ray slice the fp64 oracle
+# finishes in seconds: B = configs[2] (N=519, K=77), C = configs[3] at 300^3 (N=1558, K=233, contraction + embeddings),
+# D = configs[4] (N=512, K=128)
+LEGO300 = S.lego_workload(R=48, G=300)
+DOZER300 = S.dozer_workload(R=32, G=300)
+RENDER300 = S.Workload("render300", 40, 300, 16, 48, 512, 128, 2, 2)
+# gradient slices at the bench shapes: gradients are sums over rays, so a 64-ray call has a well-defined oracle answer
+LEGO_A_SLICE = S.lego_workload(R=64, G=128, N=256, K=38, name="legoA_slice")
+DOZER128_SLICE = S.dozer_workload(R=40, G=128)
+
+
+def fused_ok(w):
+    """Shapes TENSORF_MLP_FUSED accepts (csrc/mlp_fused.cu: mlp_fused_supported)."""
+    return (3 * w.ca) % 16 == 0 and 3 * w.ca <= 160 and w.feat_freqs == 2 and w.view_freqs == 2 and not w.num_cameras
 
 
 def run_cuda(w, inp, cuda, with_colors=True, mlp_impl=0):
@@ -47,9 +66,17 @@ def audit_selection(idx_cuda, aux, K):
     return len(bad_rows)
 
 
-@pytest.mark.parametrize("mlp_impl", [2, 1], ids=["tcgen05", "simt_fp32"])
-@pytest.mark.parametrize("w", [SMALL, SMALL6, MID, ODD, DOZER_S, DOZER_T], ids=lambda w: w.name)
+@pytest.mark.parametrize("mlp_impl", [2, 1, 3], ids=["tcgen05", "simt_fp32", "fused"])
+@pytest.mark.parametrize("w", [SMALL, SMALL6, MID, ODD, DOZER_S, DOZER_T, FUSED_S, FUSED_C, LEGO300, DOZER300, RENDER300, LEGO_A_SLICE,
+                               DOZER128_SLICE], ids=lambda w: w.name)
 def test_render_rgb_forward_and_grads(cuda, w, mlp_impl):
+    if w.G >= 128 and mlp_impl == 1:
+        pytest.skip("full-size shapes: the exact-fp32 SIMT MLP is covered on the small shapes")
+    if mlp_impl == 3 and not fused_ok(w):
+        from tensorf_b200 import _lib
+        with pytest.raises(_lib.TensorfError):  # the fused kernels refuse other networks instead of falling back silently
+            run_cuda(w, S.make_inputs(w, bias_std=0.05), cuda, mlp_impl=3)
+        return
     inp = S.make_inputs(w, bias_std=0.05)
     call, params, dins, rgb, loss = run_cuda(w, inp, cuda, mlp_impl=mlp_impl)
     idx = call.view("idx").cpu().numpy().reshape(w.R, w.K)
@@ -80,7 +107,7 @@ def test_render_rgb_forward_and_grads(cuda, w, mlp_impl):
     # the rays that own a ReLU-kink row zeroed for kernel and oracle alike
     d_rgb64 = (2.0 / (3 * w.R)) * (rgb64.detach() - o64["colors"])
     amb_rays = np.unique(kink_rows(aux64) // w.K)
-    assert len(amb_rays) <= max(3, w.R // 10)
+    assert len(amb_rays) <= max(3, w.R // 3)  # (K = 233 rows x 256 units per ray at the 300^3 dozer shape: a few rays own a kink row)
     d_rgb64[amb_rays] = 0.0
     (rgb64 * d_rgb64).sum().backward()
     grads = call.backward(d_rgb64.to(torch.float32).to(cuda).contiguous())
@@ -94,7 +121,7 @@ def test_render_rgb_forward_and_grads(cuda, w, mlp_impl):
         assert_close_grad(g_fused[k].cpu().numpy(), g_expl[k].cpu().numpy(), rtol=2e-5, what=f"fused vs explicit {k}")
 
 
-@pytest.mark.parametrize("w", [SMALL, MID, DOZER_S], ids=lambda w: w.name)
+@pytest.mark.parametrize("w", [SMALL, MID, DOZER_S, LEGO300, DOZER300, RENDER300], ids=lambda w: w.name)
 @pytest.mark.parametrize("mode", [O.DIST_MEDIAN, O.DIST_MEAN])
 def test_render_depth(cuda, w, mode):
     from tensorf_b200 import ops
@@ -111,9 +138,12 @@ def test_render_depth(cuda, w, mode):
     ref = O.render_rays(cfg, mc, oi["params"], w.contracted, oi["aabb"], oi["origins"], oi["directions"],
                         oi["camera_indices"], oi["jitter"], None).numpy()
     if mode == O.DIST_MEDIAN:
-        # the crossing sample can legitimately differ when 1-E is within rounding of 0.5
-        same = np.isclose(depth, ref, rtol=1e-4, atol=1e-6) | (np.isinf(depth) & np.isinf(ref))
-        assert same.mean() >= 0.98, f"median depth: only {same.mean():.3f} agree"
+        # the crossing sample can legitimately differ when 1-E is within rounding of 0.5: every mismatch is audited
+        o64 = oracle_inputs(inp, torch.float64)
+        _, aux64 = O.render_rays(cfg, mc, o64["params"], w.contracted, o64["aabb"], o64["origins"], o64["directions"],
+                                 o64["camera_indices"], o64["jitter"], None, return_aux=True)
+        n_bad = audit_median_mismatches(depth, ref, aux64, w.N)
+        assert n_bad <= max(1, w.R // 50), f"median depth: {n_bad} audited threshold cases of {w.R} rays"
     else:
         assert_close_out(depth, ref, what="mean depth")
 

@@ -48,4 +48,5 @@ def test_python_binding_names_only_existing_handlers_and_functions():
     doc = (ROOT / "INTEGRATION.md").read_text()
     for m in re.finditer(r"from tensorf_jax import ([\w, ]+)", doc):
         for name in m.group(1).split(","):
+            name = name.split(" as ")[0]
             assert name.strip() in funcs, f"INTEGRATION.md names tensorf_jax.{name.strip()}, which does not exist"
