@@ -228,24 +228,47 @@ def bench_optimizer(ops, dev, params, grads, peak_gbs, reps=10):
     adam_ms = e0.elapsed_time(e1) / reps
     out = {"adam": {"ms": adam_ms, "parameters": n, "GB/s": 28 * n / (adam_ms * 1e-3) / 1e9,
                     "frac_of_hbm_peak": 28 * n / (adam_ms * 1e-3) / 1e9 / peak_gbs, "launches_per_step": 2}}
+    # the same kernel where it is truly DRAM-bound: the final 300^3 grid (17.3 M parameters, 485 MB per step > L2)
+    shapes300 = {"density_vector": (3, 16, 300), "density_matrix": (3, 16, 300, 300), "appearance_vector": (3, 48, 300),
+                 "appearance_matrix": (3, 48, 300, 300)}
+    p3 = [torch.randn(s_, device=dev) * 0.1 for s_ in shapes300.values()]
+    g3 = [torch.randn(s_, device=dev) * 1e-3 for s_ in shapes300.values()]
+    call3 = ops.AdamCall(p3, [torch.zeros_like(x) for x in p3], [torch.zeros_like(x) for x in p3], [-0.02] * 4)
+    n3 = sum(x.numel() for x in p3)
+    for i in range(3):
+        call3.step(g3, count=i)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(reps):
+        call3.step(g3, count=3 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms3 = e0.elapsed_time(e1) / reps
+    out["adam_300"] = {"ms": ms3, "parameters": n3, "GB/s": 28 * n3 / (ms3 * 1e-3) / 1e9, "frac_of_hbm_peak": 28 * n3 / (ms3 * 1e-3) / 1e9 / peak_gbs,
+                       "note": "factors of the 300^3 grid: 485 MB per step, larger than L2 (back-to-back launches, no graph)"}
+    del call3, p3, g3
     G = params["density_vector"].shape[-1]
     G2 = int(round(G * 1.27))
     moved = 0
+    outs, scr = {}, None
     for which in ("density", "appearance"):
         v, m = params[f"{which}_vector"], params[f"{which}_matrix"]
         moved += 4 * (v.numel() + m.numel()) * (1 + (G2 / G) ** 2)
+        outs[which] = (torch.empty((3, v.shape[1], G2), device=dev), torch.empty((3, v.shape[1], G2, G2), device=dev))
+        nb = ops.vm_resize_scratch_bytes(v.shape[1], G, G2)
+        scr = torch.empty(max(nb, scr.numel() if scr is not None else 16), dtype=torch.uint8, device=dev)
     for i in range(2):
-        ops.vm_resize(params["density_vector"], params["density_matrix"], G2)
+        ops.vm_resize(params["density_vector"], params["density_matrix"], G2, out=outs["density"], scratch=scr)
     torch.cuda.synchronize()
     e0.record()
     for i in range(reps):
         for which in ("density", "appearance"):
-            ops.vm_resize(params[f"{which}_vector"], params[f"{which}_matrix"], G2)
+            ops.vm_resize(params[f"{which}_vector"], params[f"{which}_matrix"], G2, out=outs[which], scratch=scr)
     e1.record()
     torch.cuda.synchronize()
     rs_ms = e0.elapsed_time(e1) / reps
     out["resize"] = {"ms": rs_ms, "from": G, "to": G2, "GB/s": moved / (rs_ms * 1e-3) / 1e9,
-                     "note": "includes torch.empty of outputs/scratch per call"}
+                     "note": "both factor sets; outputs and scratch allocated once (TrainState.resize_grid reuses them for params, mu, nu)"}
     return out
 
 
@@ -311,6 +334,25 @@ class TrainBench:
         if self.peer_overlap:
             self.side, self.ev_early, self.ev_done = torch.cuda.Stream(device=dev), torch.cuda.Event(), torch.cuda.Event()
         self.flush = None if args.no_l2_flush else torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+        self.graph, self.graph_loss = None, None
+        self.use_graph = world == 1 and not args.no_graph
+
+    def capture(self):
+        """Single GPU: the whole step (13 launches + 1 memset) as ONE CUDA graph, replayed by the timed loops - the C ABI only
+        enqueues on the caller's stream, so it is capturable as is (stage timers off).  Removes the launch gaps between
+        the kernels (measured: sum of the stages vs ms_per_step)."""
+        if not self.use_graph or self.graph is not None:
+            return
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            self.step_eager()  # warm the capture stream (lazy per-function attributes)
+            with torch.cuda.graph(g, stream=side):
+                self.graph_loss = self.step_eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = g
 
     def describe_exchange(self):
         if self.world == 1:
@@ -321,6 +363,12 @@ class TrainBench:
         return f"rays sharded x{self.world}, NCCL grad allreduce" + (" in two buckets overlapped with the density scatter" if self.overlap else "")
 
     def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+            return self.graph_loss
+        return self.step_eager()
+
+    def step_eager(self):
         call, params, dins, grads, peer, fg = self.call, self.params, self.dins, self.grads, self.peer, self.fg
         if self.peer_overlap:
             rgb, loss = call.forward(params, dins, loss_out=peer.loss)
@@ -367,9 +415,28 @@ class TrainBench:
         synchronize on both sides, max over ranks.  Returns (ms_per_step, launches, {stage: (total ms, calls)}, total ms)."""
         ops = self.ops
         for _ in range(warmup):
-            self.step()
+            self.step_eager()
         self.barrier()
-        ops.profile_enable(True)
+        prof, launches_per_step = None, None
+        if self.use_graph:
+            # per-stage times and the launch count come from a short EAGER loop with the library's stage events on (they
+            # cannot be captured); the timed region below replays the captured graph
+            ops.profile_enable(True)
+            l0 = ops.launch_count()
+            for _ in range(5):
+                if self.flush is not None:
+                    self.flush.zero_()
+                self.step_eager()
+            torch.cuda.synchronize()
+            launches_per_step = (ops.launch_count() - l0) // 5
+            prof = ops.profile_read()
+            ops.profile_enable(False)
+            self.capture()
+            for _ in range(3):
+                self.step()
+            self.barrier()
+        else:
+            ops.profile_enable(True)
         launches0 = ops.launch_count()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         self.barrier()
@@ -380,9 +447,12 @@ class TrainBench:
             self.step()
             ev[i][1].record()
         self.barrier()
-        launches = ops.launch_count() - launches0
-        prof = ops.profile_read()
-        ops.profile_enable(False)
+        if self.use_graph:
+            launches = launches_per_step * steps  # kernels inside the replayed graphs
+        else:
+            launches = ops.launch_count() - launches0
+            prof = ops.profile_read()
+            ops.profile_enable(False)
         total_ms = self.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
         return total_ms / steps, launches, prof, total_ms
 
@@ -483,6 +553,7 @@ def main():
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-config3", action="store_true", help="skip the BASELINE configs[2] sub-record (300^3, 16384 global rays, strong scaling)")
+    ap.add_argument("--no-graph", action="store_true", help="N=1: launch every kernel of a step from the host instead of replaying one CUDA graph")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one exchange after the whole reverse pass")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer-p2p", "peer-multicast", "peer-overlap", "nccl"],
                     help="N>1 gradient exchange: own kernel over peer memory (auto = peer-overlap: two buckets, the early one beside the "
@@ -568,7 +639,7 @@ def main():
         enc = w.encoded_dim()
         mlp_row = 2 * (3 * w.ca * 27 + enc * 128 + 128 * 128 + 128 * 3)
         flops = {"mlp_fwd": mlp_row * w.R * w.K, "mlp_bwd": 2 * mlp_row * w.R * w.K}
-        stages = {k: {"ms": v[0] / max(v[1], 1), "share": v[0] / total_ms} for k, v in prof.items()}
+        stages = {k: {"ms": v[0] / max(v[1], 1), "share": v[0] / max(v[1], 1) / ms_per_step} for k, v in prof.items()}
         traffic_all = {}
         tp = ROOT / "profiles" / "traffic.json"  # per-step ncu numbers of the committed --set full capture (tools/traffic_from_ncu.py)
         if tp.exists():
@@ -613,7 +684,9 @@ def main():
                        "cd": w.cd, "ca": w.ca, "feat_freqs": w.feat_freqs, "view_freqs": w.view_freqs,
                        "contracted": w.contracted, "parallelism": exchange_desc,
                        "l2": "flushed (256 MiB write) between timed steps" if tb.flush is not None else "not flushed",
-                       "timed": "render_rays fwd + MSE + reverse wrt all LearnableParams leaves; Adam excluded",
+                       "timed": "render_rays fwd + MSE + reverse wrt all LearnableParams leaves; Adam excluded" +
+                                ("; the step is captured once and replayed as ONE CUDA graph (stages_ms from a separate eager loop)" if tb.use_graph else ""),
+                       "launch_gap_frac": 1.0 - sum(v_[0] / max(v_[1], 1) for v_ in prof.values()) / ms_per_step,
                        "loss": loss_host},
             "roofline_step": {"bound": "hbm", "achieved": value / world * w.train_bytes_per_ray() / 1e9, "peak": peak, "unit": "GB/s",
                               "frac": value / world * w.train_bytes_per_ray() / 1e9 / peak,

@@ -307,6 +307,11 @@ void tensorf_threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, ui
  * (jax_threefry_partitionable layout), so any (R,N) array is the flat array reshaped. */
 int tensorf_prng_uniform(tensorf_stream_t s, uint32_t k0, uint32_t k1, int64_t n, float minval, float maxval, float* out);
 int tensorf_prng_gumbel(tensorf_stream_t s, uint32_t k0, uint32_t k1, int64_t n, float* out);
+/* Elements [first, first + n) of the same uniform draw: a rank that holds rows [a, b) of a sharded (R,N) jitter
+ * (render.py:158-161 with the ray batch split over ranks) draws first = a*N, n = (b-a)*N and gets exactly its slice of
+ * what the single-device reference draws for the whole batch. */
+int tensorf_prng_uniform_slice(tensorf_stream_t s, uint32_t k0, uint32_t k1, int64_t first, int64_t n, float minval, float maxval,
+                               float* out);
 /* cameras.py:100-143 pixel_rays_wrt_world for image rows [row0,row1): M (HOST, 3x3 row-major) =
  * R_world_camera @ K^-1, origin (HOST, 3) = T_world_camera.translation(); direction = M @ [u,v,1] / (norm + 1e-8).
  * origins, directions ((row1-row0)*W, 3); camera_indices ((row1-row0)*W) or NULL. */

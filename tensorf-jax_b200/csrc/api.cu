@@ -526,6 +526,10 @@ static int render_rgb_bwd_impl(tensorf_stream_t s, const tensorf_render_desc* d,
     rb.go = d_rgb ? d_rgb : w.go;
     rb.d_rgb_sel = w.d_rgb_sel;
     rb.dz = w.dz;
+    if (mlp_impl == TENSORF_MLP_FUSED) {  // the fused MLP reverse carries its gradients scaled by a power of two near 1 / max |d_rgb_sel|
+      rb.amax = mlp_ws_carve(ms, M, w.mlp_base).aux;
+      TF_CHECK_CUDA(cudaMemsetAsync(rb.amax, 0, sizeof(float), st));
+    }
     // the packed gradient accumulators are zeroed by k_ray_bwd's threads (no memset launches)
     rb.zero0 = reinterpret_cast<float4*>(w.gpacked_a);
     rb.zero0_n4 = packed_floats(d->ca, d->G) / 4;
@@ -577,6 +581,7 @@ static int render_rgb_bwd_impl(tensorf_stream_t s, const tensorf_render_desc* d,
       StageTimer t_(st, "mlp_bwd");
       MlpGrads mg = mlp_grads(*grads);
       mg.prezeroed = true;  // by k_ray_bwd above
+      mg.amax_ready = mlp_impl == TENSORF_MLP_FUSED;
       TF_RETURN_IF_ERROR(mlp_bwd_any(mlp_impl, st, ms, mlp_params(*p), w.feat, in->directions,
                                                                                 in->camera_indices, M, d->K, mws, w.rgb_sel,
                                                                                 w.d_rgb_sel, w.d_feat, mg));
@@ -678,7 +683,11 @@ void tensorf_threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, ui
   if (out2) threefry2x32_host(k0, k1, x0, x1, out2);
 }
 int tensorf_prng_uniform(tensorf_stream_t s, uint32_t k0, uint32_t k1, int64_t n, float minval, float maxval, float* out) {
-  return prng_uniform((cudaStream_t)s, k0, k1, n, minval, maxval, out);
+  return prng_uniform((cudaStream_t)s, k0, k1, 0, n, minval, maxval, out);
+}
+int tensorf_prng_uniform_slice(tensorf_stream_t s, uint32_t k0, uint32_t k1, int64_t first, int64_t n, float minval, float maxval,
+                               float* out) {
+  return prng_uniform((cudaStream_t)s, k0, k1, first, n, minval, maxval, out);
 }
 int tensorf_prng_gumbel(tensorf_stream_t s, uint32_t k0, uint32_t k1, int64_t n, float* out) {
   return prng_gumbel((cudaStream_t)s, k0, k1, n, out);

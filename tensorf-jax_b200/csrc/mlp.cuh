@@ -52,6 +52,7 @@ struct MlpParams {
 struct MlpGrads {
   float *w0, *w1, *b1, *w2, *b2, *w3, *b3, *embed;
   bool prezeroed = false;  // the caller already zeroed every leaf on the stream (render reverse: k_ray_bwd does it)
+  bool amax_ready = false; // fused path: max |d_rgb| is already in ws.aux[0] (render reverse: k_ray_bwd computes it)
 };
 
 // rows_per_ray: viewdirs / camera_indices are indexed by row / rows_per_ray (render.py:487-496).

@@ -7,7 +7,7 @@
 namespace tf {
 
 void threefry2x32_host(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t* out2);
-int prng_uniform(cudaStream_t st, uint32_t k0, uint32_t k1, int64_t n, float minval, float maxval, float* out);
+int prng_uniform(cudaStream_t st, uint32_t k0, uint32_t k1, int64_t first, int64_t n, float minval, float maxval, float* out);
 int prng_gumbel(cudaStream_t st, uint32_t k0, uint32_t k1, int64_t n, float* out);
 int pixel_rays(cudaStream_t st, const float* M_host, const float* origin_host, int W, int row0, int row1, uint32_t camera_index,
                float* origins, float* directions, uint32_t* camera_indices);

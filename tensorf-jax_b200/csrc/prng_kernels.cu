@@ -42,20 +42,21 @@ __device__ __forceinline__ float uniform_from_bits(uint32_t bits, float lo, floa
 }
 
 template <bool GUMBEL>
-__global__ void __launch_bounds__(256) k_prng(uint32_t k0, uint32_t k1, int64_t n, float lo, float hi, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_prng(uint32_t k0, uint32_t k1, int64_t first, int64_t n, float lo, float hi, float* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    uint32_t x0 = (uint32_t)((uint64_t)i >> 32), x1 = (uint32_t)i;
+    const uint64_t ctr = (uint64_t)(first + i);  // out[i] = element first + i of the whole draw
+    uint32_t x0 = (uint32_t)(ctr >> 32), x1 = (uint32_t)ctr;
     threefry2x32(k0, k1, x0, x1);
     const float u = uniform_from_bits(x0 ^ x1, lo, hi);
     out[i] = GUMBEL ? -logf(-logf(u)) : u;
   }
 }
 
-int prng_uniform(cudaStream_t st, uint32_t k0, uint32_t k1, int64_t n, float minval, float maxval, float* out) {
-  TF_CHECK_ARG(n >= 0 && (n == 0 || out), "prng_uniform: bad arguments");
+int prng_uniform(cudaStream_t st, uint32_t k0, uint32_t k1, int64_t first, int64_t n, float minval, float maxval, float* out) {
+  TF_CHECK_ARG(n >= 0 && first >= 0 && (n == 0 || out), "prng_uniform: bad arguments");
   if (n == 0) return 0;
   const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(n, 256), (int64_t)kSMs * 16);
-  k_prng<false><<<grid, 256, 0, st>>>(k0, k1, n, minval, maxval, out);
+  k_prng<false><<<grid, 256, 0, st>>>(k0, k1, first, n, minval, maxval, out);
   TF_CHECK_LAUNCH();
   return 0;
 }
@@ -63,7 +64,7 @@ int prng_gumbel(cudaStream_t st, uint32_t k0, uint32_t k1, int64_t n, float* out
   TF_CHECK_ARG(n >= 0 && (n == 0 || out), "prng_gumbel: bad arguments");
   if (n == 0) return 0;
   const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(n, 256), (int64_t)kSMs * 16);
-  k_prng<true><<<grid, 256, 0, st>>>(k0, k1, n, 1.17549435e-38f /* finfo(float32).tiny */, 1.0f, out);
+  k_prng<true><<<grid, 256, 0, st>>>(k0, k1, 0, n, 1.17549435e-38f /* finfo(float32).tiny */, 1.0f, out);
   TF_CHECK_LAUNCH();
   return 0;
 }

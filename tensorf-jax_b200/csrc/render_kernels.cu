@@ -486,6 +486,7 @@ __global__ void __launch_bounds__(128) k_ray_bwd(RayBwdArgs A) {
 
   for (int s = lane; s < Npad; s += 32) q_s[s] = 0.f;
   __syncwarp();
+  float dmax = 0.f;
   for (int k = lane; k < A.K; k += 32) {
     int64_t m = (int64_t)r * A.K + k;
     float pt = A.pt_sel[m];
@@ -493,10 +494,17 @@ __global__ void __launch_bounds__(128) k_ray_bwd(RayBwdArgs A) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float ck = A.rgb_sel[3 * m + c];
-      A.d_rgb_sel[3 * m + c] = go[c] * u * pt;
+      const float dsel = go[c] * u * pt;
+      A.d_rgb_sel[3 * m + c] = dsel;
+      dmax = fmaxf(dmax, fabsf(dsel));
       gpt += go[c] * (u * ck - Wc[c] * AoB2);
     }
     q_s[A.idx[m]] = gpt;
+  }
+  if (A.amax != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    if (lane == 0 && dmax > 0.f) atomicMax(reinterpret_cast<unsigned int*>(A.amax), __float_as_uint(dmax));
   }
   float gE = 0.f;
 #pragma unroll

@@ -58,6 +58,7 @@ struct RayBwdArgs : SceneArgs {
   const float* stats;    // (R,8)
   const float* go;       // (R,3)
   float* d_rgb_sel;      // (M,3)
+  float* amax;           // or null: receives max |d_rgb_sel| (bits, atomicMax; zeroed by the caller) - the fused MLP reverse scales by it
   float* dz;             // (R,N)
   // packed gradient accumulators zeroed by this kernel's threads before their ray work (the stores overlap the
   // latency-bound reverse scan instead of costing two memsets): float4 counts, either may be 0

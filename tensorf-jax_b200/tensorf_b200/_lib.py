@@ -128,6 +128,7 @@ SIGNATURES = {
     "tensorf_vm_resize": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i64]),
     "tensorf_threefry2x32": (None, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]),
     "tensorf_prng_uniform": (_i, [_vp, C.c_uint32, C.c_uint32, _i64, C.c_float, C.c_float, _vp]),
+    "tensorf_prng_uniform_slice": (_i, [_vp, C.c_uint32, C.c_uint32, _i64, _i64, C.c_float, C.c_float, _vp]),
     "tensorf_prng_gumbel": (_i, [_vp, C.c_uint32, C.c_uint32, _i64, _vp]),
     "tensorf_pixel_rays": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _i, _i, _i, C.c_uint32, _vp, _vp, _vp]),
     "tensorf_gather_rays": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),

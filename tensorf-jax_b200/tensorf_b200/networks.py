@@ -72,14 +72,19 @@ class FeatureMlp:
         enc, u = self.encoded_dim(), self.units
 
         def n(shape, var):
-            return torch.randn(shape, generator=prng_key, device=dev) * math.sqrt(var)
+            # flax kaiming_normal / lecun_normal = variance_scaling(..., "truncated_normal"): N(0, 1) truncated to
+            # [-2, 2], scaled by sqrt(var) / 0.87962566 (the truncated distribution's standard deviation)
+            x = torch.empty(shape, device=dev)
+            torch.nn.init.trunc_normal_(x, mean=0.0, std=1.0, a=-2.0, b=2.0, generator=prng_key)
+            return x * (math.sqrt(var) / 0.87962566103423978)
 
         p = {"Dense_0": {"kernel": n((fin, self.feature_squash_dim), 1.0 / fin)},
              "Dense_1": {"kernel": n((enc, u), 2.0 / enc), "bias": torch.zeros(u, device=dev)},
              "Dense_2": {"kernel": n((u, u), 2.0 / u), "bias": torch.zeros(u, device=dev)},
              "Dense_3": {"kernel": n((u, 3), 1.0 / u), "bias": torch.zeros(3, device=dev)}}
         if self.num_cameras is not None:
-            p["Embed_0"] = {"embedding": n((self.num_cameras, u), 1.0 / u)}
+            # flax nn.Embed: variance_scaling(1.0, "fan_in", "normal", out_axis=0) = N(0, 1/units), not truncated
+            p["Embed_0"] = {"embedding": torch.randn((self.num_cameras, u), generator=prng_key, device=dev) * math.sqrt(1.0 / u)}
         return {"params": p}
 
     def apply(self, variables: Dict, features: torch.Tensor, viewdirs: torch.Tensor, camera_indices: torch.Tensor) -> torch.Tensor:

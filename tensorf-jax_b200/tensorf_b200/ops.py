@@ -356,21 +356,35 @@ class AdamCall:
         return self.grad_norm
 
 
-def vm_resize(vector: torch.Tensor, matrix: torch.Tensor, grid_dim: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """tensor_vm.py:183-223: (3,C,G) / (3,C,G,G) -> (3,C,grid_dim) / (3,C,grid_dim,grid_dim)."""
+def vm_resize(vector: torch.Tensor, matrix: torch.Tensor, grid_dim: int, out=None, scratch: Optional[torch.Tensor] = None
+              ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """tensor_vm.py:183-223: (3,C,G) / (3,C,G,G) -> (3,C,grid_dim) / (3,C,grid_dim,grid_dim).  `out` = (vector, matrix)
+    tensors to fill and `scratch` (uint8, `vm_resize_scratch_bytes`) let a caller that resizes several leaves of the same
+    shape (parameters and both Adam moments, training.py:245-276) allocate once."""
     lib = _lib.load()
     three, C_, G = vector.shape
     if three != 3 or tuple(matrix.shape) != (3, C_, G, G):
         raise ValueError(f"vm_resize: vector {tuple(vector.shape)} / matrix {tuple(matrix.shape)} are not a TensorVM")
-    vo = torch.empty((3, C_, grid_dim), dtype=torch.float32, device=vector.device)
-    mo = torch.empty((3, C_, grid_dim, grid_dim), dtype=torch.float32, device=vector.device)
-    nbytes = lib.tensorf_vm_resize_scratch_bytes(C_, G, grid_dim)
-    if nbytes < 0:
-        raise ValueError(f"vm_resize: unsupported shape C={C_} G={G} -> {grid_dim}")
-    scratch = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=vector.device)
+    if out is not None:
+        vo, mo = out
+        if tuple(vo.shape) != (3, C_, grid_dim) or tuple(mo.shape) != (3, C_, grid_dim, grid_dim):
+            raise ValueError("vm_resize: `out` tensors have the wrong shape")
+    else:
+        vo = torch.empty((3, C_, grid_dim), dtype=torch.float32, device=vector.device)
+        mo = torch.empty((3, C_, grid_dim, grid_dim), dtype=torch.float32, device=vector.device)
+    nbytes = vm_resize_scratch_bytes(C_, G, grid_dim)
+    if scratch is None or scratch.numel() < nbytes:
+        scratch = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=vector.device)
     check(lib.tensorf_vm_resize(_stream(), _ptr(vector, name="vector"), _ptr(matrix, name="matrix"), C_, G, grid_dim,
                                 vo.data_ptr(), mo.data_ptr(), scratch.data_ptr(), scratch.numel()))
     return vo, mo
+
+
+def vm_resize_scratch_bytes(C_: int, G: int, grid_dim: int) -> int:
+    nbytes = int(_lib.load().tensorf_vm_resize_scratch_bytes(C_, G, grid_dim))
+    if nbytes < 0:
+        raise ValueError(f"vm_resize: unsupported shape C={C_} G={G} -> {grid_dim}")
+    return nbytes
 
 
 def threefry2x32(k0: int, k1: int, x0: int, x1: int) -> Tuple[int, int]:
@@ -380,10 +394,12 @@ def threefry2x32(k0: int, k1: int, x0: int, x1: int) -> Tuple[int, int]:
     return int(out[0]), int(out[1])
 
 
-def prng_uniform(k0: int, k1: int, shape, device, minval: float = 0.0, maxval: float = 1.0) -> torch.Tensor:
-    """jax.random.uniform(key, shape, float32, minval, maxval) drawn on the device (`tensorf_prng_uniform`)."""
+def prng_uniform(k0: int, k1: int, shape, device, minval: float = 0.0, maxval: float = 1.0, first: int = 0) -> torch.Tensor:
+    """jax.random.uniform(key, shape, float32, minval, maxval) drawn on the device (`tensorf_prng_uniform`); with
+    `first` > 0 the result is elements [first, first + prod(shape)) of a larger flat draw (a rank's row slice of a
+    sharded (R,N) jitter, `tensorf_prng_uniform_slice`)."""
     out = torch.empty(tuple(shape), dtype=torch.float32, device=device)
-    check(_lib.load().tensorf_prng_uniform(_stream(), k0, k1, out.numel(), minval, maxval, out.data_ptr()))
+    check(_lib.load().tensorf_prng_uniform_slice(_stream(), k0, k1, int(first), out.numel(), minval, maxval, out.data_ptr()))
     return out
 
 

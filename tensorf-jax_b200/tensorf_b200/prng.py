@@ -106,11 +106,15 @@ def render_noise(prng_key, ray_count: int, density_samples: int, contracted: boo
         raise TypeError("prng_key must be a tensorf_b200.prng.Key, a RenderNoise, or a JAX key (JAX not importable)") from e
 
 
-def render_noise_device(prng_key: Key, ray_count: int, density_samples: int, contracted: bool, device, need_gumbel: bool = True):
+def render_noise_device(prng_key: Key, ray_count: int, density_samples: int, contracted: bool, device, need_gumbel: bool = True,
+                        first_ray: int = 0):
     """`render_noise` drawn ON THE DEVICE by libtensorf_b200.so (`tensorf_prng_uniform/gumbel`): same keys, same
     counter layout, no host draw and no H2D copy of the (R,N) jitter.  Returns {"jitter": tensor, "gumbel": tensor|None}."""
     from . import ops
     k_sample, k_rgb = split(prng_key)  # render.py:120 (two cipher blocks: stays on the host)
     jshape: Tuple[int, ...] = (ray_count, density_samples) if contracted else (density_samples,)
-    return {"jitter": ops.prng_uniform(k_sample.k0, k_sample.k1, jshape, device),
+    # sharded batches (first_ray = this rank's first row of the global batch): the rank draws ITS rows of the global (R,N)
+    # jitter, so the ranks together reproduce the single-device draw instead of every rank reusing rows [0, R_local)
+    first = first_ray * density_samples if contracted else 0
+    return {"jitter": ops.prng_uniform(k_sample.k0, k_sample.k1, jshape, device, first=first),
             "gumbel": ops.prng_gumbel(k_rgb.k0, k_rgb.k1, (density_samples,), device) if need_gumbel else None}

@@ -74,6 +74,10 @@ _POOL: Dict[tuple, list] = {}
 
 def _acquire(desc, device) -> ops.RenderCall:
     key = (tuple(getattr(desc, f) for f, _ in desc._fields_ if f != "loss_scale"), str(device))
+    # a new grid size (every upsampling step changes G, and with it N and K) retires the workspaces of the old one: they
+    # are 1-8 GB each and would otherwise stay cached for the life of the process
+    for k in [k for k in _POOL if k[1] == str(device) and k[0][3] != desc.G]:
+        del _POOL[k]
     pool = _POOL.setdefault(key, [])
     call = pool.pop() if pool else ops.RenderCall(desc, device)
     call.desc = desc
@@ -111,12 +115,13 @@ def _device_noise(noise: prng.RenderNoise, device) -> Dict[str, torch.Tensor]:
     return out
 
 
-def _noise_inputs(prng_key, ray_count: int, density_samples: int, contracted: bool, need_gumbel: bool, device) -> Dict[str, torch.Tensor]:
+def _noise_inputs(prng_key, ray_count: int, density_samples: int, contracted: bool, need_gumbel: bool, device,
+                  first_ray: int = 0) -> Dict[str, torch.Tensor]:
     """The jitter / Gumbel input arrays of the C ABI for a key.  A `prng.Key` is expanded on the device
     (`tensorf_prng_uniform/gumbel`: no host draw, no H2D copy of the (R,N) jitter); explicit `RenderNoise`
     arrays and JAX keys take the host route."""
     if isinstance(prng_key, prng.Key):
-        d = prng.render_noise_device(prng_key, ray_count, density_samples, contracted, device, need_gumbel)
+        d = prng.render_noise_device(prng_key, ray_count, density_samples, contracted, device, need_gumbel, first_ray=first_ray)
         return {k: v for k, v in d.items() if v is not None}
     return _device_noise(prng.render_noise(prng_key, ray_count, density_samples, contracted, need_gumbel=need_gumbel), device)
 

@@ -45,12 +45,24 @@ class TrainState:
     _peer: Optional[object] = dataclasses.field(default=None, repr=False, compare=False)  # dist.PeerAdam
     _fg: Optional[object] = dataclasses.field(default=None, repr=False, compare=False)    # dist.FlatGrads (world_size > 1)
 
+    @property
+    def rank(self) -> int:
+        """This process's position in the sharded ray batch (0 when not distributed)."""
+        import torch.distributed as dist
+        return dist.get_rank() if (self.world_size > 1 and dist.is_available() and dist.is_initialized()) else 0
+
     @staticmethod
     def initialize(config: train_config.TensorfConfig, grid_dim: int, prng_key, num_cameras: int,
                    device="cuda", world_size: int = 1) -> "TrainState":
-        """training.py:35-99."""
-        seed = prng_key if isinstance(prng_key, int) else 0
-        gen = torch.Generator(device=device).manual_seed(seed)
+        """training.py:35-99.  The initial values come from a torch generator seeded from the key (every rank must pass
+        the same key): the distributions are the reference's (networks.py:9-10 variance-scaling truncated normals,
+        N(0, 0.1^2) factors), the random streams are torch's, not jax.random's."""
+        if isinstance(prng_key, prng.Key):  # split(key, 5)[0] as training.py:44-60 does for the first sub-key; its words seed torch
+            k = prng.split(prng_key, 5)[0]
+            seed = (int(k.k0) << 32) | int(k.k1)
+        else:
+            seed = int(prng_key)
+        gen = torch.Generator(device=device).manual_seed(seed & ((1 << 63) - 1))
         mlp = networks.FeatureMlp(feature_n_freqs=config.feature_n_freqs, viewdir_n_freqs=config.viewdir_n_freqs,
                                   num_cameras=num_cameras if config.camera_embeddings else None)
         dummy = torch.zeros((1, config.appearance_feat_dim * 3), device=device)
@@ -95,7 +107,8 @@ class TrainState:
         inputs = {"origins": rays.origins.contiguous(), "directions": rays.directions.contiguous(),
                   "camera_indices": rays.camera_indices.to(torch.int32).contiguous(), "aabb": self.aabb,
                   "colors": minibatch.colors.contiguous()}
-        inputs.update(render._noise_inputs(render_prng_key, R, N, self.config.scene_contraction, True, dev))
+        # sharded batches: rank r owns rows [r*R, (r+1)*R) of the global batch and draws those rows of the global jitter
+        inputs.update(render._noise_inputs(render_prng_key, R, N, self.config.scene_contraction, True, dev, first_ray=self.rank * R))
         if self.config.scene_contraction:
             base, delta = render.contracted_schedule(self.config.render_near, self.config.render_far, N)
             inputs["base_ts"], inputs["deltas"] = torch.from_numpy(base).to(dev), torch.from_numpy(delta).to(dev)

@@ -34,12 +34,8 @@ def _x_perm():
     """Kernel column order of the encoded MLP input (csrc/mlp_fused.cu, fz::perm): kernel column -> reference column."""
     out = []
     for kp in range(160):
-        s, e = divmod(kp, 80)
-        if e >= 75:
-            out.append(-1)
-            continue
-        d, v = 15 * s + e // 5, e % 5
-        out.append(d if v == 0 else 30 + 4 * d + (v - 1))
+        d, v = 8 * (kp // 40) + (kp % 40) // 5, kp % 5
+        out.append(-1 if d >= 30 else d if v == 0 else 30 + 4 * d + (v - 1))
     return np.array(out)
 
 
@@ -90,7 +86,7 @@ def test_fused_mlp_forward(cuda, ca, rays, rpr, inference):
     rgb = call.forward(params, T(feat, device=cuda), T(vd, device=cuda), None, rpr)
     torch.cuda.synchronize()
     assert_close_out(rgb.cpu().numpy(), ref.numpy(), what="fused mlp rgb")
-    assert np.abs(rgb.cpu().numpy() - ref.numpy()).max() < 2e-6
+    assert np.abs(rgb.cpu().numpy() - ref.numpy()).max() < 5e-6
     if inference:
         return
     off = (C.c_int64 * 10)()
@@ -103,13 +99,12 @@ def test_fused_mlp_forward(cuda, ca, rays, rpr, inference):
         h1_ref = np.maximum(aux["z1"].numpy(), 0)
         h2_ref = np.maximum(aux["z2"].numpy(), 0)
     fs = ws[off[0]: off[0] + tiles * 4096].reshape(tiles, 8, 128, 4).transpose(0, 2, 1, 3).reshape(tiles * 128, 32)[:M]
-    sq = [n for n in range(32) if n < 15 or 16 <= n < 28]  # kernel column order of the squashed features (fz::sq_nat)
-    assert np.abs(fs[:, sq] - f_ref).max() < 2e-6 * max(1.0, np.abs(f_ref).max())
-    assert np.all(fs[:, 15] == 0) and np.all(fs[:, 28:] == 0)
+    assert np.abs(fs[:, :27] - f_ref).max() < 2e-6 * max(1.0, np.abs(f_ref).max())
+    assert np.all(fs[:, 27:] == 0)
     xs = _unslab(ws[off[2]:].view(np.uint8), tiles, 160)[:M]
     perm = _x_perm()
     assert np.abs(xs[:, perm >= 0] - x_ref[:, perm[perm >= 0]]).max() < 3e-6
-    assert np.all(xs[:, 75] == 1.0) and np.all(xs[:, 76:80] == 0) and np.all(xs[:, 155:] == 0)
+    assert np.all(xs[:, 150] == 1.0) and np.all(xs[:, 151:] == 0)
     h1 = _unslab(ws[off[4]:].view(np.uint8), tiles, 128)[:M]
     h2 = _unslab(ws[off[5]:].view(np.uint8), tiles, 128)[:M]
     assert np.abs(h1 - h1_ref).max() < 5e-6 * max(1.0, np.abs(h1_ref).max())

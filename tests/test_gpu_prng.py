@@ -85,3 +85,19 @@ def test_pixel_rays_match_oracle(cuda, W, H):
     assert abs(cam.compute_fov_x_radians() - 0.6911) < 1e-6
     small = cam.resize_with_fixed_fov(max(W // 2, 1), max(H // 2, 1))
     assert abs(small.compute_fov_x_radians() - 0.6911) < 1e-5
+
+
+def test_uniform_slice_is_the_rows_of_the_whole_draw(cuda):
+    """A rank of a sharded contracted-scene batch draws ITS rows of the global (R,N) jitter (render.py:158-161):
+    `tensorf_prng_uniform_slice` must give exactly the corresponding elements of the single-device draw."""
+    from tensorf_b200 import ops, prng
+    key = prng.Key.from_seed(11)
+    R, N = 37, 53
+    whole = ops.prng_uniform(key.k0, key.k1, (R, N), cuda)
+    for a, b in ((0, 9), (9, 30), (30, 37)):
+        part = ops.prng_uniform(key.k0, key.k1, (b - a, N), cuda, first=a * N)
+        assert torch.equal(part, whole[a:b])
+    d0 = prng.render_noise_device(key, 10, N, True, cuda, need_gumbel=False, first_ray=0)["jitter"]
+    d1 = prng.render_noise_device(key, 10, N, True, cuda, need_gumbel=False, first_ray=10)["jitter"]
+    both = prng.render_noise_device(key, 20, N, True, cuda, need_gumbel=False)["jitter"]
+    assert torch.equal(torch.cat([d0, d1]), both)

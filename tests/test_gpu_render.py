@@ -22,7 +22,7 @@ ODD = S.Workload("odd", 33, 11, 5, 6, 50, 50, 1, 3)  # cd, ca not multiples of 4
 DOZER_S = S.Workload("dozer_s", 48, 16, 32, 48, 90, 13, 6, 6, contracted=True, num_cameras=7)
 DOZER_T = S.Workload("dozer_t", 40, 9, 4, 3, 41, 6, 2, 2, contracted=True, num_cameras=None)
 FUSED_S = S.Workload("fused_s", 96, 12, 4, 16, 45, 7, 2, 2)  # 3*ca = 48: smallest shape family of the fused MLP kernels
-FUSED_C = S.Workload("fused_c", 40, 9, 4, 32, 41, 6, 2, 2, contracted=True, num_cameras=None)
+FUSED_C = S.Workload("fused_c", 64, 10, 4, 32, 43, 6, 2, 2, contracted=True, num_cameras=None)
 
 
 # BASELINE.json shapes at grid_dim_final = 300 (training.py:115-118, render_360.py:43-51) on a ray slice the fp64 oracle
