@@ -87,7 +87,7 @@ static RenderWs carve(const tensorf_render_desc& d, float* base) {
   w.pt_sel = take(M);
   w.stats = take(R * 8);
   w.go = take(R * 3);
-  w.feat = take(M * ms.Ca);
+  w.feat = take(round_up64(M, 128) * ms.Ca);  // fused MLP: fp16 slab tiles of 128 rows (same bytes per row as fp32)
   w.d_feat = take(M * ms.Ca);
   w.rgb_sel = take(M * 3);
   w.d_rgb_sel = take(M * 3);
@@ -464,10 +464,12 @@ int tensorf_render_rgb_fwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   ap.feat = w.feat;
   {
     StageTimer t_(st, "appearance_gather");
+    ap.feat_slabs = mlp_impl == TENSORF_MLP_FUSED;  // the fused MLP kernels take the rows as two-term fp16 slab tiles
     TF_RETURN_IF_ERROR(launch_appearance(st, ap, false));
   }
 
   MlpWs mws = mlp_ws_carve(ms, M, w.mlp_base);
+  if (mlp_impl == TENSORF_MLP_FUSED) mws.feat_slabs = reinterpret_cast<const unsigned char*>(w.feat);  // written by k_appearance
   {
     StageTimer t_(st, "mlp_fwd");
     TF_RETURN_IF_ERROR(mlp_fwd_any(mlp_impl, st, ms, mlp_params(*p), w.feat, in->directions,
@@ -577,6 +579,7 @@ static int render_rgb_bwd_impl(tensorf_stream_t s, const tensorf_render_desc* d,
 
   if (do_app) {
     MlpWs mws = mlp_ws_carve(ms, M, w.mlp_base);
+    if (mlp_impl == TENSORF_MLP_FUSED) mws.feat_slabs = reinterpret_cast<const unsigned char*>(w.feat);  // written by k_appearance
     {
       StageTimer t_(st, "mlp_bwd");
       MlpGrads mg = mlp_grads(*grads);

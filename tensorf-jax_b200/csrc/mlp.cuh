@@ -42,6 +42,9 @@ struct MlpWs {
   float* df;   // (M, squash)
   uint32_t* bits1;  // (M, units/32) ReLU mask of layer 1, one bit per unit (tensor-core path); layer 2's follow (fused path)
   float* aux;       // fused path: [64] scalars (gradient scale), then the d(output) slab tiles (M, 16)
+  float* wg_partial;  // fused path: per-CTA partial weight-gradient accumulators [min(tiles, 148)][320 + 3ca][128]
+  const unsigned char* feat_slabs = nullptr;  // fused path: the feature rows already as slab tiles (render path: written by
+                                              // k_appearance); null = `feat` is fp32 (M, 3ca) and is converted into `dx`
 };
 int64_t mlp_ws_floats(const MlpShape& s, int64_t M);
 MlpWs mlp_ws_carve(const MlpShape& s, int64_t M, float* base);

@@ -150,9 +150,9 @@ int umma_probe(cudaStream_t st, const float* A, const float* B, float* D, int N,
 // ===============================================================================================================
 namespace fz {
 constexpr int kU = 128, kSq = 27, kQDims = 8, kPer = 5, kXQ = 40, kX = 160, kOnesCol = 150;
-constexpr int kWorkWarps = 16, kConvWarp0 = 16, kMmaWarp = 20, kLoadWarp = 21, kThreads = 704;
-constexpr int kRawSlots = 3, kRawBytes = 128 * 32 * 4, kHeader = 8192;
-constexpr uint32_t kAcc0 = 0, kAcc1 = 128, kAop = 256, kAopLo = 80;  // tensor-memory columns
+constexpr int kWorkWarps = 16, kMmaWarp = 16, kLoadWarp = 17, kThreads = 576;
+constexpr int kRawSlots = 3, kRawBytes = 128 * 32 * 4, kHeader = 8192;  // feature ring: pieces of 32 columns (4 column groups x hi, lo slab)
+constexpr uint32_t kAccX = 0, kAccY = 128, kAop = 256, kAopLo = 80, kAccD0 = 416;  // tensor-memory columns (Dense_0: 2 x 32 at kAccD0)
 constexpr uint32_t kB1Bytes = 2u * kX * kU * 2u, kB2Bytes = 2u * kU * kU * 2u;
 // kernel column 40*q + 5*i + v of x' (source dimension d = 8*q + i; d = 30, 31 are padding, column 150 is the constant 1)
 // -> column of the reference's [f, v, enc(f), enc(v)] (networks.py:68-76), or -1
@@ -221,7 +221,8 @@ struct FusedFwdArgs {
   int K0;  // 3*ca
   float* rgb;
   // residuals of the reverse pass (TRAIN): slab tiles per 128-row tile, ReLU masks, Dense_0 output
-  unsigned char *xs, *h1s, *h2s, *feats;
+  const unsigned char* feats;  // feature rows as slab tiles
+  unsigned char *xs, *h1s, *h2s;
   float* fs;
   uint32_t *bits1, *bits2;
 };
@@ -363,33 +364,38 @@ __device__ __forceinline__ void fused_fwd_worker(const FusedFwdArgs& g, uint32_t
   const int64_t ntiles = (g.M + 127) / 128;
   const int row = quad * 32 + lane;
   const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+  const uint32_t accX = lane_base + fz::kAccX, accY = lane_base + fz::kAccY, aop = lane_base + fz::kAop;
+  // Dense_0 accumulator of tile number `it` -> x' (the MMA warp runs Dense_0 one tile ahead)
+  auto encode = [&](int64_t t, uint32_t it) {
+    mbar_wait(&accfull[0], it & 1, 10);
+    tc_fence_after();
+    fused_epi0<Q, TRAIN>(g, lane_base + fz::kAccD0 + 32u * (it & 1), aop, t * 128 + row, t, row, xready, lane);
+  };
   uint32_t it = 0;
+  if ((int64_t)blockIdx.x < ntiles) encode(blockIdx.x, 0);
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-    const uint32_t accA = lane_base + ((it & 1) ? fz::kAcc1 : fz::kAcc0), accB = lane_base + ((it & 1) ? fz::kAcc0 : fz::kAcc1);
-    const uint32_t aop = lane_base + fz::kAop;
     const int64_t m = t * 128 + row;
     const uint32_t ph = it & 1;
-    // Dense_0 -> x'
-    mbar_wait(&accfull[0], ph, 10);
-    tc_fence_after();
-    fused_epi0<Q, TRAIN>(g, accA, aop, m, t, row, xready, lane);
     // Dense_1 -> h1
     mbar_wait(&accfull[1], ph, 11);
     tc_fence_after();
-    fused_epi_hidden<Q, TRAIN, false>(accB, aop, s_b1, s_w3, TRAIN ? g.h1s + (size_t)t * (fz::kU * 512) + (size_t)row * 16 : nullptr,
+    fused_epi_hidden<Q, TRAIN, false>(accX, aop, s_b1, s_w3, TRAIN ? g.h1s + (size_t)t * (fz::kU * 512) + (size_t)row * 16 : nullptr,
                                       TRAIN ? g.bits1 + m * 4 : nullptr, kready, lane, nullptr);
-    // Dense_2 -> h2 -> Dense_3 + sigmoid
+    // Dense_2 complete: h1 in the operand region is dead.  The NEXT tile's x' goes in first, so that its Dense_1 runs on
+    // the tensor pipe while this tile's output layer is evaluated on the CUDA cores.
     float o3[3] = {0.f, 0.f, 0.f};
     mbar_wait(&accfull[2], ph, 12);
     tc_fence_after();
-    fused_epi_hidden<Q, TRAIN, true>(accA, aop, s_b2, s_w3, TRAIN ? g.h2s + (size_t)t * (fz::kU * 512) + (size_t)row * 16 : nullptr,
+    if (t + gridDim.x < ntiles) encode(t + gridDim.x, it + 1);
+    // Dense_2 -> h2 -> Dense_3 + sigmoid
+    fused_epi_hidden<Q, TRAIN, true>(accY, aop, s_b2, s_w3, TRAIN ? g.h2s + (size_t)t * (fz::kU * 512) + (size_t)row * 16 : nullptr,
                                      TRAIN ? g.bits2 + m * 4 : nullptr, kready, lane, o3);
     tc_fence_before();
     if (Q != 0) {
       float* sp = s_part + (Q - 1) * 384 + 3 * row;
       sp[0] = o3[0]; sp[1] = o3[1]; sp[2] = o3[2];
     }
-    asm volatile("bar.sync 1, 512;" ::: "memory");
+    asm volatile("bar.sync 1, 512;" ::: "memory");  // also: every quarter has read accumulator Y before the next Dense_2 can start
     if (Q == 0 && m < g.M) {
 #pragma unroll
       for (int c = 0; c < 3; ++c)
@@ -399,14 +405,14 @@ __device__ __forceinline__ void fused_fwd_worker(const FusedFwdArgs& g, uint32_t
 }
 
 template <bool TRAIN>
-__global__ void __launch_bounds__(fz::kThreads, 1) k_mlp_fused_fwd(FusedFwdArgs g, const __grid_constant__ CUtensorMap tmapA) {
+__global__ void __launch_bounds__(fz::kThreads, 1) k_mlp_fused_fwd(FusedFwdArgs g) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint64_t* wfull = reinterpret_cast<uint64_t*>(smem);
-  uint64_t* rfull = wfull + 1;               // [kRawSlots]
-  uint64_t* rempty = rfull + fz::kRawSlots;  // [kRawSlots]
-  uint64_t* kready = rempty + fz::kRawSlots; // [10] feature chunks (Dense_0, 4 converter warps) / h1 chunks (Dense_2, one quarter)
-  uint64_t* xready = kready + 10;            // [10] x' chunks (Dense_1): one or two quarters each
+  uint64_t* rfull = wfull + 1;               // [kRawSlots] feature piece landed (bulk copy tx bytes)
+  uint64_t* rempty = rfull + fz::kRawSlots;  // [kRawSlots] Dense_0 MMAs have read the piece (tcgen05.commit)
+  uint64_t* kready = rempty + fz::kRawSlots; // [8]  h1 chunks (Dense_2's A operand): one quarter each
+  uint64_t* xready = kready + 8;             // [10] x' chunks (Dense_1's A operand): one or two quarters each
   uint64_t* accfull = xready + 10;           // [3]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 3);
   float* s_b1 = reinterpret_cast<float*>(smem + 512);
@@ -416,7 +422,7 @@ __global__ void __launch_bounds__(fz::kThreads, 1) k_mlp_fused_fwd(FusedFwdArgs 
   const uint32_t wbytes = fz::b0_bytes(g.K0) + fz::kB1Bytes + fz::kB2Bytes;
   unsigned char* sW = smem + fz::kHeader;
   unsigned char* raw0 = smem + ((fz::kHeader + wbytes + 1023u) & ~1023u);
-  const int nk0 = g.K0 / 16, nbox = (g.K0 + 31) / 32;
+  const int nk0 = g.K0 / 16, npiece = (g.K0 + 31) / 32;
   const int64_t ntiles = (g.M + 127) / 128;
   const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
@@ -424,12 +430,10 @@ __global__ void __launch_bounds__(fz::kThreads, 1) k_mlp_fused_fwd(FusedFwdArgs 
     mbar_init(wfull, 1);
     for (int r = 0; r < fz::kRawSlots; ++r) {
       mbar_init(&rfull[r], 1);
-      mbar_init(&rempty[r], 4);
+      mbar_init(&rempty[r], 1);
     }
-    for (int c = 0; c < 10; ++c) {
-      mbar_init(&kready[c], 4);
-      mbar_init(&xready[c], fz::x_chunk_warps(c));
-    }
+    for (int c = 0; c < 8; ++c) mbar_init(&kready[c], 4);
+    for (int c = 0; c < 10; ++c) mbar_init(&xready[c], fz::x_chunk_warps(c));
     for (int l = 0; l < 3; ++l) mbar_init(&accfull[l], 1);
     fence_barrier_init();
   }
@@ -452,71 +456,20 @@ __global__ void __launch_bounds__(fz::kThreads, 1) k_mlp_fused_fwd(FusedFwdArgs 
       case 2: fused_fwd_worker<2, TRAIN>(g, tmem, warp & 3, lane, xready, kready, accfull, s_b1, s_b2, s_w3, s_part); break;
       default: fused_fwd_worker<3, TRAIN>(g, tmem, warp & 3, lane, xready, kready, accfull, s_b1, s_b2, s_w3, s_part); break;
     }
-  } else if (warp < fz::kMmaWarp) {
-    // ================= converters: raw fp32 feature rows (TMA ring) -> Dense_0's A operand in tensor memory =============
-    const int quad = warp - fz::kConvWarp0, row = quad * 32 + lane;
-    const uint32_t aop = tmem + ((uint32_t)(quad * 32) << 16) + fz::kAop;
-    const uint32_t raw_s = smem_u32(raw0);
-    uint32_t sl = 0, rph = 0;
-    for (int64_t it = 0; it < my_tiles; ++it) {
-      if (it > 0) {  // operand region free: the previous tile's Dense_2 has read it
-        mbar_wait(&accfull[2], (uint32_t)(it - 1) & 1, 20);
-        tc_fence_after();
-      }
-      for (int b = 0; b < nbox; ++b) {
-        mbar_wait(&rfull[sl], rph, 21);
-        const uint32_t rrow = raw_s + sl * fz::kRawBytes + row * 128;
-        const int64_t t = blockIdx.x + it * gridDim.x;
-        uint4* fslab = TRAIN ? reinterpret_cast<uint4*>(g.feats + (size_t)t * ((size_t)g.K0 * 512) + (size_t)(8 * b) * 2048 + (size_t)row * 16) : nullptr;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {  // the box's two 16-column k-chunks
-          float x[16];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float4 v = lds128(rrow + (((4 * h + u) ^ (row & 7)) << 4));
-            x[4 * u] = v.x; x[4 * u + 1] = v.y; x[4 * u + 2] = v.z; x[4 * u + 3] = v.w;
-          }
-          uint32_t hi[8], lo[8];
-          split16(x, hi, lo);
-          if (h == 1) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&rempty[sl]);  // after the values were consumed (see k_tc_rowgemm)
-          }
-          const int c = 2 * b + h;
-          if (c < nk0) {
-            if (TRAIN) {  // the weight-gradient kernel reads the features as slab tiles: column groups 2c, 2c + 1
-              fslab[(4 * h) * 128] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              fslab[(4 * h + 1) * 128] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-              fslab[(4 * h + 2) * 128] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-              fslab[(4 * h + 3) * 128] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-            }
-            tmem_st8(aop + 8u * c, hi);
-            tmem_st8(aop + fz::kAopLo + 8u * c, lo);
-          }
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&kready[2 * b]);
-          if (2 * b + 1 < nk0) mbar_arrive(&kready[2 * b + 1]);
-        }
-        if (++sl == fz::kRawSlots) { sl = 0; rph ^= 1; }
-      }
-    }
   } else if (warp == fz::kLoadWarp) {
-    // ================= loader: weights once, then one TMA box (128 rows x 32 columns) per feature chunk =================
+    // ================= loader: weights once, then the feature tile of every row tile in 16 KB pieces (32 columns) =============
     if (lane == 0) {
       mbar_arrive_expect_tx(wfull, wbytes);
       for (uint32_t off = 0; off < wbytes; off += 16384u)
         bulk_copy_g2s(sW + off, g.wpack + off, min(16384u, wbytes - off), wfull);
       uint32_t sl = 0, ph = 0;
       for (int64_t it = 0; it < my_tiles; ++it) {
-        const int64_t t = blockIdx.x + it * gridDim.x;
-        for (int b = 0; b < nbox; ++b) {
+        const unsigned char* tile = g.feats + (size_t)(blockIdx.x + it * gridDim.x) * ((size_t)g.K0 * 512);
+        for (int p = 0; p < npiece; ++p) {
+          const uint32_t bytes = (uint32_t)min(32, g.K0 - 32 * p) * 512u;
           mbar_wait(&rempty[sl], ph ^ 1, 30);
-          mbar_arrive_expect_tx(&rfull[sl], fz::kRawBytes);
-          tma_load_2d(raw0 + (size_t)sl * fz::kRawBytes, &tmapA, b * 32, (int)(t * 128), &rfull[sl]);
+          mbar_arrive_expect_tx(&rfull[sl], bytes);
+          bulk_copy_g2s(raw0 + (size_t)sl * fz::kRawBytes, tile + (size_t)p * fz::kRawBytes, bytes, &rfull[sl]);
           if (++sl == fz::kRawSlots) { sl = 0; ph ^= 1; }
         }
       }
@@ -525,41 +478,56 @@ __global__ void __launch_bounds__(fz::kThreads, 1) k_mlp_fused_fwd(FusedFwdArgs 
     // ================= MMA issuer (warp-uniform loop, one elected lane issues) =================
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t idesc0 = make_idesc(128, 32, FMT_F16, FMT_F16, 0, 0), idesc1 = make_idesc(128, 128, FMT_F16, FMT_F16, 0, 0);
-    const uint32_t sw = smem_u32(sW);
+    const uint32_t sw = smem_u32(sW), sr = smem_u32(raw0);
     const uint32_t b0_lo = desc_lo(sw, 2u * slab_bytes(32)), b1_lo = desc_lo(sw + fz::b0_bytes(g.K0), 2u * slab_bytes(128)),
                    b2_lo = desc_lo(sw + fz::b0_bytes(g.K0) + fz::kB1Bytes, 2u * slab_bytes(128));
-    const uint32_t b_hi = desc_hi(128u);
+    const uint32_t b_hi = desc_hi(128u);  // K-major slabs: 8-row group stride 128 B (A tiles of 128 rows use the same high word)
     const uint32_t t32 = slab_bytes(32) >> 4, s32 = (4u * slab_bytes(32)) >> 4, t128 = slab_bytes(128) >> 4, s128 = (4u * slab_bytes(128)) >> 4;
-    const uint32_t aop = tm + fz::kAop;
-    uint32_t kph = 0, xph = 0;
-    mbar_wait(wfull, 0, 40);
-    for (int64_t it = 0; it < my_tiles; ++it) {
-      const uint32_t accA = tm + ((it & 1) ? fz::kAcc1 : fz::kAcc0), accB = tm + ((it & 1) ? fz::kAcc0 : fz::kAcc1);
-      for (int c = 0; c < nk0; ++c) {  // Dense_0
-        mbar_wait(&kready[c], (kph >> c) & 1u, 41);
-        kph ^= 1u << c;
+    const uint32_t aop = tm + fz::kAop, accX = tm + fz::kAccX, accY = tm + fz::kAccY;
+    uint32_t kph = 0, xph = 0, sl = 0, rph = 0;
+    // Dense_0 of tile `it`: A = the feature pieces in the shared-memory ring (K-major slab tiles), one 32-column accumulator per
+    // tile parity.  It is issued one tile AHEAD (between Dense_1 and Dense_2 of the previous tile), so the features of the
+    // next tile are multiplied while the workers are busy with this one.
+    auto dense0 = [&](int64_t it) {
+      const uint32_t acc = tm + fz::kAccD0 + 32u * (uint32_t)(it & 1);
+      for (int p = 0; p < npiece; ++p) {
+        mbar_wait(&rfull[sl], rph, 41);
         tc_fence_after();
-        if (elect_one()) umma_ts_split2(accA, aop + 8u * c, fz::kAopLo, b0_lo + c * s32, t32, b_hi, idesc0, c == 0);
+        const uint32_t a_lo = desc_lo(sr + sl * fz::kRawBytes, 2u * slab_bytes(128));
+        if (elect_one()) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = 2 * p + h;
+            if (c < nk0) umma_ss_split2(acc, a_lo + h * s128, t128, b_hi, b0_lo + c * s32, t32, b_hi, idesc0, c == 0);
+          }
+          umma_commit(&rempty[sl]);
+        }
         __syncwarp();
+        if (++sl == fz::kRawSlots) { sl = 0; rph ^= 1; }
       }
       if (elect_one()) umma_commit(&accfull[0]);
       __syncwarp();
+    };
+    mbar_wait(wfull, 0, 40);
+    dense0(0);
+    for (int64_t it = 0; it < my_tiles; ++it) {
       for (int i = 0; i < 10; ++i) {  // Dense_1: chunks roughly in the order the four quarters complete them
         const int c = (0x7294618350ull >> (4 * i)) & 15;  // 0,5,3,8,1,6,4,9,2,7
         mbar_wait(&xready[c], (xph >> c) & 1u, 42);
         xph ^= 1u << c;
         tc_fence_after();
-        if (elect_one()) umma_ts_split2(accB, aop + 8u * c, fz::kAopLo, b1_lo + c * s128, t128, b_hi, idesc1, i == 0);
+        if (elect_one()) umma_ts_split2(accX, aop + 8u * c, fz::kAopLo, b1_lo + c * s128, t128, b_hi, idesc1, i == 0);
         __syncwarp();
       }
       if (elect_one()) umma_commit(&accfull[1]);
       __syncwarp();
+      if (it + 1 < my_tiles) dense0(it + 1);
       for (int i = 0; i < 8; ++i) {  // Dense_2: quarter q completes chunk 2q, then 2q + 1
         const int c = (i & 3) * 2 + (i >> 2);
         mbar_wait(&kready[c], (kph >> c) & 1u, 43);
         kph ^= 1u << c;
         tc_fence_after();
-        if (elect_one()) umma_ts_split2(accA, aop + 8u * c, fz::kAopLo, b2_lo + c * s128, t128, b_hi, idesc1, i == 0);
+        if (elect_one()) umma_ts_split2(accY, aop + 8u * c, fz::kAopLo, b2_lo + c * s128, t128, b_hi, idesc1, i == 0);
         __syncwarp();
       }
       if (elect_one()) umma_commit(&accfull[2]);
@@ -573,6 +541,23 @@ __global__ void __launch_bounds__(fz::kThreads, 1) k_mlp_fused_fwd(FusedFwdArgs 
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
+}
+
+// fp32 feature rows (M, K0) -> slab tiles (standalone tensorf_mlp_fwd; the render path's k_appearance writes slabs itself)
+__global__ void __launch_bounds__(256) k_feat_to_slab(const float* feat, int64_t M, int K0, unsigned char* out) {
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (row, column group)
+  const int ncg = K0 / 8;
+  const int64_t m = item / ncg;
+  const int cg = (int)(item % ncg);
+  if (m >= round_up64(M, 128)) return;
+  float x[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) x[q] = m < M ? feat[m * K0 + cg * 8 + q] : 0.f;
+  uint4 hi, lo;
+  split8_fmt<FMT_F16>(x, hi, lo);
+  unsigned char* tile = out + (m >> 7) * ((int64_t)K0 * 512) + (m & 127) * 16;
+  *reinterpret_cast<uint4*>(tile + (int64_t)(2 * cg) * 2048) = hi;
+  *reinterpret_cast<uint4*>(tile + (int64_t)(2 * cg + 1) * 2048) = lo;
 }
 
 int mlp_fused_pack(cudaStream_t st, const MlpShape& s, const MlpParams& p, const MlpWs& ws) {
@@ -590,12 +575,17 @@ int mlp_fused_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const 
   (void)cams;
   if (M == 0) return 0;
   TF_RETURN_IF_ERROR(mlp_fused_pack(st, s, p, ws));
-  CUtensorMap tm;
-  memset(&tm, 0, sizeof(tm));
-  TF_CHECK_ARG(tc_make_a_tensor_map(&tm, feat, M, s.Ca, s.Ca, 32), "fused MLP: features must be 16-byte aligned (tensor map)");
+  const unsigned char* slabs = ws.feat_slabs;
+  if (slabs == nullptr) {  // fp32 rows from the caller: convert once (the reverse pass reads the same tiles)
+    unsigned char* out = reinterpret_cast<unsigned char*>(ws.dx);
+    const int64_t items = round_up64(M, 128) * (s.Ca / 8);
+    k_feat_to_slab<<<(unsigned)ceil_div64(items, 256), 256, 0, st>>>(feat, M, s.Ca, out);
+    TF_CHECK_LAUNCH();
+    slabs = out;
+  }
   FusedFwdArgs g{};
   g.wpack = ws.wpack; g.b1 = p.b1; g.b2 = p.b2; g.w3 = p.w3; g.b3 = p.b3;
-  g.viewdirs = viewdirs; g.rows_per_ray = rows_per_ray; g.M = M; g.K0 = s.Ca; g.rgb = rgb;
+  g.viewdirs = viewdirs; g.rows_per_ray = rows_per_ray; g.M = M; g.K0 = s.Ca; g.rgb = rgb; g.feats = slabs;
   const bool train = !s.inference;
   if (train) {
     g.xs = reinterpret_cast<unsigned char*>(ws.x);
@@ -604,22 +594,20 @@ int mlp_fused_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const 
     g.fs = ws.f;
     g.bits1 = ws.bits1;
     g.bits2 = ws.bits1 + round_up64(M, 128) * 4;
-    g.feats = reinterpret_cast<unsigned char*>(ws.dx);
   }
   const size_t smem = ((fz::kHeader + mlp_fused_wpack_bytes(s) + 1023) & ~(size_t)1023) + (size_t)fz::kRawSlots * fz::kRawBytes;
   TF_CHECK_ARG(smem <= 227 * 1024, "fused MLP: shared memory budget exceeded");
   const unsigned grid = (unsigned)std::min<int64_t>((M + 127) / 128, kSMs);
   if (train) {
     TF_CHECK_CUDA(cudaFuncSetAttribute(k_mlp_fused_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_mlp_fused_fwd<true><<<grid, fz::kThreads, smem, st>>>(g, tm);
+    k_mlp_fused_fwd<true><<<grid, fz::kThreads, smem, st>>>(g);
   } else {
     TF_CHECK_CUDA(cudaFuncSetAttribute(k_mlp_fused_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_mlp_fused_fwd<false><<<grid, fz::kThreads, smem, st>>>(g, tm);
+    k_mlp_fused_fwd<false><<<grid, fz::kThreads, smem, st>>>(g);
   }
   TF_CHECK_LAUNCH();
   return 0;
 }
-
 
 // ===============================================================================================================
 // Reverse pass, kernel 1 of 2: the activation-gradient chain of one 128-row tile,
@@ -673,19 +661,17 @@ __device__ __forceinline__ void store_chunk_slab(unsigned char* slab_row, int c,
 
 template <int Q>
 __device__ __forceinline__ void fused_bwd_worker(const FusedBwdArgs& g, uint32_t tmem, int quad, int lane, uint64_t* kready, uint64_t* dfready,
-                                                 uint64_t* accfull, const float* s_w3) {
+                                                 uint64_t* accfull, uint64_t* s3done, const float* s_w3) {
   const int64_t ntiles = (g.M + 127) / 128;
   const int row = quad * 32 + lane;
   const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
-  const uint32_t accA = lane_base + fz::kBAccA, accB = lane_base + fz::kBAccB, aop = lane_base + fz::kBAop;
+  const uint32_t aop = lane_base + fz::kBAop;
   float S, invS;
   grad_scale(g.amax, S, invS);
   const int nk0 = g.K0 / 16;
-  uint32_t it = 0;
-  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+  // ---- output layer reverse (networks.py:114-120) and relu'(h2): this quarter's 32 columns of dp2 of tile t ----
+  auto out_reverse = [&](int64_t t) {
     const int64_t m = t * 128 + row;
-    const uint32_t ph = it & 1;
-    // ---- output layer reverse (networks.py:114-120) and relu'(h2): this quarter's 32 columns of dp2 ----
     float dout[3] = {0.f, 0.f, 0.f};
     if (m < g.M) {
 #pragma unroll
@@ -694,22 +680,20 @@ __device__ __forceinline__ void fused_bwd_worker(const FusedBwdArgs& g, uint32_t
         dout[c] = S * g.d_rgb[3 * m + c] * y * (1.0f - y);
       }
     }
-    {
-      const uint32_t bw = g.bits2[m * 4 + Q];
-      unsigned char* slab_row = g.dp2s + (size_t)t * (fz::kU * 512) + (size_t)row * 16;
+    const uint32_t bw = g.bits2[m * 4 + Q];
+    unsigned char* slab_row = g.dp2s + (size_t)t * (fz::kU * 512) + (size_t)row * 16;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int n0 = 32 * Q + 16 * c;
-        float y[16];
+    for (int c = 0; c < 2; ++c) {
+      const int n0 = 32 * Q + 16 * c;
+      float y[16];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const float v = fmaf(dout[2], s_w3[3 * (n0 + q) + 2], fmaf(dout[1], s_w3[3 * (n0 + q) + 1], dout[0] * s_w3[3 * (n0 + q)]));
-          y[q] = ((bw >> (16 * c + q)) & 1u) ? v : 0.f;
-        }
-        emit8<true>(y, aop, 4 * Q + 2 * c, slab_row);
-        emit8<true>(y + 8, aop, 4 * Q + 2 * c + 1, slab_row);
-        chunk_arrive(&kready[2 * Q + c], lane);
+      for (int q = 0; q < 16; ++q) {
+        const float v = fmaf(dout[2], s_w3[3 * (n0 + q) + 2], fmaf(dout[1], s_w3[3 * (n0 + q) + 1], dout[0] * s_w3[3 * (n0 + q)]));
+        y[q] = ((bw >> (16 * c + q)) & 1u) ? v : 0.f;
       }
+      emit8<true>(y, aop, 4 * Q + 2 * c, slab_row);
+      emit8<true>(y + 8, aop, 4 * Q + 2 * c + 1, slab_row);
+      chunk_arrive(&kready[2 * Q + c], lane);
     }
     if (Q == 0) {
       float y[16];
@@ -724,6 +708,14 @@ __device__ __forceinline__ void fused_bwd_worker(const FusedBwdArgs& g, uint32_t
         if (lane == 0) atomicAdd(g.db3 + c, sum * invS);
       }
     }
+  };
+  uint32_t it = 0;
+  if ((int64_t)blockIdx.x < ntiles) out_reverse(blockIdx.x);
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    const int64_t m = t * 128 + row;
+    const uint32_t ph = it & 1;
+    // accumulators alternate with the tile parity: dh1 and d_features in P, dx' in Q_ (see the MMA warp)
+    const uint32_t accP = lane_base + (ph ? fz::kBAccB : fz::kBAccA), accQ = lane_base + (ph ? fz::kBAccA : fz::kBAccB);
     // ---- dp1 = (dp2 W2^T) * relu'(h1) ----
     mbar_wait(&accfull[0], ph, 50);
     tc_fence_after();
@@ -731,8 +723,8 @@ __device__ __forceinline__ void fused_bwd_worker(const FusedBwdArgs& g, uint32_t
       const uint32_t bw = g.bits1[m * 4 + Q];
       unsigned char* slab_row = g.dp1s + (size_t)t * (fz::kU * 512) + (size_t)row * 16;
       float y[32];
-      tmem_ld16(accA + 32 * Q, y);
-      tmem_ld16(accA + 32 * Q + 16, y + 16);
+      tmem_ld16(accP + 32 * Q, y);
+      tmem_ld16(accP + 32 * Q + 16, y + 16);
       tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -753,7 +745,7 @@ __device__ __forceinline__ void fused_bwd_worker(const FusedBwdArgs& g, uint32_t
       fv[0] = f0.x; fv[1] = f0.y; fv[2] = f0.z; fv[3] = f0.w; fv[4] = f1.x; fv[5] = f1.y; fv[6] = f1.z; fv[7] = f1.w;
       float dx[40];
 #pragma unroll
-      for (int c = 0; c < 5; ++c) tmem_ld8(accB + 40 * Q + 8 * c, dx + 8 * c);
+      for (int c = 0; c < 5; ++c) tmem_ld8(accQ + 40 * Q + 8 * c, dx + 8 * c);
       tmem_ld_wait();
       float y[8];
       constexpr int ND = Q < 3 ? 8 : 3;  // feature dimensions of this quarter (the view direction needs no gradient)
@@ -771,16 +763,19 @@ __device__ __forceinline__ void fused_bwd_worker(const FusedBwdArgs& g, uint32_t
       emit8<true>(y, aop, Q, g.dfs + (size_t)t * (32 * 512) + (size_t)row * 16);
       chunk_arrive(&dfready[Q >> 1], lane);
     }
-    // ---- d_features = df W0^T: accumulator fragments (16 rows x 256 bit) -> whole 32-byte sectors ----
+    // ---- d_features = df W0^T complete: the operand region is free, so the NEXT tile's dp2 goes in first and its dh1 product
+    // runs on the tensor pipe while this tile's d_features are written out ----
     mbar_wait(&accfull[2], ph, 52);
     tc_fence_after();
-    {
+    if (t + gridDim.x < ntiles) out_reverse(t + gridDim.x);
+    {  // accumulator fragments (16 rows x 256 bit) -> whole 32-byte sectors
       const int lrow = lane >> 2, lc = (lane & 3) * 2;
       const int c_beg = (nk0 * Q) / 4, c_end = (nk0 * (Q + 1)) / 4;
+      const uint32_t accP0 = tmem + (ph ? fz::kBAccB : fz::kBAccA);
       for (int c = c_beg; c < c_end; ++c) {
         float v[2][8];
-        tmem_ld_16x256b_x2(tmem + ((uint32_t)(quad * 32) << 16) + fz::kBAccA + 16u * c, v[0]);
-        tmem_ld_16x256b_x2(tmem + ((uint32_t)(quad * 32 + 16) << 16) + fz::kBAccA + 16u * c, v[1]);
+        tmem_ld_16x256b_x2(accP0 + ((uint32_t)(quad * 32) << 16) + 16u * c, v[0]);
+        tmem_ld_16x256b_x2(accP0 + ((uint32_t)(quad * 32 + 16) << 16) + 16u * c, v[1]);
         tmem_ld_wait();
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk)
@@ -796,7 +791,8 @@ __device__ __forceinline__ void fused_bwd_worker(const FusedBwdArgs& g, uint32_t
       }
     }
     tc_fence_before();
-    asm volatile("bar.sync 1, 512;" ::: "memory");  // every quarter has read accumulator A before the next tile's chunks release it
+    __syncwarp();
+    if (lane == 0) mbar_arrive(s3done);  // this warp has read accumulator P: the next tile's dx' product may overwrite it
   }
 }
 
@@ -807,7 +803,8 @@ __global__ void __launch_bounds__(fz::kBwdThreads, 1) k_mlp_fused_bwd(FusedBwdAr
   uint64_t* kready = wfull + 1;     // [8] dp2 / dp1 chunks (one quarter each)
   uint64_t* dfready = kready + 8;   // [2] df chunks (two quarters each)
   uint64_t* accfull = dfready + 2;  // [3]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 3);
+  uint64_t* s3done = accfull + 3;   // all 16 worker warps have read the d_features accumulator of the tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s3done + 1);
   float* s_w3 = reinterpret_cast<float*>(smem + 1024);  // [384]
   const uint32_t wbytes = fz::b0_bytes(g.K0) + fz::kB1Bytes + fz::kB2Bytes;
   unsigned char* sW = smem + fz::kHeader;
@@ -818,6 +815,7 @@ __global__ void __launch_bounds__(fz::kBwdThreads, 1) k_mlp_fused_bwd(FusedBwdAr
     for (int c = 0; c < 8; ++c) mbar_init(&kready[c], 4);
     for (int c = 0; c < 2; ++c) mbar_init(&dfready[c], 8);
     for (int l = 0; l < 3; ++l) mbar_init(&accfull[l], 1);
+    mbar_init(s3done, 16);
     fence_barrier_init();
   }
   for (int n = tid; n < 384; n += fz::kBwdThreads) s_w3[n] = g.w3[n];
@@ -829,10 +827,10 @@ __global__ void __launch_bounds__(fz::kBwdThreads, 1) k_mlp_fused_bwd(FusedBwdAr
 
   if (warp < 16) {
     switch (warp >> 2) {
-      case 0: fused_bwd_worker<0>(g, tmem, warp & 3, lane, kready, dfready, accfull, s_w3); break;
-      case 1: fused_bwd_worker<1>(g, tmem, warp & 3, lane, kready, dfready, accfull, s_w3); break;
-      case 2: fused_bwd_worker<2>(g, tmem, warp & 3, lane, kready, dfready, accfull, s_w3); break;
-      default: fused_bwd_worker<3>(g, tmem, warp & 3, lane, kready, dfready, accfull, s_w3); break;
+      case 0: fused_bwd_worker<0>(g, tmem, warp & 3, lane, kready, dfready, accfull, s3done, s_w3); break;
+      case 1: fused_bwd_worker<1>(g, tmem, warp & 3, lane, kready, dfready, accfull, s3done, s_w3); break;
+      case 2: fused_bwd_worker<2>(g, tmem, warp & 3, lane, kready, dfready, accfull, s3done, s_w3); break;
+      default: fused_bwd_worker<3>(g, tmem, warp & 3, lane, kready, dfready, accfull, s3done, s_w3); break;
     }
   } else if (warp == fz::kBwdLoadWarp) {
     if (lane == 0) {
@@ -849,26 +847,33 @@ __global__ void __launch_bounds__(fz::kBwdThreads, 1) k_mlp_fused_bwd(FusedBwdAr
     const uint32_t t32 = slab_bytes(32) >> 4, t128 = slab_bytes(128) >> 4;
     const uint32_t id2 = make_idesc(128, fz::kU, FMT_F16, FMT_F16, 0, 1), id1 = make_idesc(128, fz::kX, FMT_F16, FMT_F16, 0, 1),
                    id0 = make_idesc(128, g.K0, FMT_F16, FMT_F16, 0, 1);
-    const uint32_t accA = tm + fz::kBAccA, accB = tm + fz::kBAccB, aop = tm + fz::kBAop;
+    const uint32_t aop = tm + fz::kBAop;
     uint32_t kph = 0, dph = 0;
     mbar_wait(wfull, 0, 60);
     for (int64_t it = 0; it < my_tiles; ++it) {
+      // accumulators alternate with the tile parity: the workers feed tile it+1's dp2 while they still read tile it's
+      // d_features accumulator (P), so dh1 of the next tile goes to the other one
+      const uint32_t accP = tm + ((it & 1) ? fz::kBAccB : fz::kBAccA), accQ = tm + ((it & 1) ? fz::kBAccA : fz::kBAccB);
       for (int i = 0; i < 8; ++i) {  // dh1 = dp2 W2^T (quarter q completes chunk 2q, then 2q + 1)
         const int c = (i & 3) * 2 + (i >> 2);
         mbar_wait(&kready[c], (kph >> c) & 1u, 61);
         kph ^= 1u << c;
         tc_fence_after();
-        if (elect_one()) umma_ts_split2(accA, aop + 8u * c, fz::kAopLo, b2_lo + 16u * c, t128, bh128, id2, i == 0);
+        if (elect_one()) umma_ts_split2(accP, aop + 8u * c, fz::kAopLo, b2_lo + 16u * c, t128, bh128, id2, i == 0);
         __syncwarp();
       }
       if (elect_one()) umma_commit(&accfull[0]);
       __syncwarp();
+      if (it > 0) {  // accQ is the previous tile's d_features accumulator: every worker warp must have read it
+        mbar_wait(s3done, (uint32_t)(it - 1) & 1u, 64);
+        tc_fence_after();
+      }
       for (int i = 0; i < 8; ++i) {  // dx' = dp1 W1'^T
         const int c = (i & 3) * 2 + (i >> 2);
         mbar_wait(&kready[c], (kph >> c) & 1u, 62);
         kph ^= 1u << c;
         tc_fence_after();
-        if (elect_one()) umma_ts_split2(accB, aop + 8u * c, fz::kAopLo, b1_lo + 16u * c, t128, bh128, id1, i == 0);
+        if (elect_one()) umma_ts_split2(accQ, aop + 8u * c, fz::kAopLo, b1_lo + 16u * c, t128, bh128, id1, i == 0);
         __syncwarp();
       }
       if (elect_one()) umma_commit(&accfull[1]);
@@ -877,7 +882,7 @@ __global__ void __launch_bounds__(fz::kBwdThreads, 1) k_mlp_fused_bwd(FusedBwdAr
         mbar_wait(&dfready[c], (dph >> c) & 1u, 63);
         dph ^= 1u << c;
         tc_fence_after();
-        if (elect_one()) umma_ts_split2(accA, aop + 8u * c, fz::kAopLo, b0_lo + 16u * c, t32, bh32, id0, c == 0);
+        if (elect_one()) umma_ts_split2(accP, aop + 8u * c, fz::kAopLo, b0_lo + 16u * c, t32, bh32, id0, c == 0);
         __syncwarp();
       }
       if (elect_one()) umma_commit(&accfull[2]);
@@ -913,7 +918,50 @@ struct FusedWgradArgs {
   int64_t M;
   int K0;
   float *dw0, *dw1, *db1, *dw2, *db2, *dw3;
+  float* partial;  // [gridDim.x][320 + K0][128]
 };
+
+// Sum of the per-CTA partial accumulators of k_mlp_fused_wgrad -> the gradient leaves (overwritten), un-scaled, with the
+// kernel column orders mapped back to the reference's (fz::perm, fz::sq_nat).  One thread per (accumulator column, row).
+struct WgradReduceArgs {
+  const float* partial;
+  const float* amax;
+  int ncta, K0;
+  float *dw0, *dw1, *db1, *dw2, *db2, *dw3;
+};
+__global__ void __launch_bounds__(128) k_wgrad_reduce(WgradReduceArgs a) {
+  const int col = blockIdx.x, n = threadIdx.x;
+  const int ncols = fz::kD0 + a.K0;
+  if (col >= (int)fz::kD0 && n >= 32) return;
+  const float* p = a.partial + (size_t)col * 128 + n;
+  const size_t stride = (size_t)ncols * 128;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int c = 0;
+  for (; c + 4 <= a.ncta; c += 4) {
+    s0 += __ldcg(p + (size_t)c * stride);
+    s1 += __ldcg(p + (size_t)(c + 1) * stride);
+    s2 += __ldcg(p + (size_t)(c + 2) * stride);
+    s3 += __ldcg(p + (size_t)(c + 3) * stride);
+  }
+  for (; c < a.ncta; ++c) s0 += __ldcg(p + (size_t)c * stride);
+  float S, invS;
+  grad_scale(a.amax, S, invS);
+  const float x = ((s0 + s1) + (s2 + s3)) * invS;
+  if (col < (int)fz::kD2) {
+    if (col < 3) a.dw3[n * 3 + col] = x;
+  } else if (col < (int)fz::kD1) {
+    const int k = col - fz::kD2;
+    if (k < fz::kU) a.dw2[k * fz::kU + n] = x;
+    else if (k == fz::kU) a.db2[n] = x;
+  } else if (col < (int)fz::kD0) {
+    const int kp = col - fz::kD1, nat = fz::perm(kp);
+    if (nat >= 0) a.dw1[nat * fz::kU + n] = x;
+    else if (kp == fz::kOnesCol) a.db1[n] = x;
+  } else {
+    const int nat0 = fz::sq_nat(n);
+    if (nat0 >= 0) a.dw0[(col - fz::kD0) * fz::kSq + nat0] = x;
+  }
+}
 
 __global__ void __launch_bounds__(fz::kWgThreads, 1) k_mlp_fused_wgrad(FusedWgradArgs g) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -1033,41 +1081,21 @@ __global__ void __launch_bounds__(fz::kWgThreads, 1) k_mlp_fused_wgrad(FusedWgra
     if (elect_one()) umma_commit(done);
     __syncwarp();
   } else {
-    // ================= epilogue: accumulators -> gradient leaves (RED), once per CTA =================
+    // ================= epilogue: this CTA's partial sums -> scratch [cta][column][128 rows], plain coalesced stores ==========
+    // (148 CTAs adding 59 k values each straight into the leaves with REDs took 40 us: the L2 serialises them per address;
+    // k_wgrad_reduce sums the partials instead - ~35 MB that are still in L2 - and is deterministic)
     mbar_wait(done, 0, 90);
     tc_fence_after();
-    float S, invS;
-    grad_scale(g.amax, S, invS);
-    const int n = warp * 32 + lane;  // accumulator row = output unit of the layer (Dense_0: kernel column order)
+    const int n = warp * 32 + lane;  // accumulator row = output unit of the layer
     const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
-    const int ncols = fz::kD0 + (warp == 0 ? K0 : 0);
-    const int nat0 = fz::sq_nat(n < 32 ? n : 31);
-    // every CTA adds into the same 59 k addresses: start each CTA at a different column chunk so that the L2's per-address
-    // serialisation of the REDs is spread over the whole range instead of 148 CTAs queueing on the same lines
-    const int nchunk = ncols / 16;
-    for (int j = 0; j < nchunk; ++j) {
-      const int c0 = 16 * (int)((j + blockIdx.x * 5u) % (unsigned)nchunk);
+    const int ncols = fz::kD0 + (warp == 0 ? K0 : 0);  // rows >= 32 of the Dense_0 accumulator are meaningless
+    float* part = g.partial + (size_t)blockIdx.x * (size_t)(fz::kD0 + K0) * 128 + n;
+    for (int c0 = 0; c0 < ncols; c0 += 16) {
       float v[16];
       tmem_ld16(tl + c0, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int col = c0 + q;
-        const float x = v[q] * invS;
-        if (col < (int)fz::kD2) {
-          if (col < 3) atomicAdd(g.dw3 + n * 3 + col, x);
-        } else if (col < (int)fz::kD1) {
-          const int k = col - fz::kD2;
-          if (k < fz::kU) atomicAdd(g.dw2 + k * fz::kU + n, x);
-          else if (k == fz::kU) atomicAdd(g.db2 + n, x);
-        } else if (col < (int)fz::kD0) {
-          const int kp = col - fz::kD1, nat = fz::perm(kp);
-          if (nat >= 0) atomicAdd(g.dw1 + nat * fz::kU + n, x);
-          else if (kp == fz::kOnesCol) atomicAdd(g.db1 + n, x);
-        } else {
-          if (nat0 >= 0) atomicAdd(g.dw0 + (col - fz::kD0) * fz::kSq + nat0, x);
-        }
-      }
+      for (int q = 0; q < 16; ++q) part[(size_t)(c0 + q) * 128] = v[q];
     }
     tc_fence_before();
   }
@@ -1107,11 +1135,16 @@ int mlp_fused_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const 
   TF_CHECK_LAUNCH();
   FusedWgradArgs w{};
   w.h2s = reinterpret_cast<unsigned char*>(ws.h2); w.douts = b.douts; w.dp2s = b.dp2s; w.h1s = reinterpret_cast<unsigned char*>(ws.h1);
-  w.dp1s = b.dp1s; w.xs = reinterpret_cast<unsigned char*>(ws.x); w.dfs = b.dfs; w.feats = reinterpret_cast<unsigned char*>(ws.dx);
+  w.dp1s = b.dp1s; w.xs = reinterpret_cast<unsigned char*>(ws.x); w.dfs = b.dfs;
+  w.feats = ws.feat_slabs ? ws.feat_slabs : reinterpret_cast<const unsigned char*>(ws.dx);
   w.amax = amax; w.M = M; w.K0 = s.Ca;
   w.dw0 = gr.w0; w.dw1 = gr.w1; w.db1 = gr.b1; w.dw2 = gr.w2; w.db2 = gr.b2; w.dw3 = gr.w3;
+  w.partial = ws.wg_partial;
   TF_CHECK_CUDA(cudaFuncSetAttribute(k_mlp_fused_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::kWgSmem));
   k_mlp_fused_wgrad<<<grid, fz::kWgThreads, fz::kWgSmem, st>>>(w);
+  TF_CHECK_LAUNCH();
+  WgradReduceArgs ra{ws.wg_partial, amax, (int)grid, s.Ca, gr.w0, gr.w1, gr.b1, gr.w2, gr.b2, gr.w3};
+  k_wgrad_reduce<<<fz::kD0 + s.Ca, 128, 0, st>>>(ra);
   TF_CHECK_LAUNCH();
   return 0;
 }

@@ -10,7 +10,8 @@ namespace tf {
 
 int64_t mlp_ws_floats(const MlpShape& s, int64_t M) {
   int64_t Mp = round_up64(M, 128);
-  return Mp * ((int64_t)2 * round_up(s.squash, 16) + 2 * round_up(s.enc, 16) + 4 * s.units + 8 + 16) + 64 +
+  const int64_t wg = mlp_fused_supported(s) ? std::min<int64_t>(Mp / 128, kSMs) * (320 + s.Ca) * 128 : 0;
+  return Mp * ((int64_t)2 * round_up(s.squash, 16) + 2 * round_up(s.enc, 16) + 4 * s.units + 8 + 16) + 64 + wg +
          (int64_t)round_up64((int64_t)mlp_tc_wpack_bytes(s), 256) / 4;
 }
 MlpWs mlp_ws_carve(const MlpShape& s, int64_t M, float* base) {
@@ -32,6 +33,7 @@ MlpWs mlp_ws_carve(const MlpShape& s, int64_t M, float* base) {
   w.dp1 = p; p += Mp * s.units;
   w.bits1 = reinterpret_cast<uint32_t*>(p); p += Mp * 8;
   w.aux = p; p += Mp * 16 + 64;
+  w.wg_partial = p;
   return w;
 }
 

@@ -11,6 +11,8 @@
 
 #include <algorithm>
 
+#include <cuda_fp16.h>
+
 #include "render_kernels.cuh"
 #include "vm.cuh"
 
@@ -341,9 +343,9 @@ template <bool BWD>
 __global__ void __launch_bounds__(256) k_appearance(AppearanceArgs A) {
   const int nvec = A.Cp >> 2;
   int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (item >= A.M * nvec) return;
   int64_t m = item / nvec;
   int v = (int)(item % nvec);
+  if (m >= A.M) return;
   int r = (int)(m / A.K);
   int s = A.idx[m];
   const float* xp = A.xs + ((int64_t)r * A.N + s) * 3;  // coordinates computed once by k_density_select
@@ -389,8 +391,72 @@ __global__ void __launch_bounds__(256) k_appearance(AppearanceArgs A) {
   }
 }
 
+// The same lookup for the fused MLP kernels (csrc/mlp_fused.cu): rows are written as two-term fp16 slab tiles (per 128 rows
+// and 8 columns one hi and one lo slab of 128 x 16 B, csrc/umma_tiles.cuh) instead of fp32 rows - the same number of bytes,
+// but the MLP's loader copies them straight into its operand ring.  The gather keeps the mapping of k_appearance (item =
+// (row, float4 channel group): the 12 lanes of a row read one contiguous 192-byte texel per tap); a block owns 32 rows,
+// stages their hi / lo halves in shared memory in slab order and writes every slab segment (32 rows x 16 B = 512 B) with
+// coalesced 16-byte stores - scattering 8-byte fragments straight to global memory cost 3-4x the L2 write requests.
+// Needs C % 8 == 0.  Rows M..ceil128(M) are written as zeros (they must be finite).
+constexpr int kSlabRows = 32, kSlabPitch = kSlabRows * 16 + 16;  // +16: column groups land on different banks
+__global__ void __launch_bounds__(512) k_appearance_slab(AppearanceArgs A) {  // blockDim = 32 rows x C/4 items: one item per thread
+  extern __shared__ __align__(16) unsigned char sm_slab[];
+  const int nvec = A.C >> 2, Ca = 3 * A.C, nslab = (Ca >> 3) * 2;
+  const int64_t m0 = (int64_t)blockIdx.x * kSlabRows;
+  for (int item = threadIdx.x; item < kSlabRows * nvec; item += blockDim.x) {
+    const int rl = item / nvec, v = item % nvec;
+    const int64_t m = m0 + rl;
+    uint2 hi[3], lo[3];
+#pragma unroll
+    for (int P = 0; P < 3; ++P) hi[P] = lo[P] = make_uint2(0u, 0u);
+    if (m < A.M) {
+      const int r = (int)(m / A.K);
+      const int s = A.idx[m];
+      const float* xp = A.xs + ((int64_t)r * A.N + s) * 3;
+      float x[3] = {xp[0], xp[1], xp[2]};
+      VmTaps taps;
+      make_vm_taps(taps, x, A.G);
+#pragma unroll
+      for (int P = 0; P < 3; ++P) {
+        PairAddr pa = pair_addr(taps, P, A.G, A.Cp, v);
+        float4 lin, bil;
+        pair_values(A.packed_a, pa, lin, bil);
+        const float4 f = f4_mul(lin, bil);
+        const __half2 h01 = __floats2half2_rn(f.x, f.y), h23 = __floats2half2_rn(f.z, f.w);
+        const float2 r01 = __half22float2(h01), r23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(f.x - r01.x, f.y - r01.y), l23 = __floats2half2_rn(f.z - r23.x, f.w - r23.y);
+        hi[P] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+        lo[P] = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+      }
+    }
+#pragma unroll
+    for (int P = 0; P < 3; ++P) {
+      const int cg = (P * A.C + 4 * v) >> 3;
+      unsigned char* d = sm_slab + (size_t)(2 * cg) * kSlabPitch + rl * 16 + (v & 1) * 8;
+      *reinterpret_cast<uint2*>(d) = hi[P];
+      *reinterpret_cast<uint2*>(d + kSlabPitch) = lo[P];
+    }
+  }
+  __syncthreads();
+  unsigned char* tile = reinterpret_cast<unsigned char*>(A.feat) + (m0 >> 7) * ((int64_t)Ca * 512) + (m0 & 127) * 16;
+  for (int i = threadIdx.x; i < nslab * kSlabRows; i += blockDim.x) {
+    const int sl = i / kSlabRows, rl = i % kSlabRows;
+    *reinterpret_cast<uint4*>(tile + (int64_t)sl * 2048 + rl * 16) = *reinterpret_cast<const uint4*>(sm_slab + (size_t)sl * kSlabPitch + rl * 16);
+  }
+}
+
 int launch_appearance(cudaStream_t st, const AppearanceArgs& A, bool bwd) {
   if (A.M == 0) return 0;
+  if (!bwd && A.feat_slabs) {
+    TF_CHECK_ARG(A.C % 8 == 0 && A.Cp == A.C, "appearance slab rows need ca %% 8 == 0");
+    const size_t smem = (size_t)(3 * A.C / 8) * 2 * kSlabPitch;
+    TF_CHECK_ARG(smem <= 96 * 1024, "appearance slab rows: too many channels");
+    if (smem > 48 * 1024) TF_CHECK_CUDA(cudaFuncSetAttribute(k_appearance_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TF_CHECK_ARG(kSlabRows * (A.C / 4) <= 512, "appearance slab rows: ca=%d too wide", A.C);
+    k_appearance_slab<<<(unsigned)(round_up64(A.M, 128) / kSlabRows), kSlabRows * (A.C / 4), smem, st>>>(A);
+    TF_CHECK_LAUNCH();
+    return 0;
+  }
   int64_t items = A.M * (A.Cp / 4);
   unsigned grid = (unsigned)ceil_div64(items, 256);
   if (bwd)

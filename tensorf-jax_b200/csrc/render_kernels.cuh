@@ -33,7 +33,9 @@ struct AppearanceArgs : SceneArgs {
   const float* xs;     // (R,N,3) grid coordinates saved by the forward gather
   int C, Cp;
   int64_t M;
-  float* feat;           // fwd: (M,3C)
+  float* feat;           // fwd: (M,3C) fp32, or with feat_slabs the fused MLP's operand format: per 128 rows and 8 columns one
+                         // hi and one lo slab of 128 x 16 B (csrc/umma_tiles.cuh), rows M..ceil128(M) zero
+  bool feat_slabs;
   const float* d_feat;   // bwd
   float* d_packed;       // bwd (+=)
 };
