@@ -329,30 +329,67 @@ class TrainBench:
                 self.grads = self.peer.grads
             else:
                 self.peer = None
-        # the early bucket's exchange on a side stream beside the density scatter (as the NCCL path does)
-        self.peer_overlap = self.peer is not None and exchange_arg in ("peer-overlap", "auto") and not args.no_overlap
-        if self.peer_overlap:
+        # exchange transport (P2P vs NVSwitch multicast) and schedule (one exchange after the reverse pass vs the early
+        # bucket on a side stream, a few CTAs wide, beside the density scatter) are MEASURED at start-up under --exchange auto:
+        # which one wins depends on the world size and the payload (12.8 MB at 128^3, 69.5 MB at 300^3)
+        self.tuning = {}
+        if self.peer is not None and exchange_arg == "auto":
+            self.tuning["transport_us"] = self.peer.autotune_transport()
+            self.exchange = "peer-multicast" if self.peer.multicast else "peer-p2p"
+        self.peer_overlap = self.peer is not None and exchange_arg == "peer-overlap" and not args.no_overlap
+        self.overlap_ctas = 32
+        if self.peer is not None:
             self.side, self.ev_early, self.ev_done = torch.cuda.Stream(device=dev), torch.cuda.Event(), torch.cuda.Event()
         self.flush = None if args.no_l2_flush else torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
         self.graph, self.graph_loss = None, None
-        self.use_graph = world == 1 and not args.no_graph
+        self.use_graph = not args.no_graph and (world == 1 or self.peer is not None)
+        if self.peer is not None and exchange_arg == "auto" and not args.no_overlap:
+            t = {}
+            for name, ov in (("serial", False), ("overlap", True)):
+                self.peer_overlap = ov
+                for _ in range(2):
+                    self.step_eager()
+                self.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(6):
+                    self.step_eager()
+                e1.record()
+                self.barrier()
+                t[name] = self.max_over_ranks(e0.elapsed_time(e1) / 6)
+            self.peer_overlap = t["overlap"] < t["serial"]
+            self.tuning["schedule_ms"] = t
 
     def capture(self):
-        """Single GPU: the whole step (13 launches + 1 memset) as ONE CUDA graph, replayed by the timed loops - the C ABI only
-        enqueues on the caller's stream, so it is capturable as is (stage timers off).  Removes the launch gaps between
-        the kernels (measured: sum of the stages vs ms_per_step)."""
+        """The whole step (12 kernel launches + 1 memset per rank, plus the exchange kernels and their cross-rank barriers at
+        N > 1) as ONE CUDA graph, replayed by the timed loops - the C ABI only enqueues on the caller's stream, so it is
+        capturable as is (stage timers off).  Removes the launch gaps between the kernels.  If any rank cannot capture
+        (e.g. a symmetric-memory barrier that refuses stream capture), every rank falls back to eager launches."""
         if not self.use_graph or self.graph is not None:
             return
-        side = torch.cuda.Stream(device=self.dev)
-        side.wait_stream(torch.cuda.current_stream())
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.stream(side):
-            self.step_eager()  # warm the capture stream (lazy per-function attributes)
-            with torch.cuda.graph(g, stream=side):
-                self.graph_loss = self.step_eager()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        self.graph = g
+        ok, g = 1, None
+        try:
+            cap = torch.cuda.Stream(device=self.dev)
+            cap.wait_stream(torch.cuda.current_stream())
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(cap):
+                self.step_eager()  # warm the capture stream (lazy per-function attributes)
+                torch.cuda.synchronize()
+                self.barrier()
+                with torch.cuda.graph(g, stream=cap):
+                    self.graph_loss = self.step_eager()
+            torch.cuda.current_stream().wait_stream(cap)
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] rank {self.rank}: CUDA-graph capture failed ({repr(e)[:300]}); eager launches", file=sys.stderr)
+            ok = 0
+        if self.world > 1:
+            t = torch.tensor([ok], device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+            ok = int(t.item())
+        self.graph = g if ok else None
+        if not ok:
+            self.use_graph = False
 
     def describe_exchange(self):
         if self.world == 1:
@@ -376,7 +413,7 @@ class TrainBench:
             self.ev_early.record()
             with torch.cuda.stream(self.side):
                 self.side.wait_event(self.ev_early)
-                peer.allreduce("early", channel=1)
+                peer.allreduce("early", channel=1, max_ctas=self.overlap_ctas)
                 self.ev_done.record()
             call.backward(None, grads, phase=2)
             peer.allreduce("late", channel=0)
@@ -435,7 +472,7 @@ class TrainBench:
             for _ in range(3):
                 self.step()
             self.barrier()
-        else:
+        if not self.use_graph:
             ops.profile_enable(True)
         launches0 = ops.launch_count()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
@@ -531,13 +568,16 @@ def multi_rank_parity(ops, dev, world, rank, dist):
         adam = ops.AdamCall(p1, [torch.zeros_like(x) for x in p1], [torch.zeros_like(x) for x in p1], [lrs[k] for k in names])
         adam.step([g1[k] for k in names], count=0)
         torch.cuda.synchronize()
-        step_inf = 0.0
+        step_inf = step_l2 = 0.0
         for k, x in zip(names, p1):
             upd_ref, upd = (x - params[k]).double(), (new_params[k] - params[k]).double()
             step_inf = max(step_inf, float((upd - upd_ref).abs().max() / upd_ref.abs().max().clamp_min(1e-300)))
-        out = {"max_rel_inf": rel_inf, "max_rel_l2": rel_l2, "adam_update_max_rel_inf": step_inf, "rays_global": w.R, "ranks": world,
+            step_l2 = max(step_l2, float((upd - upd_ref).norm() / upd_ref.norm().clamp_min(1e-300)))
+        out = {"max_rel_inf": rel_inf, "max_rel_l2": rel_l2, "adam_update_max_rel_inf": step_inf, "adam_update_max_rel_l2": step_l2, "rays_global": w.R, "ranks": world,
                "covers": "k_peer_allreduce (summed gradient) and k_adam_peer (parameter update) vs one rank over the concatenated rays",
-               "note": "sums are re-associated across ranks: differences are fp32 rounding of the ray partition"}
+               "note": "sums are re-associated across ranks: gradient differences are fp32 rounding of the ray partition; the first Adam "
+                       "update is lr * g / (|g| + 1e-8), which amplifies that rounding for the few elements with |g| ~ 1e-8 (inf norm) "
+                       "and not otherwise (L2 norm)"}
     del peer
     return out
 
@@ -610,6 +650,7 @@ def main():
         n_par = sum(int(np.prod(s_)) for s_ in ops.param_shapes(tb3.desc).values())
         config3 = {"workload": w3.name, "scaling": "strong", "R_global": Rg, "R_per_gpu": w3.R, "N": w3.N, "K": w3.K, "G": 300,
                    "value": Rg / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3, "exchange_bytes": 4 * n_par, "exchange": tb3.describe_exchange(),
+                   "exchange_tuning": tb3.tuning, "cuda_graph": tb3.graph is not None,
                    "stages_ms": st3,
                    "roofline_step_frac": Rg / world / (ms3 * 1e-3) * w3.train_bytes_per_ray() / 1e9 / measured_peaks()[0]}
         del tb3
@@ -682,10 +723,10 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": w.name, "R_per_gpu": w.R, "R_global": R_global, "N": w.N, "K": w.K, "G": w.G,
                        "cd": w.cd, "ca": w.ca, "feat_freqs": w.feat_freqs, "view_freqs": w.view_freqs,
-                       "contracted": w.contracted, "parallelism": exchange_desc,
+                       "contracted": w.contracted, "parallelism": exchange_desc, "exchange_tuning": tb.tuning,
                        "l2": "flushed (256 MiB write) between timed steps" if tb.flush is not None else "not flushed",
                        "timed": "render_rays fwd + MSE + reverse wrt all LearnableParams leaves; Adam excluded" +
-                                ("; the step is captured once and replayed as ONE CUDA graph (stages_ms from a separate eager loop)" if tb.use_graph else ""),
+                                ("; the step is captured once and replayed as ONE CUDA graph per rank (stages_ms from a separate eager loop)" if tb.graph is not None else ""),
                        "launch_gap_frac": 1.0 - sum(v_[0] / max(v_[1], 1) for v_ in prof.values()) / ms_per_step,
                        "loss": loss_host},
             "roofline_step": {"bound": "hbm", "achieved": value / world * w.train_bytes_per_ray() / 1e9, "peak": peak, "unit": "GB/s",

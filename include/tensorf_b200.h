@@ -278,6 +278,10 @@ int tensorf_adam_step_peer(tensorf_stream_t s, const tensorf_peer_adam_desc* d, 
  * total a multiple of 4.  Same barrier contract as tensorf_adam_step_peer.  Runs on the caller's stream, so it
  * is ordered with the reverse pass without a second stream. */
 int tensorf_peer_allreduce(tensorf_stream_t s, int rank, int world, int64_t total, float* const* peers, float* mc);
+/* Upper bound on the CTAs of the exchange kernels launched from this thread from now on (0 = default, 4 per SM): an exchange
+ * running on a side stream beside a compute kernel (the early bucket beside the density scatter) should trickle through a
+ * few SMs instead of competing for issue slots on all of them. */
+int tensorf_peer_set_max_ctas(int max_ctas);
 /* The same exchange with the two cross-rank barriers INSIDE the kernel (no barrier launches around it):
  * signal_peers[world] (HOST array) = every rank's signal pad, 32 uint32 in symmetric memory, zeroed once before the
  * first call ([0,16) "buffer complete", [16,32) "stores landed", slot = signalling rank); local_flags = 2 uint32 of this

@@ -658,6 +658,7 @@ int tensorf_adam_step_peer(tensorf_stream_t s, const tensorf_peer_adam_desc* d, 
   return adam_step_peer((cudaStream_t)s, d, leaf_offsets, neg_lrs, grad_peers, param_peers, grad_mc, param_mc, mu_shard,
                         nu_shard, norm_slot_peers, scratch, scratch_bytes);
 }
+int tensorf_peer_set_max_ctas(int max_ctas) { return peer_set_max_ctas(max_ctas); }
 int tensorf_peer_allreduce(tensorf_stream_t s, int rank, int world, int64_t total, float* const* peers, float* mc) {
   return peer_allreduce((cudaStream_t)s, rank, world, total, peers, mc, nullptr, nullptr, 0);
 }

@@ -34,6 +34,7 @@ int64_t peer_adam_scratch_bytes(int64_t shard_floats);
 int adam_step_peer(cudaStream_t st, const tensorf_peer_adam_desc* d, const int64_t* leaf_offsets, const float* neg_lrs,
                    const float* const* grad_peers, float* const* param_peers, const float* grad_mc, float* param_mc,
                    float* mu_shard, float* nu_shard, float* const* norm_slot_peers, void* scratch, int64_t scratch_bytes);
+int peer_set_max_ctas(int max_ctas);
 int peer_allreduce(cudaStream_t st, int rank, int world, int64_t total, float* const* peers, float* mc,
                    uint32_t* const* signal_peers, uint32_t* local_flags, uint32_t epoch);
 int peer_grad_norm(cudaStream_t st, const float* norm_slots, int world, float* grad_norm);

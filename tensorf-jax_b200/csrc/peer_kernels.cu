@@ -14,6 +14,8 @@
 // k_scatter_walk issues one 16-byte RED per texel VISIT (~0.4 GB of REDs per step at lego 128^3); the local L2
 // combines them into a 12.7 MB dense gradient, so reducing after the L2 moves 30x fewer bytes over the links.
 // Ordering across ranks is the caller's (one barrier before, one after; see include/tensorf_b200.h).
+#include <algorithm>
+
 #include "optim.cuh"
 
 namespace tf {
@@ -400,6 +402,15 @@ int adam_step_peer(cudaStream_t st, const tensorf_peer_adam_desc* d, const int64
   return 0;
 }
 
+// Upper bound on the CTAs of the next exchange kernels launched from this thread (0 = default, 4 per SM): an exchange
+// that runs on a side stream BESIDE a compute kernel should trickle through a few SMs instead of taking issue slots on all.
+static thread_local int g_peer_max_ctas = 0;
+int peer_set_max_ctas(int max_ctas) {
+  TF_CHECK_ARG(max_ctas >= 0, "peer_set_max_ctas: negative");
+  g_peer_max_ctas = max_ctas;
+  return 0;
+}
+
 int peer_allreduce(cudaStream_t st, int rank, int world, int64_t total, float* const* peers, float* mc,
                    uint32_t* const* signal_peers, uint32_t* local_flags, uint32_t epoch) {
   TF_CHECK_ARG(peers, "peer_allreduce: null argument");
@@ -435,7 +446,8 @@ int peer_allreduce(cudaStream_t st, int rank, int world, int64_t total, float* c
   a.n_tiles = (int)tiles;
   // 4 CTAs of 256 threads x <= 48 registers per SM: every block of the grid is resident at once, so the blocks
   // spinning on the in-kernel gate never keep block 0 (dispatched first in any case) off an SM
-  const int64_t cap = (int64_t)kSMs * 4;
+  int64_t cap = (int64_t)kSMs * 4;
+  if (g_peer_max_ctas > 0) cap = std::min<int64_t>(cap, g_peer_max_ctas);
   const int grid = (int)(tiles < 1 ? 1 : (tiles < cap ? tiles : cap));
   StageTimer t(st, "peer_allreduce");
   const bool use_mc = mc != nullptr;

@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(256) k_appearance(AppearanceArgs A) {
 // coalesced 16-byte stores - scattering 8-byte fragments straight to global memory cost 3-4x the L2 write requests.
 // Needs C % 8 == 0.  Rows M..ceil128(M) are written as zeros (they must be finite).
 constexpr int kSlabRows = 32, kSlabPitch = kSlabRows * 16 + 16;  // +16: column groups land on different banks
-__global__ void __launch_bounds__(512) k_appearance_slab(AppearanceArgs A) {  // blockDim = 32 rows x C/4 items: one item per thread
+__global__ void __launch_bounds__(384, 3) k_appearance_slab(AppearanceArgs A) {  // blockDim = 32 rows x C/4 items: one item per thread
   extern __shared__ __align__(16) unsigned char sm_slab[];
   const int nvec = A.C >> 2, Ca = 3 * A.C, nslab = (Ca >> 3) * 2;
   const int64_t m0 = (int64_t)blockIdx.x * kSlabRows;
@@ -452,7 +452,7 @@ int launch_appearance(cudaStream_t st, const AppearanceArgs& A, bool bwd) {
     const size_t smem = (size_t)(3 * A.C / 8) * 2 * kSlabPitch;
     TF_CHECK_ARG(smem <= 96 * 1024, "appearance slab rows: too many channels");
     if (smem > 48 * 1024) TF_CHECK_CUDA(cudaFuncSetAttribute(k_appearance_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TF_CHECK_ARG(kSlabRows * (A.C / 4) <= 512, "appearance slab rows: ca=%d too wide", A.C);
+    TF_CHECK_ARG(kSlabRows * (A.C / 4) <= 384, "appearance slab rows: ca=%d too wide", A.C);
     k_appearance_slab<<<(unsigned)(round_up64(A.M, 128) / kSlabRows), kSlabRows * (A.C / 4), smem, st>>>(A);
     TF_CHECK_LAUNCH();
     return 0;

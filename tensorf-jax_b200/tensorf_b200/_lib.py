@@ -122,6 +122,7 @@ SIGNATURES = {
     "tensorf_adam_step_peer": (_i, [_vp, C.POINTER(PeerAdamDesc), C.POINTER(_i64), C.POINTER(C.c_float), C.POINTER(_vp),
                                     C.POINTER(_vp), _vp, _vp, _vp, _vp, C.POINTER(_vp), _vp, _i64]),
     "tensorf_peer_allreduce": (_i, [_vp, _i, _i, _i64, C.POINTER(_vp), _vp]),
+    "tensorf_peer_set_max_ctas": (_i, [_i]),
     "tensorf_peer_allreduce_sync": (_i, [_vp, _i, _i, _i64, C.POINTER(_vp), _vp, C.POINTER(_vp), _vp, C.c_uint32]),
     "tensorf_peer_grad_norm": (_i, [_vp, _vp, _i, _vp]),
     "tensorf_vm_resize_scratch_bytes": (_i64, [_i, _i, _i]),

@@ -189,13 +189,15 @@ class PeerAdam:
             mc = int(self._hdl.multicast_ptr or 0)
             if want_mc and mc == 0:
                 raise RuntimeError("PeerAdam: multicast requested but the symmetric allocation has no multicast address")
-            if want_mc:
+            if mc:
                 mc_base = mc + own_off
+            self._want_mc = bool(want_mc)
         else:
             self.buf = torch.empty(n_all, dtype=torch.float32, device=self.device)
             peer_ptrs = [self.buf.data_ptr()]
         self.buf.zero_()
-        self.multicast = mc_base != 0
+        self.has_multicast = mc_base != 0
+        self.multicast = self.has_multicast and getattr(self, "_want_mc", False)  # default transport of allreduce() / step()
         self.params_flat = self.buf[:self.total]
         self.grads_flat = self.buf[self.total:2 * self.total]
         self.aux = self.buf[2 * self.total:2 * self.total + 16]
@@ -248,7 +250,36 @@ class PeerAdam:
         if self._hdl is not None:
             self._hdl.barrier(channel=0)
 
-    def allreduce(self, which: str = "all", channel: int = 0) -> None:
+    def autotune_transport(self, reps: int = 5) -> Dict[str, float]:
+        """Times the exchange of the whole buffer over both transports (P2P loads / stores vs NVSwitch multicast
+        `multimem.ld_reduce` / `multimem.st`) and makes the faster one (max over ranks) the default.  Which one wins depends
+        on the world size and the payload: P2P at 2-4 GPUs and 12.8 MB, the in-switch reduction for larger worlds / payloads.
+        The buffer's contents are summed `2 * (reps + 1)` times: call before the first step.  Returns the timings (us)."""
+        import torch.distributed as dist
+        out = {}
+        if self.world == 1 or not self.has_multicast:
+            return out
+        for name, mc in (("p2p", False), ("multicast", True)):
+            self.multicast = mc
+            self.grads_flat.zero_()
+            self.allreduce()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            e0.record()
+            for _ in range(reps):
+                self.allreduce()
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / reps * 1e3], dtype=torch.float64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            out[name] = float(t.item())
+        self.multicast = out["multicast"] < out["p2p"]
+        self.grads_flat.zero_()
+        self.aux.zero_()
+        return out
+
+    def allreduce(self, which: str = "all", channel: int = 0, max_ctas: int = 0) -> None:
         """Sum `grads` and `aux` (the loss slot) over the ranks in place, on the current stream: barrier (all
         gradients written), one kernel (each rank reduces 1/world of the range from every peer and stores the sums
         to every peer), barrier (all stores landed).  `which` = "late" (the leading density leaves) / "early"
@@ -264,17 +295,23 @@ class PeerAdam:
         if which == "all" and self.sync == "kernel":  # both barriers inside the kernel (signal pads in the symmetric buffer)
             self._epoch += 1
             _lib.check(self.lib.tensorf_peer_allreduce_sync(_stream(), self.rank, self.world, self.total + 16, self._g,
-                                                            self._x_mc, self._sig, self._local_flags.data_ptr(),
+                                                            self._x_mc if self.multicast else None, self._sig, self._local_flags.data_ptr(),
                                                             self._epoch & 0xFFFFFFFF))
             return
         lo, hi = {"all": (0, self.total + 16), "late": (0, self._density_end), "early": (self._density_end, self.total + 16)}[which]
         if hi == lo:
             return
         ptrs = self._g if lo == 0 else (C.c_void_p * self.world)(*[int(p) + 4 * lo for p in self._g])
-        mc = self._x_mc if (lo == 0 or self._x_mc is None) else C.c_void_p(self._x_mc.value + 4 * lo)
+        mc = None if not self.multicast else (self._x_mc if lo == 0 else C.c_void_p(self._x_mc.value + 4 * lo))
         if self._hdl is not None:
             self._hdl.barrier(channel=channel)
-        _lib.check(self.lib.tensorf_peer_allreduce(_stream(), self.rank, self.world, hi - lo, ptrs, mc))
+        if max_ctas:  # an exchange that overlaps a compute kernel: a few CTAs only
+            _lib.check(self.lib.tensorf_peer_set_max_ctas(int(max_ctas)))
+        try:
+            _lib.check(self.lib.tensorf_peer_allreduce(_stream(), self.rank, self.world, hi - lo, ptrs, mc))
+        finally:
+            if max_ctas:
+                _lib.check(self.lib.tensorf_peer_set_max_ctas(0))
         if self._hdl is not None:
             self._hdl.barrier(channel=channel)
 
@@ -303,7 +340,7 @@ class PeerAdam:
             rank=self.rank, world=self.world, total=self.total, shard_begin=self.shard[0], shard_end=self.shard[1])
         self.barrier()  # all ranks' gradients are complete
         _lib.check(self.lib.tensorf_adam_step_peer(_stream(), C.byref(d), self._offs, self._neg_lrs, self._g, self._p,
-                                                   self._g_mc, self._p_mc, self.mu.data_ptr(), self.nu.data_ptr(), self._s,
+                                                   self._g_mc if self.multicast else None, self._p_mc if self.multicast else None, self.mu.data_ptr(), self.nu.data_ptr(), self._s,
                                                    self.scratch.data_ptr(), self.scratch.numel()))
         self.barrier()  # all parameter and slot stores have landed everywhere
         _lib.check(self.lib.tensorf_peer_grad_norm(_stream(), self.slots.data_ptr(), self.world, self.grad_norm.data_ptr()))
