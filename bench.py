@@ -277,14 +277,14 @@ class TrainBench:
     workload, set up once: parameters replicated, this rank's ray shard resident in HBM (and mirrored in one pinned host
     buffer for the end-to-end loop), all gradient leaves in one flat buffer."""
 
-    def __init__(self, args, w, world, rank, dev, dist, exchange_arg):
+    def __init__(self, args, w, world, rank, dev, dist, exchange_arg, packed=False):
         from tensorf_b200 import dist as tdist, ops
         from tensorf_b200.data import HostStage
         self.ops, self.dist, self.w, self.world, self.rank, self.dev = ops, dist, w, world, rank, dev
         self.R_global = w.R * world
         inp = S.make_inputs(w, seed_rays=1 + rank)
         desc = ops.make_desc(R=w.R, N=w.N, K=w.K, G=w.G, cd=w.cd, ca=w.ca, contracted=w.contracted, feat_freqs=w.feat_freqs,
-                             view_freqs=w.view_freqs, num_cameras=w.num_cameras, loss_scale=1.0 / (3 * self.R_global))
+                             view_freqs=w.view_freqs, num_cameras=w.num_cameras, loss_scale=1.0 / (3 * self.R_global), packed_factors=packed)
         self.desc = desc
         self.call = ops.RenderCall(desc, dev)
 
@@ -295,6 +295,8 @@ class TrainBench:
             return t.to(dev)
 
         self.params = {k: dv(v) for k, v in inp["params"].items()}
+        if packed:  # parameters (and gradients) live in the kernel-native texel-major layout: no pack / unpack passes per step
+            self.params = ops.pack_params(self.params)
         self.host_keys = ["origins", "directions", "camera_indices", "colors", "jitter", "gumbel"]
         # e2e path: the minibatch lives in ONE pinned host buffer mirrored by one device buffer (data.HostStage), so a
         # step's inputs are a single H2D copy; the device views are what both timed loops read
@@ -345,8 +347,8 @@ class TrainBench:
         self.use_graph = not args.no_graph and (world == 1 or self.peer is not None)
         if self.peer is not None and exchange_arg == "auto" and not args.no_overlap:
             t = {}
-            for name, ov in (("serial", False), ("overlap", True)):
-                self.peer_overlap = ov
+            for name, sync, ov in (("serial", "barrier", False), ("overlap", "barrier", True), ("serial_kernel_sync", "kernel", False)):
+                self.peer.sync, self.peer_overlap = sync, ov
                 for _ in range(2):
                     self.step_eager()
                 self.barrier()
@@ -357,7 +359,9 @@ class TrainBench:
                 e1.record()
                 self.barrier()
                 t[name] = self.max_over_ranks(e0.elapsed_time(e1) / 6)
-            self.peer_overlap = t["overlap"] < t["serial"]
+            best = min(t, key=t.get)
+            self.peer.sync = "kernel" if best == "serial_kernel_sync" else "barrier"
+            self.peer_overlap = best == "overlap"
             self.tuning["schedule_ms"] = t
 
     def capture(self):
@@ -593,6 +597,7 @@ def main():
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-config3", action="store_true", help="skip the BASELINE configs[2] sub-record (300^3, 16384 global rays, strong scaling)")
+    ap.add_argument("--no-packed", action="store_true", help="skip the packed-factor-layout sub-record")
     ap.add_argument("--no-graph", action="store_true", help="N=1: launch every kernel of a step from the host instead of replaying one CUDA graph")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one exchange after the whole reverse pass")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer-p2p", "peer-multicast", "peer-overlap", "nccl"],
@@ -654,6 +659,19 @@ def main():
                    "stages_ms": st3,
                    "roofline_step_frac": Rg / world / (ms3 * 1e-3) * w3.train_bytes_per_ray() / 1e9 / measured_peaks()[0]}
         del tb3
+        torch.cuda.empty_cache()
+
+    # ---- the same step with parameters / gradients kept in the kernel-native packed layout (TENSORF_FLAG_PACKED_FACTORS) ----
+    packed_rec = None
+    if not args.no_packed:
+        tbp = TrainBench(args, w, world, rank, dev, dist, args.exchange, packed=True)
+        msp, _, profp, _ = tbp.timed(max(6, steps // 2), 3)
+        packed_rec = {"value": R_global / (msp * 1e-3), "unit": UNIT, "ms_per_step": msp,
+                      "stages_ms": {k: round(v[0] / max(v[1], 1), 4) for k, v in sorted(profp.items(), key=lambda kv: -kv[1][0])},
+                      "note": "TENSORF_FLAG_PACKED_FACTORS: factors, their gradients (and, in a training loop, the Adam moments - every optimiser "
+                              "operation is elementwise) stay in the texel-major layout the kernels read; the per-step pack and unpack passes "
+                              "disappear.  The headline `value` keeps the reference's channel-first layout at the boundary."}
+        del tbp
         torch.cuda.empty_cache()
 
     parity = multi_rank_parity(ops, dev, world, rank, dist) if world > 1 else None
@@ -741,6 +759,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if packed_rec is not None:
+            out["packed_layout"] = packed_rec
         if config3 is not None:
             out["config3"] = config3
         if parity is not None:

@@ -45,7 +45,13 @@ enum tensorf_render_mode { TENSORF_MODE_RGB = 0, TENSORF_MODE_DIST_MEDIAN = 1, T
 
 /* TENSORF_FLAG_INFERENCE: forward only (render_360.py, render_rays_batched): residuals that only the reverse pass
  * reads (ReLU masks, second hidden layer) are not written; tensorf_render_rgb_bwd / tensorf_mlp_bwd then fail. */
-enum tensorf_render_flags { TENSORF_FLAG_INFERENCE = 1 };
+/* TENSORF_FLAG_PACKED_FACTORS: the factor leaves are ALREADY in the kernel-native texel-major layout (tensorf_vm_pack;
+ * tensorf_vm_packed_floats floats per TensorVM: lines [3][G][Cp] then planes [3][G][G][Cp]): `*_vector` points to that
+ * buffer and `*_matrix` is NULL or `*_vector + 3*G*Cp`.  The same holds for the gradient struct, whose packed buffers are
+ * zeroed and accumulated in place.  A training loop that keeps parameters, gradients and Adam moments packed (every
+ * optimiser operation is elementwise) skips the pack and unpack passes of each step: 2 x 12.7 MB at 128^3, 2 x 69 MB at
+ * 300^3; tensorf_vm_unpack converts back at the boundary (checkpoints, grid resampling). */
+enum tensorf_render_flags { TENSORF_FLAG_INFERENCE = 1, TENSORF_FLAG_PACKED_FACTORS = 2 };
 
 /* MLP arithmetic: exact fp32 on CUDA cores; tcgen05 tensor cores with split-bf16 operands, one kernel per layer;
  * or the per-row-tile fused tcgen05 kernels (split-fp16 operands, activations stay in tensor memory between the
@@ -284,11 +290,13 @@ int tensorf_peer_allreduce(tensorf_stream_t s, int rank, int world, int64_t tota
 int tensorf_peer_set_max_ctas(int max_ctas);
 /* The same exchange with the two cross-rank barriers INSIDE the kernel (no barrier launches around it):
  * signal_peers[world] (HOST array) = every rank's signal pad, 32 uint32 in symmetric memory, zeroed once before the
- * first call ([0,16) "buffer complete", [16,32) "stores landed", slot = signalling rank); local_flags = 2 uint32 of this
- * rank's own device memory, zeroed once; epoch = 1, 2, 3, ... the call number, identical on every rank.  Block 0
+ * first call ([0,16) "buffer complete", [16,32) "stores landed", slot = signalling rank); local_flags = 4 uint32 of this
+ * rank's own device memory, zeroed once; epoch = 1, 2, 3, ... the call number, identical on every rank, or 0 = the
+ * kernel keeps the call number itself in local_flags[2] (then every call on every rank must pass 0).  Block 0
  * signals / awaits "complete" with st.release.sys / ld.acquire.sys and opens a gate for the grid; the last block to
  * finish its stores signals / awaits "landed", so stream completion of the kernel means every buffer holds every sum.
- * Every rank must make the call (even with an empty shard).  Not CUDA-graph capturable (epoch is a launch argument). */
+ * Every rank must make the call (even with an empty shard).  With epoch = 0 the launch has no per-call argument and is
+ * CUDA-graph capturable (every replay advances the device-side counter). */
 int tensorf_peer_allreduce_sync(tensorf_stream_t s, int rank, int world, int64_t total, float* const* peers, float* mc,
                                 uint32_t* const* signal_peers, uint32_t* local_flags, uint32_t epoch);
 /* grad_norm[0] = sqrt(sum of the `world` slots, in rank order, fp64 accumulation): identical on every rank. */

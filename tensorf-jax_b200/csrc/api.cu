@@ -96,6 +96,15 @@ static RenderWs carve(const tensorf_render_desc& d, float* base) {
   return w;
 }
 
+// TENSORF_FLAG_PACKED_FACTORS: the caller's factor buffers ARE the packed copies (no pack / unpack passes)
+static bool packed_factors(const tensorf_render_desc& d) { return (d.flags & TENSORF_FLAG_PACKED_FACTORS) != 0; }
+static int check_packed_leaf(const tensorf_render_desc& d, const float* vec, const float* mat, int C, const char* what) {
+  TF_CHECK_ARG(vec != nullptr, "%s: packed factor buffer is NULL", what);
+  TF_CHECK_ARG((reinterpret_cast<uintptr_t>(vec) & 15) == 0, "%s: packed factor buffer must be 16-byte aligned", what);
+  TF_CHECK_ARG(mat == nullptr || mat == vec + packed_line_floats(C, d.G), "%s: with TENSORF_FLAG_PACKED_FACTORS the matrix pointer must be NULL or vector + 3*G*Cp", what);
+  return 0;
+}
+
 static int check_desc(const tensorf_render_desc* d) {
   TF_CHECK_ARG(d != nullptr, "desc is NULL");
   TF_CHECK_ARG(d->R >= 0 && d->N >= 1 && d->G >= 2, "bad shape R=%d N=%d G=%d", d->R, d->N, d->G);
@@ -396,13 +405,17 @@ int tensorf_render_depth(tensorf_stream_t s, const tensorf_render_desc* d, const
   TF_RETURN_IF_ERROR(check_desc(d));
   TF_CHECK_ARG(d->mode == TENSORF_MODE_DIST_MEDIAN || d->mode == TENSORF_MODE_DIST_MEAN, "render_depth needs a DIST_* mode");
   TF_RETURN_IF_ERROR(check_inputs(d, in));
-  TF_CHECK_ARG(p && p->density_vector && p->density_matrix, "density factors must be non-NULL");
+  TF_CHECK_ARG(p != nullptr, "params is NULL");
+  const bool packed = packed_factors(*d);
+  if (packed) TF_RETURN_IF_ERROR(check_packed_leaf(*d, p->density_vector, p->density_matrix, d->cd, "params density"));
+  else TF_CHECK_ARG(p->density_vector && p->density_matrix, "density factors must be non-NULL");
   TF_CHECK_ARG(workspace && (depth || d->R == 0), "NULL buffer");
   cudaStream_t st = (cudaStream_t)s;
   tensorf_render_desc dd = *d;
   dd.K = 1;
   RenderWs w = carve(dd, (float*)workspace);
-  TF_RETURN_IF_ERROR(vm_pack(st, p->density_vector, p->density_matrix, w.packed_d, d->cd, d->G));
+  if (packed) w.packed_d = p->density_vector;
+  else TF_RETURN_IF_ERROR(vm_pack(st, p->density_vector, p->density_matrix, w.packed_d, d->cd, d->G));
   DensityArgs a{};
   fill_scene(a, dd, *in);
   a.packed_d = w.packed_d;
@@ -420,18 +433,28 @@ int tensorf_render_rgb_fwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   TF_CHECK_ARG(d->mode == TENSORF_MODE_RGB, "render_rgb_fwd needs mode RGB");
   TF_RETURN_IF_ERROR(check_inputs(d, in));
   TF_RETURN_IF_ERROR(check_mlp_params(*d, p, "params"));
-  TF_CHECK_ARG(p->density_vector && p->density_matrix && p->appearance_vector && p->appearance_matrix,
-               "factor leaves must be non-NULL");
+  const bool packed = packed_factors(*d);
+  if (packed) {
+    TF_RETURN_IF_ERROR(check_packed_leaf(*d, p->density_vector, p->density_matrix, d->cd, "params density"));
+    TF_RETURN_IF_ERROR(check_packed_leaf(*d, p->appearance_vector, p->appearance_matrix, d->ca, "params appearance"));
+  } else {
+    TF_CHECK_ARG(p->density_vector && p->density_matrix && p->appearance_vector && p->appearance_matrix,
+                 "factor leaves must be non-NULL");
+  }
   TF_CHECK_ARG(workspace && (rgb || d->R == 0), "NULL buffer");
   TF_CHECK_ARG(!in->colors || loss, "loss must be non-NULL when colors are given");
   cudaStream_t st = (cudaStream_t)s;
   RenderWs w = carve(*d, (float*)workspace);
+  if (packed) {
+    w.packed_d = p->density_vector;
+    w.packed_a = p->appearance_vector;
+  }
   const MlpShape ms = mlp_shape(*d);
   int mlp_impl;
   TF_RETURN_IF_ERROR(mlp_pick(*d, ms, &mlp_impl));
   const int64_t M = (int64_t)d->R * d->K;
 
-  {
+  if (!packed) {
     StageTimer t_(st, "pack");
     TF_RETURN_IF_ERROR(vm_pack2(st, p->density_vector, p->density_matrix, w.packed_d, d->cd, p->appearance_vector,
                                 p->appearance_matrix, w.packed_a, d->ca, d->G));
@@ -505,12 +528,26 @@ static int render_rgb_bwd_impl(tensorf_stream_t s, const tensorf_render_desc* d,
   TF_RETURN_IF_ERROR(check_inputs(d, in));
   TF_RETURN_IF_ERROR(check_mlp_params(*d, p, "params"));
   TF_RETURN_IF_ERROR(check_mlp_params(*d, grads, "grads"));
-  TF_CHECK_ARG(grads->density_vector && grads->density_matrix && grads->appearance_vector && grads->appearance_matrix,
-               "factor gradient leaves must be non-NULL");
+  const bool packed = packed_factors(*d);
+  if (packed) {
+    TF_RETURN_IF_ERROR(check_packed_leaf(*d, p->density_vector, p->density_matrix, d->cd, "params density"));
+    TF_RETURN_IF_ERROR(check_packed_leaf(*d, p->appearance_vector, p->appearance_matrix, d->ca, "params appearance"));
+    TF_RETURN_IF_ERROR(check_packed_leaf(*d, grads->density_vector, grads->density_matrix, d->cd, "grads density"));
+    TF_RETURN_IF_ERROR(check_packed_leaf(*d, grads->appearance_vector, grads->appearance_matrix, d->ca, "grads appearance"));
+  } else {
+    TF_CHECK_ARG(grads->density_vector && grads->density_matrix && grads->appearance_vector && grads->appearance_matrix,
+                 "factor gradient leaves must be non-NULL");
+  }
   TF_CHECK_ARG(workspace != nullptr, "workspace is NULL");
   TF_CHECK_ARG(d_rgb || in->colors, "either d_rgb or inputs->colors (fused loss) is required");
   cudaStream_t st = (cudaStream_t)s;
   RenderWs w = carve(*d, (float*)workspace);
+  if (packed) {  // parameters are read, gradients accumulated, straight in the caller's packed buffers
+    w.packed_d = p->density_vector;
+    w.packed_a = p->appearance_vector;
+    w.gpacked_d = grads->density_vector;
+    w.gpacked_a = grads->appearance_vector;
+  }
   const MlpShape ms = mlp_shape(*d);
   int mlp_impl;
   TF_RETURN_IF_ERROR(mlp_pick(*d, ms, &mlp_impl));
@@ -613,6 +650,7 @@ static int render_rgb_bwd_impl(tensorf_stream_t s, const tensorf_render_desc* d,
     StageTimer t_(st, "density_scatter");
     TF_RETURN_IF_ERROR(launch_density_scatter(st, db));
   }
+  if (packed) return 0;  // the gradients are already where the caller wants them
   StageTimer t_(st, "unpack");
   if (phase == 0)
     return vm_unpack2(st, w.gpacked_d, grads->density_vector, grads->density_matrix, d->cd, w.gpacked_a,

@@ -929,24 +929,35 @@ struct WgradReduceArgs {
   int ncta, K0;
   float *dw0, *dw1, *db1, *dw2, *db2, *dw3;
 };
-__global__ void __launch_bounds__(128) k_wgrad_reduce(WgradReduceArgs a) {
-  const int col = blockIdx.x, n = threadIdx.x;
+__global__ void __launch_bounds__(1024) k_wgrad_reduce(WgradReduceArgs a) {
+  // block = (128 rows, 8 slices of the CTA range): 8x the loads in flight of a single pass over the partials (the sum is
+  // latency-bound: ~148 strided 512-byte reads per column), combined through shared memory in a fixed order (deterministic)
+  __shared__ float s_red[8][128];
+  const int col = blockIdx.x, n = threadIdx.x, j = threadIdx.y;
   const int ncols = fz::kD0 + a.K0;
-  if (col >= (int)fz::kD0 && n >= 32) return;
+  const bool live = !(col >= (int)fz::kD0 && n >= 32);
   const float* p = a.partial + (size_t)col * 128 + n;
   const size_t stride = (size_t)ncols * 128;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int c = 0;
-  for (; c + 4 <= a.ncta; c += 4) {
-    s0 += __ldcg(p + (size_t)c * stride);
-    s1 += __ldcg(p + (size_t)(c + 1) * stride);
-    s2 += __ldcg(p + (size_t)(c + 2) * stride);
-    s3 += __ldcg(p + (size_t)(c + 3) * stride);
+  if (live) {
+    int c = j;
+    for (; c + 24 < a.ncta; c += 32) {
+      s0 += __ldcg(p + (size_t)c * stride);
+      s1 += __ldcg(p + (size_t)(c + 8) * stride);
+      s2 += __ldcg(p + (size_t)(c + 16) * stride);
+      s3 += __ldcg(p + (size_t)(c + 24) * stride);
+    }
+    for (; c < a.ncta; c += 8) s0 += __ldcg(p + (size_t)c * stride);
   }
-  for (; c < a.ncta; ++c) s0 += __ldcg(p + (size_t)c * stride);
+  s_red[j][n] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (j != 0 || !live) return;
+  float tot = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) tot += s_red[q][n];
   float S, invS;
   grad_scale(a.amax, S, invS);
-  const float x = ((s0 + s1) + (s2 + s3)) * invS;
+  const float x = tot * invS;
   if (col < (int)fz::kD2) {
     if (col < 3) a.dw3[n * 3 + col] = x;
   } else if (col < (int)fz::kD1) {
@@ -1144,7 +1155,7 @@ int mlp_fused_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const 
   k_mlp_fused_wgrad<<<grid, fz::kWgThreads, fz::kWgSmem, st>>>(w);
   TF_CHECK_LAUNCH();
   WgradReduceArgs ra{ws.wg_partial, amax, (int)grid, s.Ca, gr.w0, gr.w1, gr.b1, gr.w2, gr.b2, gr.w3};
-  k_wgrad_reduce<<<fz::kD0 + s.Ca, 128, 0, st>>>(ra);
+  k_wgrad_reduce<<<fz::kD0 + s.Ca, dim3(128, 8), 0, st>>>(ra);
   TF_CHECK_LAUNCH();
   return 0;
 }

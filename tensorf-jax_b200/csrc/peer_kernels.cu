@@ -205,18 +205,18 @@ __device__ __forceinline__ bool epoch_reached(uint32_t seen, uint32_t epoch) { r
 // waits for the same from every rank, then opens the gate for the other blocks of this grid.  All blocks are
 // co-resident (grid <= 4 per SM, see peer_allreduce) and block 0 is dispatched first: the spinning blocks cannot
 // starve it, and block 0 only depends on the block 0 of every other rank's kernel.
-__device__ __forceinline__ void peer_entry_barrier(const PeerReduceArgs& a, int world) {
+__device__ __forceinline__ void peer_entry_barrier(const PeerReduceArgs& a, int world, uint32_t epoch) {
   if (blockIdx.x == 0) {
     if ((int)threadIdx.x < world) {
-      st_release_sys(a.sig[threadIdx.x] + a.rank, a.epoch);
-      while (!epoch_reached(ld_acquire_sys(a.sig[a.rank] + threadIdx.x), a.epoch)) {
+      st_release_sys(a.sig[threadIdx.x] + a.rank, epoch);
+      while (!epoch_reached(ld_acquire_sys(a.sig[a.rank] + threadIdx.x), epoch)) {
       }
     }
     __syncthreads();
-    if (threadIdx.x == 0) st_release_gpu(a.local, a.epoch);
+    if (threadIdx.x == 0) st_release_gpu(a.local, epoch);
   } else {
     if (threadIdx.x == 0) {
-      while (!epoch_reached(ld_acquire_gpu(a.local), a.epoch)) {
+      while (!epoch_reached(ld_acquire_gpu(a.local), epoch)) {
       }
     }
     __syncthreads();
@@ -224,7 +224,7 @@ __device__ __forceinline__ void peer_entry_barrier(const PeerReduceArgs& a, int 
 }
 // Exit: the last block of this grid to finish its stores tells every rank "my stores have landed" and waits for the
 // same from every rank, so the kernel (and with it the stream) only completes once every buffer holds every sum.
-__device__ __forceinline__ void peer_exit_barrier(const PeerReduceArgs& a, int world) {
+__device__ __forceinline__ void peer_exit_barrier(const PeerReduceArgs& a, int world, uint32_t epoch) {
   __shared__ bool s_last;
   __threadfence_system();
   __syncthreads();
@@ -236,9 +236,15 @@ __device__ __forceinline__ void peer_exit_barrier(const PeerReduceArgs& a, int w
   __syncthreads();
   if (!s_last) return;
   if ((int)threadIdx.x < world) {
-    st_release_sys(a.sig[threadIdx.x] + 16 + a.rank, a.epoch);
-    while (!epoch_reached(ld_acquire_sys(a.sig[a.rank] + 16 + threadIdx.x), a.epoch)) {
+    st_release_sys(a.sig[threadIdx.x] + 16 + a.rank, epoch);
+    while (!epoch_reached(ld_acquire_sys(a.sig[a.rank] + 16 + threadIdx.x), epoch)) {
     }
+  }
+  // device-side call counter (epoch argument 0): every block of this grid read it at entry and has arrived here, so the
+  // last block may advance it for the next launch on the stream
+  if (a.epoch == 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) a.local[2] = epoch;
   }
 }
 constexpr int kPeerRedV4 = 4;  // float4 per thread and tile
@@ -248,7 +254,10 @@ template <int W, bool MC>
 __global__ void __launch_bounds__(kPeerThreads) k_peer_allreduce(const __grid_constant__ PeerReduceArgs a) {
   const int world = W > 0 ? W : a.world;
   const bool sync = a.sig[0] != nullptr;
-  if (sync) peer_entry_barrier(a, world);
+  // epoch 0: the call number lives in device memory (local[2] = calls completed so far), which makes the launch
+  // CUDA-graph capturable - every replay sees the next epoch without a new launch argument
+  const uint32_t epoch = !sync ? 0u : (a.epoch ? a.epoch : ld_acquire_gpu(a.local + 2) + 1u);
+  if (sync) peer_entry_barrier(a, world, epoch);
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int64_t base = a.begin + (int64_t)tile * kPeerRedTile;
     float4 acc[kPeerRedV4];
@@ -284,7 +293,7 @@ __global__ void __launch_bounds__(kPeerThreads) k_peer_allreduce(const __grid_co
       }
     }
   }
-  if (sync) peer_exit_barrier(a, world);
+  if (sync) peer_exit_barrier(a, world, epoch);
 }
 
 __global__ void k_peer_grad_norm(const float* __restrict__ slots, int world, float* __restrict__ out) {

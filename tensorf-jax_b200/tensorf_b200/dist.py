@@ -293,10 +293,9 @@ class PeerAdam:
         if self.world == 1:
             return
         if which == "all" and self.sync == "kernel":  # both barriers inside the kernel (signal pads in the symmetric buffer)
-            self._epoch += 1
+            # epoch 0: the kernel keeps the call number in its own device memory, so the launch is CUDA-graph capturable
             _lib.check(self.lib.tensorf_peer_allreduce_sync(_stream(), self.rank, self.world, self.total + 16, self._g,
-                                                            self._x_mc if self.multicast else None, self._sig, self._local_flags.data_ptr(),
-                                                            self._epoch & 0xFFFFFFFF))
+                                                            self._x_mc if self.multicast else None, self._sig, self._local_flags.data_ptr(), 0))
             return
         lo, hi = {"all": (0, self.total + 16), "late": (0, self._density_end), "early": (self._density_end, self.total + 16)}[which]
         if hi == lo:

@@ -17,6 +17,7 @@ from ._lib import PARAM_FIELDS, AdamDesc, Params, RenderDesc, RenderInputs, chec
 MODE_RGB, MODE_DIST_MEDIAN, MODE_DIST_MEAN = 0, 1, 2
 MLP_AUTO, MLP_SIMT_FP32, MLP_TCGEN05, MLP_FUSED = 0, 1, 2, 3
 FLAG_INFERENCE = 1  # forward only: residuals of the reverse pass are not kept
+FLAG_PACKED_FACTORS = 2  # TENSORF_FLAG_PACKED_FACTORS: factor leaves are the kernel-native packed copies
 
 
 def _stream() -> C.c_void_p:
@@ -37,10 +38,14 @@ def _ptr(t: Optional[torch.Tensor], dtype=torch.float32, name: str = "tensor") -
 
 def make_desc(R: int, N: int, K: int, G: int, cd: int, ca: int, mode: int = MODE_RGB, contracted: bool = False,
               feat_freqs: int = 6, view_freqs: int = 6, num_cameras: Optional[int] = None, loss_scale: float = 0.0,
-              squash: int = 27, units: int = 128, mlp_impl: int = MLP_AUTO, inference: bool = False) -> RenderDesc:
+              squash: int = 27, units: int = 128, mlp_impl: int = MLP_AUTO, inference: bool = False,
+              packed_factors: bool = False) -> RenderDesc:
+    """`packed_factors`: the factor leaves of params / grads are the kernel-native packed copies (`vm_pack`), named
+    'density_packed' / 'appearance_packed' (1-D); the pack and unpack passes of every step are skipped."""
     return RenderDesc(R=R, N=N, K=K, G=G, cd=cd, ca=ca, mode=mode, contracted=int(bool(contracted)), squash=squash,
                       units=units, feat_freqs=feat_freqs, view_freqs=view_freqs, num_cameras=int(num_cameras or 0),
-                      mlp_impl=mlp_impl, loss_scale=loss_scale, flags=FLAG_INFERENCE if inference else 0)
+                      mlp_impl=mlp_impl, loss_scale=loss_scale,
+                      flags=(FLAG_INFERENCE if inference else 0) | (FLAG_PACKED_FACTORS if packed_factors else 0))
 
 
 def encoded_dim(desc: RenderDesc) -> int:
@@ -50,12 +55,15 @@ def encoded_dim(desc: RenderDesc) -> int:
 def param_shapes(desc: RenderDesc) -> Dict[str, Tuple[int, ...]]:
     """Leaf shapes of LearnableParams (render.py:39-46) in the reference's layouts."""
     G, cd, ca, u = desc.G, desc.cd, desc.ca, desc.units
-    s = {
-        "density_vector": (3, cd, G), "density_matrix": (3, cd, G, G),
-        "appearance_vector": (3, ca, G), "appearance_matrix": (3, ca, G, G),
+    if desc.flags & FLAG_PACKED_FACTORS:
+        s = {"density_packed": (vm_packed_floats(cd, G),), "appearance_packed": (vm_packed_floats(ca, G),)}
+    else:
+        s = {"density_vector": (3, cd, G), "density_matrix": (3, cd, G, G),
+             "appearance_vector": (3, ca, G), "appearance_matrix": (3, ca, G, G)}
+    s.update({
         "w0": (3 * ca, desc.squash), "w1": (encoded_dim(desc), u), "b1": (u,), "w2": (u, u), "b2": (u,),
         "w3": (u, 3), "b3": (3,),
-    }
+    })
     if desc.num_cameras > 0:
         s["embed"] = (desc.num_cameras, u)
     return s
@@ -64,7 +72,18 @@ def param_shapes(desc: RenderDesc) -> Dict[str, Tuple[int, ...]]:
 def _params_struct(desc: RenderDesc, params: Dict[str, torch.Tensor], what: str = "params", factors: bool = True) -> Params:
     shapes = param_shapes(desc)
     ps = Params()
+    packed = bool(desc.flags & FLAG_PACKED_FACTORS)
     for name in PARAM_FIELDS:
+        if packed and factors and name in ("density_vector", "appearance_vector"):
+            # TENSORF_FLAG_PACKED_FACTORS: `*_vector` carries the packed buffer, `*_matrix` stays NULL
+            key = name.replace("_vector", "_packed")
+            if key not in params:
+                raise KeyError(f"{what} is missing leaf '{key}'")
+            t = params[key]
+            if tuple(t.shape) != shapes[key]:
+                raise ValueError(f"{what}['{key}'] has shape {tuple(t.shape)}, expected {shapes[key]}")
+            setattr(ps, name, _ptr(t, name=f"{what}['{key}']"))
+            continue
         if name not in shapes or (not factors and name.startswith(("density_", "appearance_"))):
             setattr(ps, name, None)
             continue
@@ -75,6 +94,22 @@ def _params_struct(desc: RenderDesc, params: Dict[str, torch.Tensor], what: str 
             raise ValueError(f"{what}['{name}'] has shape {tuple(t.shape)}, expected {shapes[name]}")
         setattr(ps, name, _ptr(t, name=f"{what}['{name}']"))
     return ps
+
+
+def pack_params(params: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Reference-layout leaves -> the leaves a `packed_factors` call takes (MLP leaves are shared, not copied)."""
+    out = {k: v for k, v in params.items() if not k.startswith(("density_", "appearance_"))}
+    out["density_packed"] = vm_pack(params["density_vector"], params["density_matrix"])
+    out["appearance_packed"] = vm_pack(params["appearance_vector"], params["appearance_matrix"])
+    return out
+
+
+def unpack_params(packed: Dict[str, torch.Tensor], cd: int, ca: int, G: int) -> Dict[str, torch.Tensor]:
+    """Inverse of `pack_params` (checkpoints, grid resampling, comparison with the reference layout)."""
+    out = {k: v for k, v in packed.items() if not k.endswith("_packed")}
+    out["density_vector"], out["density_matrix"] = vm_unpack(packed["density_packed"], cd, G)
+    out["appearance_vector"], out["appearance_matrix"] = vm_unpack(packed["appearance_packed"], ca, G)
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -280,11 +315,17 @@ class RenderCall:
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
         d = self.desc
         ps = Params()
-        for name in ("density_vector", "density_matrix"):
-            t = params[name]
-            if tuple(t.shape) != param_shapes(d)[name]:
-                raise ValueError(f"params['{name}'] has shape {tuple(t.shape)}")
-            setattr(ps, name, _ptr(t, name=name))
+        if d.flags & FLAG_PACKED_FACTORS:
+            t = params["density_packed"]
+            if tuple(t.shape) != param_shapes(d)["density_packed"]:
+                raise ValueError(f"params['density_packed'] has shape {tuple(t.shape)}")
+            ps.density_vector = _ptr(t, name="density_packed")
+        else:
+            for name in ("density_vector", "density_matrix"):
+                t = params[name]
+                if tuple(t.shape) != param_shapes(d)[name]:
+                    raise ValueError(f"params['{name}'] has shape {tuple(t.shape)}")
+                setattr(ps, name, _ptr(t, name=name))
         ri = self._inputs(inputs)
         if out is not None and (tuple(out.shape) != (d.R,) or not out.is_contiguous()):
             raise ValueError(f"out must be a contiguous {(d.R,)} tensor")

@@ -225,3 +225,37 @@ def test_inference_flag_matches_training_forward(cuda):
     train.backward()
     with pytest.raises(_lib.TensorfError, match="INFERENCE"):
         infer.backward()
+
+
+def test_packed_factor_layout_matches_reference_layout(cuda):
+    """TENSORF_FLAG_PACKED_FACTORS: parameters given (and gradients returned) in the kernel-native packed layout - no pack /
+    unpack passes - must give bit-identical colours and the packed image of the reference-layout gradients."""
+    from tensorf_b200 import ops
+    w = S.Workload("packed", 96, 12, 4, 16, 45, 7, 2, 2)
+    inp = S.make_inputs(w, bias_std=0.05)
+    params, dins = device_inputs(w, inp, cuda)
+    kw = dict(R=w.R, N=w.N, K=w.K, G=w.G, cd=w.cd, ca=w.ca, feat_freqs=2, view_freqs=2, loss_scale=1.0 / (3 * w.R))
+    ref = ops.RenderCall(ops.make_desc(**kw), cuda)
+    rgb, loss = ref.forward(params, dins)
+    g_ref = ref.backward()
+    pk = ops.RenderCall(ops.make_desc(packed_factors=True, **kw), cuda)
+    pparams = ops.pack_params(params)
+    rgb_p, loss_p = pk.forward(pparams, dins)
+    g_p = pk.backward()
+    assert torch.equal(rgb, rgb_p)
+    assert abs(float(loss) - float(loss_p)) <= 1e-6 * abs(float(loss))  # the loss is an atomic sum: order-dependent in the last bits
+    assert set(g_p) == set(ops.param_shapes(pk.desc))
+    back = ops.unpack_params(g_p, w.cd, w.ca, w.G)
+    for k in g_ref:
+        np.testing.assert_allclose(back[k].cpu().numpy(), g_ref[k].cpu().numpy(), rtol=0, atol=2e-6 * float(g_ref[k].abs().max()), err_msg=k)
+    # the two-half reverse pass and the distance modes take the packed layout too
+    g2 = {k: torch.full_like(v, float("nan")) for k, v in g_p.items()}
+    pk.backward(None, g2, phase=1)
+    pk.backward(None, g2, phase=2)
+    for k in g_p:
+        np.testing.assert_allclose(g2[k].cpu().numpy(), g_p[k].cpu().numpy(), rtol=0, atol=2e-6 * float(g_p[k].abs().max()), err_msg=k)
+    for mode in (ops.MODE_DIST_MEDIAN, ops.MODE_DIST_MEAN):
+        kwd = {k: v for k, v in kw.items() if k != "loss_scale"}
+        a = ops.RenderCall(ops.make_desc(mode=mode, **kwd), cuda).depth(params, dins)
+        b = ops.RenderCall(ops.make_desc(mode=mode, packed_factors=True, **kwd), cuda).depth(pparams, dins)
+        assert torch.equal(a, b)

@@ -288,11 +288,13 @@ def test_backward_phases_match_whole_pass(cuda):
 
 @pytest.mark.skipif(os.environ.get("CUDA_LAUNCH_BLOCKING") == "1",
                     reason="the simulated ranks must run concurrently (they meet inside their kernels)")
+@pytest.mark.parametrize("device_epoch", [False, True], ids=["epoch_arg", "epoch_on_device"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_inkernel_sync_ranks_on_streams(cuda, world):
+def test_inkernel_sync_ranks_on_streams(cuda, world, device_epoch):
     """tensorf_peer_allreduce_sync: the two cross-rank barriers inside the kernel (signal pads, epochs, grid gate).
     `world` simulated ranks launch on separate streams of one GPU and have to meet inside their kernels; three calls
-    in a row exercise the epoch logic and the arrival-counter reset."""
+    in a row exercise the epoch logic and the arrival-counter reset.  `device_epoch`: epoch argument 0, the kernel keeps
+    the call number in local_flags[2] (the CUDA-graph capturable form)."""
     from tensorf_b200 import _lib
     lib = _lib.load()
     rng = np.random.default_rng(9)
@@ -311,10 +313,10 @@ def test_inkernel_sync_ranks_on_streams(cuda, world):
         torch.cuda.synchronize()
         for r in range(world):
             _lib.check(lib.tensorf_peer_allreduce_sync(C.c_void_p(streams[r].cuda_stream), r, world, total, ptrs, None, sig_ptrs,
-                                                       local[r].data_ptr(), epoch))
+                                                       local[r].data_ptr(), 0 if device_epoch else epoch))
         torch.cuda.synchronize()
         for r in range(world):
             assert np.array_equal(bufs[r].cpu().numpy(), want), (epoch, r)
             assert sig[r][:world].tolist() == [epoch] * world and sig[r][16:16 + world].tolist() == [epoch] * world
-            assert local[r][:2].tolist() == [epoch, 0]
+            assert local[r][:3].tolist() == [epoch, 0, epoch if device_epoch else 0]
     assert lib.tensorf_peer_allreduce_sync(None, 0, world, total, ptrs, None, None, None, 4) == -1

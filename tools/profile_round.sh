@@ -11,7 +11,7 @@ python bench.py --steps 20 --warmup 5 --workload $WL > $OUT/${TAG}_bench_1gpu.js
 tail -c 400 $OUT/${TAG}_bench_1gpu.json
 NL=$(python -c "import json,sys; d=json.load(open('$OUT/${TAG}_bench_1gpu.json')); print(d['gpu_launches']//d['steps'])")
 echo "launches per step: $NL"
-CMD="python bench.py --steps 1 --warmup 3 --no-render --no-cpu-baseline --no-config3 --workload $WL"
+CMD="python bench.py --steps 1 --warmup 3 --no-render --no-cpu-baseline --no-config3 --no-packed --workload $WL"
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 600 --csv --log-file $OUT/${TAG}_launches.csv \
     $CMD > $OUT/${TAG}_ncu_bench.log 2>&1
 SKIP=$(python tools/launch_table.py $OUT/${TAG}_launches.csv $NL skip)

@@ -15,6 +15,7 @@ try:
     print("parallelism:", d["config"]["parallelism"])
     print("stages:", d["stages_ms"])
     if "config3" in d: print("config3:", {k: d["config3"][k] for k in ("value", "ms_per_step", "R_per_gpu", "exchange")}, d["config3"]["stages_ms"])
+    if "packed_layout" in d: print("packed:", d["packed_layout"]["value"], d["packed_layout"]["ms_per_step"])
     if "parity_check" in d: print("parity:", d["parity_check"])
     if "render" in d: print("render:", {k: (v["mpix_per_s"], v["ms_per_frame"]) for k, v in d["render"].items() if isinstance(v, dict)})
 except Exception as e:
@@ -23,5 +24,5 @@ except Exception as e:
 PY
 }
 run auto "$@"
-run p2p --exchange peer-p2p --no-render --no-config3 "$@"
-run nccl --exchange nccl --no-render --no-config3 "$@"
+run p2p --exchange peer-p2p --no-render --no-config3 --no-packed "$@"
+run nccl --exchange nccl --no-render --no-config3 --no-packed "$@"
