@@ -346,32 +346,42 @@ class TrainBench:
         self.graph, self.graph_loss = None, None
         self.use_graph = not args.no_graph and (world == 1 or self.peer is not None)
         if self.peer is not None and exchange_arg == "auto" and not args.no_overlap:
-            t = {}
+            # every schedule is timed the way it will run: captured as a CUDA graph and replayed (eager timings rank them
+            # differently: launch gaps hide or expose the barrier launches)
+            t, graphs = {}, {}
             for name, sync, ov in (("serial", "barrier", False), ("overlap", "barrier", True), ("serial_kernel_sync", "kernel", False)):
                 self.peer.sync, self.peer_overlap = sync, ov
                 for _ in range(2):
                     self.step_eager()
                 self.barrier()
+                g, loss = self._capture_graph() if self.use_graph else (None, None)
+                graphs[name] = (g, loss)
+                run = g.replay if g is not None else self.step_eager
+                for _ in range(2):
+                    run()
+                self.barrier()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                for _ in range(6):
-                    self.step_eager()
+                for _ in range(8):
+                    run()
                 e1.record()
                 self.barrier()
-                t[name] = self.max_over_ranks(e0.elapsed_time(e1) / 6)
+                t[name] = self.max_over_ranks(e0.elapsed_time(e1) / 8)
             best = min(t, key=t.get)
             self.peer.sync = "kernel" if best == "serial_kernel_sync" else "barrier"
             self.peer_overlap = best == "overlap"
+            self.graph, self.graph_loss = graphs[best]
+            if self.graph is None:
+                self.use_graph = False
             self.tuning["schedule_ms"] = t
+            self.tuning["timed_as"] = "cuda graph replay" if self.graph is not None else "eager launches"
 
-    def capture(self):
+    def _capture_graph(self):
         """The whole step (12 kernel launches + 1 memset per rank, plus the exchange kernels and their cross-rank barriers at
-        N > 1) as ONE CUDA graph, replayed by the timed loops - the C ABI only enqueues on the caller's stream, so it is
-        capturable as is (stage timers off).  Removes the launch gaps between the kernels.  If any rank cannot capture
-        (e.g. a symmetric-memory barrier that refuses stream capture), every rank falls back to eager launches."""
-        if not self.use_graph or self.graph is not None:
-            return
-        ok, g = 1, None
+        N > 1) as ONE CUDA graph - the C ABI only enqueues on the caller's stream, so it is capturable as is (stage timers
+        off).  Returns (graph, loss tensor), or (None, None) on every rank if any rank cannot capture (e.g. a
+        symmetric-memory barrier that refuses stream capture)."""
+        ok, g, loss = 1, None, None
         try:
             cap = torch.cuda.Stream(device=self.dev)
             cap.wait_stream(torch.cuda.current_stream())
@@ -381,7 +391,7 @@ class TrainBench:
                 torch.cuda.synchronize()
                 self.barrier()
                 with torch.cuda.graph(g, stream=cap):
-                    self.graph_loss = self.step_eager()
+                    loss = self.step_eager()
             torch.cuda.current_stream().wait_stream(cap)
             torch.cuda.synchronize()
         except Exception as e:  # noqa: BLE001
@@ -391,8 +401,14 @@ class TrainBench:
             t = torch.tensor([ok], device=self.dev)
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
             ok = int(t.item())
-        self.graph = g if ok else None
-        if not ok:
+        return (g, loss) if ok else (None, None)
+
+    def capture(self):
+        """Captures the step once (unless the schedule tuning already did); the timed loops replay the graph."""
+        if not self.use_graph or self.graph is not None:
+            return
+        self.graph, self.graph_loss = self._capture_graph()
+        if self.graph is None:
             self.use_graph = False
 
     def describe_exchange(self):

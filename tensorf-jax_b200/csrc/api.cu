@@ -56,6 +56,26 @@ StageTimer::~StageTimer() {
   if (rec_ >= 0) cudaEventRecord(g_prof.recs[rec_].e1, st_);
 }
 
+// One internal side stream (+ three fork / join events) per host thread and device, created on first use.
+struct SideStream {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+};
+static SideStream* side_stream() {
+  static thread_local SideStream ss[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStream& s = ss[dev];
+  if (s.stream == nullptr) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (auto& e : s.ev)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    s.device = dev;
+  }
+  return &s;
+}
+
 static inline int64_t al(int64_t floats) { return round_up64(floats, 64); }  // 256-byte granules
 
 struct RenderWs {
@@ -602,7 +622,14 @@ static int render_rgb_bwd_impl(tensorf_stream_t s, const tensorf_render_desc* d,
     TF_CHECK_CUDA(cudaMemsetAsync(w.gpacked_d, 0, sizeof(float) * packed_floats(d->cd, d->G), st));
   }
 
-  if (do_den && phase == 0) {
+  // Whole pass with the fused MLP (and no stage timers): two branches after k_ray_bwd that only meet again at the end.
+  //   launch stream : activation-gradient chain -> weight gradients (HBM-bound, 6 warps per SM) -> reduce
+  //   side stream   :                              density scatter -> appearance scatter (needs the chain's d_features)
+  // The scatters are issue-bound at L2 rates and leave the DRAM pipe idle, the weight-gradient kernel streams 0.54 GB with
+  // a handful of warps: they share the SMs.  Fork / join are event dependencies, so the schedule is CUDA-graph capturable.
+  const bool fork = phase == 0 && mlp_impl == TENSORF_MLP_FUSED && !g_prof.on && !getenv("TENSORF_NO_FORK") && M > 0;
+  SideStream* ss = fork ? side_stream() : nullptr;
+  auto density_scatter = [&](cudaStream_t s_) -> int {
     DensityBwdArgs db{};
     fill_scene(db, *d, *in);
     db.packed_d = w.packed_d;
@@ -610,22 +637,10 @@ static int render_rgb_bwd_impl(tensorf_stream_t s, const tensorf_render_desc* d,
     db.xs = w.xs;
     db.d_packed = w.gpacked_d;
     db.Cp = packed_cp(d->cd);
-    StageTimer t_(st, "density_scatter");
-    TF_RETURN_IF_ERROR(launch_density_scatter(st, db));
-  }
-
-  if (do_app) {
-    MlpWs mws = mlp_ws_carve(ms, M, w.mlp_base);
-    if (mlp_impl == TENSORF_MLP_FUSED) mws.feat_slabs = reinterpret_cast<const unsigned char*>(w.feat);  // written by k_appearance
-    {
-      StageTimer t_(st, "mlp_bwd");
-      MlpGrads mg = mlp_grads(*grads);
-      mg.prezeroed = true;  // by k_ray_bwd above
-      mg.amax_ready = mlp_impl == TENSORF_MLP_FUSED;
-      TF_RETURN_IF_ERROR(mlp_bwd_any(mlp_impl, st, ms, mlp_params(*p), w.feat, in->directions,
-                                                                                in->camera_indices, M, d->K, mws, w.rgb_sel,
-                                                                                w.d_rgb_sel, w.d_feat, mg));
-    }
+    StageTimer t_(s_, "density_scatter");
+    return launch_density_scatter(s_, db);
+  };
+  auto appearance_scatter = [&](cudaStream_t s_) -> int {
     AppearanceArgs ap{};
     fill_scene(ap, *d, *in);
     ap.packed_a = w.packed_a;
@@ -636,20 +651,49 @@ static int render_rgb_bwd_impl(tensorf_stream_t s, const tensorf_render_desc* d,
     ap.M = M;
     ap.d_feat = w.d_feat;
     ap.d_packed = w.gpacked_a;
-    StageTimer t_(st, "appearance_scatter");
-    TF_RETURN_IF_ERROR(launch_appearance_scatter(st, ap));
+    StageTimer t_(s_, "appearance_scatter");
+    return launch_appearance_scatter(s_, ap);
+  };
+  if (ss != nullptr) {
+    MlpWs mws = mlp_ws_carve(ms, M, w.mlp_base);
+    mws.feat_slabs = reinterpret_cast<const unsigned char*>(w.feat);
+    MlpGrads mg = mlp_grads(*grads);
+    mg.prezeroed = true;  // by k_ray_bwd above
+    mg.amax_ready = true;
+    // Launch order = placement order: the MLP kernels are launched first so that their one CTA per SM is resident
+    // everywhere (chain: 576 threads x 72 registers, weight gradients: 192 x 98) and the scatter CTAs fill what is left of
+    // the register file (one / two density-scatter CTAs per SM instead of three; the scatters use no shared memory).
+    static const int fork_mode = getenv("TENSORF_FORK_MODE") ? atoi(getenv("TENSORF_FORK_MODE")) : 2;
+    if (fork_mode == 2) TF_CHECK_CUDA(cudaEventRecord(ss->ev[0], st));  // k_ray_bwd done: dz is final
+    TF_RETURN_IF_ERROR(mlp_fused_bwd_chain(st, ms, mlp_params(*p), M, mws, w.rgb_sel, w.d_rgb_sel, w.d_feat, mg));
+    if (fork_mode == 2) {  // density scatter beside the chain kernel already
+      TF_CHECK_CUDA(cudaStreamWaitEvent(ss->stream, ss->ev[0], 0));
+      TF_RETURN_IF_ERROR(density_scatter(ss->stream));
+    }
+    TF_CHECK_CUDA(cudaEventRecord(ss->ev[1], st));  // d_features are final
+    TF_RETURN_IF_ERROR(mlp_fused_bwd_wgrad(st, ms, M, mws, mg));
+    TF_CHECK_CUDA(cudaStreamWaitEvent(ss->stream, ss->ev[1], 0));
+    if (fork_mode != 2) TF_RETURN_IF_ERROR(density_scatter(ss->stream));
+    TF_RETURN_IF_ERROR(appearance_scatter(ss->stream));
+    TF_CHECK_CUDA(cudaEventRecord(ss->ev[2], ss->stream));
+    TF_CHECK_CUDA(cudaStreamWaitEvent(st, ss->ev[2], 0));
+  } else {
+    if (do_den && phase == 0) TF_RETURN_IF_ERROR(density_scatter(st));
+    if (do_app) {
+      MlpWs mws = mlp_ws_carve(ms, M, w.mlp_base);
+      if (mlp_impl == TENSORF_MLP_FUSED) mws.feat_slabs = reinterpret_cast<const unsigned char*>(w.feat);  // written by k_appearance
+      {
+        StageTimer t_(st, "mlp_bwd");
+        MlpGrads mg = mlp_grads(*grads);
+        mg.prezeroed = true;  // by k_ray_bwd above
+        mg.amax_ready = mlp_impl == TENSORF_MLP_FUSED;
+        TF_RETURN_IF_ERROR(mlp_bwd_any(mlp_impl, st, ms, mlp_params(*p), w.feat, in->directions, in->camera_indices, M, d->K, mws,
+                                       w.rgb_sel, w.d_rgb_sel, w.d_feat, mg));
+      }
+      TF_RETURN_IF_ERROR(appearance_scatter(st));
+    }
   }
-  if (phase == 2) {
-    DensityBwdArgs db{};
-    fill_scene(db, *d, *in);
-    db.packed_d = w.packed_d;
-    db.dz = w.dz;
-    db.xs = w.xs;
-    db.d_packed = w.gpacked_d;
-    db.Cp = packed_cp(d->cd);
-    StageTimer t_(st, "density_scatter");
-    TF_RETURN_IF_ERROR(launch_density_scatter(st, db));
-  }
+  if (phase == 2) TF_RETURN_IF_ERROR(density_scatter(st));
   if (packed) return 0;  // the gradients are already where the caller wants them
   StageTimer t_(st, "unpack");
   if (phase == 0)

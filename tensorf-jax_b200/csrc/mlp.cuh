@@ -78,6 +78,9 @@ size_t mlp_fused_wpack_bytes(const MlpShape& s);
 int mlp_fused_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs,
                   const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, float* rgb);
 bool mlp_fused_bwd_ready();
+int mlp_fused_bwd_chain(cudaStream_t st, const MlpShape& s, const MlpParams& p, int64_t M, const MlpWs& ws, const float* rgb,
+                        const float* d_rgb, float* d_feat, const MlpGrads& g);
+int mlp_fused_bwd_wgrad(cudaStream_t st, const MlpShape& s, int64_t M, const MlpWs& ws, const MlpGrads& g);
 int mlp_fused_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs,
                   const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, const float* rgb, const float* d_rgb,
                   float* d_feat, const MlpGrads& g);

@@ -796,7 +796,7 @@ __device__ __forceinline__ void fused_bwd_worker(const FusedBwdArgs& g, uint32_t
   }
 }
 
-__global__ void __launch_bounds__(fz::kBwdThreads, 1) k_mlp_fused_bwd(FusedBwdArgs g) {
+__global__ void __maxnreg__(72) k_mlp_fused_bwd(FusedBwdArgs g) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint64_t* wfull = reinterpret_cast<uint64_t*>(smem);
@@ -1119,9 +1119,13 @@ __global__ void __launch_bounds__(fz::kWgThreads, 1) k_mlp_fused_wgrad(FusedWgra
 }
 
 bool mlp_fused_bwd_ready() { return true; }
-int mlp_fused_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs, const uint32_t* cams,
-                  int64_t M, int rows_per_ray, const MlpWs& ws, const float* rgb, const float* d_rgb, float* d_feat, const MlpGrads& gr) {
-  (void)feat; (void)viewdirs; (void)cams; (void)rows_per_ray;
+
+// The reverse pass in its two halves, so that a caller can run the (HBM-bound, 6-warp) weight-gradient kernel on one stream
+// while the (issue-bound) scatter kernels that only need d_features run on another (render_rgb_bwd_impl):
+//   mlp_fused_bwd_chain: max|d_rgb| (unless the caller has it) + k_mlp_fused_bwd  -> d_features, slab tiles of dp2 / dp1 / df / d(out), db3
+//   mlp_fused_bwd_wgrad: k_mlp_fused_wgrad + k_wgrad_reduce                       -> dW0, dW1, db1, dW2, db2, dW3
+int mlp_fused_bwd_chain(cudaStream_t st, const MlpShape& s, const MlpParams& p, int64_t M, const MlpWs& ws, const float* rgb,
+                        const float* d_rgb, float* d_feat, const MlpGrads& gr) {
   TF_CHECK_ARG(!s.inference, "mlp reverse pass after a forward with TENSORF_FLAG_INFERENCE (residuals were not kept)");
   TF_CHECK_ARG(mlp_fused_supported(s), "fused MLP: unsupported network shape");
   if (!gr.prezeroed) TF_RETURN_IF_ERROR(mlp_zero_grads(st, s, gr));
@@ -1144,9 +1148,18 @@ int mlp_fused_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const 
   TF_CHECK_CUDA(cudaFuncSetAttribute(k_mlp_fused_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
   k_mlp_fused_bwd<<<grid, fz::kBwdThreads, smem_b, st>>>(b);
   TF_CHECK_LAUNCH();
+  return 0;
+}
+
+int mlp_fused_bwd_wgrad(cudaStream_t st, const MlpShape& s, int64_t M, const MlpWs& ws, const MlpGrads& gr) {
+  if (M == 0) return 0;
+  const unsigned grid = (unsigned)std::min<int64_t>((M + 127) / 128, kSMs);
+  float* amax = ws.aux;
   FusedWgradArgs w{};
-  w.h2s = reinterpret_cast<unsigned char*>(ws.h2); w.douts = b.douts; w.dp2s = b.dp2s; w.h1s = reinterpret_cast<unsigned char*>(ws.h1);
-  w.dp1s = b.dp1s; w.xs = reinterpret_cast<unsigned char*>(ws.x); w.dfs = b.dfs;
+  w.h2s = reinterpret_cast<unsigned char*>(ws.h2); w.douts = reinterpret_cast<unsigned char*>(ws.aux + 64);
+  w.dp2s = reinterpret_cast<unsigned char*>(ws.dp2); w.h1s = reinterpret_cast<unsigned char*>(ws.h1);
+  w.dp1s = reinterpret_cast<unsigned char*>(ws.dp1); w.xs = reinterpret_cast<unsigned char*>(ws.x);
+  w.dfs = reinterpret_cast<unsigned char*>(ws.df);
   w.feats = ws.feat_slabs ? ws.feat_slabs : reinterpret_cast<const unsigned char*>(ws.dx);
   w.amax = amax; w.M = M; w.K0 = s.Ca;
   w.dw0 = gr.w0; w.dw1 = gr.w1; w.db1 = gr.b1; w.dw2 = gr.w2; w.db2 = gr.b2; w.dw3 = gr.w3;
@@ -1158,6 +1171,13 @@ int mlp_fused_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const 
   k_wgrad_reduce<<<fz::kD0 + s.Ca, dim3(128, 8), 0, st>>>(ra);
   TF_CHECK_LAUNCH();
   return 0;
+}
+
+int mlp_fused_bwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs, const uint32_t* cams,
+                  int64_t M, int rows_per_ray, const MlpWs& ws, const float* rgb, const float* d_rgb, float* d_feat, const MlpGrads& gr) {
+  (void)feat; (void)viewdirs; (void)cams; (void)rows_per_ray;
+  TF_RETURN_IF_ERROR(mlp_fused_bwd_chain(st, s, p, M, ws, rgb, d_rgb, d_feat, gr));
+  return mlp_fused_bwd_wgrad(st, s, M, ws, gr);
 }
 
 }  // namespace tf
