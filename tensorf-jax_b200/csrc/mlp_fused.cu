@@ -974,7 +974,11 @@ __global__ void __launch_bounds__(1024) k_wgrad_reduce(WgradReduceArgs a) {
   }
 }
 
+#ifdef TF_WG_MAXREG
+__global__ void __maxnreg__(TF_WG_MAXREG) k_mlp_fused_wgrad(FusedWgradArgs g) {
+#else
 __global__ void __launch_bounds__(fz::kWgThreads, 1) k_mlp_fused_wgrad(FusedWgradArgs g) {
+#endif
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint64_t* afull = reinterpret_cast<uint64_t*>(smem);  // [2]

@@ -658,8 +658,11 @@ struct WalkArgs : SceneArgs {
 #ifndef TF_SW_MINB
 #define TF_SW_MINB 2  // measured on B200: 2 -> step 1.318 ms; 1: 1.409; 3: 1.354; 4: 1.393
 #endif
+#ifndef TF_DSW_MINB
+#define TF_DSW_MINB 3
+#endif
 template <int LPS, bool APP>
-__global__ void __launch_bounds__(256, APP ? 2 : 3) k_scatter_walk(WalkArgs A) {  // measured: density 3 CTAs/SM, appearance 2
+__global__ void __launch_bounds__(256, APP ? 2 : TF_DSW_MINB) k_scatter_walk(WalkArgs A) {  // measured: density 3 CTAs/SM, appearance 2
   const int nvec = A.Cp >> 2;
   const int vblocks = (nvec + LPS - 1) / LPS;
   const int sub = threadIdx.x % LPS;

@@ -86,12 +86,12 @@ class TensorVM:
     def channel_dim(self) -> int:
         return self.stacked_single_vm.channel_dim() * 3
 
-    def resize(self, grid_dim: int) -> "TensorVM":
+    def resize(self, grid_dim: int, scratch: Optional[torch.Tensor] = None) -> "TensorVM":
         """tensor_vm.py:91-100 / :183-223: align-corners linear resampling of all three pairs
-        (`tensorf_vm_resize`)."""
+        (`tensorf_vm_resize`).  `scratch`: a uint8 buffer to reuse across several resizes (`ops.vm_resize_scratch_bytes`)."""
         sv = self.stacked_single_vm
         with torch.no_grad():
-            v, m = ops.vm_resize(sv.vector.detach().contiguous(), sv.matrix.detach().contiguous(), int(grid_dim))
+            v, m = ops.vm_resize(sv.vector.detach().contiguous(), sv.matrix.detach().contiguous(), int(grid_dim), scratch=scratch)
         v.requires_grad_(sv.vector.requires_grad)
         m.requires_grad_(sv.matrix.requires_grad)
         return TensorVM(stacked_single_vm=TensorVMSingle(vector=v, matrix=m))

@@ -219,12 +219,18 @@ class TrainState:
         if self._peer is not None:
             return self._resize_grid_peer(new_grid_dim)
         lp = self.learnable_params
-        lp.density_tensor = lp.density_tensor.resize(new_grid_dim)
-        lp.appearance_tensor = lp.appearance_tensor.resize(new_grid_dim)
+        # one scratch buffer for the six resamplings (parameters and both moments of both factor sets): the outputs are
+        # the new leaves and must be fresh tensors, the intermediate of the separable resampling need not be
+        g_old = lp.density_tensor.grid_dim()
+        nbytes = max(ops.vm_resize_scratch_bytes(t.channel_dim(), g_old, int(new_grid_dim))
+                     for t in (lp.density_tensor.stacked_single_vm, lp.appearance_tensor.stacked_single_vm))
+        scratch = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.aabb.device)
+        lp.density_tensor = lp.density_tensor.resize(new_grid_dim, scratch=scratch)
+        lp.appearance_tensor = lp.appearance_tensor.resize(new_grid_dim, scratch=scratch)
         for mom in ("mu", "nu"):
             st = self.optimizer_state[mom]
             for which in ("density", "appearance"):
-                v, m = ops.vm_resize(st[f"{which}_vector"], st[f"{which}_matrix"], int(new_grid_dim))
+                v, m = ops.vm_resize(st[f"{which}_vector"], st[f"{which}_matrix"], int(new_grid_dim), scratch=scratch)
                 st[f"{which}_vector"], st[f"{which}_matrix"] = v, m
         self._adam = None  # leaf buffers changed: rebuild the pointer tables
         return self
