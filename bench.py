@@ -168,7 +168,7 @@ def bench_render(ops, dev, world, rank, dist, frames=2, warm=1):
     noise = {"jitter": torch.from_numpy(jitter).to(dev), "gumbel": torch.from_numpy(gumbel).to(dev)}
     cams = [S.frame_camera(W_, H, angle=0.3 + 2 * 3.14159265 * i / 120) for i in range(frames + warm)]  # consecutive poses of the orbit
     out = {"workload": w.name, "frame": [H, W_], "rays_per_chunk": w.R, "frames_timed": frames,
-           "tiling": f"16-row stripes round-robin over {world} rank(s), no collective",
+           "tiling": f"{__import__('tensorf_b200.dist', fromlist=['x']).balanced_stripe(H, world)}-row stripes round-robin over {world} rank(s) (every rank the same number of rows), no collective",
            "e2e": "pixel rays generated on the device, one D2H copy of the rank's rows per frame into pinned memory (inside the timed region)"}
     for label, mode in (("rgb", trender.RenderMode.RGB), ("dist_median", trender.RenderMode.DIST_MEDIAN), ("dist_mean", trender.RenderMode.DIST_MEAN)):
         cfg = trender.RenderConfig(near=0.1, far=10.0, mode=mode, density_samples_per_ray=w.N, appearance_samples_per_ray=w.K)

@@ -207,8 +207,12 @@ class FrameRenderer:
     Every chunk uses the same jitter / Gumbel vectors (same key), as render_rays_batched does."""
 
     def __init__(self, appearance_mlp: networks.FeatureMlp, learnable_params: LearnableParams, aabb: torch.Tensor, config: RenderConfig,
-                 image_height: int, image_width: int, *, batch_size: int = 16384, rank: int = 0, world: int = 1, stripe: int = 16):
+                 image_height: int, image_width: int, *, batch_size: int = 16384, rank: int = 0, world: int = 1,
+                 stripe: Optional[int] = None):
         from . import dist as tdist
+        if stripe is None:  # the largest stripe (<= 16 rows) that deals every rank the same number of rows
+            stripe = tdist.balanced_stripe(image_height, world)
+        self.stripe = stripe
         self.config, self.aabb, self.device = config, aabb.to(torch.float32).contiguous(), aabb.device
         self.H, self.W, self.batch = image_height, image_width, batch_size
         self.rows: List[Tuple[int, int]] = tdist.stripe_rows(image_height, rank, world, stripe)

@@ -38,6 +38,12 @@ def test_stripe_rows_cover_every_row_once():
     # 800 rows over 8 ranks: 50 stripes, 6 or 7 per rank -> at most one stripe of imbalance
     sizes = [sum(b - a for a, b in tdist.stripe_rows(800, r, 8)) for r in range(8)]
     assert max(sizes) - min(sizes) <= 16 and sum(sizes) == 800
+    # the balanced stripe height deals every rank the same number of rows whenever a power-of-two stripe can
+    assert [tdist.balanced_stripe(800, w) for w in (1, 2, 4, 8)] == [16, 16, 8, 4]
+    for w in (2, 4, 8):
+        s = tdist.balanced_stripe(800, w)
+        assert len({sum(b - a for a, b in tdist.stripe_rows(800, r, w, s)) for r in range(w)}) == 1
+    assert tdist.balanced_stripe(21, 2) == 16  # nothing divides: keep the default
 
 
 def test_shard_rays_slices_only_per_ray_arrays():

@@ -156,12 +156,16 @@ def test_simulated_ranks_on_one_device(cuda, world, shapes):
         assert torch.equal(mu_cat, ref_m) and torch.equal(nu_cat, ref_v)
 
 
+@pytest.mark.parametrize("max_ctas", [0, 3], ids=["full_grid", "3_ctas"])
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
-def test_simulated_allreduce_on_one_device(cuda, world):
+def test_simulated_allreduce_on_one_device(cuda, world, max_ctas):
     """tensorf_peer_allreduce with `world` buffers on one GPU: after every rank's launch all buffers hold the
-    rank-ordered fp32 sum."""
+    rank-ordered fp32 sum.  `max_ctas`: the grid cap an exchange overlapped with a compute kernel uses
+    (tensorf_peer_set_max_ctas) must not change the result."""
     from tensorf_b200 import _lib
     lib = _lib.load()
+    _lib.check(lib.tensorf_peer_set_max_ctas(max_ctas))
+    assert lib.tensorf_peer_set_max_ctas(-1) == -1
     rng = np.random.default_rng(8)
     for total in (4, 8 * 4096 + 20, 1_000_004):
         xs = [(rng.normal(size=total) * 10.0 ** rng.integers(-3, 3)).astype(np.float32) for _ in range(world)]
@@ -175,6 +179,7 @@ def test_simulated_allreduce_on_one_device(cuda, world):
         torch.cuda.synchronize()
         for r in range(world):
             assert np.array_equal(bufs[r].cpu().numpy(), want), (total, r)
+    _lib.check(lib.tensorf_peer_set_max_ctas(0))
     assert lib.tensorf_peer_allreduce(None, 0, world, 6, ptrs, None) == -1
     assert lib.tensorf_peer_allreduce(None, world, world, 8, ptrs, None) == -1
 
