@@ -330,6 +330,13 @@ int tensorf_prng_uniform_slice(tensorf_stream_t s, uint32_t k0, uint32_t k1, int
 int tensorf_pixel_rays(tensorf_stream_t s, const float* M, const float* origin, int W, int row0, int row1,
                        uint32_t camera_index, float* origins, float* directions, uint32_t* camera_indices);
 
+/* The same for the rows a rank owns when a frame is dealt to `world` ranks in interleaved stripes of `stripe` rows (stripe k
+ * = rows [k*stripe, (k+1)*stripe) belongs to rank k % world; render_360-style frames sharded with no collective): the
+ * rank's rows are written contiguously, in image order, by ONE launch.  *n_rays (HOST, may be NULL) receives rows * W; with
+ * origins == directions == NULL the call only reports it. */
+int tensorf_pixel_rays_striped(tensorf_stream_t s, const float* M, const float* origin, int W, int H, int stripe, int rank, int world,
+                               uint32_t camera_index, float* origins, float* directions, uint32_t* camera_indices, int64_t* n_rays);
+
 /* ---- training data path -------------------------------------------------------- */
 /* data.py:301-337 keeps every training ray in memory; training.py:318-323 draws shuffled minibatches.  Here the
  * table (origins, directions (n_table,3); camera_indices (n_table) or NULL; colors (n_table,3) or NULL) lives on

@@ -778,6 +778,10 @@ int tensorf_prng_uniform_slice(tensorf_stream_t s, uint32_t k0, uint32_t k1, int
 int tensorf_prng_gumbel(tensorf_stream_t s, uint32_t k0, uint32_t k1, int64_t n, float* out) {
   return prng_gumbel((cudaStream_t)s, k0, k1, n, out);
 }
+int tensorf_pixel_rays_striped(tensorf_stream_t s, const float* M, const float* origin, int W, int H, int stripe, int rank, int world,
+                               uint32_t camera_index, float* origins, float* directions, uint32_t* camera_indices, int64_t* n_rays) {
+  return pixel_rays_striped((cudaStream_t)s, M, origin, W, H, stripe, rank, world, camera_index, origins, directions, camera_indices, n_rays);
+}
 int tensorf_pixel_rays(tensorf_stream_t s, const float* M, const float* origin, int W, int row0, int row1,
                        uint32_t camera_index, float* origins, float* directions, uint32_t* camera_indices) {
   return pixel_rays((cudaStream_t)s, M, origin, W, row0, row1, camera_index, origins, directions, camera_indices);

@@ -43,6 +43,7 @@ struct MlpWs {
   uint32_t* bits1;  // (M, units/32) ReLU mask of layer 1, one bit per unit (tensor-core path); layer 2's follow (fused path)
   float* aux;       // fused path: [64] scalars (gradient scale), then the d(output) slab tiles (M, 16)
   float* wg_partial;  // fused path: per-CTA partial weight-gradient accumulators [min(tiles, 148)][320 + 3ca][128]
+  bool wpack_ready = false;  // fused path: the caller has already run mlp_fused_pack on this workspace (on a side stream)
   const unsigned char* feat_slabs = nullptr;  // fused path: the feature rows already as slab tiles (render path: written by
                                               // k_appearance); null = `feat` is fp32 (M, 3ca) and is converted into `dx`
 };
@@ -77,6 +78,7 @@ bool mlp_fused_supported(const MlpShape& s);
 size_t mlp_fused_wpack_bytes(const MlpShape& s);
 int mlp_fused_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const float* feat, const float* viewdirs,
                   const uint32_t* cams, int64_t M, int rows_per_ray, const MlpWs& ws, float* rgb);
+int mlp_fused_pack(cudaStream_t st, const MlpShape& s, const MlpParams& p, const MlpWs& ws);
 bool mlp_fused_bwd_ready();
 int mlp_fused_bwd_chain(cudaStream_t st, const MlpShape& s, const MlpParams& p, int64_t M, const MlpWs& ws, const float* rgb,
                         const float* d_rgb, float* d_feat, const MlpGrads& g);

@@ -574,7 +574,7 @@ int mlp_fused_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const 
                   int64_t M, int rows_per_ray, const MlpWs& ws, float* rgb) {
   (void)cams;
   if (M == 0) return 0;
-  TF_RETURN_IF_ERROR(mlp_fused_pack(st, s, p, ws));
+  if (!ws.wpack_ready) TF_RETURN_IF_ERROR(mlp_fused_pack(st, s, p, ws));
   const unsigned char* slabs = ws.feat_slabs;
   if (slabs == nullptr) {  // fp32 rows from the caller: convert once (the reverse pass reads the same tiles)
     unsigned char* out = reinterpret_cast<unsigned char*>(ws.dx);

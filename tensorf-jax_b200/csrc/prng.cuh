@@ -11,6 +11,8 @@ int prng_uniform(cudaStream_t st, uint32_t k0, uint32_t k1, int64_t first, int64
 int prng_gumbel(cudaStream_t st, uint32_t k0, uint32_t k1, int64_t n, float* out);
 int pixel_rays(cudaStream_t st, const float* M_host, const float* origin_host, int W, int row0, int row1, uint32_t camera_index,
                float* origins, float* directions, uint32_t* camera_indices);
+int pixel_rays_striped(cudaStream_t st, const float* M_host, const float* origin_host, int W, int H, int stripe, int rank, int world,
+                       uint32_t camera_index, float* origins, float* directions, uint32_t* camera_indices, int64_t* n_rays);
 
 int gather_rays(cudaStream_t st, const float* origins, const float* directions, const uint32_t* cams, const float* colors,
                 int64_t n_table, const int64_t* idx, int64_t R, float* o_out, float* d_out, uint32_t* c_out, float* col_out,

@@ -5,6 +5,8 @@
 //     H2D copy of the (R,N) jitter of render.py:158-161 and the (N,) vectors of :375-379, :462-468.
 //   - pixel rays of one camera (cameras.py:100-143) for a band of image rows: replaces the CPU-pinned
 //     jit of cameras.py:124 and the per-frame H2D copy render_360.py makes.
+#include <algorithm>
+
 #include "prng.cuh"
 
 namespace tf {
@@ -76,13 +78,17 @@ struct PixelRayArgs {
   float origin[3];
   int W, row0, row1;
   uint32_t cam;
+  // striped variant: output row r (0 <= r < row1 - row0) is image row (r / stripe * world + rank) * stripe + r % stripe
+  int stripe, rank, world;  // stripe == 0: contiguous band starting at row0
 };
 __global__ void __launch_bounds__(256) k_pixel_rays(const __grid_constant__ PixelRayArgs a, float* __restrict__ origins,
                                                     float* __restrict__ directions, uint32_t* __restrict__ cams) {
   const int64_t n = (int64_t)(a.row1 - a.row0) * a.W;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float u = (float)(i % a.W), v = (float)(a.row0 + i / a.W);
+  const int r_local = (int)(i / a.W);
+  const int row = a.stripe > 0 ? (r_local / a.stripe * a.world + a.rank) * a.stripe + r_local % a.stripe : a.row0 + r_local;
+  const float u = (float)(i % a.W), v = (float)row;
   float d[3];
 #pragma unroll
   for (int r = 0; r < 3; ++r) d[r] = __fadd_rn(__fadd_rn(__fmul_rn(a.M[3 * r], u), __fmul_rn(a.M[3 * r + 1], v)), a.M[3 * r + 2]);
@@ -105,7 +111,29 @@ int pixel_rays(cudaStream_t st, const float* M_host, const float* origin_host, i
   for (int i = 0; i < 9; ++i) a.M[i] = M_host[i];
   for (int i = 0; i < 3; ++i) a.origin[i] = origin_host[i];
   a.W = W; a.row0 = row0; a.row1 = row1; a.cam = camera_index;
+  a.stripe = 0; a.rank = 0; a.world = 1;
   k_pixel_rays<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(a, origins, directions, camera_indices);
+  TF_CHECK_LAUNCH();
+  return 0;
+}
+
+int pixel_rays_striped(cudaStream_t st, const float* M_host, const float* origin_host, int W, int H, int stripe, int rank, int world,
+                       uint32_t camera_index, float* origins, float* directions, uint32_t* camera_indices, int64_t* n_rays) {
+  TF_CHECK_ARG(M_host && origin_host, "pixel_rays_striped: null argument");
+  TF_CHECK_ARG(W >= 1 && H >= 1 && stripe >= 1 && world >= 1 && rank >= 0 && rank < world, "pixel_rays_striped: bad arguments");
+  // rows of this rank: whole stripes k*world + rank, the last one possibly cut by the image height
+  int rows = 0;
+  for (int k = rank; k * stripe < H; k += world) rows += std::min(stripe, H - k * stripe);
+  if (n_rays) *n_rays = (int64_t)rows * W;
+  if (!origins && !directions) return 0;  // size query
+  TF_CHECK_ARG(origins && directions, "pixel_rays_striped: null output");
+  if (rows == 0) return 0;
+  PixelRayArgs a;
+  for (int i = 0; i < 9; ++i) a.M[i] = M_host[i];
+  for (int i = 0; i < 3; ++i) a.origin[i] = origin_host[i];
+  a.W = W; a.row0 = 0; a.row1 = rows; a.cam = camera_index;
+  a.stripe = stripe; a.rank = rank; a.world = world;
+  k_pixel_rays<<<(unsigned)ceil_div64((int64_t)rows * W, 256), 256, 0, st>>>(a, origins, directions, camera_indices);
   TF_CHECK_LAUNCH();
   return 0;
 }

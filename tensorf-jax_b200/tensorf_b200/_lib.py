@@ -132,6 +132,7 @@ SIGNATURES = {
     "tensorf_prng_uniform_slice": (_i, [_vp, C.c_uint32, C.c_uint32, _i64, _i64, C.c_float, C.c_float, _vp]),
     "tensorf_prng_gumbel": (_i, [_vp, C.c_uint32, C.c_uint32, _i64, _vp]),
     "tensorf_pixel_rays": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _i, _i, _i, C.c_uint32, _vp, _vp, _vp]),
+    "tensorf_pixel_rays_striped": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _i, _i, _i, _i, _i, C.c_uint32, _vp, _vp, _vp, C.POINTER(_i64)]),
     "tensorf_gather_rays": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "tensorf_rgba_over_white": (_i, [_vp, _vp, _i64, _vp]),
 }

@@ -471,6 +471,23 @@ def pixel_rays(M, origin, width: int, rows: Tuple[int, int], camera_index: int, 
     return o, d, c
 
 
+def pixel_rays_striped(M, origin, width: int, height: int, stripe: int, rank: int, world: int, camera_index: int, out) -> int:
+    """cameras.py:124-143 for the rows `rank` owns when a frame is dealt to `world` ranks in interleaved `stripe`-row stripes
+    (`dist.stripe_rows`), written contiguously into `out` = (origins (n,3), directions (n,3), camera_indices (n,)) by ONE
+    launch (`tensorf_pixel_rays_striped`).  Returns n."""
+    o, d, c = out
+    Mh = (C.c_float * 9)(*[float(x) for x in M])
+    oh = (C.c_float * 3)(*[float(x) for x in origin])
+    n = C.c_int64(0)
+    lib = _lib.load()
+    check(lib.tensorf_pixel_rays_striped(_stream(), Mh, oh, width, height, stripe, rank, world, camera_index, None, None, None, C.byref(n)))
+    if tuple(o.shape) != (n.value, 3) or tuple(d.shape) != (n.value, 3) or tuple(c.shape) != (n.value,):
+        raise ValueError(f"pixel_rays_striped: outputs must hold {n.value} rays")
+    check(lib.tensorf_pixel_rays_striped(_stream(), Mh, oh, width, height, stripe, rank, world, camera_index, o.data_ptr(), d.data_ptr(),
+                                         c.data_ptr(), None))
+    return int(n.value)
+
+
 def launch_count() -> int:
     """Kernels this thread has enqueued through the library so far."""
     return int(_lib.load().tensorf_launch_count())

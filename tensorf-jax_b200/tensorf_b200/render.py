@@ -212,7 +212,7 @@ class FrameRenderer:
         from . import dist as tdist
         if stripe is None:  # the largest stripe (<= 16 rows) that deals every rank the same number of rows
             stripe = tdist.balanced_stripe(image_height, world)
-        self.stripe = stripe
+        self.stripe, self.rank, self.world = stripe, rank, world
         self.config, self.aabb, self.device = config, aabb.to(torch.float32).contiguous(), aabb.device
         self.H, self.W, self.batch = image_height, image_width, batch_size
         self.rows: List[Tuple[int, int]] = tdist.stripe_rows(image_height, rank, world, stripe)
@@ -245,11 +245,9 @@ class FrameRenderer:
         """Renders this rank's rows of one frame; returns the pinned host tensor (n, 3) or (n,) in `rows` order.
         `noise`: device tensors 'jitter' (N,) and, for RGB, 'gumbel' (N,)."""
         M, origin = camera.ray_matrices()
-        a = 0
-        for r0, r1 in self.rows:  # this rank's stripes of the pixel grid -> one contiguous ray table
-            b = a + (r1 - r0) * self.W
-            ops.pixel_rays(M.reshape(-1), origin, self.W, (r0, r1), int(camera_index), self.device, out=(self.o[a:b], self.d[a:b], self.c[a:b]))
-            a = b
+        # this rank's stripes of the pixel grid -> one contiguous ray table, one launch
+        ops.pixel_rays_striped(M.reshape(-1), origin, self.W, self.H, self.stripe, self.rank, self.world, int(camera_index),
+                               (self.o, self.d, self.c))
         for a in range(0, self.n, self.batch):
             b = min(self.n, a + self.batch)
             call = self.calls[b - a]
