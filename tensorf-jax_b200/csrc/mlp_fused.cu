@@ -176,7 +176,7 @@ size_t mlp_fused_wpack_bytes(const MlpShape& s) { return (size_t)fz::b0_bytes(s.
 // Weights -> fp16 two-term slab tiles [B0 | B1 | B2]: tile rows = output unit n, columns = input k (K-major B of the
 // forward; the same bytes are the MN-major B of the reverse products, umma_tiles.cuh).
 struct FusedPackArgs {
-  const float *w0, *w1, *w2;
+  const float *w0, *w1, *w2, *b1;
   int Ca;
   unsigned char* out;
 };
@@ -198,7 +198,8 @@ __global__ void __launch_bounds__(256) k_fused_pack(FusedPackArgs a) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int nat = fz::perm(c8 * 8 + q);
-      x[q] = nat >= 0 ? a.w1[nat * fz::kU + n] : 0.f;
+      // the row of x's constant-1 column carries Dense_1's bias: the tensor core adds it
+      x[q] = nat >= 0 ? a.w1[nat * fz::kU + n] : (c8 * 8 + q == fz::kOnesCol ? a.b1[n] : 0.f);
     }
   } else {
     item -= n0 + n1;
@@ -320,7 +321,7 @@ __device__ __forceinline__ void fused_epi0(const FusedFwdArgs& g, uint32_t acc_l
 // hidden-layer accumulator -> bias, ReLU, mask bits -> next layer's A operand (this quarter's 32 columns = 2 k-chunks).
 // LAST: no next layer; the output layer (networks.py:114-120) is accumulated into o3 instead.
 template <int Q, bool TRAIN, bool LAST>
-__device__ __forceinline__ void fused_epi_hidden(uint32_t acc_lane, uint32_t aop_lane, const float* s_bias, const float* s_w3, unsigned char* slab_row,
+__device__ __forceinline__ void fused_epi_hidden(uint32_t acc_lane, uint32_t aop_lane, const float* s_bias /* null: already in the product */, const float* s_w3, unsigned char* slab_row,
                                                  uint32_t* bits_row, uint64_t* kready, int lane, float* o3) {
   uint32_t bw = 0u;
   float y[32];
@@ -332,7 +333,7 @@ __device__ __forceinline__ void fused_epi_hidden(uint32_t acc_lane, uint32_t aop
     const int n0 = 32 * Q + 16 * c;
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
-      const float v = fmaxf(y[16 * c + q] + s_bias[n0 + q], 0.f);
+      const float v = fmaxf(LAST ? y[16 * c + q] + s_bias[n0 + q] : y[16 * c + q], 0.f);  // Dense_1's bias rides in W1' (ones column of x')
       y[16 * c + q] = v;
       if (TRAIN && v > 0.f) bw |= 1u << (16 * c + q);
       if (LAST) {
@@ -563,7 +564,7 @@ __global__ void __launch_bounds__(256) k_feat_to_slab(const float* feat, int64_t
 int mlp_fused_pack(cudaStream_t st, const MlpShape& s, const MlpParams& p, const MlpWs& ws) {
   TF_CHECK_ARG(mlp_fused_supported(s), "fused MLP: unsupported network shape");
   TF_CHECK_ARG(ws.wpack_bytes >= mlp_fused_wpack_bytes(s), "fused MLP: weight scratch too small");
-  FusedPackArgs a{p.w0, p.w1, p.w2, s.Ca, ws.wpack};
+  FusedPackArgs a{p.w0, p.w1, p.w2, p.b1, s.Ca, ws.wpack};
   const int items = 32 * (s.Ca / 8) + fz::kU * (fz::kX / 8) + fz::kU * (fz::kU / 8);
   k_fused_pack<<<(items + 255) / 256, 256, 0, st>>>(a);
   TF_CHECK_LAUNCH();
