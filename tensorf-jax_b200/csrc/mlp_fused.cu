@@ -275,8 +275,8 @@ __device__ __forceinline__ void fast_sincos(float x, float& sn, float& cs) {
 }
 
 // Dense_0 accumulator -> Fourier-encoded input x' (this quarter's 40 columns)
-template <int Q, bool TRAIN>
-__device__ __forceinline__ void fused_epi0(const FusedFwdArgs& g, uint32_t acc_lane, uint32_t aop_lane, int64_t m, int64_t tile, int row,
+template <bool TRAIN>
+__device__ __forceinline__ void fused_epi0(const FusedFwdArgs& g, int Q, uint32_t acc_lane, uint32_t aop_lane, int64_t m, int64_t tile, int row,
                                            uint64_t* xready, int lane) {
   float f[8];
   tmem_ld8(acc_lane + 8u * Q, f);
@@ -320,8 +320,8 @@ __device__ __forceinline__ void fused_epi0(const FusedFwdArgs& g, uint32_t acc_l
 
 // hidden-layer accumulator -> bias, ReLU, mask bits -> next layer's A operand (this quarter's 32 columns = 2 k-chunks).
 // LAST: no next layer; the output layer (networks.py:114-120) is accumulated into o3 instead.
-template <int Q, bool TRAIN, bool LAST>
-__device__ __forceinline__ void fused_epi_hidden(uint32_t acc_lane, uint32_t aop_lane, const float* s_bias /* null: already in the product */, const float* s_w3, unsigned char* slab_row,
+template <bool TRAIN, bool LAST>
+__device__ __forceinline__ void fused_epi_hidden(int Q, uint32_t acc_lane, uint32_t aop_lane, const float* s_bias /* null: already in the product */, const float* s_w3, unsigned char* slab_row,
                                                  uint32_t* bits_row, uint64_t* kready, int lane, float* o3) {
   uint32_t bw = 0u;
   float y[32];
@@ -359,8 +359,11 @@ __device__ __forceinline__ void fused_epi_hidden(uint32_t acc_lane, uint32_t aop
   if (TRAIN) bits_row[Q] = bw;
 }
 
-template <int Q, bool TRAIN>
-__device__ __forceinline__ void fused_fwd_worker(const FusedFwdArgs& g, uint32_t tmem, int quad, int lane, uint64_t* xready, uint64_t* kready,
+// The column quarter Q is a RUN-TIME value on purpose: with four template instances the kernel was 133 KB of SASS and 43 % of
+// its warp stalls were instruction fetches (ncu: stall_no_inst) - sixteen warps walking four copies of the same unrolled
+// epilogues do not fit the instruction cache.
+template <bool TRAIN>
+__device__ __forceinline__ void fused_fwd_worker(const FusedFwdArgs& g, int Q, uint32_t tmem, int quad, int lane, uint64_t* xready, uint64_t* kready,
                                                  uint64_t* accfull, const float* s_b1, const float* s_b2, const float* s_w3, float* s_part) {
   const int64_t ntiles = (g.M + 127) / 128;
   const int row = quad * 32 + lane;
@@ -370,37 +373,43 @@ __device__ __forceinline__ void fused_fwd_worker(const FusedFwdArgs& g, uint32_t
   auto encode = [&](int64_t t, uint32_t it) {
     mbar_wait(&accfull[0], it & 1, 10);
     tc_fence_after();
-    fused_epi0<Q, TRAIN>(g, lane_base + fz::kAccD0 + 32u * (it & 1), aop, t * 128 + row, t, row, xready, lane);
+    fused_epi0<TRAIN>(g, Q, lane_base + fz::kAccD0 + 32u * (it & 1), aop, t * 128 + row, t, row, xready, lane);
   };
-  uint32_t it = 0;
-  if ((int64_t)blockIdx.x < ntiles) encode(blockIdx.x, 0);
-  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+  const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  // Software pipeline over the CTA's tiles, written so that every epilogue appears ONCE in the code (instruction cache):
+  // step k finishes Dense_1 of tile k-1, encodes tile k, then finishes tile k-1.
+  for (int64_t k = 0; k <= my_tiles; ++k) {
+    const int64_t t = blockIdx.x + (k - 1) * (int64_t)gridDim.x;  // the tile being finished (k >= 1)
     const int64_t m = t * 128 + row;
-    const uint32_t ph = it & 1;
-    // Dense_1 -> h1
-    mbar_wait(&accfull[1], ph, 11);
-    tc_fence_after();
-    fused_epi_hidden<Q, TRAIN, false>(accX, aop, s_b1, s_w3, TRAIN ? g.h1s + (size_t)t * (fz::kU * 512) + (size_t)row * 16 : nullptr,
-                                      TRAIN ? g.bits1 + m * 4 : nullptr, kready, lane, nullptr);
-    // Dense_2 complete: h1 in the operand region is dead.  The NEXT tile's x' goes in first, so that its Dense_1 runs on
-    // the tensor pipe while this tile's output layer is evaluated on the CUDA cores.
+    const uint32_t ph = (uint32_t)(k - 1) & 1u;
     float o3[3] = {0.f, 0.f, 0.f};
-    mbar_wait(&accfull[2], ph, 12);
-    tc_fence_after();
-    if (t + gridDim.x < ntiles) encode(t + gridDim.x, it + 1);
-    // Dense_2 -> h2 -> Dense_3 + sigmoid
-    fused_epi_hidden<Q, TRAIN, true>(accY, aop, s_b2, s_w3, TRAIN ? g.h2s + (size_t)t * (fz::kU * 512) + (size_t)row * 16 : nullptr,
-                                     TRAIN ? g.bits2 + m * 4 : nullptr, kready, lane, o3);
-    tc_fence_before();
-    if (Q != 0) {
-      float* sp = s_part + (Q - 1) * 384 + 3 * row;
-      sp[0] = o3[0]; sp[1] = o3[1]; sp[2] = o3[2];
+    if (k > 0) {
+      // Dense_1 -> h1
+      mbar_wait(&accfull[1], ph, 11);
+      tc_fence_after();
+      fused_epi_hidden<TRAIN, false>(Q, accX, aop, s_b1, s_w3, TRAIN ? g.h1s + (size_t)t * (fz::kU * 512) + (size_t)row * 16 : nullptr,
+                                     TRAIN ? g.bits1 + m * 4 : nullptr, kready, lane, nullptr);
+      // Dense_2 complete: h1 in the operand region is dead.  The NEXT tile's x' goes in first, so that its Dense_1 runs on
+      // the tensor pipe while this tile's output layer is evaluated on the CUDA cores.
+      mbar_wait(&accfull[2], ph, 12);
+      tc_fence_after();
     }
-    asm volatile("bar.sync 1, 512;" ::: "memory");  // also: every quarter has read accumulator Y before the next Dense_2 can start
-    if (Q == 0 && m < g.M) {
+    if (k < my_tiles) encode(blockIdx.x + k * (int64_t)gridDim.x, (uint32_t)k);
+    if (k > 0) {
+      // Dense_2 -> h2 -> Dense_3 + sigmoid
+      fused_epi_hidden<TRAIN, true>(Q, accY, aop, s_b2, s_w3, TRAIN ? g.h2s + (size_t)t * (fz::kU * 512) + (size_t)row * 16 : nullptr,
+                                    TRAIN ? g.bits2 + m * 4 : nullptr, kready, lane, o3);
+      tc_fence_before();
+      if (Q != 0) {
+        float* sp = s_part + (Q - 1) * 384 + 3 * row;
+        sp[0] = o3[0]; sp[1] = o3[1]; sp[2] = o3[2];
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");  // also: every quarter has read accumulator Y before the next Dense_2 can start
+      if (Q == 0 && m < g.M) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        g.rgb[3 * m + c] = 1.0f / (1.0f + expf(-(o3[c] + s_part[3 * row + c] + s_part[384 + 3 * row + c] + s_part[768 + 3 * row + c] + s_w3[384 + c])));
+        for (int c = 0; c < 3; ++c)
+          g.rgb[3 * m + c] = 1.0f / (1.0f + expf(-(o3[c] + s_part[3 * row + c] + s_part[384 + 3 * row + c] + s_part[768 + 3 * row + c] + s_w3[384 + c])));
+      }
     }
   }
 }
@@ -451,12 +460,7 @@ __global__ void __launch_bounds__(fz::kThreads, 1) k_mlp_fused_fwd(FusedFwdArgs 
 
   if (warp < fz::kWorkWarps) {
     // ================= row workers: thread = row; quarter q (warps 4q..4q+3) owns a quarter of every layer's columns ========
-    switch (warp >> 2) {
-      case 0: fused_fwd_worker<0, TRAIN>(g, tmem, warp & 3, lane, xready, kready, accfull, s_b1, s_b2, s_w3, s_part); break;
-      case 1: fused_fwd_worker<1, TRAIN>(g, tmem, warp & 3, lane, xready, kready, accfull, s_b1, s_b2, s_w3, s_part); break;
-      case 2: fused_fwd_worker<2, TRAIN>(g, tmem, warp & 3, lane, xready, kready, accfull, s_b1, s_b2, s_w3, s_part); break;
-      default: fused_fwd_worker<3, TRAIN>(g, tmem, warp & 3, lane, xready, kready, accfull, s_b1, s_b2, s_w3, s_part); break;
-    }
+    fused_fwd_worker<TRAIN>(g, warp >> 2, tmem, warp & 3, lane, xready, kready, accfull, s_b1, s_b2, s_w3, s_part);
   } else if (warp == fz::kLoadWarp) {
     // ================= loader: weights once, then the feature tile of every row tile in 16 KB pieces (32 columns) =============
     if (lane == 0) {
@@ -660,8 +664,7 @@ __device__ __forceinline__ void store_chunk_slab(unsigned char* slab_row, int c,
   p[384] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
 }
 
-template <int Q>
-__device__ __forceinline__ void fused_bwd_worker(const FusedBwdArgs& g, uint32_t tmem, int quad, int lane, uint64_t* kready, uint64_t* dfready,
+__device__ __forceinline__ void fused_bwd_worker(const FusedBwdArgs& g, int Q, uint32_t tmem, int quad, int lane, uint64_t* kready, uint64_t* dfready,
                                                  uint64_t* accfull, uint64_t* s3done, const float* s_w3) {
   const int64_t ntiles = (g.M + 127) / 128;
   const int row = quad * 32 + lane;
@@ -710,90 +713,96 @@ __device__ __forceinline__ void fused_bwd_worker(const FusedBwdArgs& g, uint32_t
       }
     }
   };
-  uint32_t it = 0;
-  if ((int64_t)blockIdx.x < ntiles) out_reverse(blockIdx.x);
-  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+  const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  // Software pipeline over the CTA's tiles with every stage appearing once in the code: step k finishes dp1 and df of tile
+  // k-1, writes tile k's dp2, then stores tile k-1's d_features.
+  for (int64_t k = 0; k <= my_tiles; ++k) {
+    const int64_t t = blockIdx.x + (k - 1) * (int64_t)gridDim.x;  // the tile being finished (k >= 1)
     const int64_t m = t * 128 + row;
-    const uint32_t ph = it & 1;
+    const uint32_t ph = (uint32_t)(k - 1) & 1u;
     // accumulators alternate with the tile parity: dh1 and d_features in P, dx' in Q_ (see the MMA warp)
     const uint32_t accP = lane_base + (ph ? fz::kBAccB : fz::kBAccA), accQ = lane_base + (ph ? fz::kBAccA : fz::kBAccB);
-    // ---- dp1 = (dp2 W2^T) * relu'(h1) ----
-    mbar_wait(&accfull[0], ph, 50);
-    tc_fence_after();
-    {
-      const uint32_t bw = g.bits1[m * 4 + Q];
-      unsigned char* slab_row = g.dp1s + (size_t)t * (fz::kU * 512) + (size_t)row * 16;
-      float y[32];
-      tmem_ld16(accP + 32 * Q, y);
-      tmem_ld16(accP + 32 * Q + 16, y + 16);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-#pragma unroll
-        for (int q = 0; q < 16; ++q) y[16 * c + q] = ((bw >> (16 * c + q)) & 1u) ? y[16 * c + q] : 0.f;
-        emit8<true>(y + 16 * c, aop, 4 * Q + 2 * c, slab_row);
-        emit8<true>(y + 16 * c + 8, aop, 4 * Q + 2 * c + 1, slab_row);
-        chunk_arrive(&kready[2 * Q + c], lane);
-      }
-    }
-    // ---- Fourier reverse (networks.py:13-35, :68-76): df_d = dx_d + cos(f) dx_sin1 + 2 cos(2f) dx_sin2 - sin(f) dx_cos1 - 2 sin(2f) dx_cos2 ----
-    mbar_wait(&accfull[1], ph, 51);
-    tc_fence_after();
-    {
-      float fv[8];
-      const float4* fp = reinterpret_cast<const float4*>(g.fs + (size_t)t * 4096 + (size_t)(2 * Q) * 512) + row;
-      const float4 f0 = fp[0], f1 = fp[128];
-      fv[0] = f0.x; fv[1] = f0.y; fv[2] = f0.z; fv[3] = f0.w; fv[4] = f1.x; fv[5] = f1.y; fv[6] = f1.z; fv[7] = f1.w;
-      float dx[40];
-#pragma unroll
-      for (int c = 0; c < 5; ++c) tmem_ld8(accQ + 40 * Q + 8 * c, dx + 8 * c);
-      tmem_ld_wait();
-      float y[8];
-      constexpr int ND = Q < 3 ? 8 : 3;  // feature dimensions of this quarter (the view direction needs no gradient)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (i < ND) {
-          float sn, cs;
-          fast_sincos(fv[i], sn, cs);
-          const float sn2 = 2.0f * sn * cs, cs2 = fmaf(-2.0f * sn, sn, 1.0f);
-          y[i] = dx[5 * i] + cs * dx[5 * i + 1] + 2.0f * cs2 * dx[5 * i + 2] - sn * dx[5 * i + 3] - 2.0f * sn2 * dx[5 * i + 4];
-        } else {
-          y[i] = 0.f;
-        }
-      }
-      emit8<true>(y, aop, Q, g.dfs + (size_t)t * (32 * 512) + (size_t)row * 16);
-      chunk_arrive(&dfready[Q >> 1], lane);
-    }
-    // ---- d_features = df W0^T complete: the operand region is free, so the NEXT tile's dp2 goes in first and its dh1 product
-    // runs on the tensor pipe while this tile's d_features are written out ----
-    mbar_wait(&accfull[2], ph, 52);
-    tc_fence_after();
-    if (t + gridDim.x < ntiles) out_reverse(t + gridDim.x);
-    {  // accumulator fragments (16 rows x 256 bit) -> whole 32-byte sectors
-      const int lrow = lane >> 2, lc = (lane & 3) * 2;
-      const int c_beg = (nk0 * Q) / 4, c_end = (nk0 * (Q + 1)) / 4;
-      const uint32_t accP0 = tmem + (ph ? fz::kBAccB : fz::kBAccA);
-      for (int c = c_beg; c < c_end; ++c) {
-        float v[2][8];
-        tmem_ld_16x256b_x2(accP0 + ((uint32_t)(quad * 32) << 16) + 16u * c, v[0]);
-        tmem_ld_16x256b_x2(accP0 + ((uint32_t)(quad * 32 + 16) << 16) + 16u * c, v[1]);
+    if (k > 0) {
+      // ---- dp1 = (dp2 W2^T) * relu'(h1) ----
+      mbar_wait(&accfull[0], ph, 50);
+      tc_fence_after();
+      {
+        const uint32_t bw = g.bits1[m * 4 + Q];
+        unsigned char* slab_row = g.dp1s + (size_t)t * (fz::kU * 512) + (size_t)row * 16;
+        float y[32];
+        tmem_ld16(accP + 32 * Q, y);
+        tmem_ld16(accP + 32 * Q + 16, y + 16);
         tmem_ld_wait();
 #pragma unroll
-        for (int blk = 0; blk < 2; ++blk)
+        for (int c = 0; c < 2; ++c) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int64_t mr = t * 128 + quad * 32 + blk * 16 + h * 8 + lrow;
-            if (mr < g.M) {
-              float* dst = g.d_feat + mr * g.K0 + 16 * c + lc;
-              *reinterpret_cast<float2*>(dst) = make_float2(v[blk][h * 2] * invS, v[blk][h * 2 + 1] * invS);
-              *reinterpret_cast<float2*>(dst + 8) = make_float2(v[blk][4 + h * 2] * invS, v[blk][4 + h * 2 + 1] * invS);
-            }
-          }
+          for (int q = 0; q < 16; ++q) y[16 * c + q] = ((bw >> (16 * c + q)) & 1u) ? y[16 * c + q] : 0.f;
+          emit8<true>(y + 16 * c, aop, 4 * Q + 2 * c, slab_row);
+          emit8<true>(y + 16 * c + 8, aop, 4 * Q + 2 * c + 1, slab_row);
+          chunk_arrive(&kready[2 * Q + c], lane);
+        }
       }
+      // ---- Fourier reverse (networks.py:13-35, :68-76): df_d = dx_d + cos(f) dx_sin1 + 2 cos(2f) dx_sin2 - sin(f) dx_cos1 - 2 sin(2f) dx_cos2 ----
+      mbar_wait(&accfull[1], ph, 51);
+      tc_fence_after();
+      {
+        float fv[8];
+        const float4* fp = reinterpret_cast<const float4*>(g.fs + (size_t)t * 4096 + (size_t)(2 * Q) * 512) + row;
+        const float4 f0 = fp[0], f1 = fp[128];
+        fv[0] = f0.x; fv[1] = f0.y; fv[2] = f0.z; fv[3] = f0.w; fv[4] = f1.x; fv[5] = f1.y; fv[6] = f1.z; fv[7] = f1.w;
+        float dx[40];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) tmem_ld8(accQ + 40 * Q + 8 * c, dx + 8 * c);
+        tmem_ld_wait();
+        float y[8];
+        const int ND = Q < 3 ? 8 : 3;  // feature dimensions of this quarter (the view direction needs no gradient)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i < ND) {
+            float sn, cs;
+            fast_sincos(fv[i], sn, cs);
+            const float sn2 = 2.0f * sn * cs, cs2 = fmaf(-2.0f * sn, sn, 1.0f);
+            y[i] = dx[5 * i] + cs * dx[5 * i + 1] + 2.0f * cs2 * dx[5 * i + 2] - sn * dx[5 * i + 3] - 2.0f * sn2 * dx[5 * i + 4];
+          } else {
+            y[i] = 0.f;
+          }
+        }
+        emit8<true>(y, aop, Q, g.dfs + (size_t)t * (32 * 512) + (size_t)row * 16);
+        chunk_arrive(&dfready[Q >> 1], lane);
+      }
+      // ---- d_features = df W0^T complete: the operand region is free, so the NEXT tile's dp2 goes in first and its dh1 product
+      // runs on the tensor pipe while this tile's d_features are written out ----
+      mbar_wait(&accfull[2], ph, 52);
+      tc_fence_after();
     }
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(s3done);  // this warp has read accumulator P: the next tile's dx' product may overwrite it
+    if (k < my_tiles) out_reverse(blockIdx.x + k * (int64_t)gridDim.x);
+    if (k > 0) {
+      {  // accumulator fragments (16 rows x 256 bit) -> whole 32-byte sectors
+        const int lrow = lane >> 2, lc = (lane & 3) * 2;
+        const int c_beg = (nk0 * Q) / 4, c_end = (nk0 * (Q + 1)) / 4;
+        const uint32_t accP0 = tmem + (ph ? fz::kBAccB : fz::kBAccA);
+        for (int c = c_beg; c < c_end; ++c) {
+          float v[2][8];
+          tmem_ld_16x256b_x2(accP0 + ((uint32_t)(quad * 32) << 16) + 16u * c, v[0]);
+          tmem_ld_16x256b_x2(accP0 + ((uint32_t)(quad * 32 + 16) << 16) + 16u * c, v[1]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int blk = 0; blk < 2; ++blk)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int64_t mr = t * 128 + quad * 32 + blk * 16 + h * 8 + lrow;
+              if (mr < g.M) {
+                float* dst = g.d_feat + mr * g.K0 + 16 * c + lc;
+                *reinterpret_cast<float2*>(dst) = make_float2(v[blk][h * 2] * invS, v[blk][h * 2 + 1] * invS);
+                *reinterpret_cast<float2*>(dst + 8) = make_float2(v[blk][4 + h * 2] * invS, v[blk][4 + h * 2 + 1] * invS);
+              }
+            }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s3done);  // this warp has read accumulator P: the next tile's dx' product may overwrite it
+    }
   }
 }
 
@@ -827,12 +836,7 @@ __global__ void __maxnreg__(72) k_mlp_fused_bwd(FusedBwdArgs g) {
   const uint32_t tmem = *tmem_slot;
 
   if (warp < 16) {
-    switch (warp >> 2) {
-      case 0: fused_bwd_worker<0>(g, tmem, warp & 3, lane, kready, dfready, accfull, s3done, s_w3); break;
-      case 1: fused_bwd_worker<1>(g, tmem, warp & 3, lane, kready, dfready, accfull, s3done, s_w3); break;
-      case 2: fused_bwd_worker<2>(g, tmem, warp & 3, lane, kready, dfready, accfull, s3done, s_w3); break;
-      default: fused_bwd_worker<3>(g, tmem, warp & 3, lane, kready, dfready, accfull, s3done, s_w3); break;
-    }
+    fused_bwd_worker(g, warp >> 2, tmem, warp & 3, lane, kready, dfready, accfull, s3done, s_w3);
   } else if (warp == fz::kBwdLoadWarp) {
     if (lane == 0) {
       mbar_arrive_expect_tx(wfull, wbytes);
