@@ -660,23 +660,53 @@ static int render_rgb_bwd_impl(tensorf_stream_t s, const tensorf_render_desc* d,
     MlpGrads mg = mlp_grads(*grads);
     mg.prezeroed = true;  // by k_ray_bwd above
     mg.amax_ready = true;
+    mws.beside_scatter = true;
     // Launch order = placement order: the MLP kernels are launched first so that their one CTA per SM is resident
     // everywhere (chain: 576 threads x 72 registers, weight gradients: 192 x 98) and the scatter CTAs fill what is left of
     // the register file (one / two density-scatter CTAs per SM instead of three; the scatters use no shared memory).
+    // (Measured and dropped: a third branch for the appearance scatter, and the MLP branch on a high-priority stream so
+    // that the weight-gradient CTAs are placed before the density scatter's pending ones - the branch ends 110 us earlier
+    // but the join does not move: the overlapped region is bound by the SMs' total work, not by the dependencies.)
     static const int fork_mode = getenv("TENSORF_FORK_MODE") ? atoi(getenv("TENSORF_FORK_MODE")) : 2;
+    // TENSORF_FORK_TIMES=1 (eager launches only): prints where each branch of the PREVIOUS call ended, relative to the fork
+    static const bool fork_times = getenv("TENSORF_FORK_TIMES") != nullptr;
+    static thread_local cudaEvent_t tev[6] = {nullptr};
+    static thread_local int tcalls = 0;
+    auto mark = [&](int i, cudaStream_t s_) {
+      if (fork_times) cudaEventRecord(tev[i], s_);
+    };
+    if (fork_times) {
+      if (tev[0] == nullptr) {
+        for (auto& e : tev) cudaEventCreate(&e);
+      } else if (cudaEventSynchronize(tev[5]) == cudaSuccess && (++tcalls % 8) == 0) {
+        float t[6] = {0};
+        for (int i = 1; i < 6; ++i) cudaEventElapsedTime(&t[i], tev[0], tev[i]);
+        fprintf(stderr, "tensorf_b200 fork (us from k_ray_bwd's end): chain %.1f  wgrad+reduce %.1f | density scatter %.1f  appearance scatter %.1f | join %.1f\n",
+                1e3f * t[1], 1e3f * t[2], 1e3f * t[3], 1e3f * t[4], 1e3f * t[5]);
+      }
+    }
+    mark(0, st);
     if (fork_mode == 2) TF_CHECK_CUDA(cudaEventRecord(ss->ev[0], st));  // k_ray_bwd done: dz is final
     TF_RETURN_IF_ERROR(mlp_fused_bwd_chain(st, ms, mlp_params(*p), M, mws, w.rgb_sel, w.d_rgb_sel, w.d_feat, mg));
+    mark(1, st);
     if (fork_mode == 2) {  // density scatter beside the chain kernel already
       TF_CHECK_CUDA(cudaStreamWaitEvent(ss->stream, ss->ev[0], 0));
       TF_RETURN_IF_ERROR(density_scatter(ss->stream));
+      mark(3, ss->stream);
     }
     TF_CHECK_CUDA(cudaEventRecord(ss->ev[1], st));  // d_features are final
     TF_RETURN_IF_ERROR(mlp_fused_bwd_wgrad(st, ms, M, mws, mg));
+    mark(2, st);
     TF_CHECK_CUDA(cudaStreamWaitEvent(ss->stream, ss->ev[1], 0));
-    if (fork_mode != 2) TF_RETURN_IF_ERROR(density_scatter(ss->stream));
+    if (fork_mode != 2) {
+      TF_RETURN_IF_ERROR(density_scatter(ss->stream));
+      mark(3, ss->stream);
+    }
     TF_RETURN_IF_ERROR(appearance_scatter(ss->stream));
+    mark(4, ss->stream);
     TF_CHECK_CUDA(cudaEventRecord(ss->ev[2], ss->stream));
     TF_CHECK_CUDA(cudaStreamWaitEvent(st, ss->ev[2], 0));
+    mark(5, st);
   } else {
     if (do_den && phase == 0) TF_RETURN_IF_ERROR(density_scatter(st));
     if (do_app) {

@@ -148,6 +148,9 @@ int umma_probe(cudaStream_t st, const float* A, const float* B, float* D, int N,
 // is zero; in the weight-gradient product it yields the bias gradient as one more column sum).  fz_perm maps a
 // kernel column to the reference's column of networks.py:68-76 ([f, v, enc(f), enc(v)]).
 // ===============================================================================================================
+// Residual / gradient slab tiles are written once and read back a kernel or more later: streaming stores (evict-first in
+// the L2), so that they do not displace the factor and gradient planes the gather / scatter kernels keep there.
+#define TF_SLAB_ST(ptr, val) __stcs((ptr), (val))
 namespace fz {
 constexpr int kU = 128, kSq = 27, kQDims = 8, kPer = 5, kXQ = 40, kX = 160, kOnesCol = 150;
 constexpr int kWorkWarps = 16, kMmaWarp = 16, kLoadWarp = 17, kThreads = 576;
@@ -261,8 +264,8 @@ __device__ __forceinline__ void emit8(const float* y, uint32_t aop_lane, int cg,
   tmem_st4(aop_lane + fz::kAopLo + 4u * cg, lo);
   if (TRAIN) {
     uint4* p = reinterpret_cast<uint4*>(slab_row + (size_t)(2 * cg) * 2048);
-    p[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    p[128] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    TF_SLAB_ST(&p[0], make_uint4(hi[0], hi[1], hi[2], hi[3]));
+    TF_SLAB_ST(&p[128], make_uint4(lo[0], lo[1], lo[2], lo[3]));
   }
 }
 // sin / cos of a squashed feature or view-direction component (networks.py:13-35: sin(2^j x), sin(2^j x + pi/2), j < 2):
@@ -350,10 +353,10 @@ __device__ __forceinline__ void fused_epi_hidden(int Q, uint32_t acc_lane, uint3
       uint32_t hi[8], lo[8];
       split16(y + 16 * c, hi, lo);
       uint4* p = reinterpret_cast<uint4*>(slab_row + (size_t)(4 * (2 * Q + c)) * 2048);
-      p[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      p[128] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      p[256] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-      p[384] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+      TF_SLAB_ST(&p[0], make_uint4(hi[0], hi[1], hi[2], hi[3]));
+      TF_SLAB_ST(&p[128], make_uint4(lo[0], lo[1], lo[2], lo[3]));
+      TF_SLAB_ST(&p[256], make_uint4(hi[4], hi[5], hi[6], hi[7]));
+      TF_SLAB_ST(&p[384], make_uint4(lo[4], lo[5], lo[6], lo[7]));
     }
   }
   if (TRAIN) bits_row[Q] = bw;
@@ -658,10 +661,10 @@ struct FusedBwdArgs {
 
 __device__ __forceinline__ void store_chunk_slab(unsigned char* slab_row, int c, const uint32_t* hi, const uint32_t* lo) {
   uint4* p = reinterpret_cast<uint4*>(slab_row + (size_t)(4 * c) * 2048);
-  p[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  p[128] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-  p[256] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-  p[384] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+  TF_SLAB_ST(&p[0], make_uint4(hi[0], hi[1], hi[2], hi[3]));
+  TF_SLAB_ST(&p[128], make_uint4(lo[0], lo[1], lo[2], lo[3]));
+  TF_SLAB_ST(&p[256], make_uint4(hi[4], hi[5], hi[6], hi[7]));
+  TF_SLAB_ST(&p[384], make_uint4(lo[4], lo[5], lo[6], lo[7]));
 }
 
 __device__ __forceinline__ void fused_bwd_worker(const FusedBwdArgs& g, int Q, uint32_t tmem, int quad, int lane, uint64_t* kready, uint64_t* dfready,
@@ -924,6 +927,7 @@ struct FusedWgradArgs {
   int K0;
   float *dw0, *dw1, *db1, *dw2, *db2, *dw3;
   float* partial;  // [gridDim.x][320 + K0][128]
+  int group;       // B pieces per MMA: 2 (N = 64) when the kernel runs alone, 1 beside a scatter kernel
 };
 
 // Sum of the per-CTA partial accumulators of k_mlp_fused_wgrad -> the gradient leaves (overwritten), un-scaled, with the
@@ -1027,16 +1031,20 @@ __global__ void __launch_bounds__(fz::kWgThreads, 1) k_mlp_fused_wgrad(FusedWgra
     // ================= loader =================
     if (lane == 0) {
       uint32_t ab = 0, aph = 0, sl = 0, bph = 0;
+      // read-once streams: evict-first, so that they do not push the gradient planes of the scatter kernel running beside
+      // this one out of the L2 (-12 us per step)
+      const uint64_t pol = l2_policy_evict_first();
+      auto copy = [&](void* dst, const void* src, uint32_t bytes, uint64_t* bar) { bulk_copy_g2s_hint(dst, src, bytes, bar, pol); };
       auto load_a = [&](const unsigned char* src, uint32_t bytes) {
         mbar_wait(&aempty[ab], aph ^ 1, 70);
         mbar_arrive_expect_tx(&afull[ab], bytes);
-        for (uint32_t off = 0; off < bytes; off += fz::kPiece) bulk_copy_g2s(sA + ab * fz::kATile + off, src + off, fz::kPiece, &afull[ab]);
+        for (uint32_t off = 0; off < bytes; off += fz::kPiece) copy(sA + ab * fz::kATile + off, src + off, fz::kPiece, &afull[ab]);
         if (++ab == 2) { ab = 0; aph ^= 1; }
       };
       auto load_b = [&](const unsigned char* src, uint32_t bytes) {
         mbar_wait(&bempty[sl], bph ^ 1, 71);
         mbar_arrive_expect_tx(&bfull[sl], bytes);
-        bulk_copy_g2s(sB + sl * fz::kPiece, src, bytes, &bfull[sl]);
+        copy(sB + sl * fz::kPiece, src, bytes, &bfull[sl]);
         if (++sl == fz::kWgSlots) { sl = 0; bph ^= 1; }
       };
       for (int64_t it = 0; it < my_tiles; ++it) {
@@ -1079,6 +1087,36 @@ __global__ void __launch_bounds__(fz::kWgThreads, 1) k_mlp_fused_wgrad(FusedWgra
         piece(sb + sl * fz::kPiece, dcol, idesc, &bempty[sl]);
         if (++sl == fz::kWgSlots) { sl = 0; bph ^= 1; }
       };
+      // `cols` columns of B in 32-column pieces (the last one may be shorter).  Two pieces in adjacent slots go into ONE
+      // instruction stream of N = 64: every MMA re-reads its 128 x 16 A operand from shared memory whatever N is, and at
+      // N = 32 the kernel was bound by exactly those reads (ncu: tensor-core shared-memory wavefronts at 59 % of peak
+      // with the HMMA pipe never idle).
+      auto ring_cols = [&](uint32_t dcol, int cols) {
+        for (int c = 0; c < cols;) {
+          const int left = cols - c;
+          if (g.group > 1 && left > 32 && sl + 1 < (uint32_t)fz::kWgSlots) {
+            const int n = min(64, left);
+            mbar_wait(&bfull[sl], bph, 81);
+            mbar_wait(&bfull[sl + 1], bph, 82);
+            tc_fence_after();
+            const uint32_t a_lo = desc_lo(sa + ab * fz::kATile, 128u), b_lo = desc_lo(sb + sl * fz::kPiece, 128u);
+            const uint32_t idesc = make_idesc(128, n, FMT_F16, FMT_F16, 1, 1);
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) umma_ss_split2(tm + dcol + c, a_lo + 16u * ks, term, a_hi, b_lo + 16u * ks, term, a_hi, idesc, first && ks == 0);
+              umma_commit(&bempty[sl]);
+              umma_commit(&bempty[sl + 1]);
+            }
+            __syncwarp();
+            sl += 2;
+            if (sl == (uint32_t)fz::kWgSlots) { sl = 0; bph ^= 1; }
+            c += n;
+          } else {
+            ring_piece(dcol + c, left >= 32 ? id32 : make_idesc(128, left, FMT_F16, FMT_F16, 1, 1));
+            c += min(32, left);
+          }
+        }
+      };
       auto release_a = [&]() {
         if (elect_one()) umma_commit(&aempty[ab]);
         __syncwarp();
@@ -1088,14 +1126,14 @@ __global__ void __launch_bounds__(fz::kWgThreads, 1) k_mlp_fused_wgrad(FusedWgra
       ring_piece(fz::kD3, id16);
       release_a();
       wait_a();  // dp2^T [h1 | 1]
-      for (int j = 0; j < 4; ++j) ring_piece(fz::kD2 + 32u * j, id32);
+      ring_cols(fz::kD2, 128);
       piece(so, fz::kD2 + 128u, id16, nullptr);
       release_a();
       wait_a();  // dp1^T x'
-      for (int j = 0; j < 5; ++j) ring_piece(fz::kD1 + 32u * j, id32);
+      ring_cols(fz::kD1, fz::kX);
       release_a();
       wait_a();  // df^T features (rows >= 32 of this accumulator are meaningless and never read)
-      for (int j = 0; j < npf; ++j) ring_piece(fz::kD0 + 32u * j, (K0 - 32 * j) >= 32 ? id32 : id16);
+      ring_cols(fz::kD0, K0);
       release_a();
     }
     if (elect_one()) umma_commit(done);
@@ -1173,6 +1211,11 @@ int mlp_fused_bwd_wgrad(cudaStream_t st, const MlpShape& s, int64_t M, const Mlp
   w.amax = amax; w.M = M; w.K0 = s.Ca;
   w.dw0 = gr.w0; w.dw1 = gr.w1; w.db1 = gr.b1; w.dw2 = gr.w2; w.db2 = gr.b2; w.dw3 = gr.w3;
   w.partial = ws.wg_partial;
+  // Alone, the kernel is 20 us faster with two B pieces per MMA (N = 64).  Beside the appearance scatter of the forked
+  // reverse pass the whole step is 19 us SLOWER with it (measured in both orders): the scatter is the critical branch
+  // and latency-bound on its DRAM reads, and a weight-gradient kernel that pulls its 538 MB faster starves it.
+  static const int grp_env = getenv("TENSORF_WG_GROUP") ? atoi(getenv("TENSORF_WG_GROUP")) : 0;
+  w.group = grp_env ? grp_env : (ws.beside_scatter ? 1 : 2);
   TF_CHECK_CUDA(cudaFuncSetAttribute(k_mlp_fused_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::kWgSmem));
   k_mlp_fused_wgrad<<<grid, fz::kWgThreads, fz::kWgSmem, st>>>(w);
   TF_CHECK_LAUNCH();

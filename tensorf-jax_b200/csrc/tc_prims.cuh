@@ -61,6 +61,20 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
                : "memory");
 }
 
+// The same with an L2 eviction policy: streams that are read once (residual tiles of the weight-gradient kernel) are marked
+// evict-first so that they do not push the factor / gradient planes of a scatter kernel running beside them out of the L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_copy_g2s_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+
 // TMA tiled load (UTMALDG): one 2-D box of a tensor map -> shared memory, completion on an mbarrier.
 // c0 = innermost (column) coordinate, c1 = row coordinate, in elements; out-of-bounds parts are zero-filled.
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
