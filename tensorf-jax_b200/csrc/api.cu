@@ -76,6 +76,11 @@ static SideStream* side_stream() {
   return &s;
 }
 
+int pdl_level() {
+  static const int lv = getenv("TENSORF_PDL") != nullptr ? atoi(getenv("TENSORF_PDL")) : 2;
+  return lv;
+}
+
 static inline int64_t al(int64_t floats) { return round_up64(floats, 64); }  // 256-byte granules
 
 struct RenderWs {
@@ -474,6 +479,17 @@ int tensorf_render_rgb_fwd(tensorf_stream_t s, const tensorf_render_desc* d, con
   TF_RETURN_IF_ERROR(mlp_pick(*d, ms, &mlp_impl));
   const int64_t M = (int64_t)d->R * d->K;
 
+  // Programmatic dependent launch of the fused MLP kernels (their set-up - 166 KB of weights into shared memory, tensor
+  // memory, barriers - overlaps the tail of the kernel before them).  The weights are packed first thing, so that the only
+  // output of its predecessor the forward kernel waits for are the feature tiles.
+  if (in->colors) TF_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));  // (not between two kernels of the chain)
+  MlpWs mws = mlp_ws_carve(ms, M, w.mlp_base);
+  if (mlp_impl == TENSORF_MLP_FUSED && pdl_enabled() && M > 0) {
+    StageTimer t_(st, "mlp_pack");
+    TF_RETURN_IF_ERROR(mlp_fused_pack(st, ms, mlp_params(*p), mws));
+    mws.wpack_ready = true;
+    mws.pdl = true;
+  }
   if (!packed) {
     StageTimer t_(st, "pack");
     TF_RETURN_IF_ERROR(vm_pack2(st, p->density_vector, p->density_matrix, w.packed_d, d->cd, p->appearance_vector,
@@ -511,7 +527,6 @@ int tensorf_render_rgb_fwd(tensorf_stream_t s, const tensorf_render_desc* d, con
     TF_RETURN_IF_ERROR(launch_appearance(st, ap, false));
   }
 
-  MlpWs mws = mlp_ws_carve(ms, M, w.mlp_base);
   if (mlp_impl == TENSORF_MLP_FUSED) mws.feat_slabs = reinterpret_cast<const unsigned char*>(w.feat);  // written by k_appearance
   {
     StageTimer t_(st, "mlp_fwd");
@@ -519,7 +534,6 @@ int tensorf_render_rgb_fwd(tensorf_stream_t s, const tensorf_render_desc* d, con
                                                                               in->camera_indices, M, d->K, mws, w.rgb_sel));
   }
   StageTimer t_(st, "composite");
-  if (in->colors) TF_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
   CompositeArgs c{};
   c.rgb_sel = w.rgb_sel;
   c.pt_sel = w.pt_sel;
@@ -661,6 +675,7 @@ static int render_rgb_bwd_impl(tensorf_stream_t s, const tensorf_render_desc* d,
     mg.prezeroed = true;  // by k_ray_bwd above
     mg.amax_ready = true;
     mws.beside_scatter = true;
+    mws.pdl = true;
     // Launch order = placement order: the MLP kernels are launched first so that their one CTA per SM is resident
     // everywhere (chain: 576 threads x 72 registers, weight gradients: 192 x 98) and the scatter CTAs fill what is left of
     // the register file (one / two density-scatter CTAs per SM instead of three; the scatters use no shared memory).
@@ -712,6 +727,8 @@ static int render_rgb_bwd_impl(tensorf_stream_t s, const tensorf_render_desc* d,
     if (do_app) {
       MlpWs mws = mlp_ws_carve(ms, M, w.mlp_base);
       if (mlp_impl == TENSORF_MLP_FUSED) mws.feat_slabs = reinterpret_cast<const unsigned char*>(w.feat);  // written by k_appearance
+      // with stage timers on, time the kernel variants of the forked pass (which the timers alone keep this call from using)
+      mws.beside_scatter = g_prof.on && phase == 0 && !getenv("TENSORF_NO_FORK");
       {
         StageTimer t_(st, "mlp_bwd");
         MlpGrads mg = mlp_grads(*grads);

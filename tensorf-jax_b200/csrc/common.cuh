@@ -27,6 +27,32 @@ void set_error(const char* fmt, ...);  // thread-local message, api.cu
     }                                                                                     \
   } while (0)
 
+// Programmatic dependent launch.  A kernel launched through launch_pdl may be scheduled while the kernel before it in the
+// stream drains (its set-up overlaps that tail, and the launch latency disappears); it calls pdl_wait() before it touches
+// anything its predecessor wrote or reads - a no-op under a normal launch - and every CTA calls it, so that completion of
+// the kernel implies completion of everything before it.  pdl_launch_dependents() in a kernel lets its successor's CTAs be
+// scheduled as SMs free up instead of when the whole grid has exited.  Captured into CUDA graphs as programmatic edges.
+int pdl_level();  // api.cu: TENSORF_PDL = 0 off, 1 the two fused MLP row kernels only, 2 (default) the per-ray kernels too
+inline bool pdl_enabled() { return pdl_level() > 0; }
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename A>
+inline cudaError_t launch_pdl(void (*kernel)(A), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const A& arg, bool pdl = true, int level = 1) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_level() >= level) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, arg);
+}
+#endif
+
 // Launch errors are collected right after enqueue; no device synchronisation.
 void count_launch();  // thread-local kernel-launch counter (tensorf_launch_count), api.cu
 #define TF_CHECK_LAUNCH()               \

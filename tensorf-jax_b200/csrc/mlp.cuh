@@ -44,6 +44,7 @@ struct MlpWs {
   float* aux;       // fused path: [64] scalars (gradient scale), then the d(output) slab tiles (M, 16)
   float* wg_partial;  // fused path: per-CTA partial weight-gradient accumulators [min(tiles, 148)][320 + 3ca][128]
   bool wpack_ready = false;  // fused path: the caller has already run mlp_fused_pack on this workspace (on a side stream)
+  bool pdl = false;  // fused path: launch the row kernels as programmatic dependents of the kernel before them in the stream
   bool beside_scatter = false;  // fused path: the weight-gradient kernel shares the GPU with a scatter kernel (forked reverse pass)
   const unsigned char* feat_slabs = nullptr;  // fused path: the feature rows already as slab tiles (render path: written by
                                               // k_appearance); null = `feat` is fp32 (M, 3ca) and is converted into `dx`

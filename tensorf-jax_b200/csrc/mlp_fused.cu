@@ -419,6 +419,7 @@ __device__ __forceinline__ void fused_fwd_worker(const FusedFwdArgs& g, int Q, u
 
 template <bool TRAIN>
 __global__ void __launch_bounds__(fz::kThreads, 1) k_mlp_fused_fwd(FusedFwdArgs g) {
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint64_t* wfull = reinterpret_cast<uint64_t*>(smem);
@@ -470,6 +471,7 @@ __global__ void __launch_bounds__(fz::kThreads, 1) k_mlp_fused_fwd(FusedFwdArgs 
       mbar_arrive_expect_tx(wfull, wbytes);
       for (uint32_t off = 0; off < wbytes; off += 16384u)
         bulk_copy_g2s(sW + off, g.wpack + off, min(16384u, wbytes - off), wfull);
+      pdl_wait();  // the feature tiles are the predecessor's output (the weights were packed earlier in the stream)
       uint32_t sl = 0, ph = 0;
       for (int64_t it = 0; it < my_tiles; ++it) {
         const unsigned char* tile = g.feats + (size_t)(blockIdx.x + it * gridDim.x) * ((size_t)g.K0 * 512);
@@ -608,10 +610,10 @@ int mlp_fused_fwd(cudaStream_t st, const MlpShape& s, const MlpParams& p, const 
   const unsigned grid = (unsigned)std::min<int64_t>((M + 127) / 128, kSMs);
   if (train) {
     TF_CHECK_CUDA(cudaFuncSetAttribute(k_mlp_fused_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_mlp_fused_fwd<true><<<grid, fz::kThreads, smem, st>>>(g);
+    TF_CHECK_CUDA(launch_pdl(k_mlp_fused_fwd<true>, dim3(grid), dim3(fz::kThreads), smem, st, g, ws.pdl));
   } else {
     TF_CHECK_CUDA(cudaFuncSetAttribute(k_mlp_fused_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_mlp_fused_fwd<false><<<grid, fz::kThreads, smem, st>>>(g);
+    TF_CHECK_CUDA(launch_pdl(k_mlp_fused_fwd<false>, dim3(grid), dim3(fz::kThreads), smem, st, g, ws.pdl));
   }
   TF_CHECK_LAUNCH();
   return 0;
@@ -673,6 +675,7 @@ __device__ __forceinline__ void fused_bwd_worker(const FusedBwdArgs& g, int Q, u
   const int row = quad * 32 + lane;
   const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
   const uint32_t aop = lane_base + fz::kBAop;
+  pdl_wait();  // d_rgb, max|d_rgb| and the zeroed db3 are the predecessor's (k_ray_bwd's) output
   float S, invS;
   grad_scale(g.amax, S, invS);
   const int nk0 = g.K0 / 16;
@@ -1193,7 +1196,7 @@ int mlp_fused_bwd_chain(cudaStream_t st, const MlpShape& s, const MlpParams& p, 
   const size_t smem_b = fz::kHeader + mlp_fused_wpack_bytes(s);
   const unsigned grid = (unsigned)std::min<int64_t>((M + 127) / 128, kSMs);
   TF_CHECK_CUDA(cudaFuncSetAttribute(k_mlp_fused_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-  k_mlp_fused_bwd<<<grid, fz::kBwdThreads, smem_b, st>>>(b);
+  TF_CHECK_CUDA(launch_pdl(k_mlp_fused_bwd, dim3(grid), dim3(fz::kBwdThreads), smem_b, st, b, ws.pdl));
   TF_CHECK_LAUNCH();
   return 0;
 }

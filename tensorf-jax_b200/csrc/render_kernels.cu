@@ -400,6 +400,9 @@ __global__ void __launch_bounds__(256) k_appearance(AppearanceArgs A) {
 // Needs C % 8 == 0.  Rows M..ceil128(M) are written as zeros (they must be finite).
 constexpr int kSlabRows = 32, kSlabPitch = kSlabRows * 16 + 16;  // +16: column groups land on different banks
 __global__ void __launch_bounds__(384, 3) k_appearance_slab(AppearanceArgs A) {  // blockDim = 32 rows x C/4 items: one item per thread
+  // (this kernel itself is launched normally: as a programmatic dependent its 3 CTAs per SM sit on the SMs of
+  //  k_density_select's last wave while they wait - measured 11 us slower per step)
+  pdl_launch_dependents();  // the fused MLP kernel may load its weights while this grid's last wave drains
   extern __shared__ __align__(16) unsigned char sm_slab[];
   const int nvec = A.C >> 2, Ca = 3 * A.C, nslab = (Ca >> 3) * 2;
   const int64_t m0 = (int64_t)blockIdx.x * kSlabRows;
@@ -471,6 +474,8 @@ int launch_appearance(cudaStream_t st, const AppearanceArgs& A, bool bwd) {
 // composite (render.py:233-246, :529-546) + fused MSE (training.py:140)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_composite_fwd(CompositeArgs A) {
+  pdl_launch_dependents();
+  pdl_wait();  // rgb of the MLP kernel before this one
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = blockIdx.x * 4 + warp;
   __shared__ float loss_part[4];
@@ -512,7 +517,7 @@ __global__ void __launch_bounds__(128) k_composite_fwd(CompositeArgs A) {
 
 int launch_composite_fwd(cudaStream_t st, const CompositeArgs& A) {
   if (A.R == 0) return 0;
-  k_composite_fwd<<<(A.R + 3) / 4, 128, 0, st>>>(A);
+  TF_CHECK_CUDA(launch_pdl(k_composite_fwd, dim3((unsigned)((A.R + 3) / 4)), dim3(128), 0, st, A, true, 2));
   TF_CHECK_LAUNCH();
   return 0;
 }
@@ -521,6 +526,8 @@ int launch_composite_fwd(cudaStream_t st, const CompositeArgs& A) {
 // k_ray_bwd: reverse of composite/unbias/segment probabilities
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_ray_bwd(RayBwdArgs A) {
+  pdl_launch_dependents();  // the reverse MLP kernel may set itself up while this grid drains (it waits before reading)
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Npad = round_up(A.N, 32);
@@ -629,7 +636,7 @@ int launch_ray_bwd(cudaStream_t st, const RayBwdArgs& A) {
   }
   size_t smem = 4 * (size_t)2 * round_up(A.N, 32) * sizeof(float);
   if (smem > 48 * 1024) TF_CHECK_CUDA(cudaFuncSetAttribute(k_ray_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_ray_bwd<<<(A.R + 3) / 4, 128, smem, st>>>(A);
+  TF_CHECK_CUDA(launch_pdl(k_ray_bwd, dim3((unsigned)((A.R + 3) / 4)), dim3(128), smem, st, A, true, 2));
   TF_CHECK_LAUNCH();
   return 0;
 }
