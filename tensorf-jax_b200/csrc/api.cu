@@ -665,6 +665,7 @@ static int render_rgb_bwd_impl(tensorf_stream_t s, const tensorf_render_desc* d,
     ap.M = M;
     ap.d_feat = w.d_feat;
     ap.d_packed = w.gpacked_a;
+    ap.beside_mlp = fork || (g_prof.on && phase == 0 && mlp_impl == TENSORF_MLP_FUSED && !getenv("TENSORF_NO_FORK"));
     StageTimer t_(s_, "appearance_scatter");
     return launch_appearance_scatter(s_, ap);
   };

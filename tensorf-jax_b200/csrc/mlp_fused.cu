@@ -986,11 +986,9 @@ __global__ void __launch_bounds__(1024) k_wgrad_reduce(WgradReduceArgs a) {
   }
 }
 
-#ifdef TF_WG_MAXREG
-__global__ void __maxnreg__(TF_WG_MAXREG) k_mlp_fused_wgrad(FusedWgradArgs g) {
-#else
-__global__ void __launch_bounds__(fz::kWgThreads, 1) k_mlp_fused_wgrad(FusedWgradArgs g) {
-#endif
+// 64-register cap (48 used, no spills; 98 without it): 192 x 48 registers leave room for two 96-register CTAs of the
+// appearance scatter on the same SM (forked reverse pass).
+__global__ void __maxnreg__(64) k_mlp_fused_wgrad(FusedWgradArgs g) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint64_t* afull = reinterpret_cast<uint64_t*>(smem);  // [2]

@@ -660,16 +660,15 @@ struct WalkArgs : SceneArgs {
   const int32_t* idx;   // appearance
   const float* d_feat;  // appearance (M, 3C)
   int C, Cp, seg_len, segs, count;  // count = N (density) or K (appearance)
+  bool slim;                         // appearance: the 96-register variant (runs beside the fused MLP's weight-gradient kernel)
 };
 
-#ifndef TF_SW_MINB
-#define TF_SW_MINB 2  // measured on B200: 2 -> step 1.318 ms; 1: 1.409; 3: 1.354; 4: 1.393
-#endif
-#ifndef TF_DSW_MINB
-#define TF_DSW_MINB 3
-#endif
-template <int LPS, bool APP>
-__global__ void __launch_bounds__(256, APP ? 2 : TF_DSW_MINB) k_scatter_walk(WalkArgs A) {  // measured: density 3 CTAs/SM, appearance 2
+// Register budgets (256 threads): density 80 = 3 CTAs per SM; appearance 128 (114 used) = 2 CTAs per SM when the kernel has
+// the GPU to itself, and SLIM = 96 for the forked reverse pass, where TWO of its CTAs then fit beside the weight-gradient
+// kernel's CTA (192 threads x 48 registers): alone the slim variant is 12 us slower (0.094 -> 0.106 ms), beside that kernel
+// the step is 15 us faster.  (Density at 72 or 76 registers - three CTAs beside the weight-gradient kernel - spills and loses.)
+template <int LPS, bool APP, bool SLIM = false>
+__global__ void __maxnreg__(APP ? (SLIM ? 96 : 128) : 80) k_scatter_walk(WalkArgs A) {  // measured: density 3 CTAs/SM, appearance 2
   const int nvec = A.Cp >> 2;
   const int vblocks = (nvec + LPS - 1) / LPS;
   const int sub = threadIdx.x % LPS;
@@ -883,10 +882,14 @@ static int launch_walk(cudaStream_t st, WalkArgs A) {
   const int vblocks = (nvec + lps - 1) / lps;
   int64_t items = (int64_t)A.R * A.segs * 3 * vblocks;
   unsigned grid = (unsigned)ceil_div64(items, 256 / lps);
-  switch (lps) {
-    case 4: k_scatter_walk<4, APP><<<grid, 256, 0, st>>>(A); break;
-    case 2: k_scatter_walk<2, APP><<<grid, 256, 0, st>>>(A); break;
-    default: k_scatter_walk<1, APP><<<grid, 256, 0, st>>>(A); break;
+  if (APP && A.slim && lps == 4) {
+    k_scatter_walk<4, APP, APP><<<grid, 256, 0, st>>>(A);
+  } else {
+    switch (lps) {
+      case 4: k_scatter_walk<4, APP><<<grid, 256, 0, st>>>(A); break;
+      case 2: k_scatter_walk<2, APP><<<grid, 256, 0, st>>>(A); break;
+      default: k_scatter_walk<1, APP><<<grid, 256, 0, st>>>(A); break;
+    }
   }
   TF_CHECK_LAUNCH();
   return 0;
@@ -916,6 +919,7 @@ int launch_appearance_scatter(cudaStream_t st, const AppearanceArgs& D) {
   A.C = D.C;
   A.Cp = D.Cp;
   A.count = D.K;
+  A.slim = D.beside_mlp;
   return launch_walk<true>(st, A);
 }
 

@@ -38,6 +38,7 @@ struct AppearanceArgs : SceneArgs {
   bool feat_slabs;
   const float* d_feat;   // bwd
   float* d_packed;       // bwd (+=)
+  bool beside_mlp = false;  // bwd: launched beside the fused MLP's weight-gradient kernel (forked reverse pass): 96-register variant
 };
 
 struct CompositeArgs {

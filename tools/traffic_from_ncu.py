@@ -7,7 +7,7 @@ import csv, json, re, sys
 
 STAGE = [  # kernel-name regex -> bench.py stage (api.cu StageTimer names)
     (r"k_density_select", "density_select"), (r"k_appearance_slab|k_appearance<0>|k_appearance<false>", "appearance_gather"),
-    (r"k_scatter_walk<4, ?0>|k_scatter_walk<4, ?false>", "density_scatter"), (r"k_scatter_walk<4, ?1>|k_scatter_walk<4, ?true>", "appearance_scatter"),
+    (r"k_scatter_walk<\d, ?(0|false)[,>]", "density_scatter"), (r"k_scatter_walk<\d, ?(1|true)[,>]", "appearance_scatter"),
     (r"k_fused_pack", "mlp_pack"), (r"k_mlp_fused_fwd", "mlp_fwd"), (r"k_mlp_fused_bwd|k_mlp_fused_wgrad|k_wgrad_reduce|k_fused_amax", "mlp_bwd"),
     (r"k_tc_rowgemm<3|k_encode_fwd|k_pack_all", "mlp_fwd"), (r"k_tc_rowgemm<2|k_tc_redgemm|k_encode_bwd|k_out_bwd", "mlp_bwd"),
     (r"k_composite_fwd", "composite"), (r"k_ray_bwd", "ray_bwd"), (r"k_pack<0", "pack"), (r"k_pack<1", "unpack"),
