@@ -663,17 +663,20 @@ struct WalkArgs : SceneArgs {
   bool slim;                         // appearance: the 96-register variant (runs beside the fused MLP's weight-gradient kernel)
 };
 
-// Register budgets (256 threads): density 80 = 3 CTAs per SM; appearance 128 (114 used) = 2 CTAs per SM when the kernel has
-// the GPU to itself, and SLIM = 96 for the forked reverse pass, where TWO of its CTAs then fit beside the weight-gradient
-// kernel's CTA (192 threads x 48 registers): alone the slim variant is 12 us slower (0.094 -> 0.106 ms), beside that kernel
-// the step is 15 us faster.  (Density at 72 or 76 registers - three CTAs beside the weight-gradient kernel - spills and loses.)
+// Register budgets: density 80 (768 threads per SM); appearance 128 (114 used; 512 threads per SM) when the kernel has the
+// GPU to itself, and SLIM = 96 for the forked reverse pass, where 512 of its threads then fit beside the weight-gradient
+// kernel's CTA (192 threads x 48 registers) instead of 256: alone the slim variant is 12 us slower (0.094 -> 0.106 ms),
+// beside that kernel the step is 15 us faster.  (Density at 72 or 76 registers spills and loses.)
+// CTA size (launch_walk): 64 threads for the density walk, 128 for the appearance walk - small CTAs fill the register
+// file left over by the MLP kernels at a finer grain and shorten the tail: 256 -> 64 / 128 threads took another 18 us off
+// the step (the density walk alone: 0.152 -> 0.144 ms).
 template <int LPS, bool APP, bool SLIM = false>
 __global__ void __maxnreg__(APP ? (SLIM ? 96 : 128) : 80) k_scatter_walk(WalkArgs A) {  // measured: density 3 CTAs/SM, appearance 2
   const int nvec = A.Cp >> 2;
   const int vblocks = (nvec + LPS - 1) / LPS;
   const int sub = threadIdx.x % LPS;
   const int per_ray = A.segs * 3 * vblocks;
-  int64_t item = (int64_t)blockIdx.x * (256 / LPS) + threadIdx.x / LPS;
+  int64_t item = (int64_t)blockIdx.x * (blockDim.x / LPS) + threadIdx.x / LPS;
   if (item >= (int64_t)A.R * per_ray) return;
   const int r = (int)(item / per_ray);
   int rem = (int)(item % per_ray);
@@ -881,14 +884,19 @@ static int launch_walk(cudaStream_t st, WalkArgs A) {
   A.segs = (A.count + A.seg_len - 1) / A.seg_len;
   const int vblocks = (nvec + lps - 1) / lps;
   int64_t items = (int64_t)A.R * A.segs * 3 * vblocks;
-  unsigned grid = (unsigned)ceil_div64(items, 256 / lps);
-  if (APP && A.slim && lps == 4) {
-    k_scatter_walk<4, APP, APP><<<grid, 256, 0, st>>>(A);
+  // tuning switches: TENSORF_DSW_BLOCK / TENSORF_ASW_BLOCK (CTA size of the density / appearance walk), TENSORF_ASW_SLIM=0
+  static const int den_block = getenv("TENSORF_DSW_BLOCK") ? atoi(getenv("TENSORF_DSW_BLOCK")) : 64;
+  static const int app_block = getenv("TENSORF_ASW_BLOCK") ? atoi(getenv("TENSORF_ASW_BLOCK")) : 128;
+  const int block = APP ? app_block : den_block;
+  unsigned grid = (unsigned)ceil_div64(items, block / lps);
+  static const int slim_env = getenv("TENSORF_ASW_SLIM") ? atoi(getenv("TENSORF_ASW_SLIM")) : 1;
+  if (APP && A.slim && slim_env && lps == 4) {
+    k_scatter_walk<4, APP, APP><<<grid, block, 0, st>>>(A);
   } else {
     switch (lps) {
-      case 4: k_scatter_walk<4, APP><<<grid, 256, 0, st>>>(A); break;
-      case 2: k_scatter_walk<2, APP><<<grid, 256, 0, st>>>(A); break;
-      default: k_scatter_walk<1, APP><<<grid, 256, 0, st>>>(A); break;
+      case 4: k_scatter_walk<4, APP><<<grid, block, 0, st>>>(A); break;
+      case 2: k_scatter_walk<2, APP><<<grid, block, 0, st>>>(A); break;
+      default: k_scatter_walk<1, APP><<<grid, block, 0, st>>>(A); break;
     }
   }
   TF_CHECK_LAUNCH();
